@@ -1,0 +1,71 @@
+"""MetricCalculator / CalculateResult -- mirrors the reference's calculator.py
+(/root/reference/open_pcc_metric/calculator.py:15-108): recursive, memoised
+resolution of the metric graph and the result table.
+
+Deviations, both deliberate:
+* the memo is PER INSTANCE.  In the reference it is a class attribute
+  (calculator.py:60, quirk Q2), so a second calculator in one process returns the
+  first pair's values; sequence evaluation needs the per-instance form.
+* reductions that the GPU already produced are taken from ``calculate_fused``
+  before the dependency graph is walked (``use_fused=False`` restores the pure
+  graph walk over per-point arrays).
+"""
+from __future__ import annotations
+
+import typing
+
+import pandas as pd
+
+from .cloud_pair import CloudPair
+from .metric import AbstractMetric, PrimaryMetric, SecondaryMetric, SymmetricMetric
+
+
+class CalculateResult:
+    def __init__(self, metrics: typing.List[AbstractMetric]):
+        self._metrics = metrics
+
+    def as_dict(self) -> typing.Dict[tuple, typing.Any]:
+        return {m._key(): m.value for m in self._metrics}
+
+    def as_df(self) -> pd.DataFrame:
+        rows = {"label": [], "is_left": [], "point-to-plane": [], "value": []}
+        for m in self._metrics:
+            label = type(m).__name__
+            if isinstance(m, SymmetricMetric):
+                label = type(m.metrics[0]).__name__ + "(symmetric)"
+            rows["label"].append(label)
+            rows["is_left"].append(getattr(m, "is_left", ""))
+            rows["point-to-plane"].append(getattr(m, "point_to_plane", ""))
+            rows["value"].append(str(m.value))
+        return pd.DataFrame(rows)
+
+    def __str__(self) -> str:
+        return str(self.as_df())
+
+
+class MetricCalculator:
+    def __init__(self, cloud_pair: CloudPair, use_fused: bool = True):
+        self._cloud_pair = cloud_pair
+        self._calculated_metrics: typing.Dict[tuple, AbstractMetric] = {}
+        self._use_fused = use_fused and hasattr(cloud_pair, "fused")
+
+    def _metric_recursive_calculate(self, metric: AbstractMetric) -> AbstractMetric:
+        key = metric._key()
+        done = self._calculated_metrics.get(key)
+        if done is not None:
+            return done
+        if isinstance(metric, PrimaryMetric):
+            metric.calculate(self._cloud_pair)
+        elif isinstance(metric, SecondaryMetric):
+            fused = getattr(metric, "calculate_fused", None) if self._use_fused else None
+            if fused is None or not fused(self._cloud_pair):
+                deps = {name: self._metric_recursive_calculate(dep)
+                        for name, dep in metric._get_dependencies().items()}
+                metric.calculate(**deps)
+        else:
+            raise RuntimeError(f"Metric of unknown AbstractMetric subclass {type(metric).__name__}")
+        self._calculated_metrics[key] = metric
+        return metric
+
+    def calculate(self, metrics_list: typing.List[AbstractMetric]) -> CalculateResult:
+        return CalculateResult([self._metric_recursive_calculate(m) for m in metrics_list])

@@ -1,0 +1,925 @@
+// pccm_api.cu -- host orchestration + C ABI (include/pccm.h) of libpccm.so.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared ...
+// There is no CPU path: every entry point needs a CUDA device.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pccm_kernels.cuh"
+
+using namespace pccm;
+
+// --------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------
+struct PendingTimer {
+    cudaEvent_t a, b;
+    double* dest;
+};
+
+struct pccm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int profiling = 0;
+    pccm_timings tm{};
+    std::vector<PendingTimer> pending;
+    std::vector<cudaEvent_t> event_pool;
+    // per-point outputs of the last pair_eval
+    int32_t* pp_idx[2] = {nullptr, nullptr};
+    double* pp_d2[2] = {nullptr, nullptr};
+    int64_t pp_n[2] = {0, 0};
+    // small pinned + device scratch for result structs
+    void* pinned = nullptr;
+    void* dscratch = nullptr;
+    static constexpr size_t kScratch = 1 << 16;
+    int sm_count = 148;
+    int cell_override_shift = -1;   // debugging: PCCM_CELL_SHIFT
+    double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
+};
+
+static thread_local std::string g_err;
+
+static int fail(pccm_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, PCCM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct StageTimer {
+    pccm_ctx* ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    double* dest;
+    bool on;
+    StageTimer(pccm_ctx* c, double* d, int level = 2) : ctx(c), dest(d), on(c->profiling >= level) {
+        if (!on) return;
+        a = get();
+        b = get();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->pending.push_back({a, b, dest});
+    }
+    cudaEvent_t get() {
+        if (!ctx->event_pool.empty()) {
+            cudaEvent_t e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+static void resolve_timers(pccm_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) *p.dest += ms;
+        ctx->event_pool.push_back(p.a);
+        ctx->event_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+template <class T>
+static cudaError_t dalloc(pccm_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMallocAsync(reinterpret_cast<void**>(p), count * sizeof(T), ctx->stream);
+}
+static void dfree(pccm_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// --------------------------------------------------------------------------------------
+// cloud
+// --------------------------------------------------------------------------------------
+struct pccm_cloud {
+    int64_t n = 0;
+    // raw input, alive until the index is built
+    const void* raw_xyz = nullptr;
+    void* raw_owned = nullptr;
+    int raw_dtype = PCCM_F64;
+    int64_t raw_stride = 0;
+    // raw colours until classified
+    const void* raw_rgb = nullptr;
+    void* raw_rgb_owned = nullptr;
+    int raw_rgb_dtype = PCCM_F64;
+    int64_t raw_rgb_stride = 0;
+    // statistics
+    StatsPartial* d_stats = nullptr;
+    StatsPartial* h_stats = nullptr;  // pinned
+    int stats_blocks = 0;
+    cudaEvent_t stats_done = nullptr;
+    bool stats_ready = false;
+    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    int data_kind = PCCM_KIND_F64;
+    bool rgb_u8_ok = false;
+    // attributes (original order)
+    uchar4* rgb_u8 = nullptr;
+    double* rgb_f64 = nullptr;
+    double* normals = nullptr;
+    bool has_colors = false, has_normals = false;
+    // index
+    int index_kind = -1;
+    RowGrid grid{};
+    void* recs = nullptr;
+    uint32_t* row_start = nullptr;
+    double cell_size = 0;
+};
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case PCCM_F64: return 8;
+        case PCCM_F32: return 4;
+        case PCCM_I32: return 4;
+        case PCCM_U16: return 2;
+        case PCCM_U8: return 1;
+    }
+    return 0;
+}
+
+static int ensure_stats(pccm_ctx* ctx, pccm_cloud* c) {
+    if (c->stats_ready) return PCCM_OK;
+    if (c->n == 0) {
+        c->data_kind = PCCM_KIND_INT;
+        c->stats_ready = true;
+        return PCCM_OK;
+    }
+    CK(cudaEventSynchronize(c->stats_done));
+    bool not_int = false, not_f32 = false, not_fin = false, rgb_bad = false;
+    for (int a = 0; a < 3; ++a) { c->mn[a] = INFINITY; c->mx[a] = -INFINITY; }
+    for (int b = 0; b < c->stats_blocks; ++b) {
+        const StatsPartial& p = c->h_stats[b];
+        for (int a = 0; a < 3; ++a) { c->mn[a] = std::min(c->mn[a], p.mn[a]); c->mx[a] = std::max(c->mx[a], p.mx[a]); }
+        not_int |= p.not_int != 0; not_f32 |= p.not_f32 != 0; not_fin |= p.not_finite != 0; rgb_bad |= p.rgb_not_u8 != 0;
+    }
+    if (not_fin) return fail(ctx, PCCM_ERR_NONFINITE, "cloud has NaN or Inf coordinates");
+    c->data_kind = !not_int ? PCCM_KIND_INT : (!not_f32 ? PCCM_KIND_F32 : PCCM_KIND_F64);
+    c->rgb_u8_ok = !rgb_bad;
+    c->stats_ready = true;
+    return PCCM_OK;
+}
+
+// colours: uchar4 when every channel is k/255, else packed float64
+static int finish_colors(pccm_ctx* ctx, pccm_cloud* c) {
+    if (!c->has_colors || c->rgb_u8 || c->rgb_f64 || c->n == 0) return PCCM_OK;
+    const int threads = 256;
+    const int blocks = (int)((c->n + threads - 1) / threads);
+    if (c->raw_rgb_dtype == PCCM_U8 || c->rgb_u8_ok) {
+        CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n));
+        pack_rgb_u8_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->n, c->rgb_u8);
+    } else {
+        CK(dalloc(ctx, &c->rgb_f64, (size_t)c->n * 3));
+        pack_f64x3_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, PCCM_F64, c->raw_rgb_stride, c->n, c->rgb_f64);
+    }
+    ctx->tm.total_launches++;
+    CK(cudaGetLastError());
+    dfree(ctx, c->raw_rgb_owned);
+    c->raw_rgb_owned = nullptr;
+    c->raw_rgb = nullptr;
+    return PCCM_OK;
+}
+
+static int upload_rows(pccm_ctx* ctx, const void* src, int dtype, int64_t n, int64_t* stride, int mem_kind,
+                       const void** dev, void** owned) {
+    const size_t es = dtype_size(dtype);
+    if (es == 0) return fail(ctx, PCCM_ERR_INVALID, "bad dtype %d", dtype);
+    if (*stride == 0) *stride = (int64_t)(3 * es);
+    if (*stride < (int64_t)(3 * es) || (*stride % (int64_t)es) != 0) return fail(ctx, PCCM_ERR_INVALID, "bad row stride %lld", (long long)*stride);
+    *owned = nullptr;
+    if (mem_kind == PCCM_DEVICE) {
+        *dev = src;
+        return PCCM_OK;
+    }
+    unsigned char* d = nullptr;
+    const size_t bytes = (size_t)n * (size_t)*stride;
+    CK(dalloc(ctx, &d, bytes));
+    CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = d;
+    *owned = d;
+    return PCCM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// C ABI: context
+// --------------------------------------------------------------------------------------
+extern "C" int pccm_version(void) { return PCCM_VERSION; }
+
+extern "C" const char* pccm_last_error(const pccm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
+    pccm_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, PCCM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, PCCM_ERR_CUDA, "no CUDA device (%s); libpccm has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, PCCM_ERR_INVALID, "device %d out of range (%d)", device, count);
+    ctx = new pccm_ctx();
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, PCCM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return fail(nullptr, PCCM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        ctx->own_stream = true;
+    }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMallocHost(&ctx->pinned, pccm_ctx::kScratch) != cudaSuccess || cudaMalloc(&ctx->dscratch, pccm_ctx::kScratch) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, PCCM_ERR_CUDA, "scratch allocation failed");
+    }
+    if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
+    if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
+    *out = ctx;
+    return PCCM_OK;
+}
+
+extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
+    if (!ctx) return PCCM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    resolve_timers(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (int d = 0; d < 2; ++d) { dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]); }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(ctx->pinned);
+    cudaFree(ctx->dscratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PCCM_OK;
+}
+
+extern "C" int pccm_ctx_synchronize(pccm_ctx* ctx) {
+    if (!ctx) return fail(nullptr, PCCM_ERR_INVALID, "ctx is NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PCCM_OK;
+}
+extern "C" int pccm_ctx_set_profiling(pccm_ctx* ctx, int level) {
+    if (!ctx) return fail(nullptr, PCCM_ERR_INVALID, "ctx is NULL");
+    ctx->profiling = level;
+    return PCCM_OK;
+}
+extern "C" int pccm_ctx_reset_timings(pccm_ctx* ctx) {
+    if (!ctx) return fail(nullptr, PCCM_ERR_INVALID, "ctx is NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    resolve_timers(ctx);
+    ctx->tm = pccm_timings{};
+    return PCCM_OK;
+}
+extern "C" int pccm_ctx_get_timings(pccm_ctx* ctx, pccm_timings* out) {
+    if (!ctx || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaStreamSynchronize(ctx->stream));
+    resolve_timers(ctx);
+    *out = ctx->tm;
+    return PCCM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// C ABI: cloud
+// --------------------------------------------------------------------------------------
+extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
+    if (!ctx || !c) return PCCM_OK;
+    cudaSetDevice(ctx->device);
+    dfree(ctx, c->raw_owned);
+    dfree(ctx, c->raw_rgb_owned);
+    dfree(ctx, c->d_stats);
+    dfree(ctx, c->rgb_u8);
+    dfree(ctx, c->rgb_f64);
+    dfree(ctx, c->normals);
+    dfree(ctx, c->recs);
+    dfree(ctx, c->row_start);
+    if (c->h_stats) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(c->h_stats);
+    }
+    if (c->stats_done) cudaEventDestroy(c->stats_done);
+    delete c;
+    return PCCM_OK;
+}
+
+static int set_normals_impl(pccm_ctx* ctx, pccm_cloud* c, const void* normals, int dtype, int64_t stride, int mem_kind) {
+    if (dtype != PCCM_F64 && dtype != PCCM_F32) return fail(ctx, PCCM_ERR_INVALID, "normals must be F64 or F32");
+    const void* dev = nullptr;
+    void* owned = nullptr;
+    int rc = upload_rows(ctx, normals, dtype, c->n, &stride, mem_kind, &dev, &owned);
+    if (rc) return rc;
+    if (!c->normals) CK(dalloc(ctx, &c->normals, (size_t)c->n * 3));
+    if (c->n) {
+        pack_f64x3_kernel<<<(int)((c->n + 255) / 256), 256, 0, ctx->stream>>>(dev, dtype, stride, c->n, c->normals);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    dfree(ctx, owned);
+    c->has_normals = true;
+    return PCCM_OK;
+}
+
+extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, int64_t n, int64_t xyz_stride,
+                                 const void* rgb, int rgb_dtype, int64_t rgb_stride,
+                                 const void* normals, int nrm_dtype, int64_t nrm_stride,
+                                 int mem_kind, pccm_cloud** out) {
+    if (!ctx || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (n < 0 || n > 0x7fffffffLL) return fail(ctx, PCCM_ERR_INVALID, "n=%lld out of range", (long long)n);
+    if (n > 0 && !xyz) return fail(ctx, PCCM_ERR_INVALID, "xyz is NULL");
+    if (xyz_dtype == PCCM_U8 || dtype_size(xyz_dtype) == 0) return fail(ctx, PCCM_ERR_INVALID, "bad xyz dtype %d", xyz_dtype);
+    if (rgb && rgb_dtype != PCCM_F64 && rgb_dtype != PCCM_U8) return fail(ctx, PCCM_ERR_INVALID, "rgb must be F64 or U8");
+    CK(cudaSetDevice(ctx->device));
+    pccm_cloud* c = new pccm_cloud();
+    c->n = n;
+    int rc = PCCM_OK;
+    {
+        StageTimer t(ctx, &ctx->tm.upload_ms);
+        c->raw_dtype = xyz_dtype;
+        c->raw_stride = xyz_stride;
+        if (n) rc = upload_rows(ctx, xyz, xyz_dtype, n, &c->raw_stride, mem_kind, &c->raw_xyz, &c->raw_owned);
+        if (!rc && rgb && n) {
+            c->raw_rgb_dtype = rgb_dtype;
+            c->raw_rgb_stride = rgb_stride;
+            rc = upload_rows(ctx, rgb, rgb_dtype, n, &c->raw_rgb_stride, mem_kind, &c->raw_rgb, &c->raw_rgb_owned);
+        }
+        c->has_colors = rgb != nullptr;
+        if (!rc && normals) rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind);
+    }
+    if (rc) { pccm_cloud_destroy(ctx, c); return rc; }
+    if (n) {
+        StageTimer t(ctx, &ctx->tm.stats_ms);
+        c->stats_blocks = (int)std::min<int64_t>((n + kStatsThreads - 1) / kStatsThreads, (int64_t)ctx->sm_count * 4);
+        cudaError_t e = dalloc(ctx, &c->d_stats, (size_t)c->stats_blocks);
+        if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->h_stats), sizeof(StatsPartial) * c->stats_blocks);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->stats_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
+        stats_kernel<<<c->stats_blocks, kStatsThreads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+                                                                         c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->d_stats);
+        ctx->tm.total_launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsPartial) * c->stats_blocks, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->stats_done, ctx->stream);
+        if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats launch: %s", cudaGetErrorString(e)); }
+    }
+    *out = c;
+    return PCCM_OK;
+}
+
+extern "C" int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* c, pccm_cloud_info* out) {
+    if (!ctx || !c || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_stats(ctx, c);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->n = c->n;
+    out->data_kind = c->data_kind;
+    out->index_kind = c->index_kind;
+    out->has_colors = c->has_colors;
+    out->colors_u8 = c->rgb_u8 != nullptr || (c->has_colors && (c->raw_rgb_dtype == PCCM_U8 || c->rgb_u8_ok) && !c->rgb_f64);
+    out->has_normals = c->has_normals;
+    out->indexed = c->index_kind >= 0;
+    out->ny = c->grid.ny;
+    out->nz = c->grid.nz;
+    out->cell_size = c->cell_size;
+    for (int a = 0; a < 3; ++a) { out->aabb_min[a] = c->mn[a]; out->aabb_max[a] = c->mx[a]; }
+    return PCCM_OK;
+}
+
+extern "C" int pccm_cloud_set_normals(pccm_ctx* ctx, pccm_cloud* c, const void* normals, int nrm_dtype, int64_t nrm_stride, int mem_kind) {
+    if (!ctx || !c || (!normals && c->n)) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind);
+    if (rc) return rc;
+    if (mem_kind == PCCM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PCCM_OK;
+}
+
+static int copy_out(pccm_ctx* ctx, void* dst, const void* src_dev, size_t bytes, int mem_kind) {
+    if (bytes == 0) return PCCM_OK;
+    CK(cudaMemcpyAsync(dst, src_dev, bytes, mem_kind == PCCM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (mem_kind == PCCM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PCCM_OK;
+}
+
+extern "C" int pccm_cloud_get_normals(pccm_ctx* ctx, pccm_cloud* c, double* out, int mem_kind) {
+    if (!ctx || !c || (!out && c->n)) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    if (!c->has_normals) return fail(ctx, PCCM_ERR_STATE, "cloud has no normals");
+    CK(cudaSetDevice(ctx->device));
+    return copy_out(ctx, out, c->normals, (size_t)c->n * 3 * sizeof(double), mem_kind);
+}
+
+// --------------------------------------------------------------------------------------
+// index build
+// --------------------------------------------------------------------------------------
+static int bits_for(uint64_t v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+template <class KeyT>
+static int sort_pairs(pccm_ctx* ctx, KeyT* keys_in, KeyT* keys_out, uint32_t* vals_in, uint32_t* vals_out, uint32_t n, int end_bit) {
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, ctx->stream));
+    unsigned char* tmp = nullptr;
+    CK(dalloc(ctx, &tmp, bytes));
+    CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, ctx->stream));
+    dfree(ctx, tmp);
+    ctx->tm.library_launches += 1 + (end_bit + 7) / 8;
+    return PCCM_OK;
+}
+
+static int exclusive_scan(pccm_ctx* ctx, uint32_t* data, size_t count) {
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, data, data, (int)count, ctx->stream));
+    unsigned char* tmp = nullptr;
+    CK(dalloc(ctx, &tmp, bytes));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, data, data, (int)count, ctx->stream));
+    dfree(ctx, tmp);
+    ctx->tm.library_launches += 2;
+    return PCCM_OK;
+}
+
+static constexpr int64_t kMaxRows = 1ll << 26;
+
+// choose h from the point density: surface-like clouds have spacing ~ sqrt(area / n)
+static double auto_cell(const pccm_cloud* c) {
+    double ex = c->mx[0] - c->mn[0] + 1e-300, ey = c->mx[1] - c->mn[1] + 1e-300, ez = c->mx[2] - c->mn[2] + 1e-300;
+    double area = 2.0 * (ex * ey + ey * ez + ex * ez);
+    double spacing = std::sqrt(area / (double)std::max<int64_t>(c->n, 1)) / 1.4;
+    return 2.0 * spacing;
+}
+
+extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_size, int force_kind) {
+    if (!ctx || !c) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_stats(ctx, c);
+    if (rc) return rc;
+    rc = finish_colors(ctx, c);
+    if (rc) return rc;
+    int kind = c->data_kind;
+    if (force_kind != PCCM_KIND_AUTO) {
+        if (force_kind < c->data_kind || force_kind > PCCM_KIND_F64)
+            return fail(ctx, PCCM_ERR_INVALID, "force_kind %d not allowed for data kind %d", force_kind, c->data_kind);
+        kind = force_kind;
+    }
+    if (c->index_kind >= 0) {
+        if (c->index_kind == kind) return PCCM_OK;
+        return fail(ctx, PCCM_ERR_STATE, "cloud already indexed with kind %d", c->index_kind);
+    }
+    if (c->n && !c->raw_xyz) return fail(ctx, PCCM_ERR_STATE, "raw coordinates already released");
+    const uint32_t n = (uint32_t)c->n;
+    RowGrid g{};
+    g.n = n;
+    if (n == 0) {
+        g.ny = g.nz = 1; g.h = g.inv_h = 1; g.shift = 0;
+        c->grid = g; c->index_kind = kind; c->cell_size = 1;
+        CK(dalloc(ctx, &c->row_start, 2));
+        CK(cudaMemsetAsync(c->row_start, 0, 2 * sizeof(uint32_t), ctx->stream));
+        return PCCM_OK;
+    }
+    double h = cell_size > 0 ? cell_size : auto_cell(c) * ctx->cell_scale;
+    int xbits = 0;
+    if (kind == PCCM_KIND_INT) {
+        int shift = (int)std::lround(std::log2(std::max(h, 1.0)));
+        if (cell_size <= 0 && ctx->cell_override_shift >= 0) shift = ctx->cell_override_shift;
+        shift = std::max(0, std::min(shift, 15));
+        for (;; ++shift) {
+            g.shift = shift;
+            g.iy0 = ((int)c->mn[1] >> shift) << shift;
+            g.iz0 = ((int)c->mn[2] >> shift) << shift;
+            g.ny = (((int)c->mx[1] - g.iy0) >> shift) + 1;
+            g.nz = (((int)c->mx[2] - g.iz0) >> shift) + 1;
+            if ((int64_t)g.ny * g.nz <= kMaxRows) break;
+        }
+        g.h = (double)(1 << g.shift); g.inv_h = 1.0 / g.h; g.y0 = g.iy0; g.z0 = g.iz0;
+        xbits = std::max(1, bits_for((uint64_t)c->mx[0]));
+    } else {
+        double ey = c->mx[1] - c->mn[1], ez = c->mx[2] - c->mn[2];
+        if (!(h > 0) || !std::isfinite(h)) h = 1.0;
+        for (;;) {
+            double ny = std::floor(ey / h) + 1, nz = std::floor(ez / h) + 1;
+            if (ny * nz <= (double)kMaxRows) { g.ny = (int)ny; g.nz = (int)nz; break; }
+            h *= 1.5;
+        }
+        g.h = h; g.inv_h = 1.0 / h; g.y0 = c->mn[1]; g.z0 = c->mn[2];
+        double mag = 0;
+        for (int a = 1; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(c->mn[a]), std::fabs(c->mx[a])));
+        g.slack = 1e-9 * (mag + h);
+    }
+    c->cell_size = g.h;
+    const size_t nrows = (size_t)g.ny * g.nz;
+    const int rowbits = std::max(1, bits_for(nrows - 1));
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+
+    CK(dalloc(ctx, &c->row_start, nrows + 1));
+    uint32_t *vals_a = nullptr, *vals_b = nullptr;
+    CK(dalloc(ctx, &vals_a, (size_t)n));
+    CK(dalloc(ctx, &vals_b, (size_t)n));
+    uint32_t* sorted_vals = vals_b;
+    {
+        StageTimer t(ctx, &ctx->tm.keys_ms);
+        CK(cudaMemsetAsync(c->row_start, 0, (nrows + 1) * sizeof(uint32_t), ctx->stream));
+    }
+    if (kind == PCCM_KIND_INT && rowbits + xbits <= 32) {
+        uint32_t *ka = nullptr, *kb = nullptr;
+        CK(dalloc(ctx, &ka, (size_t)n));
+        CK(dalloc(ctx, &kb, (size_t)n));
+        {
+            StageTimer t(ctx, &ctx->tm.keys_ms);
+            keys_int_kernel<uint32_t><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, xbits, ka, vals_a, c->row_start);
+            ctx->tm.total_launches++;
+        }
+        {
+            StageTimer t(ctx, &ctx->tm.sort_ms);
+            rc = sort_pairs<uint32_t>(ctx, ka, kb, vals_a, vals_b, n, rowbits + xbits);
+        }
+        dfree(ctx, ka); dfree(ctx, kb);
+        if (rc) return rc;
+    } else if (kind == PCCM_KIND_INT || kind == PCCM_KIND_F32) {
+        unsigned long long *ka = nullptr, *kb = nullptr;
+        CK(dalloc(ctx, &ka, (size_t)n));
+        CK(dalloc(ctx, &kb, (size_t)n));
+        int end_bit;
+        {
+            StageTimer t(ctx, &ctx->tm.keys_ms);
+            if (kind == PCCM_KIND_INT) {
+                keys_int_kernel<unsigned long long><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, xbits, ka, vals_a, c->row_start);
+                end_bit = rowbits + xbits;
+            } else {
+                keys_f32_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, ka, vals_a, c->row_start);
+                end_bit = 32 + rowbits;
+            }
+            ctx->tm.total_launches++;
+        }
+        {
+            StageTimer t(ctx, &ctx->tm.sort_ms);
+            rc = sort_pairs<unsigned long long>(ctx, ka, kb, vals_a, vals_b, n, end_bit);
+        }
+        dfree(ctx, ka); dfree(ctx, kb);
+        if (rc) return rc;
+    } else {  // F64: LSD in two stable sorts -- by full-precision x, then by row
+        unsigned long long *ka = nullptr, *kb = nullptr;
+        uint32_t *rowkeys = nullptr, *rk_a = nullptr, *rk_b = nullptr;
+        CK(dalloc(ctx, &ka, (size_t)n));
+        CK(dalloc(ctx, &kb, (size_t)n));
+        CK(dalloc(ctx, &rowkeys, (size_t)n));
+        CK(dalloc(ctx, &rk_a, (size_t)n));
+        CK(dalloc(ctx, &rk_b, (size_t)n));
+        {
+            StageTimer t(ctx, &ctx->tm.keys_ms);
+            keys_f64_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, ka, rowkeys, vals_a, c->row_start);
+            ctx->tm.total_launches++;
+        }
+        {
+            StageTimer t(ctx, &ctx->tm.sort_ms);
+            rc = sort_pairs<unsigned long long>(ctx, ka, kb, vals_a, vals_b, n, 64);
+            if (!rc) {
+                gather_u32_kernel<<<blocks, threads, 0, ctx->stream>>>(rowkeys, vals_b, n, rk_a);
+                ctx->tm.total_launches++;
+                rc = sort_pairs<uint32_t>(ctx, rk_a, rk_b, vals_b, vals_a, n, rowbits);
+            }
+        }
+        sorted_vals = vals_a;
+        dfree(ctx, ka); dfree(ctx, kb); dfree(ctx, rowkeys); dfree(ctx, rk_a); dfree(ctx, rk_b);
+        if (rc) return rc;
+    }
+    CK(cudaGetLastError());
+    {
+        StageTimer t(ctx, &ctx->tm.table_ms);
+        rc = exclusive_scan(ctx, c->row_start, nrows + 1);
+        if (rc) return rc;
+    }
+    {
+        StageTimer t(ctx, &ctx->tm.reorder_ms);
+        if (kind == PCCM_KIND_INT) {
+            uint4* r = nullptr;
+            CK(dalloc(ctx, &r, (size_t)n));
+            reorder_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, c->rgb_u8, r);
+            c->recs = r;
+        } else if (kind == PCCM_KIND_F32) {
+            float4* r = nullptr;
+            CK(dalloc(ctx, &r, (size_t)n));
+            reorder_kernel<KF32><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, nullptr, r);
+            c->recs = r;
+        } else {
+            RecF64* r = nullptr;
+            CK(dalloc(ctx, &r, (size_t)n));
+            reorder_kernel<KF64><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, nullptr, r);
+            c->recs = r;
+        }
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    dfree(ctx, vals_a); dfree(ctx, vals_b);
+    dfree(ctx, c->raw_owned);
+    c->raw_owned = nullptr;
+    c->raw_xyz = nullptr;
+    c->grid = g;
+    c->index_kind = kind;
+    return PCCM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// queries
+// --------------------------------------------------------------------------------------
+static CloudView view_of(const pccm_cloud* c) {
+    CloudView v;
+    v.grid = c->grid;
+    v.recs = c->recs;
+    v.row_start = c->row_start;
+    v.rgb_u8 = c->rgb_u8;
+    v.rgb_f64 = c->rgb_f64;
+    v.normals = c->normals;
+    return v;
+}
+
+static int launch_query(pccm_ctx* ctx, int kind, const QueryParams& P, uint32_t nblocks) {
+    if (nblocks == 0) return PCCM_OK;
+    if (kind == PCCM_KIND_INT) pair_query_kernel<KInt><<<nblocks, kQueryThreads, 0, ctx->stream>>>(P);
+    else if (kind == PCCM_KIND_F32) pair_query_kernel<KF32><<<nblocks, kQueryThreads, 0, ctx->stream>>>(P);
+    else pair_query_kernel<KF64><<<nblocks, kQueryThreads, 0, ctx->stream>>>(P);
+    ctx->tm.query_launches++;
+    ctx->tm.total_launches++;
+    CK(cudaGetLastError());
+    return PCCM_OK;
+}
+
+static int check_pair(pccm_ctx* ctx, pccm_cloud* q, pccm_cloud* s) {
+    if (q->index_kind < 0 || s->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "both clouds must be indexed (pccm_cloud_build_index)");
+    if (q->index_kind != s->index_kind)
+        return fail(ctx, PCCM_ERR_STATE, "clouds indexed with different kinds (%d vs %d); rebuild with force_kind", q->index_kind, s->index_kind);
+    return PCCM_OK;
+}
+
+extern "C" int pccm_nn(pccm_ctx* ctx, pccm_cloud* query, pccm_cloud* search, int32_t* idx_out, double* d2_out, int mem_kind) {
+    if (!ctx || !query || !search) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_pair(ctx, query, search);
+    if (rc) return rc;
+    if (query->n == 0) return PCCM_OK;
+    if (search->n == 0) return fail(ctx, PCCM_ERR_INDEX, "search cloud is empty (reference: IndexError at cloud_pair.py:23)");
+    const uint32_t nq = (uint32_t)query->n;
+    const uint32_t nblocks = (nq + kQueryThreads - 1) / kQueryThreads;
+    int32_t* d_idx = nullptr;
+    double* d_d2 = nullptr;
+    BlockPartial* partials = nullptr;
+    CK(dalloc(ctx, &partials, (size_t)nblocks));
+    if (idx_out) { if (mem_kind == PCCM_DEVICE) d_idx = idx_out; else CK(dalloc(ctx, &d_idx, (size_t)nq)); }
+    if (d2_out) { if (mem_kind == PCCM_DEVICE) d_d2 = d2_out; else CK(dalloc(ctx, &d_d2, (size_t)nq)); }
+    QueryParams P{};
+    P.q = view_of(query); P.s = view_of(search);
+    P.qbegin = 0; P.qend = nq; P.flags = 0; P.normals_mode = 0; P.color_scale = 1;
+    P.idx_out = d_idx; P.d2_out = d_d2; P.partials = partials;
+    {
+        StageTimer t(ctx, &ctx->tm.query_ms, 1);
+        rc = launch_query(ctx, query->index_kind, P, nblocks);
+    }
+    if (!rc && mem_kind == PCCM_HOST) {
+        if (idx_out) rc = copy_out(ctx, idx_out, d_idx, (size_t)nq * sizeof(int32_t), PCCM_HOST);
+        if (!rc && d2_out) rc = copy_out(ctx, d2_out, d_d2, (size_t)nq * sizeof(double), PCCM_HOST);
+        dfree(ctx, d_idx); dfree(ctx, d_d2);
+    }
+    dfree(ctx, partials);
+    return rc;
+}
+
+extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint32_t flags,
+                              const double* color_matrix, double color_scale, int normals_mode,
+                              int rank, int world, pccm_pair_result* out) {
+    if (!ctx || !a || !b || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, PCCM_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_pair(ctx, a, b);
+    if (rc) return rc;
+    if (a->n == 0 || b->n == 0) return fail(ctx, PCCM_ERR_INDEX, "empty cloud (reference: IndexError at cloud_pair.py:23)");
+    if (flags & PCCM_EVAL_D2) {
+        if (!a->has_normals || !b->has_normals) return fail(ctx, PCCM_ERR_STATE, "D2 needs normals on both clouds (set or estimate them)");
+    }
+    if (flags & PCCM_EVAL_COLOR) {
+        if (!a->has_colors || !b->has_colors) return fail(ctx, PCCM_ERR_STATE, "colour metrics need colours on both clouds");
+        if (!color_matrix) return fail(ctx, PCCM_ERR_INVALID, "color_matrix is NULL");
+    }
+    pccm_cloud* cl[2] = {a, b};
+    // metric.py:148-152 indexes the OTHER cloud's normals with the query index: a direction
+    // whose search cloud is shorter than its query cloud raises IndexError in the reference.
+    uint32_t dflags[2] = {flags, flags};
+    for (int d = 0; d < 2; ++d)
+        if ((flags & PCCM_EVAL_D2) && normals_mode == PCCM_NORMALS_BY_QUERY_INDEX && cl[1 - d]->n < cl[d]->n)
+            dflags[d] &= ~(uint32_t)PCCM_EVAL_D2;
+    BlockPartial* partials[2] = {nullptr, nullptr};
+    uint32_t nblocks[2];
+    uint32_t qb[2], qe[2];
+    for (int d = 0; d < 2; ++d) {
+        const uint64_t n = (uint64_t)cl[d]->n;
+        qb[d] = (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
+        qe[d] = (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
+        nblocks[d] = (qe[d] - qb[d] + kQueryThreads - 1) / kQueryThreads;
+        CK(dalloc(ctx, &partials[d], (size_t)nblocks[d]));
+        if (flags & PCCM_EVAL_PERPOINT) {
+            if (ctx->pp_n[d] != cl[d]->n) {
+                dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]);
+                CK(dalloc(ctx, &ctx->pp_idx[d], (size_t)n));
+                CK(dalloc(ctx, &ctx->pp_d2[d], (size_t)n));
+                ctx->pp_n[d] = cl[d]->n;
+            }
+            if (world > 1) {  // entries outside this rank's slice stay -1 / NaN
+                CK(cudaMemsetAsync(ctx->pp_idx[d], 0xff, n * sizeof(int32_t), ctx->stream));
+                CK(cudaMemsetAsync(ctx->pp_d2[d], 0xff, n * sizeof(double), ctx->stream));
+            }
+        }
+    }
+    {
+        StageTimer t(ctx, &ctx->tm.query_ms, 1);
+        for (int d = 0; d < 2 && !rc; ++d) {
+            QueryParams P{};
+            P.q = view_of(cl[d]); P.s = view_of(cl[1 - d]);
+            P.qbegin = qb[d]; P.qend = qe[d];
+            P.flags = dflags[d]; P.normals_mode = normals_mode;
+            if (color_matrix) memcpy(P.T, color_matrix, sizeof P.T);
+            P.color_scale = color_scale;
+            P.idx_out = (flags & PCCM_EVAL_PERPOINT) ? ctx->pp_idx[d] : nullptr;
+            P.d2_out = (flags & PCCM_EVAL_PERPOINT) ? ctx->pp_d2[d] : nullptr;
+            P.partials = partials[d];
+            rc = launch_query(ctx, a->index_kind, P, nblocks[d]);
+        }
+    }
+    if (!rc) {
+        StageTimer t(ctx, &ctx->tm.finalize_ms);
+        FinalizeParams F;
+        F.partials[0] = partials[0]; F.partials[1] = partials[1];
+        F.nblocks[0] = nblocks[0]; F.nblocks[1] = nblocks[1];
+        F.out = static_cast<BlockPartial*>(ctx->dscratch);
+        finalize_kernel<<<2, kFinalThreads, 0, ctx->stream>>>(F);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    dfree(ctx, partials[0]); dfree(ctx, partials[1]);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const BlockPartial* r = static_cast<const BlockPartial*>(ctx->pinned);
+    memset(out, 0, sizeof *out);
+    for (int d = 0; d < 2; ++d) {
+        pccm_dir_result& o = out->dir[d];
+        o.n = (int64_t)(qe[d] - qb[d]);
+        o.n_total = cl[d]->n;
+        o.d1_exact_int = a->index_kind == PCCM_KIND_INT;
+        o.d2_valid = (dflags[d] & PCCM_EVAL_D2) != 0;
+        o.sum_d1_u64 = r[d].sum_d1_u64;
+        o.sum_d1 = o.d1_exact_int ? (double)r[d].sum_d1_u64 : r[d].sum_d1;
+        o.max_d1 = r[d].max_d1;
+        o.sum_d2 = r[d].sum_d2; o.max_d2 = r[d].max_d2;
+        for (int k = 0; k < 3; ++k) { o.color_sum[k] = r[d].csum[k]; o.color_max[k] = r[d].cmax[k]; }
+    }
+    return PCCM_OK;
+}
+
+extern "C" int pccm_pair_get(pccm_ctx* ctx, int which, int direction, void* out, int mem_kind) {
+    if (!ctx || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    if (direction < 0 || direction > 1) return fail(ctx, PCCM_ERR_INVALID, "direction must be 0 or 1");
+    if (!ctx->pp_idx[direction]) return fail(ctx, PCCM_ERR_STATE, "no per-point results: call pccm_pair_eval with PCCM_EVAL_PERPOINT");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->pp_n[direction];
+    if (which == PCCM_GET_IDX) return copy_out(ctx, out, ctx->pp_idx[direction], n * sizeof(int32_t), mem_kind);
+    if (which == PCCM_GET_D2) return copy_out(ctx, out, ctx->pp_d2[direction], n * sizeof(double), mem_kind);
+    return fail(ctx, PCCM_ERR_INVALID, "bad selector %d", which);
+}
+
+// --------------------------------------------------------------------------------------
+// self k-NN family
+// --------------------------------------------------------------------------------------
+static int launch_knn(pccm_ctx* ctx, pccm_cloud* c, KnnParams& P) {
+    const uint32_t cnt = P.end - P.begin;
+    if (cnt == 0) return PCCM_OK;
+    const uint32_t nblocks = (cnt + kKnnThreads - 1) / kKnnThreads;
+    const size_t dsz = c->index_kind == PCCM_KIND_INT ? sizeof(uint32_t) : sizeof(double);
+    const size_t smem = (size_t)P.k * kKnnThreads * (dsz + 2 * sizeof(uint32_t));
+    if (smem > 200 * 1024) return fail(ctx, PCCM_ERR_UNSUPPORTED, "k=%d too large", P.k);
+    StageTimer t(ctx, &ctx->tm.knn_ms, 1);
+    if (c->index_kind == PCCM_KIND_INT) {
+        CK(cudaFuncSetAttribute(knn_self_kernel<KInt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_self_kernel<KInt><<<nblocks, kKnnThreads, smem, ctx->stream>>>(P);
+    } else if (c->index_kind == PCCM_KIND_F32) {
+        CK(cudaFuncSetAttribute(knn_self_kernel<KF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_self_kernel<KF32><<<nblocks, kKnnThreads, smem, ctx->stream>>>(P);
+    } else {
+        CK(cudaFuncSetAttribute(knn_self_kernel<KF64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_self_kernel<KF64><<<nblocks, kKnnThreads, smem, ctx->stream>>>(P);
+    }
+    ctx->tm.knn_launches++;
+    ctx->tm.total_launches++;
+    CK(cudaGetLastError());
+    return PCCM_OK;
+}
+
+static int check_range(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end) {
+    if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
+    if (begin < 0 || end < begin || end > c->n) return fail(ctx, PCCM_ERR_INVALID, "bad range [%lld, %lld)", (long long)begin, (long long)end);
+    return PCCM_OK;
+}
+
+extern "C" int pccm_knn_self(pccm_ctx* ctx, pccm_cloud* c, int k, int32_t* idx_out, double* d2_out, int mem_kind) {
+    if (!ctx || !c || !idx_out || !d2_out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    if (k < 1) return fail(ctx, PCCM_ERR_INVALID, "k must be >= 1");
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_range(ctx, c, 0, c->n);
+    if (rc) return rc;
+    if (c->n == 0) return PCCM_OK;
+    const size_t cnt = (size_t)c->n * (size_t)k;
+    int32_t* d_idx = idx_out;
+    double* d_d2 = d2_out;
+    if (mem_kind == PCCM_HOST) { CK(dalloc(ctx, &d_idx, cnt)); CK(dalloc(ctx, &d_d2, cnt)); }
+    KnnParams P{};
+    P.c = view_of(c); P.begin = 0; P.end = (uint32_t)c->n; P.k = k; P.mode = KNN_LIST;
+    P.idx_out = d_idx; P.d2_out = d_d2;
+    rc = launch_knn(ctx, c, P);
+    if (mem_kind == PCCM_HOST) {
+        if (!rc) rc = copy_out(ctx, idx_out, d_idx, cnt * sizeof(int32_t), PCCM_HOST);
+        if (!rc) rc = copy_out(ctx, d2_out, d_d2, cnt * sizeof(double), PCCM_HOST);
+        dfree(ctx, d_idx); dfree(ctx, d_d2);
+    }
+    return rc;
+}
+
+extern "C" int pccm_self_nn_minmax(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end,
+                                   double* min_out, double* max_out, double* per_point, int mem_kind) {
+    if (!ctx || !c || !min_out || !max_out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_range(ctx, c, begin, end);
+    if (rc) return rc;
+    if (end == begin) { *min_out = INFINITY; *max_out = -INFINITY; return PCCM_OK; }
+    const uint32_t nblocks = (uint32_t)((end - begin + kKnnThreads - 1) / kKnnThreads);
+    double* mm = nullptr;
+    double* d_pp = nullptr;
+    CK(dalloc(ctx, &mm, (size_t)nblocks * 2));
+    if (per_point) { if (mem_kind == PCCM_DEVICE) d_pp = per_point; else CK(dalloc(ctx, &d_pp, (size_t)c->n)); }
+    KnnParams P{};
+    P.c = view_of(c); P.begin = (uint32_t)begin; P.end = (uint32_t)end; P.k = 2; P.mode = KNN_BOUNDARY;
+    P.d2_out = d_pp; P.minmax = mm;
+    rc = launch_knn(ctx, c, P);
+    if (!rc) {
+        minmax_finalize_kernel<<<1, 256, 0, ctx->stream>>>(mm, nblocks, static_cast<double*>(ctx->dscratch) + 1024);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(static_cast<double*>(ctx->pinned) + 1024, static_cast<double*>(ctx->dscratch) + 1024, 2 * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        if (per_point && mem_kind == PCCM_HOST) rc = copy_out(ctx, per_point, d_pp, (size_t)c->n * sizeof(double), PCCM_HOST);
+        CK(cudaStreamSynchronize(ctx->stream));
+        *min_out = (static_cast<double*>(ctx->pinned) + 1024)[0];
+        *max_out = (static_cast<double*>(ctx->pinned) + 1024)[1];
+    }
+    if (per_point && mem_kind == PCCM_HOST) dfree(ctx, d_pp);
+    dfree(ctx, mm);
+    return rc;
+}
+
+extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_t begin, int64_t end) {
+    if (!ctx || !c) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    if (k < 1) return fail(ctx, PCCM_ERR_INVALID, "k must be >= 1");
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_range(ctx, c, begin, end);
+    if (rc) return rc;
+    if (!c->normals) {
+        // zero-filled so that ranks estimating disjoint slices can combine buffers by summation
+        CK(dalloc(ctx, &c->normals, (size_t)c->n * 3));
+        CK(cudaMemsetAsync(c->normals, 0, (size_t)c->n * 3 * sizeof(double), ctx->stream));
+    }
+    KnnParams P{};
+    P.c = view_of(c); P.begin = (uint32_t)begin; P.end = (uint32_t)end; P.k = k; P.mode = KNN_NORMALS;
+    P.normals_out = c->normals;
+    rc = launch_knn(ctx, c, P);
+    if (!rc) c->has_normals = true;
+    return rc;
+}

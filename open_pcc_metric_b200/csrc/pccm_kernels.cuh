@@ -1,0 +1,483 @@
+// pccm_kernels.cuh -- sm_100a kernels of libpccm.so (index build, fused symmetric
+// NN query with D1 / D2 / colour epilogues and block reductions, self k-NN with the
+// boundary-distance and normal-estimation epilogues).  Host orchestration and the
+// C ABI are in pccm_api.cu; the per-query search logic is in pccm_core.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pccm_core.cuh"
+#include "../../include/pccm.h"
+
+namespace pccm {
+
+constexpr int kStatsThreads = 256;
+constexpr int kQueryThreads = 128;
+constexpr int kKnnThreads = 64;
+
+// ------------------------------------------------------------------------------------
+// raw input access
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_coord(const void* base, int dtype, int64_t stride, int64_t i, int axis) {
+    const char* p = static_cast<const char*>(base) + i * stride;
+    switch (dtype) {
+        case PCCM_F64: return reinterpret_cast<const double*>(p)[axis];
+        case PCCM_F32: return (double)reinterpret_cast<const float*>(p)[axis];
+        case PCCM_I32: return (double)reinterpret_cast<const int32_t*>(p)[axis];
+        case PCCM_U16: return (double)reinterpret_cast<const uint16_t*>(p)[axis];
+        default:       return (double)reinterpret_cast<const uint8_t*>(p)[axis];
+    }
+}
+
+struct StatsPartial {
+    double mn[3], mx[3];
+    uint32_t not_int, not_f32, not_finite, rgb_not_u8;
+};
+
+// K0: bounding box + classification of coordinates (and colours) in one pass.
+__global__ void __launch_bounds__(kStatsThreads)
+stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
+             const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    uint32_t not_int = 0, not_f32 = 0, not_fin = 0, rgb_bad = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double v = load_coord(xyz, dtype, stride, i, a);
+            if (!isfinite(v)) not_fin = 1;
+            mn[a] = fmin(mn[a], v);
+            mx[a] = fmax(mx[a], v);
+            if (!(v >= 0.0 && v <= 32767.0 && v == floor(v))) not_int = 1;
+            if ((double)(float)v != v) not_f32 = 1;
+        }
+        if (rgb != nullptr && rgb_dtype == PCCM_F64) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double c = load_coord(rgb, PCCM_F64, rgb_stride, i, a);
+                double k = rint(c * 255.0);
+                if (!(k >= 0.0 && k <= 255.0 && k / 255.0 == c)) rgb_bad = 1;
+            }
+        }
+    }
+    __shared__ double s_mn[3][kStatsThreads / 32], s_mx[3][kStatsThreads / 32];
+    __shared__ uint32_t s_flags[4];
+    if (threadIdx.x < 4) s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fmin(mn[a], __shfl_down_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmax(mx[a], __shfl_down_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+    }
+    if (not_int) atomicOr(&s_flags[0], 1u);
+    if (not_f32) atomicOr(&s_flags[1], 1u);
+    if (not_fin) atomicOr(&s_flags[2], 1u);
+    if (rgb_bad) atomicOr(&s_flags[3], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatsPartial p;
+        for (int a = 0; a < 3; ++a) {
+            double lo = s_mn[a][0], hi = s_mx[a][0];
+            for (int w = 1; w < kStatsThreads / 32; ++w) { lo = fmin(lo, s_mn[a][w]); hi = fmax(hi, s_mx[a][w]); }
+            p.mn[a] = lo; p.mx[a] = hi;
+        }
+        p.not_int = s_flags[0]; p.not_f32 = s_flags[1]; p.not_finite = s_flags[2]; p.rgb_not_u8 = s_flags[3];
+        out[blockIdx.x] = p;
+    }
+}
+
+// colours -> uchar4 (original order).  F64 input must have passed the k/255 test.
+__global__ void pack_rgb_u8_kernel(const void* rgb, int rgb_dtype, int64_t stride, int64_t n, uchar4* out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uchar4 c;
+    if (rgb_dtype == PCCM_U8) {
+        const uint8_t* p = static_cast<const uint8_t*>(rgb) + i * stride;
+        c = make_uchar4(p[0], p[1], p[2], 0);
+    } else {
+        c.x = (unsigned char)rint(load_coord(rgb, PCCM_F64, stride, i, 0) * 255.0);
+        c.y = (unsigned char)rint(load_coord(rgb, PCCM_F64, stride, i, 1) * 255.0);
+        c.z = (unsigned char)rint(load_coord(rgb, PCCM_F64, stride, i, 2) * 255.0);
+        c.w = 0;
+    }
+    out[i] = c;
+}
+
+// strided rows of 3 (F64 / F32) -> packed double[n][3]
+__global__ void pack_f64x3_kernel(const void* src, int dtype, int64_t stride, int64_t n, double* out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[3 * i + 0] = load_coord(src, dtype, stride, i, 0);
+    out[3 * i + 1] = load_coord(src, dtype, stride, i, 1);
+    out[3 * i + 2] = load_coord(src, dtype, stride, i, 2);
+}
+
+// ------------------------------------------------------------------------------------
+// K1: sort keys + row histogram
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t flip_f32(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long flip_f64(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+template <class KeyT>
+__global__ void keys_int_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, RowGrid g, int xbits,
+                                KeyT* keys, uint32_t* vals, uint32_t* row_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = (int)load_coord(xyz, dtype, stride, i, 0);
+    int y = (int)load_coord(xyz, dtype, stride, i, 1);
+    int z = (int)load_coord(xyz, dtype, stride, i, 2);
+    uint32_t cy = (uint32_t)((y - g.iy0) >> g.shift), cz = (uint32_t)((z - g.iz0) >> g.shift);
+    uint32_t row = cz * (uint32_t)g.ny + cy;
+    keys[i] = ((KeyT)row << xbits) | (KeyT)x;
+    vals[i] = i;
+    atomicAdd(row_count + row, 1u);
+}
+
+__device__ __forceinline__ uint32_t float_row(const RowGrid& g, double y, double z) {
+    int cy = (int)floor((y - g.y0) * g.inv_h), cz = (int)floor((z - g.z0) * g.inv_h);
+    cy = cy < 0 ? 0 : (cy >= g.ny ? g.ny - 1 : cy);
+    cz = cz < 0 ? 0 : (cz >= g.nz ? g.nz - 1 : cz);
+    return (uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy;
+}
+
+__global__ void keys_f32_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, RowGrid g,
+                                unsigned long long* keys, uint32_t* vals, uint32_t* row_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = load_coord(xyz, dtype, stride, i, 0);
+    uint32_t row = float_row(g, load_coord(xyz, dtype, stride, i, 1), load_coord(xyz, dtype, stride, i, 2));
+    keys[i] = ((unsigned long long)row << 32) | flip_f32((float)x);
+    vals[i] = i;
+    atomicAdd(row_count + row, 1u);
+}
+
+__global__ void keys_f64_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, RowGrid g,
+                                unsigned long long* xkeys, uint32_t* rowkeys, uint32_t* vals, uint32_t* row_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = load_coord(xyz, dtype, stride, i, 0);
+    uint32_t row = float_row(g, load_coord(xyz, dtype, stride, i, 1), load_coord(xyz, dtype, stride, i, 2));
+    xkeys[i] = flip_f64(x);
+    rowkeys[i] = row;
+    vals[i] = i;
+    atomicAdd(row_count + row, 1u);
+}
+
+__global__ void gather_u32_kernel(const uint32_t* src, const uint32_t* idx, uint32_t n, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+// ------------------------------------------------------------------------------------
+// K3: gather raw points into sorted records
+// ------------------------------------------------------------------------------------
+template <class K> struct RecPack;
+template <> struct RecPack<KInt> {
+    static __device__ __forceinline__ uint4 make(double x, double y, double z, uint32_t idx, uint32_t rgba) {
+        return make_uint4((uint32_t)(int)x | ((uint32_t)(int)y << 16), (uint32_t)(int)z, idx, rgba);
+    }
+};
+template <> struct RecPack<KF32> {
+    static __device__ __forceinline__ float4 make(double x, double y, double z, uint32_t idx, uint32_t) {
+        return make_float4((float)x, (float)y, (float)z, __uint_as_float(idx));
+    }
+};
+template <> struct RecPack<KF64> {
+    static __device__ __forceinline__ RecF64 make(double x, double y, double z, uint32_t idx, uint32_t) {
+        RecF64 r; r.x = x; r.y = y; r.z = z; r.idx = idx; return r;
+    }
+};
+
+template <class K>
+__global__ void reorder_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, const uint32_t* __restrict__ vals,
+                               const uchar4* __restrict__ rgb_u8, typename K::Rec* __restrict__ recs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t src = vals[i];
+    uint32_t rgba = 0;
+    if (rgb_u8 != nullptr) { uchar4 c = rgb_u8[src]; rgba = c.x | (c.y << 8) | (c.z << 16); }
+    recs[i] = RecPack<K>::make(load_coord(xyz, dtype, stride, src, 0), load_coord(xyz, dtype, stride, src, 1),
+                               load_coord(xyz, dtype, stride, src, 2), src, rgba);
+}
+
+// ------------------------------------------------------------------------------------
+// deterministic block reductions
+// ------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_down_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < THREADS / 32; ++w) r = dadd(r, sm[w]);
+    return r;  // valid in thread 0
+}
+template <int THREADS>
+__device__ __forceinline__ double block_max(double v, double* sm) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = -INFINITY;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < THREADS / 32; ++w) r = fmax(r, sm[w]);
+    return r;
+}
+template <int THREADS>
+__device__ __forceinline__ double block_min(double v, double* sm) { return -block_max<THREADS>(-v, sm); }
+template <int THREADS>
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < THREADS / 32; ++w) r += sm[w];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------
+// K5: fused NN query + D1 / D2 / colour epilogue + block reduction
+// ------------------------------------------------------------------------------------
+struct CloudView {        // device-side view of an indexed cloud
+    RowGrid grid;
+    const void* recs;
+    const uint32_t* row_start;
+    const uchar4* rgb_u8;   // original order, or null
+    const double* rgb_f64;  // original order [n][3], or null
+    const double* normals;  // original order [n][3], or null
+};
+
+struct BlockPartial {
+    unsigned long long sum_d1_u64;
+    double sum_d1, max_d1, sum_d2, max_d2, csum[3], cmax[3];
+};
+
+struct QueryParams {
+    CloudView q, s;
+    uint32_t qbegin, qend;    // range of the query cloud's sorted order
+    uint32_t flags;
+    int32_t normals_mode;
+    double T[9];
+    double color_scale;
+    int32_t* idx_out;         // original query order, or null
+    double* d2_out;
+    BlockPartial* partials;   // one per block
+};
+
+__device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uint32_t packed, bool have_packed, double* out) {
+    if (c.rgb_u8 != nullptr) {
+        uint32_t p;
+        if (have_packed) p = packed;
+        else { uchar4 u = __ldg(c.rgb_u8 + idx); p = u.x | (u.y << 8) | (u.z << 16); }
+        out[0] = (double)(p & 0xffu) / 255.0;
+        out[1] = (double)((p >> 8) & 0xffu) / 255.0;
+        out[2] = (double)((p >> 16) & 0xffu) / 255.0;
+    } else {
+        out[0] = __ldg(c.rgb_f64 + 3 * (size_t)idx);
+        out[1] = __ldg(c.rgb_f64 + 3 * (size_t)idx + 1);
+        out[2] = __ldg(c.rgb_f64 + 3 * (size_t)idx + 2);
+    }
+}
+
+template <class K> __device__ __forceinline__ uint32_t rec_rgba(const typename K::Rec&) { return 0; }
+template <> __device__ __forceinline__ uint32_t rec_rgba<KInt>(const uint4& r) { return r.w; }
+
+template <class K>
+__global__ void __launch_bounds__(kQueryThreads)
+pair_query_kernel(const __grid_constant__ QueryParams P) {
+    typedef typename K::Rec Rec;
+    typedef typename K::Q Q;
+    const Rec* __restrict__ qrecs = static_cast<const Rec*>(P.q.recs);
+    const Rec* __restrict__ srecs = static_cast<const Rec*>(P.s.recs);
+    const uint32_t t = P.qbegin + blockIdx.x * kQueryThreads + threadIdx.x;
+    const bool active = t < P.qend;
+
+    unsigned long long d1_u64 = 0;
+    double d1 = 0, pe2 = 0, cd2[3] = {0, 0, 0}, cd2s[3] = {0, 0, 0};
+    double d1_max = -INFINITY, pe2_max = -INFINITY, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (active) {
+        const Rec qr = load_rec(qrecs + t);
+        const Q q = K::rec_q(qr);
+        const uint32_t qidx = K::rec_idx(qr);
+        Best1<K> best;
+        best.init();
+        search<K>(P.s.grid, P.s.row_start, srecs, q, best);
+        d1 = K::d2_as_double(best.d2);
+        d1_max = d1;
+        if (K::kind == KIND_INT) d1_u64 = (unsigned long long)best.d2;
+        if (P.idx_out) P.idx_out[qidx] = (int32_t)best.idx;
+        if (P.d2_out) P.d2_out[qidx] = d1;
+        if (P.flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
+            const Rec nr = load_rec(srecs + best.pos);
+            if (P.flags & PCCM_EVAL_D2) {
+                const Q nq = K::rec_q(nr);
+                double e[3] = {dsub((double)q.x, (double)nq.x), dsub((double)q.y, (double)nq.y), dsub((double)q.z, (double)nq.z)};
+                const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? best.idx : qidx;
+                double nv[3] = {__ldg(P.s.normals + 3 * (size_t)ni), __ldg(P.s.normals + 3 * (size_t)ni + 1),
+                                __ldg(P.s.normals + 3 * (size_t)ni + 2)};
+                pe2 = plane_err2(e, nv);
+                pe2_max = pe2;
+            }
+            if (P.flags & PCCM_EVAL_COLOR) {
+                double cq[3], cn[3];
+                load_color(P.q, qidx, rec_rgba<K>(qr), K::kind == KIND_INT, cq);
+                load_color(P.s, best.idx, rec_rgba<K>(nr), K::kind == KIND_INT, cn);
+                color_diff2(P.T, cq, cn, P.color_scale, cd2, cd2s);
+                cmax[0] = cd2s[0]; cmax[1] = cd2s[1]; cmax[2] = cd2s[2];
+            }
+        }
+    }
+    __shared__ double sm[kQueryThreads / 32];
+    __shared__ unsigned long long smu[kQueryThreads / 32];
+    BlockPartial bp;
+    bp.sum_d1_u64 = block_sum_u64<kQueryThreads>(d1_u64, smu);
+    bp.sum_d1 = block_sum<kQueryThreads>(d1, sm);
+    bp.max_d1 = block_max<kQueryThreads>(d1_max, sm);
+    bp.sum_d2 = 0; bp.max_d2 = -INFINITY;
+    bp.csum[0] = bp.csum[1] = bp.csum[2] = 0;
+    bp.cmax[0] = bp.cmax[1] = bp.cmax[2] = -INFINITY;
+    if (P.flags & PCCM_EVAL_D2) {
+        bp.sum_d2 = block_sum<kQueryThreads>(pe2, sm);
+        bp.max_d2 = block_max<kQueryThreads>(pe2_max, sm);
+    }
+    if (P.flags & PCCM_EVAL_COLOR) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            bp.csum[k] = block_sum<kQueryThreads>(cd2[k], sm);
+            bp.cmax[k] = block_max<kQueryThreads>(cmax[k], sm);
+        }
+    }
+    if (threadIdx.x == 0) P.partials[blockIdx.x] = bp;
+}
+
+// K8: fixed-order reduction of the per-block partials (one block per direction).
+struct FinalizeParams {
+    const BlockPartial* partials[2];
+    uint32_t nblocks[2];
+    BlockPartial* out;   // [2]
+};
+constexpr int kFinalThreads = 256;
+__global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_constant__ FinalizeParams P) {
+    const int d = blockIdx.x;
+    const BlockPartial* in = P.partials[d];
+    const uint32_t nb = P.nblocks[d];
+    BlockPartial a;
+    a.sum_d1_u64 = 0; a.sum_d1 = 0; a.sum_d2 = 0; a.max_d1 = -INFINITY; a.max_d2 = -INFINITY;
+    for (int k = 0; k < 3; ++k) { a.csum[k] = 0; a.cmax[k] = -INFINITY; }
+    for (uint32_t i = threadIdx.x; i < nb; i += kFinalThreads) {
+        const BlockPartial b = in[i];
+        a.sum_d1_u64 += b.sum_d1_u64;
+        a.sum_d1 = dadd(a.sum_d1, b.sum_d1);
+        a.sum_d2 = dadd(a.sum_d2, b.sum_d2);
+        a.max_d1 = fmax(a.max_d1, b.max_d1);
+        a.max_d2 = fmax(a.max_d2, b.max_d2);
+        for (int k = 0; k < 3; ++k) { a.csum[k] = dadd(a.csum[k], b.csum[k]); a.cmax[k] = fmax(a.cmax[k], b.cmax[k]); }
+    }
+    __shared__ double sm[kFinalThreads / 32];
+    __shared__ unsigned long long smu[kFinalThreads / 32];
+    BlockPartial r;
+    r.sum_d1_u64 = block_sum_u64<kFinalThreads>(a.sum_d1_u64, smu);
+    r.sum_d1 = block_sum<kFinalThreads>(a.sum_d1, sm);
+    r.sum_d2 = block_sum<kFinalThreads>(a.sum_d2, sm);
+    r.max_d1 = block_max<kFinalThreads>(a.max_d1, sm);
+    r.max_d2 = block_max<kFinalThreads>(a.max_d2, sm);
+    for (int k = 0; k < 3; ++k) {
+        r.csum[k] = block_sum<kFinalThreads>(a.csum[k], sm);
+        r.cmax[k] = block_max<kFinalThreads>(a.cmax[k], sm);
+    }
+    if (threadIdx.x == 0) P.out[d] = r;
+}
+
+// ------------------------------------------------------------------------------------
+// K7: self k-NN with fused epilogues
+// ------------------------------------------------------------------------------------
+enum KnnMode : int { KNN_LIST = 0, KNN_BOUNDARY = 1, KNN_NORMALS = 2 };
+
+struct KnnParams {
+    CloudView c;
+    uint32_t begin, end;   // range of sorted order
+    int32_t k;
+    int32_t mode;
+    int32_t* idx_out;      // KNN_LIST: [n][k] original order
+    double* d2_out;        // KNN_LIST: [n][k];  KNN_BOUNDARY: optional per-point sqrt distance [n]
+    double* normals_out;   // KNN_NORMALS: [n][3] original order
+    double* minmax;        // KNN_BOUNDARY: per-block {min, max}
+};
+
+template <class K>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_self_kernel(const __grid_constant__ KnnParams P) {
+    typedef typename K::Rec Rec;
+    typedef typename K::Q Q;
+    typedef typename K::D D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = P.k;
+    D* d2s = reinterpret_cast<D*>(smem_raw);
+    uint32_t* idxs = reinterpret_cast<uint32_t*>(d2s + (size_t)k * kKnnThreads);
+    uint32_t* poss = idxs + (size_t)k * kKnnThreads;
+    const Rec* __restrict__ recs = static_cast<const Rec*>(P.c.recs);
+    const uint32_t t = P.begin + blockIdx.x * kKnnThreads + threadIdx.x;
+    const bool active = t < P.end;
+    double bmin = INFINITY, bmax = -INFINITY;
+    if (active) {
+        const Rec qr = load_rec(recs + t);
+        const Q q = K::rec_q(qr);
+        const uint32_t qidx = K::rec_idx(qr);
+        TopK<K> acc;
+        acc.init(d2s + threadIdx.x, idxs + threadIdx.x, poss + threadIdx.x, kKnnThreads, k);
+        search<K>(P.c.grid, P.c.row_start, recs, q, acc);
+        if (P.mode == KNN_LIST) {
+            for (int j = 0; j < k; ++j) {
+                const bool have = j < acc.count;
+                P.idx_out[(size_t)qidx * k + j] = have ? (int32_t)idxs[j * kKnnThreads + threadIdx.x] : -1;
+                P.d2_out[(size_t)qidx * k + j] = have ? K::d2_as_double(d2s[j * kKnnThreads + threadIdx.x]) : INFINITY;
+            }
+        } else if (P.mode == KNN_BOUNDARY) {
+            // ComputeNearestNeighborDistance: sqrt of the second entry, 0 when it is absent
+            double v = acc.count > 1 ? sqrt(K::d2_as_double(d2s[1 * kKnnThreads + threadIdx.x])) : 0.0;
+            bmin = v; bmax = v;
+            if (P.d2_out) P.d2_out[qidx] = v;
+        } else {
+            double cum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < acc.count; ++j) {
+                const Rec nr = load_rec(recs + poss[j * kKnnThreads + threadIdx.x]);
+                const Q nq = K::rec_q(nr);
+                cumulant_add(cum, (double)nq.x, (double)nq.y, (double)nq.z);
+            }
+            double nv[3];
+            normal_from_cumulants(cum, acc.count, nv);
+            P.normals_out[3 * (size_t)qidx + 0] = nv[0];
+            P.normals_out[3 * (size_t)qidx + 1] = nv[1];
+            P.normals_out[3 * (size_t)qidx + 2] = nv[2];
+        }
+    }
+    if (P.mode == KNN_BOUNDARY) {
+        __shared__ double sm[kKnnThreads / 32];
+        double mn = block_min<kKnnThreads>(bmin, sm);
+        double mx = block_max<kKnnThreads>(bmax, sm);
+        if (threadIdx.x == 0) { P.minmax[2 * blockIdx.x] = mn; P.minmax[2 * blockIdx.x + 1] = mx; }
+    }
+}
+
+__global__ void minmax_finalize_kernel(const double* in, uint32_t nb, double* out) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < nb; i += 256) { mn = fmin(mn, in[2 * i]); mx = fmax(mx, in[2 * i + 1]); }
+    __shared__ double sm[8];
+    double a = block_min<256>(mn, sm);
+    double b = block_max<256>(mx, sm);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+}  // namespace pccm

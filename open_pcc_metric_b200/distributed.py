@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing: one process per GPU, query slices
+per rank, and the only data that crosses NVLink -- the tiny per-direction partial
+records (C3), the self-NN min/max, and (when normals are estimated) one all-reduce
+of disjointly filled normal buffers (C2).  torch.distributed does the transport
+(NCCL on GPUs; the same code runs over gloo on CPU tensors in the tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SUM_SLOTS = (0, 2, 4, 5, 6)      # sum_d1, sum_d2, colour sums
+MAX_SLOTS = (1, 3, 7, 8, 9)      # max_d1, max_d2, colour maxima
+
+
+def slice_range(n: int, rank: int, world: int):
+    """Contiguous equal-count slice of a cloud's sorted order (same rule as pccm_pair_eval)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def exchange_partials(vals, world: int, group=None, device="cpu"):
+    """vals: per direction dict(sum_u64, d2_valid, sum_d1, max_d1, sum_d2, max_d2, csum[3], cmax[3]).
+    All-gathers every rank's record and reduces on the host: integer sums exactly
+    (Python ints), float sums in fixed rank order (deterministic for a given world)."""
+    import torch
+    import torch.distributed as dist
+    fl = torch.tensor([[v["sum_d1"], v["max_d1"], v["sum_d2"], v["max_d2"], *v["csum"], *v["cmax"]] for v in vals],
+                      dtype=torch.float64, device=device)
+    it = torch.tensor([[v["sum_u64"], int(v["d2_valid"])] for v in vals], dtype=torch.int64, device=device)
+    fl_all = [torch.empty_like(fl) for _ in range(world)]
+    it_all = [torch.empty_like(it) for _ in range(world)]
+    dist.all_gather(fl_all, fl, group=group)
+    dist.all_gather(it_all, it, group=group)
+    fl_all = torch.stack(fl_all).cpu().numpy()   # (world, ndir, 10)
+    it_all = torch.stack(it_all).cpu().numpy()
+    out = []
+    for d, v in enumerate(vals):
+        r = dict(v)
+        r["sum_u64"] = int(sum(int(x) for x in it_all[:, d, 0]))
+        r["d2_valid"] = bool(it_all[:, d, 1].min())
+        acc = np.zeros(10)
+        acc[list(MAX_SLOTS)] = -np.inf
+        for w in range(world):
+            row = fl_all[w, d]
+            for j in SUM_SLOTS:
+                acc[j] = acc[j] + row[j]
+            for j in MAX_SLOTS:
+                acc[j] = max(acc[j], row[j])
+        r["sum_d1"], r["max_d1"], r["sum_d2"], r["max_d2"] = acc[0], acc[1], acc[2], acc[3]
+        r["csum"], r["cmax"] = acc[4:7].copy(), acc[7:10].copy()
+        out.append(r)
+    return out
+
+
+def exchange_minmax(mn: float, mx: float, group=None, device="cpu"):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([-mn, mx], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    t = t.cpu().numpy()
+    return -float(t[0]), float(t[1])
+
+
+def combine_disjoint(t, group=None):
+    """Every element was written by exactly one rank and is zero elsewhere: x + 0 == x."""
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t

@@ -1,0 +1,131 @@
+"""Point-cloud file reader standing in for ``o3d.io.read_point_cloud``
+(reference handler.py:57).
+
+PLY (ascii, binary_little_endian, binary_big_endian) with x/y/z of any scalar type,
+optional red/green/blue (uchar -> /255, floats kept) and nx/ny/nz; plus whitespace
+separated ``.xyz`` / ``.txt`` (x y z [r g b]).  Returns a ``geometry.PointCloud``
+holding float64 arrays like Open3D does.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .geometry import PointCloud
+
+_PLY_TYPES = {
+    "char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2",
+    "ushort": "u2", "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4",
+    "float": "f4", "float32": "f4", "double": "f8", "float64": "f8",
+}
+
+
+def _read_ply(path: str) -> PointCloud:
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None
+        elements = []  # (name, count, [(prop, type) | (prop, 'list', count_t, item_t)])
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: truncated header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] == "comment" or tok[0] == "obj_info":
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append((tok[1], int(tok[2]), []))
+            elif tok[0] == "property":
+                if tok[1] == "list":
+                    elements[-1][2].append((tok[4], "list", tok[2], tok[3]))
+                else:
+                    elements[-1][2].append((tok[2], tok[1]))
+            elif tok[0] == "end_header":
+                break
+        if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{path}: unsupported PLY format {fmt}")
+        vertex = None
+        for name, count, props in elements:
+            if name != "vertex":
+                if vertex is None:
+                    raise ValueError(f"{path}: element '{name}' precedes 'vertex' (unsupported)")
+                break
+            if any(p[1] == "list" for p in props):
+                raise ValueError(f"{path}: list property inside vertex element")
+            names = [p[0] for p in props]
+            if fmt == "ascii":
+                data = np.loadtxt(f, dtype=np.float64, max_rows=count, ndmin=2) if count else np.zeros((0, len(names)))
+                vertex = {n: data[:, i] for i, n in enumerate(names)}
+                u8 = {p[0] for p in props if _PLY_TYPES[p[1]] == "u1"}
+            else:
+                end = "<" if fmt == "binary_little_endian" else ">"
+                dt = np.dtype([(p[0], end + _PLY_TYPES[p[1]]) for p in props])
+                raw = np.frombuffer(f.read(dt.itemsize * count), dtype=dt, count=count)
+                vertex = {n: raw[n] for n in names}
+                u8 = {p[0] for p in props if _PLY_TYPES[p[1]] == "u1"}
+        if vertex is None:
+            raise ValueError(f"{path}: no vertex element")
+
+    def cols(keys):
+        return np.stack([np.asarray(vertex[k], dtype=np.float64) for k in keys], axis=1)
+
+    pc = PointCloud(cols(("x", "y", "z")))
+    if all(k in vertex for k in ("red", "green", "blue")):
+        c = cols(("red", "green", "blue"))
+        if "red" in u8:
+            c = c / 255.0
+        pc.colors = c
+    if all(k in vertex for k in ("nx", "ny", "nz")):
+        pc.normals = cols(("nx", "ny", "nz"))
+    return pc
+
+
+def _read_xyz(path: str) -> PointCloud:
+    data = np.loadtxt(path, dtype=np.float64, ndmin=2)
+    pc = PointCloud(data[:, :3])
+    if data.shape[1] >= 6:
+        c = data[:, 3:6]
+        pc.colors = c / 255.0 if c.max() > 1.0 else c
+    return pc
+
+
+def read_point_cloud(path: str) -> PointCloud:
+    low = path.lower()
+    if low.endswith(".ply"):
+        return _read_ply(path)
+    if low.endswith((".xyz", ".txt", ".xyzrgb")):
+        return _read_xyz(path)
+    raise ValueError(f"unsupported point cloud format: {path}")
+
+
+def write_ply(path: str, cloud, binary: bool = True) -> None:
+    """Small writer used by tests and examples (uchar colours, float normals)."""
+    pts = np.asarray(cloud.points, dtype=np.float64)
+    n = len(pts)
+    fields = [("x", "<f8"), ("y", "<f8"), ("z", "<f8")]
+    has_c = getattr(cloud, "colors", None) is not None and len(cloud.colors) == n and n > 0
+    has_n = getattr(cloud, "normals", None) is not None and len(cloud.normals) == n and n > 0
+    if has_c:
+        fields += [("red", "u1"), ("green", "u1"), ("blue", "u1")]
+    if has_n:
+        fields += [("nx", "<f8"), ("ny", "<f8"), ("nz", "<f8")]
+    rec = np.zeros(n, dtype=np.dtype(fields))
+    rec["x"], rec["y"], rec["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    if has_c:
+        c = np.rint(np.asarray(cloud.colors) * 255.0).astype(np.uint8)
+        rec["red"], rec["green"], rec["blue"] = c[:, 0], c[:, 1], c[:, 2]
+    if has_n:
+        nr = np.asarray(cloud.normals)
+        rec["nx"], rec["ny"], rec["nz"] = nr[:, 0], nr[:, 1], nr[:, 2]
+    names = {"<f8": "double", "u1": "uchar"}
+    header = ["ply", "format binary_little_endian 1.0" if binary else "format ascii 1.0", f"element vertex {n}"]
+    header += [f"property {names[t]} {k}" for k, t in fields]
+    header.append("end_header")
+    with open(path, "wb") as f:
+        f.write(("\n".join(header) + "\n").encode("ascii"))
+        if binary:
+            f.write(rec.tobytes())
+        else:
+            for r in rec:
+                f.write((" ".join(repr(v.item()) if isinstance(v, np.floating) else str(v) for v in r) + "\n").encode("ascii"))

@@ -1,0 +1,137 @@
+"""CPU tier: the per-thread search logic of the CUDA kernels (pccm_core.cuh, compiled
+for the host by tests/emul/emul.cpp) against the oracle -- every coordinate kind,
+cell sizes from far too small to far too large, ties, duplicates, outliers."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import cnn
+
+_L = ctypes.CDLL(os.path.join(os.path.dirname(__file__), "emul", "libpccm_emul.so"))
+KINT, KF32, KF64 = 0, 1, 2
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def emul_nn(kind, q, s, cell):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q))
+    _L.emul_nn(kind, _p(q), ctypes.c_int64(len(q)), _p(s), ctypes.c_int64(len(s)), ctypes.c_double(cell), _p(idx), _p(d2))
+    return idx, d2
+
+
+def emul_knn(kind, pts, k, cell):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    n = len(pts)
+    idx = np.empty((n, k), np.int32)
+    d2 = np.empty((n, k))
+    nr = np.empty((n, 3))
+    _L.emul_knn_self(kind, _p(pts), ctypes.c_int64(n), k, ctypes.c_double(cell), _p(idx), _p(d2), _p(nr))
+    return idx, d2, nr
+
+
+def _check_nn(kind, q, s, cell):
+    oi, od = cnn.knn(s, q, 1)
+    i, d = emul_nn(kind, q, s, cell)
+    assert np.array_equal(d, od[:, 0])
+    assert np.array_equal(i, oi[:, 0])
+
+
+@pytest.mark.parametrize("cell", [1, 2, 4, 16, 256])
+def test_int_nn_cells(cell):
+    rng = np.random.default_rng(1)
+    A = rng.integers(0, 64, (3000, 3)).astype(float)
+    B = rng.integers(0, 64, (2000, 3)).astype(float)
+    B[:5] += 300          # isolated far points: ring expansion must reach them
+    B = np.concatenate([B, B[:50]])  # duplicates: smallest index must win
+    _check_nn(KINT, A, B, cell)
+    _check_nn(KINT, B, A, cell)
+
+
+def test_int_extremes():
+    A = np.array([[0, 0, 0], [32767, 32767, 32767], [0, 32767, 0], [16000, 1, 2]], dtype=float)
+    B = np.array([[32767, 0, 32767], [1, 1, 1], [32766, 32767, 32767]], dtype=float)
+    for cell in (1, 64, 4096, 32768):
+        _check_nn(KINT, A, B, cell)
+        _check_nn(KINT, B, A, cell)
+    _check_nn(KINT, A, A[:1], 4)      # single-point search cloud
+    _check_nn(KINT, A[:1], A, 4)
+
+
+@pytest.mark.parametrize("kind", [KF32, KF64])
+@pytest.mark.parametrize("cell", [0.01, 0.1, 0.5, 10.0])
+def test_float_nn_cells(kind, cell):
+    rng = np.random.default_rng(2)
+    A = rng.normal(0, 1, (2500, 3))
+    B = A[rng.permutation(2500)][:2000] + rng.normal(0, 0.05, (2000, 3))
+    if kind == KF32:
+        A = A.astype(np.float32).astype(float)
+        B = B.astype(np.float32).astype(float)
+    B[:3] += 40.0
+    _check_nn(kind, A, B, cell)
+    _check_nn(kind, B, A, cell)
+
+
+def test_float_lattice_ties():
+    """float kinds on integer-valued data: exact ties must still break on the index."""
+    rng = np.random.default_rng(3)
+    A = rng.integers(-20, 20, (1500, 3)).astype(float) * 0.5
+    B = rng.integers(-20, 20, (1500, 3)).astype(float) * 0.5
+    for kind in (KF32, KF64):
+        for cell in (0.5, 2.0):
+            _check_nn(kind, A, B, cell)
+
+
+@pytest.mark.parametrize("kind,cell", [(KINT, 1), (KINT, 4), (KF32, 0.2), (KF64, 0.2)])
+def test_knn_and_normals(kind, cell):
+    rng = np.random.default_rng(4)
+    if kind == KINT:
+        P = rng.integers(0, 48, (2500, 3)).astype(float)
+    else:
+        P = rng.normal(0, 1, (2500, 3))
+        if kind == KF32:
+            P = P.astype(np.float32).astype(float)
+    for k in (2, 30):
+        oi, od = cnn.knn(P, P, k)
+        i, d, nr = emul_knn(kind, P, k, cell)
+        assert np.array_equal(d, od) and np.array_equal(i, oi)
+        if k == 30:
+            assert np.array_equal(nr, cnn.normals(P, oi))   # same arithmetic, same libm on the host
+
+
+def test_knn_fewer_points_than_k():
+    P = np.array([[0, 0, 0], [1, 0, 0], [5, 5, 5]], dtype=float)
+    i, d, nr = emul_knn(KINT, P, 30, 2)
+    assert np.array_equal(i[:, :3], [[0, 1, 2], [1, 0, 2], [2, 1, 0]]) and (i[:, 3:] == -1).all()
+    assert np.isinf(d[:, 3:]).all()
+    oi, _ = cnn.knn(P, P, 3)
+    assert np.array_equal(nr, cnn.normals(P, oi))
+
+
+coords = st.integers(min_value=0, max_value=40)
+cloud = st.lists(st.tuples(coords, coords, coords), min_size=1, max_size=60)
+
+
+@settings(max_examples=150, deadline=None)
+@given(a=cloud, b=cloud, shift=st.integers(0, 6))
+def test_property_int_nn(a, b, shift):
+    A = np.array(a, dtype=float)
+    B = np.array(b, dtype=float)
+    _check_nn(KINT, A, B, 1 << shift)
+
+
+fl = st.floats(min_value=-50, max_value=50, allow_nan=False, width=32)
+fcloud = st.lists(st.tuples(fl, fl, fl), min_size=1, max_size=40)
+
+
+@settings(max_examples=100, deadline=None)
+@given(a=fcloud, b=fcloud, cell=st.sampled_from([0.05, 1.0, 30.0]), kind=st.sampled_from([KF32, KF64]))
+def test_property_float_nn(a, b, cell, kind):
+    _check_nn(kind, np.array(a, dtype=float), np.array(b, dtype=float), cell)
