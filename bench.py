@@ -49,7 +49,7 @@ YUV = np.array([[0.25, 0.5, 0.25], [1, 0, -1], [-0.5, 1, -0.5]], dtype=np.float6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000, help="target points of the original cloud")
@@ -280,10 +280,10 @@ def main():
     total_queries = nq * args.steps * (1 if partition else world)
     value = total_queries / (ms_dev_max * 1e-3)
 
-    # query-kernel roofline (two launches per step: A->B and B->A), measured live with CUDA events
+    # query-kernel roofline (one launch per step covers A->B and B->A), measured live with CUDA events
     q_launches = max(1, tm["query_launches"])
-    q_ms_avg = tm["query_ms"] / q_launches                      # event pairs bracket the two back-to-back launches of a step
-    queries_per_launch = (nq / 2) / (world if partition else 1)
+    q_ms_avg = tm["query_ms"] / q_launches
+    queries_per_launch = nq / (world if partition else 1)
     achieved = ALG_BYTES_PER_QUERY * queries_per_launch / (q_ms_avg * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -294,6 +294,10 @@ def main():
     tp = os.path.join(ROOT, "profiles", "query_kernel_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    # per-stage device time (separate short loop with every stage bracketed by events; informational)
+    _, _, tm2, _ = timed(step_device, 5, 1, 2)
+    stages = {k: round(v / 5, 5) for k, v in tm2.items() if k.endswith("_ms")}
 
     e2e = None
     if not args.no_e2e:
@@ -337,7 +341,7 @@ def main():
                          "avg_launch_ms": q_ms_avg},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(tm["total_launches"]), "library_launches": int(tm["library_launches"]),
-            "wall_s_timed_region": wall_dev,
+            "wall_s_timed_region": wall_dev, "stage_ms_per_step": stages,
             "check": None if ps is None else {"d1_psnr_left": float(ps[0][0]), "d2_psnr_left": float(ps[0][1]),
                                               "y_psnr_left": float(ps[0][2][0])},
         }

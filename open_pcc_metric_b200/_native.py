@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpccm.so")
+LIB_PATH = os.environ.get("PCCM_LIB", os.path.join(_HERE, "libpccm.so"))  # PCCM_LIB: A/B testing of builds
 
 # enums (include/pccm.h)
 F64, F32, I32, U16, U8 = 0, 1, 2, 3, 4

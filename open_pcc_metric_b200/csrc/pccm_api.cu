@@ -46,6 +46,7 @@ struct pccm_ctx {
     int sm_count = 148;
     int cell_override_shift = -1;   // debugging: PCCM_CELL_SHIFT
     double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
+    uint32_t short_row = 8;         // rows up to this length skip the binary search (PCCM_SHORT_ROW)
 };
 
 static thread_local std::string g_err;
@@ -263,7 +264,9 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
         delete ctx;
         return fail(nullptr, PCCM_ERR_CUDA, "scratch allocation failed");
     }
+    cudaMemset(ctx->dscratch, 0, pccm_ctx::kScratch);
     if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
+    if (const char* s = getenv("PCCM_SHORT_ROW")) ctx->short_row = (uint32_t)atoi(s);
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
     return PCCM_OK;
@@ -502,6 +505,7 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
     const uint32_t n = (uint32_t)c->n;
     RowGrid g{};
     g.n = n;
+    g.short_row = ctx->short_row;
     if (n == 0) {
         g.ny = g.nz = 1; g.h = g.inv_h = 1; g.shift = 0;
         c->grid = g; c->index_kind = kind; c->cell_size = 1;
@@ -665,14 +669,42 @@ static CloudView view_of(const pccm_cloud* c) {
     return v;
 }
 
-static int launch_query(pccm_ctx* ctx, int kind, const QueryParams& P, uint32_t nblocks) {
-    if (nblocks == 0) return PCCM_OK;
-    if (kind == PCCM_KIND_INT) pair_query_kernel<KInt><<<nblocks, kQueryThreads, 0, ctx->stream>>>(P);
-    else if (kind == PCCM_KIND_F32) pair_query_kernel<KF32><<<nblocks, kQueryThreads, 0, ctx->stream>>>(P);
-    else pair_query_kernel<KF64><<<nblocks, kQueryThreads, 0, ctx->stream>>>(P);
-    ctx->tm.query_launches++;
-    ctx->tm.total_launches++;
+static constexpr size_t kTicketOffset = 4096;   // bytes into ctx->dscratch (zeroed at creation)
+static constexpr size_t kChunksOffset = 16384;  // 64 BlockPartial records of the fold
+
+// One launch covers every requested direction; the per-direction reduced records land in
+// ctx->dscratch[0..1] and are copied to ctx->pinned.
+static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
+    uint32_t max_tiles = 0, total_tiles = 0;
+    for (int d = 0; d < P.ndirs; ++d) {
+        P.dir[d].ntiles = (P.dir[d].qend - P.dir[d].qbegin + kQueryThreads - 1) / kQueryThreads;
+        max_tiles = std::max(max_tiles, P.dir[d].ntiles);
+        total_tiles += P.dir[d].ntiles;
+    }
+    P.rec_stride = max_tiles * (kQueryThreads / 32);
+    BlockPartial* partials = nullptr;
+    CK(dalloc(ctx, &partials, (size_t)P.rec_stride * 2 + 1));
+    P.partials = partials;
+    P.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->dscratch) + kTicketOffset);
+    P.out = static_cast<BlockPartial*>(ctx->dscratch);
+    P.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);
+    if (total_tiles) {
+        StageTimer t(ctx, &ctx->tm.query_ms, 1);
+        if (kind == PCCM_KIND_INT) pair_query_kernel<KInt><<<total_tiles, kQueryThreads, 0, ctx->stream>>>(P);
+        else if (kind == PCCM_KIND_F32) pair_query_kernel<KF32><<<total_tiles, kQueryThreads, 0, ctx->stream>>>(P);
+        else pair_query_kernel<KF64><<<total_tiles, kQueryThreads, 0, ctx->stream>>>(P);
+        ctx->tm.query_launches++;
+        ctx->tm.total_launches++;
+    }
     CK(cudaGetLastError());
+    {
+        StageTimer t(ctx, &ctx->tm.finalize_ms);
+        finalize_kernel<<<P.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream>>>(P);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    dfree(ctx, partials);
     return PCCM_OK;
 }
 
@@ -691,27 +723,22 @@ extern "C" int pccm_nn(pccm_ctx* ctx, pccm_cloud* query, pccm_cloud* search, int
     if (query->n == 0) return PCCM_OK;
     if (search->n == 0) return fail(ctx, PCCM_ERR_INDEX, "search cloud is empty (reference: IndexError at cloud_pair.py:23)");
     const uint32_t nq = (uint32_t)query->n;
-    const uint32_t nblocks = (nq + kQueryThreads - 1) / kQueryThreads;
     int32_t* d_idx = nullptr;
     double* d_d2 = nullptr;
-    BlockPartial* partials = nullptr;
-    CK(dalloc(ctx, &partials, (size_t)nblocks));
     if (idx_out) { if (mem_kind == PCCM_DEVICE) d_idx = idx_out; else CK(dalloc(ctx, &d_idx, (size_t)nq)); }
     if (d2_out) { if (mem_kind == PCCM_DEVICE) d_d2 = d2_out; else CK(dalloc(ctx, &d_d2, (size_t)nq)); }
     QueryParams P{};
-    P.q = view_of(query); P.s = view_of(search);
-    P.qbegin = 0; P.qend = nq; P.flags = 0; P.normals_mode = 0; P.color_scale = 1;
-    P.idx_out = d_idx; P.d2_out = d_d2; P.partials = partials;
-    {
-        StageTimer t(ctx, &ctx->tm.query_ms, 1);
-        rc = launch_query(ctx, query->index_kind, P, nblocks);
-    }
+    P.ndirs = 1;
+    P.dir[0].q = view_of(query); P.dir[0].s = view_of(search);
+    P.dir[0].qbegin = 0; P.dir[0].qend = nq; P.dir[0].flags = 0;
+    P.dir[0].idx_out = d_idx; P.dir[0].d2_out = d_d2;
+    P.normals_mode = 0; P.color_scale = 1;
+    rc = launch_query(ctx, query->index_kind, P);
     if (!rc && mem_kind == PCCM_HOST) {
         if (idx_out) rc = copy_out(ctx, idx_out, d_idx, (size_t)nq * sizeof(int32_t), PCCM_HOST);
         if (!rc && d2_out) rc = copy_out(ctx, d2_out, d_d2, (size_t)nq * sizeof(double), PCCM_HOST);
         dfree(ctx, d_idx); dfree(ctx, d_d2);
     }
-    dfree(ctx, partials);
     return rc;
 }
 
@@ -738,15 +765,18 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
     for (int d = 0; d < 2; ++d)
         if ((flags & PCCM_EVAL_D2) && normals_mode == PCCM_NORMALS_BY_QUERY_INDEX && cl[1 - d]->n < cl[d]->n)
             dflags[d] &= ~(uint32_t)PCCM_EVAL_D2;
-    BlockPartial* partials[2] = {nullptr, nullptr};
-    uint32_t nblocks[2];
-    uint32_t qb[2], qe[2];
+    QueryParams P{};
+    P.ndirs = 2;
+    P.normals_mode = normals_mode;
+    if (color_matrix) memcpy(P.T, color_matrix, sizeof P.T);
+    P.color_scale = color_scale;
     for (int d = 0; d < 2; ++d) {
         const uint64_t n = (uint64_t)cl[d]->n;
-        qb[d] = (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
-        qe[d] = (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
-        nblocks[d] = (qe[d] - qb[d] + kQueryThreads - 1) / kQueryThreads;
-        CK(dalloc(ctx, &partials[d], (size_t)nblocks[d]));
+        DirParams& D = P.dir[d];
+        D.q = view_of(cl[d]); D.s = view_of(cl[1 - d]);
+        D.qbegin = (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
+        D.qend = (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
+        D.flags = dflags[d];
         if (flags & PCCM_EVAL_PERPOINT) {
             if (ctx->pp_n[d] != cl[d]->n) {
                 dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]);
@@ -758,42 +788,18 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
                 CK(cudaMemsetAsync(ctx->pp_idx[d], 0xff, n * sizeof(int32_t), ctx->stream));
                 CK(cudaMemsetAsync(ctx->pp_d2[d], 0xff, n * sizeof(double), ctx->stream));
             }
+            D.idx_out = ctx->pp_idx[d];
+            D.d2_out = ctx->pp_d2[d];
         }
     }
-    {
-        StageTimer t(ctx, &ctx->tm.query_ms, 1);
-        for (int d = 0; d < 2 && !rc; ++d) {
-            QueryParams P{};
-            P.q = view_of(cl[d]); P.s = view_of(cl[1 - d]);
-            P.qbegin = qb[d]; P.qend = qe[d];
-            P.flags = dflags[d]; P.normals_mode = normals_mode;
-            if (color_matrix) memcpy(P.T, color_matrix, sizeof P.T);
-            P.color_scale = color_scale;
-            P.idx_out = (flags & PCCM_EVAL_PERPOINT) ? ctx->pp_idx[d] : nullptr;
-            P.d2_out = (flags & PCCM_EVAL_PERPOINT) ? ctx->pp_d2[d] : nullptr;
-            P.partials = partials[d];
-            rc = launch_query(ctx, a->index_kind, P, nblocks[d]);
-        }
-    }
-    if (!rc) {
-        StageTimer t(ctx, &ctx->tm.finalize_ms);
-        FinalizeParams F;
-        F.partials[0] = partials[0]; F.partials[1] = partials[1];
-        F.nblocks[0] = nblocks[0]; F.nblocks[1] = nblocks[1];
-        F.out = static_cast<BlockPartial*>(ctx->dscratch);
-        finalize_kernel<<<2, kFinalThreads, 0, ctx->stream>>>(F);
-        ctx->tm.total_launches++;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    dfree(ctx, partials[0]); dfree(ctx, partials[1]);
+    rc = launch_query(ctx, a->index_kind, P);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     const BlockPartial* r = static_cast<const BlockPartial*>(ctx->pinned);
     memset(out, 0, sizeof *out);
     for (int d = 0; d < 2; ++d) {
         pccm_dir_result& o = out->dir[d];
-        o.n = (int64_t)(qe[d] - qb[d]);
+        o.n = (int64_t)(P.dir[d].qend - P.dir[d].qbegin);
         o.n_total = cl[d]->n;
         o.d1_exact_int = a->index_kind == PCCM_KIND_INT;
         o.d2_valid = (dflags[d] & PCCM_EVAL_D2) != 0;

@@ -68,7 +68,7 @@ struct RowGrid {
     double h, inv_h;      // float kinds: cell size
     double slack;         // float kinds: absolute safety margin on cell boundaries
     uint32_t n;           // number of points
-    uint32_t pad_;
+    uint32_t short_row;   // rows up to this length are scanned linearly (no binary search)
 };
 
 struct alignas(16) RecF64 {
@@ -250,7 +250,16 @@ struct TopK {
 // ---- pencil visit ---------------------------------------------------------------------
 template <class K, class Acc>
 PCCM_HD void visit_run(const typename K::Rec* __restrict__ recs, uint32_t lo, uint32_t hi,
-                       const typename K::Q& q, typename K::D B2, Acc& acc) {
+                       const typename K::Q& q, typename K::D B2, Acc& acc, uint32_t short_row) {
+    if (hi - lo <= short_row) {           // short pencil: one pass, no dependent search loads
+        for (uint32_t i = lo; i < hi; ++i) {
+            typename K::Rec r = load_rec(recs + i);
+            typename K::C dx = K::rec_q(r).x - q.x;
+            if (K::lbound(dx, B2) > acc.worst()) continue;
+            acc.offer(K::dist2(q, r), K::rec_idx(r), i);
+        }
+        return;
+    }
     // first record with x >= q.x
     uint32_t a = lo, b = hi;
     while (a < b) {
@@ -288,7 +297,7 @@ PCCM_HD void search(const RowGrid& g, const uint32_t* __restrict__ row_start,
         if (B2 > acc.worst()) return;
         const uint32_t row = (uint32_t)zz * (uint32_t)ny + (uint32_t)yy;
         const uint32_t lo = load_u32(row_start + row), hi = load_u32(row_start + row + 1);
-        if (lo < hi) visit_run<K>(recs, lo, hi, q, B2, acc);
+        if (lo < hi) visit_run<K>(recs, lo, hi, q, B2, acc, g.short_row);
     };
 
     for (int r = 0;; ++r) {

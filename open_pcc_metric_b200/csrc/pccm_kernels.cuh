@@ -259,21 +259,31 @@ struct CloudView {        // device-side view of an indexed cloud
     const double* normals;  // original order [n][3], or null
 };
 
-struct BlockPartial {
+struct BlockPartial {   // one reduced record (per warp while the kernel runs, per direction at the end)
     unsigned long long sum_d1_u64;
     double sum_d1, max_d1, sum_d2, max_d2, csum[3], cmax[3];
 };
 
-struct QueryParams {
+struct DirParams {
     CloudView q, s;
-    uint32_t qbegin, qend;    // range of the query cloud's sorted order
+    uint32_t qbegin, qend;    // slice of the query cloud's sorted order
+    uint32_t ntiles;          // ceil((qend - qbegin) / kQueryThreads)
     uint32_t flags;
+    int32_t* idx_out;         // original query order, or null
+    double* d2_out;
+};
+
+struct QueryParams {
+    DirParams dir[2];
+    int32_t ndirs;
     int32_t normals_mode;
     double T[9];
     double color_scale;
-    int32_t* idx_out;         // original query order, or null
-    double* d2_out;
-    BlockPartial* partials;   // one per block
+    BlockPartial* partials;   // per-warp records: direction d at [d * rec_stride + tile * warps + warp]
+    uint32_t rec_stride;
+    BlockPartial* chunks;     // [ndirs * kFinalChunks] scratch of the fold
+    unsigned int* ticket;     // zero on entry; the last fold block resets it
+    BlockPartial* out;        // [2]
 };
 
 __device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uint32_t packed, bool have_packed, double* out) {
@@ -294,110 +304,143 @@ __device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uin
 template <class K> __device__ __forceinline__ uint32_t rec_rgba(const typename K::Rec&) { return 0; }
 template <> __device__ __forceinline__ uint32_t rec_rgba<KInt>(const uint4& r) { return r.w; }
 
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void partial_init(BlockPartial& a) {
+    a.sum_d1_u64 = 0; a.sum_d1 = 0; a.sum_d2 = 0; a.max_d1 = -INFINITY; a.max_d2 = -INFINITY;
+    for (int k = 0; k < 3; ++k) { a.csum[k] = 0; a.cmax[k] = -INFINITY; }
+}
+__device__ __forceinline__ void partial_merge(BlockPartial& a, const BlockPartial& b) {
+    a.sum_d1_u64 += b.sum_d1_u64;
+    a.sum_d1 = dadd(a.sum_d1, b.sum_d1);
+    a.sum_d2 = dadd(a.sum_d2, b.sum_d2);
+    a.max_d1 = fmax(a.max_d1, b.max_d1);
+    a.max_d2 = fmax(a.max_d2, b.max_d2);
+    for (int k = 0; k < 3; ++k) { a.csum[k] = dadd(a.csum[k], b.csum[k]); a.cmax[k] = fmax(a.cmax[k], b.cmax[k]); }
+}
+__device__ __forceinline__ void partial_warp_reduce(BlockPartial& a, uint32_t flags) {
+    a.sum_d1_u64 = warp_sum_u64(a.sum_d1_u64);
+    a.sum_d1 = warp_sum(a.sum_d1);
+    a.max_d1 = warp_max(a.max_d1);
+    if (flags & PCCM_EVAL_D2) { a.sum_d2 = warp_sum(a.sum_d2); a.max_d2 = warp_max(a.max_d2); }
+    if (flags & PCCM_EVAL_COLOR)
+        for (int k = 0; k < 3; ++k) { a.csum[k] = warp_sum(a.csum[k]); a.cmax[k] = warp_max(a.cmax[k]); }
+}
+
+// One launch covers both directions: blocks [0, dir[0].ntiles) serve direction 0, the rest
+// direction 1; a block is one tile of kQueryThreads consecutive queries of the sorted order
+// (the hardware block scheduler balances the very uneven tile costs).  Each warp reduces its 32
+// queries with shuffles only -- no block barrier -- and writes ONE record at a position fixed
+// by its tile, so the floating-point sums do not depend on scheduling.
+#ifdef PCCM_QBLOCKS
+#define PCCM_QUERY_BOUNDS __launch_bounds__(kQueryThreads, PCCM_QBLOCKS)
+#else
+#define PCCM_QUERY_BOUNDS __launch_bounds__(kQueryThreads)
+#endif
 template <class K>
-__global__ void __launch_bounds__(kQueryThreads)
+__global__ void PCCM_QUERY_BOUNDS
 pair_query_kernel(const __grid_constant__ QueryParams P) {
     typedef typename K::Rec Rec;
     typedef typename K::Q Q;
-    const Rec* __restrict__ qrecs = static_cast<const Rec*>(P.q.recs);
-    const Rec* __restrict__ srecs = static_cast<const Rec*>(P.s.recs);
-    const uint32_t t = P.qbegin + blockIdx.x * kQueryThreads + threadIdx.x;
-    const bool active = t < P.qend;
-
-    unsigned long long d1_u64 = 0;
-    double d1 = 0, pe2 = 0, cd2[3] = {0, 0, 0}, cd2s[3] = {0, 0, 0};
-    double d1_max = -INFINITY, pe2_max = -INFINITY, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (active) {
+    constexpr int kWarps = kQueryThreads / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
+    const DirParams& D = P.dir[d];
+    const uint32_t tile = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
+    const Rec* __restrict__ qrecs = static_cast<const Rec*>(D.q.recs);
+    const Rec* __restrict__ srecs = static_cast<const Rec*>(D.s.recs);
+    BlockPartial acc;
+    partial_init(acc);
+    const uint32_t t = D.qbegin + tile * kQueryThreads + threadIdx.x;
+    if (t < D.qend) {
         const Rec qr = load_rec(qrecs + t);
         const Q q = K::rec_q(qr);
         const uint32_t qidx = K::rec_idx(qr);
         Best1<K> best;
         best.init();
-        search<K>(P.s.grid, P.s.row_start, srecs, q, best);
-        d1 = K::d2_as_double(best.d2);
-        d1_max = d1;
-        if (K::kind == KIND_INT) d1_u64 = (unsigned long long)best.d2;
-        if (P.idx_out) P.idx_out[qidx] = (int32_t)best.idx;
-        if (P.d2_out) P.d2_out[qidx] = d1;
-        if (P.flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
+        search<K>(D.s.grid, D.s.row_start, srecs, q, best);
+        const double d1 = K::d2_as_double(best.d2);
+        if (K::kind == KIND_INT) acc.sum_d1_u64 = (unsigned long long)best.d2;
+        else acc.sum_d1 = d1;
+        acc.max_d1 = d1;
+        if (D.idx_out) D.idx_out[qidx] = (int32_t)best.idx;
+        if (D.d2_out) D.d2_out[qidx] = d1;
+        if (D.flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
             const Rec nr = load_rec(srecs + best.pos);
-            if (P.flags & PCCM_EVAL_D2) {
+            if (D.flags & PCCM_EVAL_D2) {
                 const Q nq = K::rec_q(nr);
                 double e[3] = {dsub((double)q.x, (double)nq.x), dsub((double)q.y, (double)nq.y), dsub((double)q.z, (double)nq.z)};
                 const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? best.idx : qidx;
-                double nv[3] = {__ldg(P.s.normals + 3 * (size_t)ni), __ldg(P.s.normals + 3 * (size_t)ni + 1),
-                                __ldg(P.s.normals + 3 * (size_t)ni + 2)};
-                pe2 = plane_err2(e, nv);
-                pe2_max = pe2;
+                double nv[3] = {__ldg(D.s.normals + 3 * (size_t)ni), __ldg(D.s.normals + 3 * (size_t)ni + 1),
+                                __ldg(D.s.normals + 3 * (size_t)ni + 2)};
+                acc.sum_d2 = plane_err2(e, nv);
+                acc.max_d2 = acc.sum_d2;
             }
-            if (P.flags & PCCM_EVAL_COLOR) {
+            if (D.flags & PCCM_EVAL_COLOR) {
                 double cq[3], cn[3];
-                load_color(P.q, qidx, rec_rgba<K>(qr), K::kind == KIND_INT, cq);
-                load_color(P.s, best.idx, rec_rgba<K>(nr), K::kind == KIND_INT, cn);
-                color_diff2(P.T, cq, cn, P.color_scale, cd2, cd2s);
-                cmax[0] = cd2s[0]; cmax[1] = cd2s[1]; cmax[2] = cd2s[2];
+                load_color(D.q, qidx, rec_rgba<K>(qr), K::kind == KIND_INT, cq);
+                load_color(D.s, best.idx, rec_rgba<K>(nr), K::kind == KIND_INT, cn);
+                color_diff2(P.T, cq, cn, P.color_scale, acc.csum, acc.cmax);
             }
         }
     }
-    __shared__ double sm[kQueryThreads / 32];
-    __shared__ unsigned long long smu[kQueryThreads / 32];
-    BlockPartial bp;
-    bp.sum_d1_u64 = block_sum_u64<kQueryThreads>(d1_u64, smu);
-    bp.sum_d1 = block_sum<kQueryThreads>(d1, sm);
-    bp.max_d1 = block_max<kQueryThreads>(d1_max, sm);
-    bp.sum_d2 = 0; bp.max_d2 = -INFINITY;
-    bp.csum[0] = bp.csum[1] = bp.csum[2] = 0;
-    bp.cmax[0] = bp.cmax[1] = bp.cmax[2] = -INFINITY;
-    if (P.flags & PCCM_EVAL_D2) {
-        bp.sum_d2 = block_sum<kQueryThreads>(pe2, sm);
-        bp.max_d2 = block_max<kQueryThreads>(pe2_max, sm);
-    }
-    if (P.flags & PCCM_EVAL_COLOR) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            bp.csum[k] = block_sum<kQueryThreads>(cd2[k], sm);
-            bp.cmax[k] = block_max<kQueryThreads>(cmax[k], sm);
-        }
-    }
-    if (threadIdx.x == 0) P.partials[blockIdx.x] = bp;
+    partial_warp_reduce(acc, D.flags);
+    if (lane == 0) P.partials[(size_t)d * P.rec_stride + (size_t)tile * kWarps + warp] = acc;
 }
 
-// K8: fixed-order reduction of the per-block partials (one block per direction).
-struct FinalizeParams {
-    const BlockPartial* partials[2];
-    uint32_t nblocks[2];
-    BlockPartial* out;   // [2]
-};
+// K8: fixed-order fold of the per-warp records.  gridDim.x = ndirs * kFinalChunks; block
+// (d, c) folds chunk c of direction d; the last block to finish folds the chunk results.
 constexpr int kFinalThreads = 256;
-__global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_constant__ FinalizeParams P) {
-    const int d = blockIdx.x;
-    const BlockPartial* in = P.partials[d];
-    const uint32_t nb = P.nblocks[d];
+constexpr int kFinalChunks = 32;
+
+__device__ __forceinline__ void block_fold(BlockPartial& a, BlockPartial* sm, BlockPartial* dst) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    partial_warp_reduce(a, PCCM_EVAL_D2 | PCCM_EVAL_COLOR);
+    __syncthreads();
+    if (lane == 0) sm[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockPartial r = sm[0];
+        for (int w = 1; w < kFinalThreads / 32; ++w) partial_merge(r, sm[w]);
+        *dst = r;
+    }
+}
+
+__global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_constant__ QueryParams P) {
+    __shared__ BlockPartial sm[kFinalThreads / 32];
+    __shared__ bool is_last;
+    const int d = blockIdx.x / kFinalChunks, c = blockIdx.x % kFinalChunks;
+    const uint32_t nrec = P.dir[d].ntiles * (kQueryThreads / 32);
+    const uint32_t per = (nrec + kFinalChunks - 1) / kFinalChunks;
+    const uint32_t lo = c * per, hi = lo + per < nrec ? lo + per : nrec;
+    const BlockPartial* in = P.partials + (size_t)d * P.rec_stride;
     BlockPartial a;
-    a.sum_d1_u64 = 0; a.sum_d1 = 0; a.sum_d2 = 0; a.max_d1 = -INFINITY; a.max_d2 = -INFINITY;
-    for (int k = 0; k < 3; ++k) { a.csum[k] = 0; a.cmax[k] = -INFINITY; }
-    for (uint32_t i = threadIdx.x; i < nb; i += kFinalThreads) {
-        const BlockPartial b = in[i];
-        a.sum_d1_u64 += b.sum_d1_u64;
-        a.sum_d1 = dadd(a.sum_d1, b.sum_d1);
-        a.sum_d2 = dadd(a.sum_d2, b.sum_d2);
-        a.max_d1 = fmax(a.max_d1, b.max_d1);
-        a.max_d2 = fmax(a.max_d2, b.max_d2);
-        for (int k = 0; k < 3; ++k) { a.csum[k] = dadd(a.csum[k], b.csum[k]); a.cmax[k] = fmax(a.cmax[k], b.cmax[k]); }
+    partial_init(a);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kFinalThreads) partial_merge(a, in[i]);
+    block_fold(a, sm, P.chunks + blockIdx.x);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(P.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int dd = 0; dd < P.ndirs; ++dd) {
+        partial_init(a);
+        if (threadIdx.x < kFinalChunks) a = P.chunks[dd * kFinalChunks + threadIdx.x];
+        block_fold(a, sm, P.out + dd);
     }
-    __shared__ double sm[kFinalThreads / 32];
-    __shared__ unsigned long long smu[kFinalThreads / 32];
-    BlockPartial r;
-    r.sum_d1_u64 = block_sum_u64<kFinalThreads>(a.sum_d1_u64, smu);
-    r.sum_d1 = block_sum<kFinalThreads>(a.sum_d1, sm);
-    r.sum_d2 = block_sum<kFinalThreads>(a.sum_d2, sm);
-    r.max_d1 = block_max<kFinalThreads>(a.max_d1, sm);
-    r.max_d2 = block_max<kFinalThreads>(a.max_d2, sm);
-    for (int k = 0; k < 3; ++k) {
-        r.csum[k] = block_sum<kFinalThreads>(a.csum[k], sm);
-        r.cmax[k] = block_max<kFinalThreads>(a.cmax[k], sm);
-    }
-    if (threadIdx.x == 0) P.out[d] = r;
+    if (threadIdx.x == 0) *P.ticket = 0;
 }
 
 // ------------------------------------------------------------------------------------

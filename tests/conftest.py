@@ -92,9 +92,14 @@ def is_d1_family(key):
 
 
 def assert_metric_close(key, got, want, rtol=1e-6, atol=1e-30, exact_d1=True):
+    """exact_d1: integer (voxelised) clouds -> the D1 family is bit exact; float clouds sum in a
+    different order than numpy's pairwise np.sum -> pass exact_d1=False."""
     g = np.asarray(got, dtype=np.float64)
     w = np.asarray(want, dtype=np.float64)
     assert g.shape == w.shape, (key, g.shape, w.shape)
+    name = key[0] if key[0] != "SymmetricMetric" else key[1]
+    if exact_d1 == "max_only" and name in ("GeoMSE", "GeoPSNR"):
+        exact_d1 = False      # float clouds: the sum order differs from numpy's, the maxima do not
     if exact_d1 and is_d1_family(key):
         assert np.array_equal(g, w), (key, g, w)
     else:

@@ -13,6 +13,8 @@
 
 using namespace pccm;
 
+static uint32_t g_short_row = 0;
+
 template <class K> struct Pack;
 template <> struct Pack<KInt> {
     static uint4 make(const double* p, uint32_t idx) {
@@ -33,12 +35,14 @@ struct Index {
     RowGrid g;
     std::vector<typename K::Rec> recs;
     std::vector<uint32_t> row_start;
+    uint32_t short_row = 0;
     void build(const double* pts, int64_t n, double cell) {
         double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int64_t i = 0; i < n; ++i)
             for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], pts[3 * i + a]); mx[a] = std::max(mx[a], pts[3 * i + a]); }
         memset(&g, 0, sizeof g);
         g.n = (uint32_t)n;
+        g.short_row = short_row;
         if (n == 0) { g.ny = g.nz = 1; g.h = g.inv_h = 1; row_start.assign(2, 0); return; }
         if (K::kind == KIND_INT) {
             int shift = (int)std::lround(std::log2(std::max(cell, 1.0)));
@@ -86,6 +90,7 @@ struct Index {
 template <class K>
 static void nn_impl(const double* q, int64_t nq, const double* s, int64_t ns, double cell, int32_t* idx, double* d2) {
     Index<K> ix;
+    ix.short_row = g_short_row;
     ix.build(s, ns, cell);
     for (int64_t i = 0; i < nq; ++i) {
         typename K::Q qq;
@@ -101,6 +106,7 @@ static void nn_impl(const double* q, int64_t nq, const double* s, int64_t ns, do
 template <class K>
 static void knn_impl(const double* pts, int64_t n, int k, double cell, int32_t* idx, double* d2, double* normals) {
     Index<K> ix;
+    ix.short_row = g_short_row;
     ix.build(pts, n, cell);
     std::vector<typename K::D> d2s(k);
     std::vector<uint32_t> idxs(k), poss(k);
@@ -126,6 +132,7 @@ static void knn_impl(const double* pts, int64_t n, int k, double cell, int32_t* 
     }
 }
 
+extern "C" void emul_set_short_row(uint32_t v) { g_short_row = v; }
 extern "C" int emul_nn(int kind, const double* q, int64_t nq, const double* s, int64_t ns, double cell, int32_t* idx, double* d2) {
     if (kind == KIND_INT) nn_impl<KInt>(q, nq, s, ns, cell, idx, d2);
     else if (kind == KIND_F32) nn_impl<KF32>(q, nq, s, ns, cell, idx, d2);

@@ -44,6 +44,14 @@ def _check_nn(kind, q, s, cell):
     assert np.array_equal(i, oi[:, 0])
 
 
+@pytest.fixture(params=[0, 8, 100000], autouse=True)
+def short_row(request):
+    """0 = always binary search + sweeps; 8 = product default; huge = always the linear scan."""
+    _L.emul_set_short_row(request.param)
+    yield request.param
+    _L.emul_set_short_row(8)
+
+
 @pytest.mark.parametrize("cell", [1, 2, 4, 16, 256])
 def test_int_nn_cells(cell):
     rng = np.random.default_rng(1)
@@ -119,7 +127,7 @@ coords = st.integers(min_value=0, max_value=40)
 cloud = st.lists(st.tuples(coords, coords, coords), min_size=1, max_size=60)
 
 
-@settings(max_examples=150, deadline=None)
+@settings(max_examples=60, deadline=None, suppress_health_check=list(__import__('hypothesis').HealthCheck))
 @given(a=cloud, b=cloud, shift=st.integers(0, 6))
 def test_property_int_nn(a, b, shift):
     A = np.array(a, dtype=float)
@@ -131,7 +139,7 @@ fl = st.floats(min_value=-50, max_value=50, allow_nan=False, width=32)
 fcloud = st.lists(st.tuples(fl, fl, fl), min_size=1, max_size=40)
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=40, deadline=None, suppress_health_check=list(__import__('hypothesis').HealthCheck))
 @given(a=fcloud, b=fcloud, cell=st.sampled_from([0.05, 1.0, 30.0]), kind=st.sampled_from([KF32, KF64]))
 def test_property_float_nn(a, b, cell, kind):
     _check_nn(kind, np.array(a, dtype=float), np.array(b, dtype=float), cell)

@@ -84,7 +84,7 @@ def test_metrics_match_reference_outputs(golden, ctx, name, use_fused):
                 continue
             got = calc._metric_recursive_calculate(m).value
             est = "est_nrm_a" in g.arr and any(x is True for x in k[2:3] + k[3:4]) and "Geo" in str(k)
-            assert_metric_close(k, got, want[k], rtol=1e-5 if est else RTOL, atol=ATOL)
+            assert_metric_close(k, got, want[k], rtol=1e-5 if est else RTOL, atol=ATOL, exact_d1=True if pair.kind == 0 else "max_only")
             n_ok += 1
         assert n_ok >= 8
         pair.close()
