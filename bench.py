@@ -220,9 +220,7 @@ def main():
     def step_device():
         a = ctx.cloud(*dA)
         b = ctx.cloud(*dB)
-        kind = max(a.info().data_kind, b.info().data_kind)
-        a.build_index(0.0, kind)
-        b.build_index(0.0, kind)
+        ctx.build_pair(a, b)
         res = ctx.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV, 1.0, N.NORMALS_BY_QUERY_INDEX, sl[0], sl[1])
         a.close()
         b.close()

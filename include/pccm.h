@@ -15,8 +15,10 @@
  *  - all device work is ordered on the context's CUDA stream; functions that
  *    fill HOST outputs synchronise that stream before returning;
  *  - a pccm_ctx is not thread safe: one context per (thread, device);
- *  - caller owns every buffer it passes; HOST inputs are copied before return,
- *    DEVICE inputs are read until pccm_cloud_build_index() returns;
+ *  - caller owns every buffer it passes; HOST inputs are copied before return;
+ *    DEVICE coordinates / colours are read until the index is built; packed float64
+ *    DEVICE normals given to pccm_cloud_create are used in place and must outlive
+ *    the cloud;
  *  - there is NO CPU fallback: without a CUDA device pccm_ctx_create fails.
  */
 #ifndef PCCM_H_
@@ -128,6 +130,11 @@ int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* cloud, pccm_cloud_info* out);
  * index.  cell_size 0 = automatic; force_kind = PCCM_KIND_AUTO or a kind >= data_kind
  * (both clouds of a pair must share one kind). */
 int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* cloud, double cell_size, int force_kind);
+
+/* Builds the indices of BOTH clouds of a pair (the two KDTreeFlann builds of cloud_pair.py:65)
+ * in joint launches: one key pass, one radix sort, one scan, one reorder.  Same result as two
+ * pccm_cloud_build_index calls with the common kind. */
+int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind);
 
 int pccm_cloud_set_normals(pccm_ctx* ctx, pccm_cloud* cloud, const void* normals, int nrm_dtype,
                            int64_t nrm_stride, int mem_kind);

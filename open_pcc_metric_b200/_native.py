@@ -26,7 +26,7 @@ ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_NONFINITE, ERR_UNSUPPORTED = -1
 EXPORTS = [
     "pccm_version", "pccm_last_error", "pccm_ctx_create", "pccm_ctx_destroy", "pccm_ctx_synchronize",
     "pccm_ctx_set_profiling", "pccm_ctx_reset_timings", "pccm_ctx_get_timings",
-    "pccm_cloud_create", "pccm_cloud_destroy", "pccm_cloud_info_get", "pccm_cloud_build_index",
+    "pccm_cloud_create", "pccm_cloud_destroy", "pccm_cloud_info_get", "pccm_cloud_build_index", "pccm_pair_build_index",
     "pccm_cloud_set_normals", "pccm_cloud_get_normals", "pccm_estimate_normals", "pccm_knn_self",
     "pccm_self_nn_minmax", "pccm_nn", "pccm_pair_eval", "pccm_pair_get",
 ]
@@ -94,6 +94,7 @@ def lib():
         "pccm_cloud_destroy": [vp, vp],
         "pccm_cloud_info_get": [vp, vp, C.POINTER(CloudInfo)],
         "pccm_cloud_build_index": [vp, vp, dbl, i32],
+        "pccm_pair_build_index": [vp, vp, vp, dbl, i32],
         "pccm_cloud_set_normals": [vp, vp, vp, i32, i64, i32],
         "pccm_cloud_get_normals": [vp, vp, vp, i32],
         "pccm_estimate_normals": [vp, vp, i32, i64, i64],
@@ -208,6 +209,11 @@ class Context:
         return Cloud(self, points, colors, normals)
 
     # --- pair level ---------------------------------------------------------
+    def build_pair(self, a: "Cloud", b: "Cloud", cell_size: float = 0.0, force_kind: int = KIND_AUTO):
+        """Index both clouds of a pair in joint launches (common coordinate kind)."""
+        self.check(self.L.pccm_pair_build_index(self.h, a.h, b.h, float(cell_size), int(force_kind)))
+        a._keep = b._keep = None
+
     def nn(self, query: "Cloud", search: "Cloud"):
         n = query.n
         idx = np.empty(n, dtype=np.int32)
@@ -252,6 +258,7 @@ class Cloud:
         self.h = h
         self.n = pb.n
         self._keep = (pb, cb, nb) if pb.mem == DEVICE else None  # device inputs are read until build_index
+        self._keep_normals = nb if pb.mem == DEVICE else None    # packed f64 device normals are used in place
 
     def info(self) -> CloudInfo:
         out = CloudInfo()

@@ -83,10 +83,9 @@ class CloudPair:
         for c in self.clouds:
             self._dev.append(self._ctx.cloud(_attr(c, "points") if _attr(c, "points") is not None else np.zeros((0, 3)),
                                              _attr(c, "colors"), _attr(c, "normals")))
+        self._ctx.build_pair(self._dev[0], self._dev[1], cell_size)
         infos = [d.info() for d in self._dev]
-        kind = max(i.data_kind for i in infos)
-        for d in self._dev:
-            d.build_index(cell_size, kind)
+        kind = infos[0].index_kind
         self._n = tuple(int(i.n) for i in infos)
         self._aabb = tuple((np.array(i.aabb_min), np.array(i.aabb_max)) for i in infos)
         self._has_normals = [bool(i.has_normals) for i in infos]

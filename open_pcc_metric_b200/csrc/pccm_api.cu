@@ -46,7 +46,8 @@ struct pccm_ctx {
     int sm_count = 148;
     int cell_override_shift = -1;   // debugging: PCCM_CELL_SHIFT
     double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
-    uint32_t short_row = 8;         // rows up to this length skip the binary search (PCCM_SHORT_ROW)
+    uint32_t short_row = 0;         // rows up to this length skip the binary search (PCCM_SHORT_ROW; measured: never a win)
+    bool use_rowsort = true;        // KInt pair build: counting sort + per-row sort instead of CUB radix (PCCM_ROWSORT=0 disables)
 };
 
 static thread_local std::string g_err;
@@ -145,13 +146,23 @@ struct pccm_cloud {
     uchar4* rgb_u8 = nullptr;
     double* rgb_f64 = nullptr;
     double* normals = nullptr;
+    bool normals_borrowed = false;   // caller's packed float64 device array (pccm_cloud_create, DEVICE)
     bool has_colors = false, has_normals = false;
     // index
     int index_kind = -1;
     RowGrid grid{};
-    void* recs = nullptr;
-    uint32_t* row_start = nullptr;
+    void* recs = nullptr;          // record array (own, or the pair's joint array)
+    uint32_t* row_start = nullptr; // pencil table; values are positions in `recs`
+    uint32_t base = 0;             // position of this cloud's first record in `recs`
+    struct SharedIndex* shared = nullptr;   // joint build: buffers owned by both clouds
+    bool rgb_in_rec = false;       // KInt records carry the 8-bit colour
     double cell_size = 0;
+};
+
+struct SharedIndex {
+    void* recs = nullptr;
+    uint32_t* table = nullptr;
+    int refs = 0;
 };
 
 static size_t dtype_size(int dt) {
@@ -267,6 +278,7 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     cudaMemset(ctx->dscratch, 0, pccm_ctx::kScratch);
     if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
     if (const char* s = getenv("PCCM_SHORT_ROW")) ctx->short_row = (uint32_t)atoi(s);
+    if (const char* s = getenv("PCCM_ROWSORT")) ctx->use_rowsort = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
     return PCCM_OK;
@@ -323,9 +335,17 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     dfree(ctx, c->d_stats);
     dfree(ctx, c->rgb_u8);
     dfree(ctx, c->rgb_f64);
-    dfree(ctx, c->normals);
-    dfree(ctx, c->recs);
-    dfree(ctx, c->row_start);
+    if (!c->normals_borrowed) dfree(ctx, c->normals);
+    if (c->shared) {
+        if (--c->shared->refs == 0) {
+            dfree(ctx, c->shared->recs);
+            dfree(ctx, c->shared->table);
+            delete c->shared;
+        }
+    } else {
+        dfree(ctx, c->recs);
+        dfree(ctx, c->row_start);
+    }
     if (c->h_stats) {
         cudaStreamSynchronize(ctx->stream);
         cudaFreeHost(c->h_stats);
@@ -335,13 +355,29 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     return PCCM_OK;
 }
 
-static int set_normals_impl(pccm_ctx* ctx, pccm_cloud* c, const void* normals, int dtype, int64_t stride, int mem_kind) {
+static int set_normals_impl(pccm_ctx* ctx, pccm_cloud* c, const void* normals, int dtype, int64_t stride, int mem_kind,
+                            bool may_borrow = false) {
     if (dtype != PCCM_F64 && dtype != PCCM_F32) return fail(ctx, PCCM_ERR_INVALID, "normals must be F64 or F32");
+    const bool packed_f64 = dtype == PCCM_F64 && (stride == 0 || stride == 24);
+    if (c->normals_borrowed) { c->normals = nullptr; c->normals_borrowed = false; }
+    if (packed_f64 && mem_kind == PCCM_DEVICE && may_borrow) {
+        // packed float64 rows already on the device: use them in place (caller keeps them alive)
+        if (c->normals) dfree(ctx, c->normals);
+        c->normals = const_cast<double*>(static_cast<const double*>(normals));
+        c->normals_borrowed = true;
+        c->has_normals = true;
+        return PCCM_OK;
+    }
+    if (!c->normals) CK(dalloc(ctx, &c->normals, (size_t)c->n * 3));
+    if (packed_f64) {   // already in the device format: one copy, no repack
+        if (c->n) CK(cudaMemcpyAsync(c->normals, normals, (size_t)c->n * 24, mem_kind == PCCM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+        c->has_normals = true;
+        return PCCM_OK;
+    }
     const void* dev = nullptr;
     void* owned = nullptr;
     int rc = upload_rows(ctx, normals, dtype, c->n, &stride, mem_kind, &dev, &owned);
     if (rc) return rc;
-    if (!c->normals) CK(dalloc(ctx, &c->normals, (size_t)c->n * 3));
     if (c->n) {
         pack_f64x3_kernel<<<(int)((c->n + 255) / 256), 256, 0, ctx->stream>>>(dev, dtype, stride, c->n, c->normals);
         ctx->tm.total_launches++;
@@ -377,7 +413,7 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
             rc = upload_rows(ctx, rgb, rgb_dtype, n, &c->raw_rgb_stride, mem_kind, &c->raw_rgb, &c->raw_rgb_owned);
         }
         c->has_colors = rgb != nullptr;
-        if (!rc && normals) rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind);
+        if (!rc && normals) rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind, true);
     }
     if (rc) { pccm_cloud_destroy(ctx, c); return rc; }
     if (n) {
@@ -484,6 +520,38 @@ static double auto_cell(const pccm_cloud* c) {
     return 2.0 * spacing;
 }
 
+// grid of one cloud for a coordinate kind (cell size 0 = automatic)
+static void choose_grid(pccm_ctx* ctx, const pccm_cloud* c, int kind, double cell_size, RowGrid& g, int& xbits) {
+    double h = cell_size > 0 ? cell_size : auto_cell(c) * ctx->cell_scale;
+    if (kind == PCCM_KIND_INT) {
+        int shift = (int)std::lround(std::log2(std::max(h, 1.0)));
+        if (cell_size <= 0 && ctx->cell_override_shift >= 0) shift = ctx->cell_override_shift;
+        shift = std::max(0, std::min(shift, 15));
+        for (;; ++shift) {
+            g.shift = shift;
+            g.iy0 = ((int)c->mn[1] >> shift) << shift;
+            g.iz0 = ((int)c->mn[2] >> shift) << shift;
+            g.ny = (((int)c->mx[1] - g.iy0) >> shift) + 1;
+            g.nz = (((int)c->mx[2] - g.iz0) >> shift) + 1;
+            if ((int64_t)g.ny * g.nz <= kMaxRows) break;
+        }
+        g.h = (double)(1 << g.shift); g.inv_h = 1.0 / g.h; g.y0 = g.iy0; g.z0 = g.iz0;
+        xbits = std::max(1, bits_for((uint64_t)c->mx[0]));
+    } else {
+        double ey = c->mx[1] - c->mn[1], ez = c->mx[2] - c->mn[2];
+        if (!(h > 0) || !std::isfinite(h)) h = 1.0;
+        for (;;) {
+            double ny = std::floor(ey / h) + 1, nz = std::floor(ez / h) + 1;
+            if (ny * nz <= (double)kMaxRows) { g.ny = (int)ny; g.nz = (int)nz; break; }
+            h *= 1.5;
+        }
+        g.h = h; g.inv_h = 1.0 / h; g.y0 = c->mn[1]; g.z0 = c->mn[2];
+        double mag = 0;
+        for (int a = 1; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(c->mn[a]), std::fabs(c->mx[a])));
+        g.slack = 1e-9 * (mag + h);
+    }
+}
+
 extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_size, int force_kind) {
     if (!ctx || !c) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
@@ -513,35 +581,8 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
         CK(cudaMemsetAsync(c->row_start, 0, 2 * sizeof(uint32_t), ctx->stream));
         return PCCM_OK;
     }
-    double h = cell_size > 0 ? cell_size : auto_cell(c) * ctx->cell_scale;
     int xbits = 0;
-    if (kind == PCCM_KIND_INT) {
-        int shift = (int)std::lround(std::log2(std::max(h, 1.0)));
-        if (cell_size <= 0 && ctx->cell_override_shift >= 0) shift = ctx->cell_override_shift;
-        shift = std::max(0, std::min(shift, 15));
-        for (;; ++shift) {
-            g.shift = shift;
-            g.iy0 = ((int)c->mn[1] >> shift) << shift;
-            g.iz0 = ((int)c->mn[2] >> shift) << shift;
-            g.ny = (((int)c->mx[1] - g.iy0) >> shift) + 1;
-            g.nz = (((int)c->mx[2] - g.iz0) >> shift) + 1;
-            if ((int64_t)g.ny * g.nz <= kMaxRows) break;
-        }
-        g.h = (double)(1 << g.shift); g.inv_h = 1.0 / g.h; g.y0 = g.iy0; g.z0 = g.iz0;
-        xbits = std::max(1, bits_for((uint64_t)c->mx[0]));
-    } else {
-        double ey = c->mx[1] - c->mn[1], ez = c->mx[2] - c->mn[2];
-        if (!(h > 0) || !std::isfinite(h)) h = 1.0;
-        for (;;) {
-            double ny = std::floor(ey / h) + 1, nz = std::floor(ez / h) + 1;
-            if (ny * nz <= (double)kMaxRows) { g.ny = (int)ny; g.nz = (int)nz; break; }
-            h *= 1.5;
-        }
-        g.h = h; g.inv_h = 1.0 / h; g.y0 = c->mn[1]; g.z0 = c->mn[2];
-        double mag = 0;
-        for (int a = 1; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(c->mn[a]), std::fabs(c->mx[a])));
-        g.slack = 1e-9 * (mag + h);
-    }
+    choose_grid(ctx, c, kind, cell_size, g, xbits);
     c->cell_size = g.h;
     const size_t nrows = (size_t)g.ny * g.nz;
     const int rowbits = std::max(1, bits_for(nrows - 1));
@@ -632,6 +673,7 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
             CK(dalloc(ctx, &r, (size_t)n));
             reorder_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, c->rgb_u8, r);
             c->recs = r;
+            c->rgb_in_rec = c->rgb_u8 != nullptr;
         } else if (kind == PCCM_KIND_F32) {
             float4* r = nullptr;
             CK(dalloc(ctx, &r, (size_t)n));
@@ -655,6 +697,191 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
     return PCCM_OK;
 }
 
+// Joint build of the two clouds of a pair (same result as two pccm_cloud_build_index calls,
+// half the launches): one key pass, one radix sort with the cloud id as the top key bit, one
+// scan of the joint row histogram, one reorder.  Falls back to separate builds for the F64
+// kind (two-pass sort), empty clouds, or clouds that are already indexed.
+template <class KeyT, int KIND>
+static int build_pair_impl(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, int xbits, int rowbits) {
+    const uint32_t n = R.n[0] + R.n[1];
+    const size_t nrows[2] = {(size_t)R.g[0].ny * R.g[0].nz, (size_t)R.g[1].ny * R.g[1].nz};
+    const size_t ntab = nrows[0] + nrows[1] + 1;
+    const int cbit = KIND == KIND_INT ? rowbits + xbits : 32 + rowbits;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    SharedIndex* sh = new SharedIndex();
+    KeyT *ka = nullptr, *kb = nullptr;
+    uint32_t *va = nullptr, *vb = nullptr;
+    CK(dalloc(ctx, &sh->table, ntab));
+    CK(dalloc(ctx, &ka, (size_t)n));
+    CK(dalloc(ctx, &kb, (size_t)n));
+    CK(dalloc(ctx, &va, (size_t)n));
+    CK(dalloc(ctx, &vb, (size_t)n));
+    {
+        StageTimer t(ctx, &ctx->tm.keys_ms);
+        CK(cudaMemsetAsync(sh->table, 0, ntab * sizeof(uint32_t), ctx->stream));
+        keys_pair_kernel<KeyT, KIND><<<blocks, threads, 0, ctx->stream>>>(R, xbits, cbit, ka, va, sh->table);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    int rc;
+    {
+        StageTimer t(ctx, &ctx->tm.sort_ms);
+        rc = sort_pairs<KeyT>(ctx, ka, kb, va, vb, n, cbit + 1);
+    }
+    dfree(ctx, ka); dfree(ctx, kb);
+    if (!rc) {
+        StageTimer t(ctx, &ctx->tm.table_ms);
+        rc = exclusive_scan(ctx, sh->table, ntab);
+    }
+    if (!rc) {
+        StageTimer t(ctx, &ctx->tm.reorder_ms);
+        if (KIND == KIND_INT) {
+            uint4* r = nullptr;
+            CK(dalloc(ctx, &r, (size_t)n));
+            reorder_pair_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(R, vb, r);
+            sh->recs = r;
+        } else {
+            float4* r = nullptr;
+            CK(dalloc(ctx, &r, (size_t)n));
+            reorder_pair_kernel<KF32><<<blocks, threads, 0, ctx->stream>>>(R, vb, r);
+            sh->recs = r;
+        }
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    dfree(ctx, va); dfree(ctx, vb);
+    if (rc) { dfree(ctx, sh->table); delete sh; return rc; }
+    sh->refs = 2;
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = cl[c];
+        p->shared = sh;
+        p->recs = sh->recs;
+        p->row_start = sh->table + R.table_off[c];
+        p->base = c ? R.n[0] : 0u;
+        p->grid = R.g[c];
+        p->cell_size = R.g[c].h;
+        p->index_kind = KIND;
+        p->rgb_in_rec = R.rgb_in_rec[c] != 0;
+        dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;
+        if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
+    }
+    return PCCM_OK;
+}
+
+// KInt pair build without the radix sort: counting sort by row (histogram ranks + scan) and a
+// hand-written per-row sort by (x, index).  Same records / table as build_pair_impl.
+static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R) {
+    const uint32_t n = R.n[0] + R.n[1];
+    const size_t nrows = (size_t)R.g[0].ny * R.g[0].nz + (size_t)R.g[1].ny * R.g[1].nz;
+    const size_t ntab = nrows + 1;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    SharedIndex* sh = new SharedIndex();
+    uint32_t *rowof = nullptr, *rank = nullptr, *long_rows = nullptr;
+    unsigned long long* items = nullptr;
+    CK(dalloc(ctx, &sh->table, ntab));
+    CK(dalloc(ctx, &rowof, (size_t)n));
+    CK(dalloc(ctx, &rank, (size_t)n));
+    CK(dalloc(ctx, &items, (size_t)n));
+    CK(dalloc(ctx, &long_rows, nrows + 1));   // [0] = count, [1..] = row ids
+    {
+        StageTimer t(ctx, &ctx->tm.keys_ms);
+        CK(cudaMemsetAsync(sh->table, 0, ntab * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(long_rows, 0, sizeof(uint32_t), ctx->stream));
+        rowrank_pair_kernel<<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    int rc;
+    {
+        StageTimer t(ctx, &ctx->tm.table_ms);
+        rc = exclusive_scan(ctx, sh->table, ntab);
+    }
+    if (!rc) {
+        StageTimer t(ctx, &ctx->tm.sort_ms);
+        scatter_pair_kernel<<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table, items);
+        const uint32_t wblocks = (uint32_t)((nrows * 32 + kRowSortThreads - 1) / kRowSortThreads);
+        rowsort_warp_kernel<<<wblocks, kRowSortThreads, 0, ctx->stream>>>(sh->table, (uint32_t)nrows, items, long_rows + 1, long_rows);
+        rowsort_block_kernel<<<ctx->sm_count * 2, kRowSortThreads, 0, ctx->stream>>>(sh->table, items, long_rows + 1, long_rows);
+        ctx->tm.total_launches += 3;
+        CK(cudaGetLastError());
+    }
+    if (!rc) {
+        StageTimer t(ctx, &ctx->tm.reorder_ms);
+        uint4* r = nullptr;
+        CK(dalloc(ctx, &r, (size_t)n));
+        reorder_items_pair_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(R, items, r);
+        sh->recs = r;
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    dfree(ctx, rowof); dfree(ctx, rank); dfree(ctx, items); dfree(ctx, long_rows);
+    if (rc) { dfree(ctx, sh->table); delete sh; return rc; }
+    sh->refs = 2;
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = cl[c];
+        p->shared = sh;
+        p->recs = sh->recs;
+        p->row_start = sh->table + R.table_off[c];
+        p->base = c ? R.n[0] : 0u;
+        p->grid = R.g[c];
+        p->cell_size = R.g[c].h;
+        p->index_kind = PCCM_KIND_INT;
+        p->rgb_in_rec = R.rgb_in_rec[c] != 0;
+        dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;
+        if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
+    }
+    return PCCM_OK;
+}
+
+extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind) {
+    if (!ctx || !a || !b) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_stats(ctx, a);
+    if (!rc) rc = ensure_stats(ctx, b);
+    if (rc) return rc;
+    int kind = std::max(a->data_kind, b->data_kind);
+    if (force_kind != PCCM_KIND_AUTO) {
+        if (force_kind < kind || force_kind > PCCM_KIND_F64) return fail(ctx, PCCM_ERR_INVALID, "force_kind %d not allowed for data kind %d", force_kind, kind);
+        kind = force_kind;
+    }
+    pccm_cloud* cl[2] = {a, b};
+    const bool separate = kind == PCCM_KIND_F64 || a == b || a->n == 0 || b->n == 0 || a->index_kind >= 0 || b->index_kind >= 0 ||
+                          (uint64_t)a->n + (uint64_t)b->n > 0x7fffffffull;
+    if (separate) {
+        rc = pccm_cloud_build_index(ctx, a, cell_size, kind);
+        if (!rc && a != b) rc = pccm_cloud_build_index(ctx, b, cell_size, kind);
+        return rc;
+    }
+    PairRaw R{};
+    int xbits = 1, rowbits = 1;
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = cl[c];
+        if (!p->raw_xyz) return fail(ctx, PCCM_ERR_STATE, "raw coordinates already released");
+        RowGrid g{};
+        g.n = (uint32_t)p->n;
+        g.short_row = ctx->short_row;
+        int xb = 0;
+        choose_grid(ctx, p, kind, cell_size, g, xb);
+        R.g[c] = g;
+        R.n[c] = (uint32_t)p->n;
+        R.xyz[c] = p->raw_xyz; R.dtype[c] = p->raw_dtype; R.stride[c] = p->raw_stride;
+        // 8-bit colours ride in the KInt record; every other combination keeps a colour array
+        R.rgb_in_rec[c] = kind == PCCM_KIND_INT && p->has_colors && (p->raw_rgb_dtype == PCCM_U8 || p->rgb_u8_ok);
+        R.rgb[c] = p->raw_rgb; R.rgb_dtype[c] = p->raw_rgb_dtype; R.rgb_stride[c] = p->raw_rgb_stride;
+        if (!R.rgb_in_rec[c]) { rc = finish_colors(ctx, p); if (rc) return rc; }
+        xbits = std::max(xbits, xb);
+        rowbits = std::max(rowbits, bits_for((uint64_t)g.ny * g.nz - 1));
+    }
+    R.table_off[0] = 0;
+    R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
+    if (kind == PCCM_KIND_INT) {
+        if (ctx->use_rowsort) return build_pair_rowsort(ctx, cl, R);
+        if (rowbits + xbits + 1 <= 32) return build_pair_impl<uint32_t, KIND_INT>(ctx, cl, R, xbits, rowbits);
+        return build_pair_impl<unsigned long long, KIND_INT>(ctx, cl, R, xbits, rowbits);
+    }
+    return build_pair_impl<unsigned long long, KIND_F32>(ctx, cl, R, xbits, rowbits);
+}
+
 // --------------------------------------------------------------------------------------
 // queries
 // --------------------------------------------------------------------------------------
@@ -665,6 +892,7 @@ static CloudView view_of(const pccm_cloud* c) {
     v.row_start = c->row_start;
     v.rgb_u8 = c->rgb_u8;
     v.rgb_f64 = c->rgb_f64;
+    v.rgb_mode = !c->has_colors ? 0 : (c->rgb_in_rec ? 1 : (c->rgb_u8 ? 2 : 3));
     v.normals = c->normals;
     return v;
 }
@@ -681,7 +909,7 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
         max_tiles = std::max(max_tiles, P.dir[d].ntiles);
         total_tiles += P.dir[d].ntiles;
     }
-    P.rec_stride = max_tiles * (kQueryThreads / 32);
+    P.rec_stride = max_tiles;
     BlockPartial* partials = nullptr;
     CK(dalloc(ctx, &partials, (size_t)P.rec_stride * 2 + 1));
     P.partials = partials;
@@ -730,7 +958,7 @@ extern "C" int pccm_nn(pccm_ctx* ctx, pccm_cloud* query, pccm_cloud* search, int
     QueryParams P{};
     P.ndirs = 1;
     P.dir[0].q = view_of(query); P.dir[0].s = view_of(search);
-    P.dir[0].qbegin = 0; P.dir[0].qend = nq; P.dir[0].flags = 0;
+    P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq; P.dir[0].flags = 0;
     P.dir[0].idx_out = d_idx; P.dir[0].d2_out = d_d2;
     P.normals_mode = 0; P.color_scale = 1;
     rc = launch_query(ctx, query->index_kind, P);
@@ -774,8 +1002,8 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
         const uint64_t n = (uint64_t)cl[d]->n;
         DirParams& D = P.dir[d];
         D.q = view_of(cl[d]); D.s = view_of(cl[1 - d]);
-        D.qbegin = (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
-        D.qend = (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
+        D.qbegin = cl[d]->base + (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
+        D.qend = cl[d]->base + (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
         D.flags = dflags[d];
         if (flags & PCCM_EVAL_PERPOINT) {
             if (ctx->pp_n[d] != cl[d]->n) {
@@ -868,7 +1096,7 @@ extern "C" int pccm_knn_self(pccm_ctx* ctx, pccm_cloud* c, int k, int32_t* idx_o
     double* d_d2 = d2_out;
     if (mem_kind == PCCM_HOST) { CK(dalloc(ctx, &d_idx, cnt)); CK(dalloc(ctx, &d_d2, cnt)); }
     KnnParams P{};
-    P.c = view_of(c); P.begin = 0; P.end = (uint32_t)c->n; P.k = k; P.mode = KNN_LIST;
+    P.c = view_of(c); P.begin = c->base; P.end = c->base + (uint32_t)c->n; P.k = k; P.mode = KNN_LIST;
     P.idx_out = d_idx; P.d2_out = d_d2;
     rc = launch_knn(ctx, c, P);
     if (mem_kind == PCCM_HOST) {
@@ -892,7 +1120,7 @@ extern "C" int pccm_self_nn_minmax(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, 
     CK(dalloc(ctx, &mm, (size_t)nblocks * 2));
     if (per_point) { if (mem_kind == PCCM_DEVICE) d_pp = per_point; else CK(dalloc(ctx, &d_pp, (size_t)c->n)); }
     KnnParams P{};
-    P.c = view_of(c); P.begin = (uint32_t)begin; P.end = (uint32_t)end; P.k = 2; P.mode = KNN_BOUNDARY;
+    P.c = view_of(c); P.begin = c->base + (uint32_t)begin; P.end = c->base + (uint32_t)end; P.k = 2; P.mode = KNN_BOUNDARY;
     P.d2_out = d_pp; P.minmax = mm;
     rc = launch_knn(ctx, c, P);
     if (!rc) {
@@ -917,13 +1145,14 @@ extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_
     CK(cudaSetDevice(ctx->device));
     int rc = check_range(ctx, c, begin, end);
     if (rc) return rc;
+    if (c->normals_borrowed) { c->normals = nullptr; c->normals_borrowed = false; }
     if (!c->normals) {
         // zero-filled so that ranks estimating disjoint slices can combine buffers by summation
         CK(dalloc(ctx, &c->normals, (size_t)c->n * 3));
         CK(cudaMemsetAsync(c->normals, 0, (size_t)c->n * 3 * sizeof(double), ctx->stream));
     }
     KnnParams P{};
-    P.c = view_of(c); P.begin = (uint32_t)begin; P.end = (uint32_t)end; P.k = k; P.mode = KNN_NORMALS;
+    P.c = view_of(c); P.begin = c->base + (uint32_t)begin; P.end = c->base + (uint32_t)end; P.k = k; P.mode = KNN_NORMALS;
     P.normals_out = c->normals;
     rc = launch_knn(ctx, c, P);
     if (!rc) c->has_normals = true;

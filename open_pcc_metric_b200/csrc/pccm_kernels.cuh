@@ -209,6 +209,238 @@ __global__ void reorder_kernel(const void* xyz, int dtype, int64_t stride, uint3
 }
 
 // ------------------------------------------------------------------------------------
+// joint index build of the two clouds of a pair: one key pass, ONE sort (cloud id in the top
+// key bit), one scan, one reorder -- half the launches of two separate builds
+// ------------------------------------------------------------------------------------
+struct PairRaw {
+    const void* xyz[2];
+    const void* rgb[2];
+    int64_t stride[2], rgb_stride[2];
+    int32_t dtype[2], rgb_dtype[2];
+    int32_t rgb_in_rec[2];     // pack the colour into the record (KInt + 8-bit colours)
+    uint32_t n[2];
+    uint32_t table_off[2];     // offset of each cloud's row table inside the joint table
+    RowGrid g[2];
+};
+
+__device__ __forceinline__ uint32_t int_row(const RowGrid& g, int y, int z) {
+    uint32_t cy = (uint32_t)((y - g.iy0) >> g.shift), cz = (uint32_t)((z - g.iz0) >> g.shift);
+    return cz * (uint32_t)g.ny + cy;
+}
+
+template <class KeyT, int KIND>
+__global__ void keys_pair_kernel(const __grid_constant__ PairRaw R, int xbits, int cbit,
+                                 KeyT* keys, uint32_t* vals, uint32_t* table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n[0] + R.n[1]) return;
+    const int c = i >= R.n[0];
+    const uint32_t li = i - (c ? R.n[0] : 0u);
+    const RowGrid& g = R.g[c];
+    uint32_t row;
+    KeyT key;
+    if constexpr (KIND == KIND_INT) {
+        const int x = (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 0);
+        row = int_row(g, (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1),
+                      (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
+        key = ((KeyT)row << xbits) | (KeyT)x;
+    } else {
+        const double x = load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 0);
+        row = float_row(g, load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1), load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
+        key = ((KeyT)row << 32) | (KeyT)flip_f32((float)x);
+    }
+    keys[i] = key | ((KeyT)c << cbit);
+    vals[i] = li;
+    atomicAdd(table + R.table_off[c] + row, 1u);
+}
+
+template <class K>
+__global__ void reorder_pair_kernel(const __grid_constant__ PairRaw R, const uint32_t* __restrict__ vals,
+                                    typename K::Rec* __restrict__ recs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n[0] + R.n[1]) return;
+    const int c = i >= R.n[0];
+    const uint32_t src = vals[i];
+    uint32_t rgba = 0;
+    if (R.rgb_in_rec[c]) {
+        if (R.rgb_dtype[c] == PCCM_U8) {
+            const uint8_t* p = static_cast<const uint8_t*>(R.rgb[c]) + (int64_t)src * R.rgb_stride[c];
+            rgba = p[0] | (p[1] << 8) | (p[2] << 16);
+        } else {
+            rgba = (uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 0) * 255.0) |
+                   ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 1) * 255.0) << 8) |
+                   ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 2) * 255.0) << 16);
+        }
+    }
+    recs[i] = RecPack<K>::make(load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 0), load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 1),
+                               load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 2), src, rgba);
+}
+
+// ------------------------------------------------------------------------------------
+// hand-written replacement of the radix sort for the pair build (KInt): counting sort by row
+// (the row histogram and its scan are needed for the pencil table anyway) + per-row sort by
+// (x, original index).  Rows are short on voxelised clouds (a 2x2 tube crosses the surface a
+// few times), so most of them fit one warp: bitonic network over lanes with shuffles.
+// ------------------------------------------------------------------------------------
+// pass 1: row of every point + its arrival rank inside the row (the histogram's atomicAdd)
+__global__ void rowrank_pair_kernel(const __grid_constant__ PairRaw R, uint32_t* __restrict__ rowof,
+                                    uint32_t* __restrict__ rank, uint32_t* table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n[0] + R.n[1]) return;
+    const int c = i >= R.n[0];
+    const uint32_t li = i - (c ? R.n[0] : 0u);
+    const uint32_t row = R.table_off[c] + int_row(R.g[c], (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1),
+                                                  (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
+    rowof[i] = row;
+    rank[i] = atomicAdd(table + row, 1u);
+}
+
+// pass 2 (after the exclusive scan of the table): scatter (x, idx) items into their row segment
+__global__ void scatter_pair_kernel(const __grid_constant__ PairRaw R, const uint32_t* __restrict__ rowof,
+                                    const uint32_t* __restrict__ rank, const uint32_t* __restrict__ table,
+                                    unsigned long long* __restrict__ items) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n[0] + R.n[1]) return;
+    const int c = i >= R.n[0];
+    const uint32_t li = i - (c ? R.n[0] : 0u);
+    const uint32_t x = (uint32_t)(int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 0);
+    items[table[rowof[i]] + rank[i]] = ((unsigned long long)x << 32) | li;
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+// pass 3: one warp per row.  <= 32 items: bitonic network over lanes (shuffles, registers);
+// <= kRowSortWarpSmem items: the same warp sorts in its private slice of shared memory
+// (no block barrier); longer rows are queued for the block kernel.
+constexpr int kRowSortThreads = 256;
+constexpr uint32_t kRowSortWarpSmem = 512;
+__global__ void __launch_bounds__(kRowSortThreads)
+rowsort_warp_kernel(const uint32_t* __restrict__ table, uint32_t nrows, unsigned long long* __restrict__ items,
+                    uint32_t* __restrict__ long_rows, uint32_t* long_count) {
+    __shared__ unsigned long long smw[kRowSortThreads / 32][kRowSortWarpSmem];
+    const uint32_t row = (blockIdx.x * kRowSortThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const uint32_t lo = table[row], hi = table[row + 1];
+    const uint32_t len = hi - lo;
+    if (len < 2) return;
+    if (len > kRowSortWarpSmem) {
+        if (lane == 0) long_rows[atomicAdd(long_count, 1u)] = row;
+        return;
+    }
+    if (len > 32) {
+        unsigned long long* sm = smw[threadIdx.x >> 5];
+        uint32_t p2 = 64;
+        while (p2 < len) p2 <<= 1;
+        for (uint32_t i = lane; i < p2; i += 32) sm[i] = i < len ? items[lo + i] : ~0ull;
+        __syncwarp();
+        for (uint32_t k = 2; k <= p2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = lane; t < (p2 >> 1); t += 32) {
+                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                    const uint32_t l = i | j;
+                    const unsigned long long a = sm[i], b = sm[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { sm[i] = b; sm[l] = a; }
+                }
+                __syncwarp();
+            }
+        for (uint32_t i = lane; i < len; i += 32) items[lo + i] = sm[i];
+        return;
+    }
+    unsigned long long v = lane < (int)len ? items[lo + lane] : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = shfl_xor_u64(v, j);
+            const bool up = ((lane & k) == 0);            // ascending block
+            const bool lower = ((lane & j) == 0);
+            const bool take_min = (up == lower);
+            v = take_min ? (v < o ? v : o) : (v > o ? v : o);
+        }
+    }
+    if (lane < (int)len) items[lo + lane] = v;
+}
+
+// pass 4: one block per long row: bitonic sort in shared memory (<= kRowSortSmem items) or,
+// for degenerate inputs (e.g. thousands of duplicates of one voxel column), in global memory
+constexpr uint32_t kRowSortSmem = 4096;
+__global__ void __launch_bounds__(kRowSortThreads)
+rowsort_block_kernel(const uint32_t* __restrict__ table, unsigned long long* __restrict__ items,
+                     const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count) {
+    __shared__ unsigned long long sm[kRowSortSmem];
+    const uint32_t count = *long_count;
+    for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
+        const uint32_t row = long_rows[w];
+        const uint32_t lo = table[row], len = table[row + 1] - lo;
+        uint32_t p2 = 64;
+        while (p2 < len) p2 <<= 1;
+        if (p2 <= kRowSortSmem) {
+            for (uint32_t i = threadIdx.x; i < p2; i += kRowSortThreads) sm[i] = i < len ? items[lo + i] : ~0ull;
+            __syncthreads();
+            for (uint32_t k = 2; k <= p2; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = threadIdx.x; i < p2; i += kRowSortThreads) {
+                        const uint32_t l = i ^ j;
+                        if (l > i) {
+                            const unsigned long long a = sm[i], b = sm[l];
+                            const bool up = (i & k) == 0;
+                            if ((a > b) == up) { sm[i] = b; sm[l] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (uint32_t i = threadIdx.x; i < len; i += kRowSortThreads) items[lo + i] = sm[i];
+            __syncthreads();
+        } else {
+            // global-memory network in the all-ascending form (first sub-stage of every merge
+            // pairs i with i ^ (k - 1)): the minimum always goes to the lower index, so the
+            // virtual +inf padding beyond len never has to move and is simply skipped
+            unsigned long long* a = items + lo;
+            for (uint32_t k = 2; k <= p2; k <<= 1) {
+                for (uint32_t i = threadIdx.x; i < len; i += kRowSortThreads) {
+                    const uint32_t l = i ^ (k - 1);
+                    if (l > i && l < len) { const unsigned long long x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+                }
+                __syncthreads();
+                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                    for (uint32_t i = threadIdx.x; i < len; i += kRowSortThreads) {
+                        const uint32_t l = i ^ j;
+                        if (l > i && l < len) { const unsigned long long x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
+
+// records from sorted (x, idx) items
+template <class K>
+__global__ void reorder_items_pair_kernel(const __grid_constant__ PairRaw R, const unsigned long long* __restrict__ items,
+                                          typename K::Rec* __restrict__ recs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n[0] + R.n[1]) return;
+    const int c = i >= R.n[0];
+    const uint32_t src = (uint32_t)items[i];
+    uint32_t rgba = 0;
+    if (R.rgb_in_rec[c]) {
+        if (R.rgb_dtype[c] == PCCM_U8) {
+            const uint8_t* p = static_cast<const uint8_t*>(R.rgb[c]) + (int64_t)src * R.rgb_stride[c];
+            rgba = p[0] | (p[1] << 8) | (p[2] << 16);
+        } else {
+            rgba = (uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 0) * 255.0) |
+                   ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 1) * 255.0) << 8) |
+                   ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 2) * 255.0) << 16);
+        }
+    }
+    recs[i] = RecPack<K>::make(load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 0), load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 1),
+                               load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 2), src, rgba);
+}
+
+// ------------------------------------------------------------------------------------
 // deterministic block reductions
 // ------------------------------------------------------------------------------------
 template <int THREADS>
@@ -254,6 +486,7 @@ struct CloudView {        // device-side view of an indexed cloud
     RowGrid grid;
     const void* recs;
     const uint32_t* row_start;
+    int32_t rgb_mode;       // 0 none, 1 packed in the record (KInt), 2 rgb_u8 array, 3 rgb_f64 array
     const uchar4* rgb_u8;   // original order, or null
     const double* rgb_f64;  // original order [n][3], or null
     const double* normals;  // original order [n][3], or null
@@ -279,26 +512,25 @@ struct QueryParams {
     int32_t normals_mode;
     double T[9];
     double color_scale;
-    BlockPartial* partials;   // per-warp records: direction d at [d * rec_stride + tile * warps + warp]
+    BlockPartial* partials;   // one record per tile: direction d at [d * rec_stride + tile]
     uint32_t rec_stride;
     BlockPartial* chunks;     // [ndirs * kFinalChunks] scratch of the fold
     unsigned int* ticket;     // zero on entry; the last fold block resets it
     BlockPartial* out;        // [2]
 };
 
-__device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uint32_t packed, bool have_packed, double* out) {
-    if (c.rgb_u8 != nullptr) {
-        uint32_t p;
-        if (have_packed) p = packed;
-        else { uchar4 u = __ldg(c.rgb_u8 + idx); p = u.x | (u.y << 8) | (u.z << 16); }
-        out[0] = (double)(p & 0xffu) / 255.0;
-        out[1] = (double)((p >> 8) & 0xffu) / 255.0;
-        out[2] = (double)((p >> 16) & 0xffu) / 255.0;
-    } else {
+__device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uint32_t packed, double* out) {
+    if (c.rgb_mode == 3) {
         out[0] = __ldg(c.rgb_f64 + 3 * (size_t)idx);
         out[1] = __ldg(c.rgb_f64 + 3 * (size_t)idx + 1);
         out[2] = __ldg(c.rgb_f64 + 3 * (size_t)idx + 2);
+        return;
     }
+    uint32_t p = packed;
+    if (c.rgb_mode == 2) { uchar4 u = __ldg(c.rgb_u8 + idx); p = u.x | (u.y << 8) | (u.z << 16); }
+    out[0] = (double)(p & 0xffu) / 255.0;
+    out[1] = (double)((p >> 8) & 0xffu) / 255.0;
+    out[2] = (double)((p >> 16) & 0xffu) / 255.0;
 }
 
 template <class K> __device__ __forceinline__ uint32_t rec_rgba(const typename K::Rec&) { return 0; }
@@ -389,14 +621,23 @@ pair_query_kernel(const __grid_constant__ QueryParams P) {
             }
             if (D.flags & PCCM_EVAL_COLOR) {
                 double cq[3], cn[3];
-                load_color(D.q, qidx, rec_rgba<K>(qr), K::kind == KIND_INT, cq);
-                load_color(D.s, best.idx, rec_rgba<K>(nr), K::kind == KIND_INT, cn);
+                load_color(D.q, qidx, rec_rgba<K>(qr), cq);
+                load_color(D.s, best.idx, rec_rgba<K>(nr), cn);
                 color_diff2(P.T, cq, cn, P.color_scale, acc.csum, acc.cmax);
             }
         }
     }
+    // warps fold with shuffles as they finish; the block's single record is written once all
+    // four are done (they could not retire earlier anyway: the block holds their resources)
     partial_warp_reduce(acc, D.flags);
-    if (lane == 0) P.partials[(size_t)d * P.rec_stride + (size_t)tile * kWarps + warp] = acc;
+    __shared__ BlockPartial sm[kWarps];
+    if (lane == 0) sm[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockPartial r = sm[0];
+        for (int w = 1; w < kWarps; ++w) partial_merge(r, sm[w]);
+        P.partials[(size_t)d * P.rec_stride + tile] = r;
+    }
 }
 
 // K8: fixed-order fold of the per-warp records.  gridDim.x = ndirs * kFinalChunks; block
@@ -421,7 +662,7 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_co
     __shared__ BlockPartial sm[kFinalThreads / 32];
     __shared__ bool is_last;
     const int d = blockIdx.x / kFinalChunks, c = blockIdx.x % kFinalChunks;
-    const uint32_t nrec = P.dir[d].ntiles * (kQueryThreads / 32);
+    const uint32_t nrec = P.dir[d].ntiles;
     const uint32_t per = (nrec + kFinalChunks - 1) / kFinalChunks;
     const uint32_t lo = c * per, hi = lo + per < nrec ? lo + per : nrec;
     const BlockPartial* in = P.partials + (size_t)d * P.rec_stride;

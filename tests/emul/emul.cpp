@@ -14,6 +14,10 @@
 using namespace pccm;
 
 static uint32_t g_short_row = 0;
+#ifdef PCCM_COUNT
+namespace pccm { Counters g_cnt; }
+extern "C" void emul_counters(unsigned long long* out, int reset) { memcpy(out, &pccm::g_cnt, sizeof(pccm::g_cnt)); if (reset) memset(&pccm::g_cnt, 0, sizeof(pccm::g_cnt)); }
+#endif
 
 template <class K> struct Pack;
 template <> struct Pack<KInt> {

@@ -146,6 +146,68 @@ def test_input_dtypes_and_strides_agree(ctx):
     assert np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1])
 
 
+@pytest.mark.parametrize("kind", ["int", "f32", "f64"])
+def test_joint_build_equals_separate_builds(ctx, kind):
+    """pccm_pair_build_index (one sort for both clouds) gives the same answers as two
+    pccm_cloud_build_index calls -- NN, k-NN, normals, fused colour sums."""
+    from open_pcc_metric_b200 import _native as N
+    rng = np.random.default_rng(11)
+    if kind == "int":
+        A = rng.integers(0, 300, (30000, 3)).astype(np.float64)
+        B = rng.integers(0, 300, (20000, 3)).astype(np.float64)
+    else:
+        A = rng.normal(0, 3, (30000, 3))
+        B = rng.normal(0, 3, (20000, 3))
+        if kind == "f32":
+            A, B = A.astype(np.float32).astype(np.float64), B.astype(np.float32).astype(np.float64)
+    ca = rng.integers(0, 256, A.shape) / 255.0
+    cb = rng.integers(0, 256, B.shape) / 255.0
+    outs = []
+    for joint in (False, True):
+        a, b = ctx.cloud(A, ca), ctx.cloud(B, cb)
+        if joint:
+            ctx.build_pair(a, b)
+        else:
+            k = max(a.info().data_kind, b.info().data_kind)
+            a.build_index(0.0, k); b.build_index(0.0, k)
+        r = ctx.pair_eval(a, b, N.EVAL_COLOR, np.eye(3), 255.0)
+        outs.append((ctx.nn(a, b), ctx.nn(b, a), b.knn_self(5), bytes(r)))
+        b.estimate_normals(12)
+        outs[-1] += (b.get_normals(),)
+        a.close(); b.close()
+    s, j = outs
+    for x, y in ((s[0], j[0]), (s[1], j[1]), (s[2], j[2])):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+    assert s[3] == j[3]
+    assert np.array_equal(s[4], j[4])
+    oi, od = cnn.knn(B, A, 1)
+    assert np.array_equal(j[0][0], oi[:, 0]) and np.array_equal(j[0][1], od[:, 0])
+
+
+def test_pair_build_long_rows(ctx):
+    """Rows of every length class of the hand-written row sort: <= 32 (warp network), <= 4096
+    (shared-memory network), longer (global-memory network), with duplicates."""
+    rng = np.random.default_rng(12)
+    line = np.stack([rng.integers(0, 30000, 9000), rng.integers(0, 2, 9000), rng.integers(0, 2, 9000)], 1)      # one 9000-long row
+    slab = np.stack([rng.integers(0, 700, 6000), 40 + rng.integers(0, 8, 6000), 40 + rng.integers(0, 8, 6000)], 1)  # ~375 per row
+    blob = rng.integers(100, 164, (4000, 3))
+    dup = np.tile(np.array([[5, 90, 90]]), (5000, 1))                                                             # 5000 duplicates
+    A = np.concatenate([line, slab, blob, dup]).astype(np.float64)
+    A = A[rng.permutation(len(A))]
+    B = np.concatenate([line[:3000] + [3, 0, 0], slab[:3000] + [0, 1, 0], blob[:2000] + 1]).astype(np.float64)
+    B = B[rng.permutation(len(B))]
+    a, b = ctx.cloud(A), ctx.cloud(B)
+    ctx.build_pair(a, b)
+    for (q, s_, Q, S) in ((a, b, A, B), (b, a, B, A)):
+        idx, d2 = ctx.nn(q, s_)
+        oi, od = cnn.knn(S, Q, 1)
+        assert np.array_equal(d2, od[:, 0]) and np.array_equal(idx, oi[:, 0])
+    ki, kd = a.knn_self(3)
+    oi, od = cnn.knn(A, A, 3)
+    assert np.array_equal(kd, od) and np.array_equal(ki, oi)
+    a.close(); b.close()
+
+
 def test_cell_size_does_not_change_results(ctx):
     rng = np.random.default_rng(2)
     A = rng.integers(0, 256, (40000, 3)).astype(np.float64)
