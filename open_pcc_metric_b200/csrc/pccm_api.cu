@@ -276,6 +276,11 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
         return fail(nullptr, PCCM_ERR_CUDA, "scratch allocation failed");
     }
     cudaMemset(ctx->dscratch, 0, pccm_ctx::kScratch);
+    {
+        double lut[256];
+        for (int k = 0; k < 256; ++k) lut[k] = (double)k / 255.0;   // the quotient Open3D / numpy store for 8-bit colours
+        cudaMemcpy(static_cast<char*>(ctx->dscratch) + 32768, lut, sizeof lut, cudaMemcpyHostToDevice);
+    }
     if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
     if (const char* s = getenv("PCCM_SHORT_ROW")) ctx->short_row = (uint32_t)atoi(s);
     if (const char* s = getenv("PCCM_ROWSORT")) ctx->use_rowsort = atoi(s) != 0;
@@ -893,12 +898,14 @@ static CloudView view_of(const pccm_cloud* c) {
     v.rgb_u8 = c->rgb_u8;
     v.rgb_f64 = c->rgb_f64;
     v.rgb_mode = !c->has_colors ? 0 : (c->rgb_in_rec ? 1 : (c->rgb_u8 ? 2 : 3));
+    v.lut255 = nullptr;
     v.normals = c->normals;
     return v;
 }
 
 static constexpr size_t kTicketOffset = 4096;   // bytes into ctx->dscratch (zeroed at creation)
 static constexpr size_t kChunksOffset = 16384;  // 64 BlockPartial records of the fold
+static constexpr size_t kLutOffset = 32768;     // double[256]: k / 255.0
 
 // One launch covers every requested direction; the per-direction reduced records land in
 // ctx->dscratch[0..1] and are copied to ctx->pinned.
@@ -913,6 +920,8 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
     BlockPartial* partials = nullptr;
     CK(dalloc(ctx, &partials, (size_t)P.rec_stride * 2 + 1));
     P.partials = partials;
+    for (int d = 0; d < P.ndirs; ++d)
+        P.dir[d].q.lut255 = P.dir[d].s.lut255 = reinterpret_cast<const double*>(static_cast<char*>(ctx->dscratch) + kLutOffset);
     P.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->dscratch) + kTicketOffset);
     P.out = static_cast<BlockPartial*>(ctx->dscratch);
     P.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);

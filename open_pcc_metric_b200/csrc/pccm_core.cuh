@@ -32,10 +32,6 @@ struct uint4 { uint32_t x, y, z, w; };
 struct float4 { float x, y, z, w; };
 #endif
 
-#ifndef PCCM_SWEEP
-#define PCCM_SWEEP 0
-#endif
-
 namespace pccm {
 
 #if defined(PCCM_COUNT) && !defined(__CUDA_ARCH__)
@@ -259,13 +255,31 @@ struct TopK {
     }
 };
 
+// ---- where the rows of the pencil table come from -----------------------------------------
+// GlobalRows reads the table and the records from global memory (read-only path).  The query
+// kernel substitutes a staged source that serves the rows around a tile from shared memory.
+template <class K>
+struct GlobalRows {
+    const uint32_t* row_start;
+    const typename K::Rec* recs;
+    int ny;
+    PCCM_HD const typename K::Rec* fetch(int yy, int zz, uint32_t& lo, uint32_t& hi) const {
+        const uint32_t row = (uint32_t)zz * (uint32_t)ny + (uint32_t)yy;
+        lo = load_u32(row_start + row);
+        hi = load_u32(row_start + row + 1);
+        return recs;
+    }
+    static PCCM_HD typename K::Rec load(const typename K::Rec* p) { return load_rec(p); }
+    static PCCM_HD typename K::C xof(const typename K::Rec* p) { return K::rec_x(p); }
+};
+
 // ---- pencil visit ---------------------------------------------------------------------
-template <class K, class Acc>
+template <class K, class Rows, class Acc>
 PCCM_HD void visit_run(const typename K::Rec* __restrict__ recs, uint32_t lo, uint32_t hi,
                        const typename K::Q& q, typename K::D B2, Acc& acc, uint32_t short_row) {
     if (hi - lo <= short_row) {           // short pencil: one pass, no dependent search loads
         for (uint32_t i = lo; i < hi; ++i) {
-            typename K::Rec r = load_rec(recs + i);
+            typename K::Rec r = Rows::load(recs + i);
             typename K::C dx = K::rec_q(r).x - q.x;
             if (K::lbound(dx, B2) > acc.worst()) continue;
             acc.offer(K::dist2(q, r), K::rec_idx(r), i);
@@ -277,83 +291,27 @@ PCCM_HD void visit_run(const typename K::Rec* __restrict__ recs, uint32_t lo, ui
     while (a < b) {
         uint32_t m = (a + b) >> 1;
         PCCM_CNT(g_cnt.bsearch_steps++);
-        if (K::rec_x(recs + m) < q.x) a = m + 1; else b = m;
+        if (Rows::xof(recs + m) < q.x) a = m + 1; else b = m;
     }
-#if PCCM_SWEEP == 0
     for (uint32_t i = a; i < hi; ++i) {   // sweep towards +x
-        typename K::Rec r = load_rec(recs + i);
+        typename K::Rec r = Rows::load(recs + i);
         typename K::C dx = K::rec_q(r).x - q.x;
         PCCM_CNT(g_cnt.cands++);
         if (K::lbound(dx, B2) > acc.worst()) break;
         acc.offer(K::dist2(q, r), K::rec_idx(r), i);
     }
     for (uint32_t i = a; i-- > lo;) {     // sweep towards -x
-        typename K::Rec r = load_rec(recs + i);
+        typename K::Rec r = Rows::load(recs + i);
         typename K::C dx = q.x - K::rec_q(r).x;
         PCCM_CNT(g_cnt.cands++);
         if (K::lbound(dx, B2) > acc.worst()) break;
         acc.offer(K::dist2(q, r), K::rec_idx(r), i);
     }
-#elif PCCM_SWEEP == 1
-    // both directions advance in the same iteration: trip count = max(right, left), two
-    // independent loads in flight
-    uint32_t ir = a, il = a;
-    bool go_r = ir < hi, go_l = il > lo;
-    while (go_r | go_l) {
-        if (go_r) {
-            typename K::Rec r = load_rec(recs + ir);
-            typename K::C dx = K::rec_q(r).x - q.x;
-            if (K::lbound(dx, B2) > acc.worst()) go_r = false;
-            else { acc.offer(K::dist2(q, r), K::rec_idx(r), ir); ++ir; go_r = ir < hi; }
-        }
-        if (go_l) {
-            typename K::Rec r = load_rec(recs + il - 1);
-            typename K::C dx = q.x - K::rec_q(r).x;
-            if (K::lbound(dx, B2) > acc.worst()) go_l = false;
-            else { --il; acc.offer(K::dist2(q, r), K::rec_idx(r), il); go_l = il > lo; }
-        }
-    }
-#else
-    // fixed window of two records on each side evaluated without branches (every lane that
-    // visits the pencil does the same work), then ordinary sweeps only where the window edge
-    // was still within reach
-    {
-        const uint32_t n = hi - lo;               // >= 1
-        uint32_t j[4];
-        bool ok[4];
-        j[0] = a;     ok[0] = a < hi;
-        j[1] = a + 1; ok[1] = a + 1 < hi;
-        j[2] = a - 1; ok[2] = a > lo;
-        j[3] = a - 2; ok[3] = a > lo + 1;
-        typename K::Rec r[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) r[t] = load_rec(recs + (ok[t] ? j[t] : lo));
-        (void)n;
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-            if (ok[t]) acc.offer(K::dist2(q, r[t]), K::rec_idx(r[t]), j[t]);
-        for (uint32_t i = a + 2; i < hi; ++i) {
-            typename K::Rec rr = load_rec(recs + i);
-            typename K::C dx = K::rec_q(rr).x - q.x;
-            if (K::lbound(dx, B2) > acc.worst()) break;
-            acc.offer(K::dist2(q, rr), K::rec_idx(rr), i);
-        }
-        if (a > lo + 2) {
-            for (uint32_t i = a - 2; i-- > lo;) {
-                typename K::Rec rr = load_rec(recs + i);
-                typename K::C dx = q.x - K::rec_q(rr).x;
-                if (K::lbound(dx, B2) > acc.worst()) break;
-                acc.offer(K::dist2(q, rr), K::rec_idx(rr), i);
-            }
-        }
-    }
-#endif
 }
 
-// Exact search of query q in the indexed cloud (g, row_start, recs).
-template <class K, class Acc>
-PCCM_HD void search(const RowGrid& g, const uint32_t* __restrict__ row_start,
-                    const typename K::Rec* __restrict__ recs, const typename K::Q& q, Acc& acc) {
+// Exact search of query q in an indexed cloud whose rows are served by `rows`.
+template <class K, class Rows, class Acc>
+PCCM_HD void search_rows(const RowGrid& g, const Rows& rows, const typename K::Q& q, Acc& acc) {
     typedef typename K::C C;
     typedef typename K::D D;
     const int ny = g.ny, nz = g.nz;
@@ -367,9 +325,9 @@ PCCM_HD void search(const RowGrid& g, const uint32_t* __restrict__ row_start,
     auto visit = [&](int yy, int zz, D B2) {
         PCCM_CNT(g_cnt.pencils_checked++);
         if (B2 > acc.worst()) { PCCM_CNT(g_cnt.skipped_by_bound++); return; }
-        const uint32_t row = (uint32_t)zz * (uint32_t)ny + (uint32_t)yy;
-        const uint32_t lo = load_u32(row_start + row), hi = load_u32(row_start + row + 1);
-        if (lo < hi) { PCCM_CNT(g_cnt.pencils_visited++); visit_run<K>(recs, lo, hi, q, B2, acc, g.short_row); }
+        uint32_t lo, hi;
+        const typename K::Rec* base = rows.fetch(yy, zz, lo, hi);
+        if (lo < hi) { PCCM_CNT(g_cnt.pencils_visited++); visit_run<K, Rows>(base, lo, hi, q, B2, acc, g.short_row); }
     };
 
     for (int r = 0;; ++r) {
@@ -377,7 +335,6 @@ PCCM_HD void search(const RowGrid& g, const uint32_t* __restrict__ row_start,
         PCCM_CNT(g_cnt.rings++);
         if (r == 0) {
             visit(cy0, cz0, bound_y(cy0) + bound_z(cz0));
-            PCCM_CNT(g_cnt.ring0_cands = g_cnt.ring0_cands + 0);
         } else {
             const int ya = ylo < 0 ? 0 : ylo, yb = yhi > ny - 1 ? ny - 1 : yhi;
             const int za = zlo + 1 < 0 ? 0 : zlo + 1, zb = zhi - 1 > nz - 1 ? nz - 1 : zhi - 1;
@@ -406,6 +363,15 @@ PCCM_HD void search(const RowGrid& g, const uint32_t* __restrict__ row_start,
         if (!open) break;
         if (K::gap_sq_gt(m, acc.worst())) break;
     }
+}
+
+// Exact search of query q in the indexed cloud (g, row_start, recs) read from global memory.
+template <class K, class Acc>
+PCCM_HD void search(const RowGrid& g, const uint32_t* __restrict__ row_start,
+                    const typename K::Rec* __restrict__ recs, const typename K::Q& q, Acc& acc) {
+    GlobalRows<K> rows;
+    rows.row_start = row_start; rows.recs = recs; rows.ny = g.ny;
+    search_rows<K>(g, rows, q, acc);
 }
 
 // ---- Open3D EstimateNormals arithmetic ---------------------------------------------------

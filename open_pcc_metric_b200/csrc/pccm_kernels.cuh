@@ -13,6 +13,10 @@ namespace pccm {
 constexpr int kStatsThreads = 256;
 constexpr int kQueryThreads = 128;
 constexpr int kKnnThreads = 64;
+#ifndef PCCM_STAGE
+#define PCCM_STAGE 0   // 1 = stage the tile's pencil window in shared memory (exact; measured 15 % slower, profiles/README.md)
+#endif
+
 
 // ------------------------------------------------------------------------------------
 // raw input access
@@ -487,6 +491,7 @@ struct CloudView {        // device-side view of an indexed cloud
     const void* recs;
     const uint32_t* row_start;
     int32_t rgb_mode;       // 0 none, 1 packed in the record (KInt), 2 rgb_u8 array, 3 rgb_f64 array
+    const double* lut255;   // lut255[k] == (double)k / 255.0 (host-computed: same IEEE quotient, no device division)
     const uchar4* rgb_u8;   // original order, or null
     const double* rgb_f64;  // original order [n][3], or null
     const double* normals;  // original order [n][3], or null
@@ -528,9 +533,9 @@ __device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uin
     }
     uint32_t p = packed;
     if (c.rgb_mode == 2) { uchar4 u = __ldg(c.rgb_u8 + idx); p = u.x | (u.y << 8) | (u.z << 16); }
-    out[0] = (double)(p & 0xffu) / 255.0;
-    out[1] = (double)((p >> 8) & 0xffu) / 255.0;
-    out[2] = (double)((p >> 16) & 0xffu) / 255.0;
+    out[0] = __ldg(c.lut255 + (p & 0xffu));
+    out[1] = __ldg(c.lut255 + ((p >> 8) & 0xffu));
+    out[2] = __ldg(c.lut255 + ((p >> 16) & 0xffu));
 }
 
 template <class K> __device__ __forceinline__ uint32_t rec_rgba(const typename K::Rec&) { return 0; }
@@ -570,6 +575,168 @@ __device__ __forceinline__ void partial_warp_reduce(BlockPartial& a, uint32_t fl
         for (int k = 0; k < 3; ++k) { a.csum[k] = warp_sum(a.csum[k]); a.cmax[k] = warp_max(a.cmax[k]); }
 }
 
+// Four values reduced over the 32 lanes with 6 exchanges instead of 20: at offsets 16 and 8 each
+// lane hands half of its values to its partner and keeps the other half (so the number of live
+// values halves while the number of lanes folded doubles), then a plain butterfly on the last
+// one.  Result: every lane ends with the total of value (lane >> 3) & 3 ... the caller reads
+// value j from lane 8 * j.  The pairing is fixed, so float sums are reproducible.
+template <bool IS_MAX>
+__device__ __forceinline__ double warp_reduce4(double v0, double v1, double v2, double v3) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    auto op = [](double a, double b) { return IS_MAX ? fmax(a, b) : dadd(a, b); };
+    // offset 16: lanes with bit 4 clear keep (v0, v1), the others keep (v2, v3)
+    const bool hi16 = (lane & 16) != 0;
+    double s0 = hi16 ? v0 : v2, s1 = hi16 ? v1 : v3;          // what I give away
+    double k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;          // what I keep
+    k0 = op(k0, __shfl_xor_sync(full, s0, 16));
+    k1 = op(k1, __shfl_xor_sync(full, s1, 16));
+    // offset 8: lanes with bit 3 clear keep k0, the others keep k1
+    const bool hi8 = (lane & 8) != 0;
+    double g = hi8 ? k0 : k1, k = hi8 ? k1 : k0;
+    k = op(k, __shfl_xor_sync(full, g, 8));
+    k = op(k, __shfl_xor_sync(full, k, 4));
+    k = op(k, __shfl_xor_sync(full, k, 2));
+    k = op(k, __shfl_xor_sync(full, k, 1));
+    return k;   // lanes 0-7: v0, 8-15: v1, 16-23: v2, 24-31: v3
+}
+
+// Query-kernel variant: one lane = one query.  Integer clouds reduce D1 with three REDUX
+// instructions (d2 < 2^32 is split in 16-bit halves so the 32-lane sums cannot overflow); the
+// float64 sums / maxima (plane error + three colour channels) go through warp_reduce4.
+template <class K>
+__device__ __forceinline__ void query_warp_reduce(BlockPartial& a, uint32_t flags, uint32_t d2_int, bool active) {
+    const unsigned full = 0xffffffffu;
+    if (K::kind == KIND_INT) {
+        const uint32_t v = active ? d2_int : 0u;
+        const unsigned lo = __reduce_add_sync(full, v & 0xffffu), hi = __reduce_add_sync(full, v >> 16);
+        a.sum_d1_u64 = (unsigned long long)lo + ((unsigned long long)hi << 16);
+        const unsigned mx = __reduce_max_sync(full, v);
+        a.max_d1 = __any_sync(full, active) ? (double)mx : -INFINITY;
+        a.sum_d1 = 0;
+    } else {
+        a.sum_d1 = warp_sum(a.sum_d1);
+        a.max_d1 = warp_max(a.max_d1);
+    }
+    if (flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
+        const double s = warp_reduce4<false>(a.sum_d2, a.csum[0], a.csum[1], a.csum[2]);
+        const double m = warp_reduce4<true>(a.max_d2, a.cmax[0], a.cmax[1], a.cmax[2]);
+        a.sum_d2 = __shfl_sync(full, s, 0);  a.csum[0] = __shfl_sync(full, s, 8);
+        a.csum[1] = __shfl_sync(full, s, 16); a.csum[2] = __shfl_sync(full, s, 24);
+        a.max_d2 = __shfl_sync(full, m, 0);  a.cmax[0] = __shfl_sync(full, m, 8);
+        a.cmax[1] = __shfl_sync(full, m, 16); a.cmax[2] = __shfl_sync(full, m, 24);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// shared-memory staging of the pencils around a tile
+//
+// ncu on the first version: DRAM 5 %, issue slots 65 %, 17 cycles per issued instruction --
+// the kernel waits on chains of DEPENDENT loads (table entry -> 4-5 binary-search probes ->
+// sweep), each a 250-cycle L2 round trip because consecutive tiles land on different SMs.
+// A tile's 128 queries are neighbours in (row, x) order, so the rows they can touch in rings
+// 0 and 1 form, for each of <= kMaxSeg z-lines, ONE contiguous run of the record array.  The
+// block copies those runs (16-byte coalesced loads, typically 0.6 k records = 10 KB) and the
+// matching slice of the row table into shared memory once, and every probe of the search then
+// costs a shared-memory access.  Rows outside the window (ring >= 2, oversized tiles) fall
+// back to global memory transparently -- results are identical by construction.
+// ------------------------------------------------------------------------------------
+#ifndef PCCM_STAGE_BYTES
+#define PCCM_STAGE_BYTES (24 * 1024)
+#endif
+constexpr int kMaxSeg = 4;
+constexpr int kMaxSegRows = 96;
+
+template <class K>
+struct StagedRows {
+    typedef typename K::Rec Rec;
+    const uint32_t* row_start;   // global fallback
+    const Rec* recs;
+    int ny;
+    int z0, nseg, ylo, yhi;      // window: zz in [z0, z0 + nseg), yy in [ylo, yhi]
+    const uint32_t* tbl;         // shared: [nseg][kMaxSegRows + 1] absolute record positions
+    const Rec* const* vbase;     // shared: vbase[k][pos] is the staged copy of recs[pos]
+    __device__ __forceinline__ const Rec* fetch(int yy, int zz, uint32_t& lo, uint32_t& hi) const {
+        const int k = zz - z0;
+        if ((unsigned)k < (unsigned)nseg && yy >= ylo && yy <= yhi) {
+            const uint32_t* t = tbl + k * (kMaxSegRows + 1) + (yy - ylo);
+            lo = t[0];
+            hi = t[1];
+            return vbase[k];
+        }
+        const uint32_t row = (uint32_t)zz * (uint32_t)ny + (uint32_t)yy;
+        lo = __ldg(row_start + row);
+        hi = __ldg(row_start + row + 1);
+        return recs;
+    }
+    static __device__ __forceinline__ Rec load(const Rec* p) { return *p; }            // generic: shared or global
+    static __device__ __forceinline__ typename K::C xof(const Rec* p) { return K::rec_x(p); }
+};
+
+template <class K>
+struct StageSmem {
+    typename K::Rec recs[PCCM_STAGE_BYTES / sizeof(typename K::Rec)];
+    uint32_t tbl[kMaxSeg][kMaxSegRows + 1];
+    const typename K::Rec* vbase[kMaxSeg];
+    uint32_t gstart[kMaxSeg], count[kMaxSeg], sbase[kMaxSeg];
+    int red[4][kQueryThreads / 32];
+    int z0, nseg, ylo, yhi;
+};
+
+// Block-wide: decide the window from the queries' cells, copy it.  Returns through `S`
+// (nseg == 0 means "not staged": every fetch goes to global memory).
+template <class K>
+__device__ __forceinline__ void stage_window(const RowGrid& g, const uint32_t* __restrict__ row_start,
+                                             const typename K::Rec* __restrict__ recs, bool active,
+                                             const typename K::Q& q, StageSmem<K>& S) {
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ny = g.ny, nz = g.nz;
+    int cy = K::cell_y(g, q.y), cz = K::cell_z(g, q.z);
+    cy = cy < 0 ? 0 : (cy >= ny ? ny - 1 : cy);
+    cz = cz < 0 ? 0 : (cz >= nz ? nz - 1 : cz);
+    const int big = 0x7fffffff;
+    const int ymn = __reduce_min_sync(full, active ? cy : big), ymx = __reduce_max_sync(full, active ? cy : -1);
+    const int zmn = __reduce_min_sync(full, active ? cz : big), zmx = __reduce_max_sync(full, active ? cz : -1);
+    if (lane == 0) { S.red[0][warp] = ymn; S.red[1][warp] = ymx; S.red[2][warp] = zmn; S.red[3][warp] = zmx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = S.red[0][0], b = S.red[1][0], c = S.red[2][0], d = S.red[3][0];
+        for (int w = 1; w < kQueryThreads / 32; ++w) {
+            a = min(a, S.red[0][w]); b = max(b, S.red[1][w]); c = min(c, S.red[2][w]); d = max(d, S.red[3][w]);
+        }
+        int nseg = 0;
+        if (b >= 0) {   // at least one active query
+            const int ylo = max(a - 1, 0), yhi = min(b + 1, ny - 1), z0 = max(c - 1, 0), z1 = min(d + 1, nz - 1);
+            const int nrows = yhi - ylo + 1;
+            nseg = z1 - z0 + 1;
+            if (nseg > kMaxSeg || nrows > kMaxSegRows) nseg = 0;
+            uint32_t total = 0;
+            for (int k = 0; k < nseg; ++k) {
+                const uint32_t first = (uint32_t)(z0 + k) * (uint32_t)ny + (uint32_t)ylo;
+                const uint32_t gs = __ldg(row_start + first), ge = __ldg(row_start + first + nrows);
+                S.gstart[k] = gs; S.count[k] = ge - gs; S.sbase[k] = total;
+                total += ge - gs;
+            }
+            if (total > PCCM_STAGE_BYTES / sizeof(typename K::Rec)) nseg = 0;
+            S.z0 = z0; S.ylo = ylo; S.yhi = yhi;
+        }
+        S.nseg = nseg;
+    }
+    __syncthreads();
+    const int nseg = S.nseg;
+    if (nseg == 0) return;
+    const int nrows = S.yhi - S.ylo + 1;
+    for (int k = 0; k < nseg; ++k) {
+        const uint32_t first = (uint32_t)(S.z0 + k) * (uint32_t)ny + (uint32_t)S.ylo;
+        for (int j = threadIdx.x; j <= nrows; j += kQueryThreads) S.tbl[k][j] = __ldg(row_start + first + j);
+        const uint32_t gs = S.gstart[k], cnt = S.count[k], sb = S.sbase[k];
+        for (uint32_t i = threadIdx.x; i < cnt; i += kQueryThreads) S.recs[sb + i] = load_rec(recs + gs + i);
+        if (threadIdx.x == 0) S.vbase[k] = S.recs + sb - gs;   // virtual base (only dereferenced inside the copied range)
+    }
+    __syncthreads();
+}
+
 // One launch covers both directions: blocks [0, dir[0].ntiles) serve direction 0, the rest
 // direction 1; a block is one tile of kQueryThreads consecutive queries of the sorted order
 // (the hardware block scheduler balances the very uneven tile costs).  Each warp reduces its 32
@@ -595,13 +762,26 @@ pair_query_kernel(const __grid_constant__ QueryParams P) {
     BlockPartial acc;
     partial_init(acc);
     const uint32_t t = D.qbegin + tile * kQueryThreads + threadIdx.x;
-    if (t < D.qend) {
-        const Rec qr = load_rec(qrecs + t);
-        const Q q = K::rec_q(qr);
-        const uint32_t qidx = K::rec_idx(qr);
-        Best1<K> best;
-        best.init();
-        search<K>(D.s.grid, D.s.row_start, srecs, q, best);
+    const bool active = t < D.qend;
+    const Rec qr = load_rec(qrecs + (active ? t : D.qbegin));
+    const Q q = K::rec_q(qr);
+    const uint32_t qidx = K::rec_idx(qr);
+    Best1<K> best;
+    best.init();
+#if PCCM_STAGE
+    __shared__ StageSmem<K> stg;
+    stage_window<K>(D.s.grid, D.s.row_start, srecs, active, q, stg);
+    if (active) {
+        StagedRows<K> rows;
+        rows.row_start = D.s.row_start; rows.recs = srecs; rows.ny = D.s.grid.ny;
+        rows.z0 = stg.z0; rows.nseg = stg.nseg; rows.ylo = stg.ylo; rows.yhi = stg.yhi;
+        rows.tbl = &stg.tbl[0][0]; rows.vbase = stg.vbase;
+        search_rows<K>(D.s.grid, rows, q, best);
+    }
+#else
+    if (active) search<K>(D.s.grid, D.s.row_start, srecs, q, best);
+#endif
+    if (active) {
         const double d1 = K::d2_as_double(best.d2);
         if (K::kind == KIND_INT) acc.sum_d1_u64 = (unsigned long long)best.d2;
         else acc.sum_d1 = d1;
@@ -629,7 +809,7 @@ pair_query_kernel(const __grid_constant__ QueryParams P) {
     }
     // warps fold with shuffles as they finish; the block's single record is written once all
     // four are done (they could not retire earlier anyway: the block holds their resources)
-    partial_warp_reduce(acc, D.flags);
+    query_warp_reduce<K>(acc, D.flags, active ? (uint32_t)acc.sum_d1_u64 : 0u, active);
     __shared__ BlockPartial sm[kWarps];
     if (lane == 0) sm[warp] = acc;
     __syncthreads();
