@@ -44,16 +44,16 @@ def _check_nn(kind, q, s, cell):
     assert np.array_equal(i, oi[:, 0])
 
 
-@pytest.fixture(params=[0, 8, 100000], autouse=True)
+@pytest.fixture(params=[0, 100000])
 def short_row(request):
-    """0 = always binary search + sweeps; 8 = product default; huge = always the linear scan."""
+    """0 = binary search + sweeps (product default); huge = always the linear scan."""
     _L.emul_set_short_row(request.param)
     yield request.param
-    _L.emul_set_short_row(8)
+    _L.emul_set_short_row(0)
 
 
 @pytest.mark.parametrize("cell", [1, 2, 4, 16, 256])
-def test_int_nn_cells(cell):
+def test_int_nn_cells(cell, short_row):
     rng = np.random.default_rng(1)
     A = rng.integers(0, 64, (3000, 3)).astype(float)
     B = rng.integers(0, 64, (2000, 3)).astype(float)
@@ -75,7 +75,7 @@ def test_int_extremes():
 
 @pytest.mark.parametrize("kind", [KF32, KF64])
 @pytest.mark.parametrize("cell", [0.01, 0.1, 0.5, 10.0])
-def test_float_nn_cells(kind, cell):
+def test_float_nn_cells(kind, cell, short_row):
     rng = np.random.default_rng(2)
     A = rng.normal(0, 1, (2500, 3))
     B = A[rng.permutation(2500)][:2000] + rng.normal(0, 0.05, (2000, 3))
