@@ -35,7 +35,7 @@ struct float4 { float x, y, z, w; };
 namespace pccm {
 
 #if defined(PCCM_COUNT) && !defined(__CUDA_ARCH__)
-struct Counters { unsigned long long pencils_checked, pencils_visited, bsearch_steps, cands, rings, queries, ring0_cands, skipped_by_bound; };
+struct Counters { unsigned long long pencils_checked, pencils_visited, bsearch_steps, cands, rings, queries, ring0_cands, skipped_by_bound, offers, inserts, shifts; };
 extern Counters g_cnt;
 #define PCCM_CNT(x) (x)
 #else
@@ -235,6 +235,7 @@ struct TopK {
     PCCM_HD typename K::D worst() const { return worst_d2; }
     PCCM_HD void offer(typename K::D d, uint32_t i, uint32_t p) {
         int j;
+        PCCM_CNT(g_cnt.offers++);
         if (count < k) {
             j = count++;
         } else {
@@ -247,9 +248,11 @@ struct TopK {
             typename K::D pd = d2s[a];
             uint32_t pi = idxs[a];
             if (pd < d || (pd == d && pi < i)) break;
+            PCCM_CNT(g_cnt.shifts++);
             d2s[j * stride] = pd; idxs[j * stride] = pi; poss[j * stride] = poss[a];
             --j;
         }
+        PCCM_CNT(g_cnt.inserts++);
         d2s[j * stride] = d; idxs[j * stride] = i; poss[j * stride] = p;
         if (count == k) worst_d2 = d2s[(k - 1) * stride];
     }
