@@ -120,25 +120,36 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
+_TORCH_MAP = None
+
+
+def _torch_map():
+    global _TORCH_MAP
+    if _TORCH_MAP is None:
+        import torch
+        _TORCH_MAP = {torch.float64: (F64, 8), torch.float32: (F32, 4), torch.int32: (I32, 4), torch.uint8: (U8, 1)}
+        if hasattr(torch, "uint16"):
+            _TORCH_MAP[torch.uint16] = (U16, 2)
+    return _TORCH_MAP
+
+
 class _Buf:
     """(pointer, dtype code, row stride in bytes, mem kind) + a reference keeping it alive."""
 
     def __init__(self, arr, allowed, what):
         if _is_torch(arr):
-            import torch
-            tmap = {torch.float64: F64, torch.float32: F32, torch.int32: I32, torch.uint8: U8}
-            if hasattr(torch, "uint16"):
-                tmap[torch.uint16] = U16
-            if arr.dtype not in tmap:
+            ent = _torch_map().get(arr.dtype)
+            if ent is None:
                 raise TypeError(f"{what}: unsupported torch dtype {arr.dtype}")
-            if arr.dim() != 2 or arr.shape[1] < 3 or arr.stride(1) != 1:
+            shape, st = arr.shape, arr.stride()
+            if len(shape) != 2 or shape[1] < 3 or st[1] != 1:
                 raise ValueError(f"{what}: expected (N, 3) rows with unit inner stride")
             self.keep = arr
             self.ptr = arr.data_ptr()
-            self.dtype = tmap[arr.dtype]
-            self.stride = arr.stride(0) * arr.element_size() if arr.shape[0] > 1 else 3 * arr.element_size()
+            self.dtype, es = ent
+            self.stride = st[0] * es if shape[0] > 1 else 3 * es
             self.mem = DEVICE if arr.is_cuda else HOST
-            self.n = arr.shape[0]
+            self.n = shape[0]
         else:
             a = np.asarray(arr)
             if a.dtype not in _NP_DTYPES:

@@ -350,3 +350,49 @@ def test_config2_full_size_properties(ctx):
     a2.build_index()
     i2, z = ctx.nn(a, a2)
     assert not z.any() and np.array_equal(i2, np.arange(len(A)))
+
+
+def test_sequence_evaluation_is_per_frame(ctx):
+    """Config-4 shape at test scale: every frame gets its own values (the reference's class-level
+    memo, quirk Q2, would repeat frame 0), equal to evaluating each pair alone."""
+    from open_pcc_metric_b200.calculator import MetricCalculator
+    from open_pcc_metric_b200.cloud_pair import CloudPair
+    from open_pcc_metric_b200.options import CalculateOptions, transform_options
+    from open_pcc_metric_b200.sequence import evaluate_sequence
+    from open_pcc_metric_b200.synth import synth_pair
+    opts = CalculateOptions(color="rgb", hausdorff=True)
+    frames = [synth_pair(7, 2500, 100 + t, phase_shift=0.02 * t) for t in range(3)]
+    df = evaluate_sequence(frames, opts, ctx=ctx, peak="resolution", resolution_bits=7)
+    assert sorted(df["frame"].unique()) == [0, 1, 2] and len(df) == 3 * 20
+    for t, (a, b) in enumerate(frames):
+        alone = MetricCalculator(CloudPair(a, b, ctx=ctx, peak="resolution", resolution_bits=7)).calculate(
+            transform_options(opts)).as_df()
+        got = df[df["frame"] == t].drop(columns="frame").reset_index(drop=True)
+        assert got.equals(alone)
+    assert df[df["frame"] == 0]["value"].tolist() != df[df["frame"] == 1]["value"].tolist()
+
+
+def test_cli_end_to_end(ctx, tmp_path):
+    """python -m open_pcc_metric_b200 on PLY files: the reference's flags and table format
+    (handler.py:5-71) with values equal to the API path."""
+    import subprocess
+    import sys
+    from open_pcc_metric_b200.calculator import MetricCalculator
+    from open_pcc_metric_b200.cloud_pair import CloudPair
+    from open_pcc_metric_b200.geometry import PointCloud
+    from open_pcc_metric_b200.io import read_point_cloud, write_ply
+    from open_pcc_metric_b200.options import CalculateOptions, transform_options
+    from open_pcc_metric_b200.synth import synth_pair
+    A, B = synth_pair(7, 3000, 5, dedup=False)
+    pa, pb = str(tmp_path / "a.ply"), str(tmp_path / "b.ply")
+    write_ply(pa, PointCloud(A.points, A.colors, A.normals))
+    write_ply(pb, PointCloud(B.points, B.colors, B.normals), binary=False)
+    out = subprocess.run([sys.executable, "-m", "open_pcc_metric_b200", "--ocloud", pa, "--pcloud", pb, "--color", "ycc",
+                          "--hausdorff", "--point-to-plane", "--csv", "--peak", "resolution", "--bits", "7"],
+                         capture_output=True, text=True, cwd=__import__("conftest").ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln]
+    assert lines[0] == ",label,is_left,point-to-plane,value" and len(lines) == 1 + 32
+    pair = CloudPair(read_point_cloud(pa), read_point_cloud(pb), ctx=ctx, peak="resolution", resolution_bits=7)
+    want = MetricCalculator(pair).calculate(transform_options(CalculateOptions("ycc", True, True))).as_df().to_csv()
+    assert out.stdout.strip() == want.strip()
