@@ -47,6 +47,7 @@ struct pccm_ctx {
     int cell_override_shift = -1;   // debugging: PCCM_CELL_SHIFT
     double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
     uint32_t short_row = 0;         // rows up to this length skip the binary search (PCCM_SHORT_ROW; measured: never a win)
+    bool normals_counting = true;   // KInt normals by counting selection (PCCM_NORMALS_COUNTING=0: list-based kernel only)
     bool use_rowsort = true;        // KInt pair build: counting sort + per-row sort instead of CUB radix (PCCM_ROWSORT=0 disables)
 };
 
@@ -284,6 +285,7 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
     if (const char* s = getenv("PCCM_SHORT_ROW")) ctx->short_row = (uint32_t)atoi(s);
     if (const char* s = getenv("PCCM_ROWSORT")) ctx->use_rowsort = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_NORMALS_COUNTING")) ctx->normals_counting = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
     return PCCM_OK;
@@ -1163,6 +1165,21 @@ extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_
     KnnParams P{};
     P.c = view_of(c); P.begin = c->base + (uint32_t)begin; P.end = c->base + (uint32_t)end; P.k = k; P.mode = KNN_NORMALS;
     P.normals_out = c->normals;
+    if (c->index_kind == PCCM_KIND_INT && k <= 255 && ctx->normals_counting && end > begin) {
+        // voxelised clouds: counting selection (no per-thread sorted list), then the generic
+        // kernel only for the points it flagged (sparse neighbourhoods, fewer than k points)
+        const uint32_t cnt = P.end - P.begin;
+        const size_t smem = (size_t)kHistBins * kNrmThreads + (size_t)k * kNrmThreads * 2 * sizeof(uint32_t);
+        {
+            StageTimer t(ctx, &ctx->tm.knn_ms, 1);
+            CK(cudaFuncSetAttribute(normals_int_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            normals_int_kernel<<<(cnt + kNrmThreads - 1) / kNrmThreads, kNrmThreads, smem, ctx->stream>>>(P);
+            ctx->tm.knn_launches++;
+            ctx->tm.total_launches++;
+            CK(cudaGetLastError());
+        }
+        P.mode = KNN_NORMALS_FLAGGED;
+    }
     rc = launch_knn(ctx, c, P);
     if (!rc) c->has_normals = true;
     return rc;

@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_co
 // ------------------------------------------------------------------------------------
 // K7: self k-NN with fused epilogues
 // ------------------------------------------------------------------------------------
-enum KnnMode : int { KNN_LIST = 0, KNN_BOUNDARY = 1, KNN_NORMALS = 2 };
+enum KnnMode : int { KNN_LIST = 0, KNN_BOUNDARY = 1, KNN_NORMALS = 2, KNN_NORMALS_FLAGGED = 3 };
 
 struct KnnParams {
     CloudView c;
@@ -893,12 +893,14 @@ knn_self_kernel(const __grid_constant__ KnnParams P) {
     uint32_t* poss = idxs + (size_t)k * kKnnThreads;
     const Rec* __restrict__ recs = static_cast<const Rec*>(P.c.recs);
     const uint32_t t = P.begin + blockIdx.x * kKnnThreads + threadIdx.x;
-    const bool active = t < P.end;
+    bool active = t < P.end;
     double bmin = INFINITY, bmax = -INFINITY;
+    const Rec qr = load_rec(recs + (active ? t : P.begin));
+    const uint32_t qidx = K::rec_idx(qr);
+    if (active && P.mode == KNN_NORMALS_FLAGGED)     // only the points normals_int_kernel could not finish
+        active = __double_as_longlong(P.normals_out[3 * (size_t)qidx]) == 0x7ff8000000000001ll;
     if (active) {
-        const Rec qr = load_rec(recs + t);
         const Q q = K::rec_q(qr);
-        const uint32_t qidx = K::rec_idx(qr);
         TopK<K> acc;
         acc.init(d2s + threadIdx.x, idxs + threadIdx.x, poss + threadIdx.x, kKnnThreads, k);
         search<K>(P.c.grid, P.c.row_start, recs, q, acc);
@@ -933,6 +935,155 @@ knn_self_kernel(const __grid_constant__ KnnParams P) {
         double mx = block_max<kKnnThreads>(bmax, sm);
         if (threadIdx.x == 0) { P.minmax[2 * blockIdx.x] = mn; P.minmax[2 * blockIdx.x + 1] = mx; }
     }
+}
+
+// ------------------------------------------------------------------------------------
+// K7': normal estimation for integer (voxelised) clouds by counting selection
+//
+// The generic k-NN kernel keeps a (d2, index)-sorted list of k = 30 entries per thread; on
+// voxel surfaces it performs ~70 insertions shifting ~600 entries per point -- the list, not
+// the search, is the cost.  Squared distances of integer clouds are small integers, so the
+// 30-NN set can be selected by COUNTING instead:
+//   pass 1  histogram of d2 (64 bins) over the candidates of rings 0, 1, 2, ... until the
+//           k-th smallest distance T is certified (every point with d2 <= T lies in the
+//           visited rings);
+//   pass 2  re-walk the window d2 <= T: points with d2 < T go straight into integer cumulants
+//           (sums of x, y, z, xx, xy, ... are exact, so their order is irrelevant); among the
+//           points with d2 == T the (k - count(d2 < T)) smallest ORIGINAL indices are kept in
+//           a short sorted list -- exactly the set the (d2, index) ordering selects.
+// The cumulants are the same exact integers the list-based kernel feeds to the eigen-solver,
+// so the normals are bit-identical to knn_self_kernel<KInt> (tested).  A point whose k-th
+// neighbour is farther than sqrt(63) (sparse data) is flagged with NaN and finished by the
+// generic kernel.
+// ------------------------------------------------------------------------------------
+constexpr int kHistBins = 64;
+constexpr int kNrmThreads = 64;
+
+template <class F>
+__device__ __forceinline__ void int_window_walk(const RowGrid& g, const uint32_t* __restrict__ row_start,
+                                                const uint4* __restrict__ recs, const KInt::Q& q, int qcy, int qcz,
+                                                int cy0, int cz0, int r, uint32_t limit, F&& f) {
+    const int ny = g.ny, nz = g.nz;
+    auto pencil = [&](int yy, int zz) {
+        if (yy < 0 || yy >= ny || zz < 0 || zz >= nz) return;
+        const uint32_t by = yy > qcy ? KInt::sq(KInt::gap_up_y(g, q.y, yy)) : (yy < qcy ? KInt::sq(KInt::gap_dn_y(g, q.y, yy)) : 0u);
+        const uint32_t bz = zz > qcz ? KInt::sq(KInt::gap_up_z(g, q.z, zz)) : (zz < qcz ? KInt::sq(KInt::gap_dn_z(g, q.z, zz)) : 0u);
+        const uint32_t B2 = by + bz;
+        if (B2 > limit) return;
+        const uint32_t row = (uint32_t)zz * (uint32_t)ny + (uint32_t)yy;
+        uint32_t lo = __ldg(row_start + row);
+        const uint32_t hi = __ldg(row_start + row + 1);
+        if (lo >= hi) return;
+        const int w = (int)floorf(sqrtf((float)(limit - B2)));
+        const int xlo = q.x - w, xhi = q.x + w;
+        uint32_t b = hi;
+        while (lo < b) {                       // first record with x >= xlo
+            const uint32_t m = (lo + b) >> 1;
+            if (KInt::rec_x(recs + m) < xlo) lo = m + 1; else b = m;
+        }
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint4 rec = __ldg(recs + i);
+            if ((int)(rec.x & 0xffffu) > xhi) break;
+            const uint32_t d2 = KInt::dist2(q, rec);
+            if (d2 <= limit) f(rec, i, d2);
+        }
+    };
+    if (r == 0) { pencil(cy0, cz0); return; }
+    for (int dy = -r; dy <= r; ++dy) { pencil(cy0 + dy, cz0 - r); pencil(cy0 + dy, cz0 + r); }
+    for (int dz = -r + 1; dz <= r - 1; ++dz) { pencil(cy0 - r, cz0 + dz); pencil(cy0 + r, cz0 + dz); }
+}
+
+__global__ void __launch_bounds__(kNrmThreads)
+normals_int_kernel(const __grid_constant__ KnnParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = P.k;
+    uint8_t* H = smem_raw + threadIdx.x;                                                   // H[bin * T]
+    uint32_t* Tidx = reinterpret_cast<uint32_t*>(smem_raw + kHistBins * kNrmThreads) + threadIdx.x;   // [k][T]
+    uint32_t* Tpos = Tidx + (size_t)k * kNrmThreads;
+    const uint4* __restrict__ recs = static_cast<const uint4*>(P.c.recs);
+    const RowGrid& g = P.c.grid;
+    const uint32_t t = P.begin + blockIdx.x * kNrmThreads + threadIdx.x;
+    if (t >= P.end) return;
+    const uint4 qr = __ldg(recs + t);
+    const KInt::Q q = KInt::rec_q(qr);
+    const uint32_t qidx = qr.z;
+    const int ny = g.ny, nz = g.nz;
+    const int qcy = KInt::cell_y(g, q.y), qcz = KInt::cell_z(g, q.z);
+    const int cy0 = qcy < 0 ? 0 : (qcy >= ny ? ny - 1 : qcy);
+    const int cz0 = qcz < 0 ? 0 : (qcz >= nz ? nz - 1 : qcz);
+    for (int b = 0; b < kHistBins; ++b) H[b * kNrmThreads] = 0;
+
+    // ---- pass 1: histogram until the k-th distance is certified ----
+    uint32_t limit = kHistBins - 1, total = 0;
+    int rfin = -1;
+    uint32_t T = 0, nless = 0;
+    bool resolved = false;
+    for (int r = 0;; ++r) {
+        int_window_walk(g, P.c.row_start, recs, q, qcy, qcz, cy0, cz0, r, limit, [&](const uint4&, uint32_t, uint32_t d2) {
+            const uint8_t c = H[d2 * kNrmThreads];
+            if (c != 255) H[d2 * kNrmThreads] = c + 1;
+            ++total;
+        });
+        // distance to everything not yet visited
+        const int ylo = cy0 - r, yhi = cy0 + r, zlo = cz0 - r, zhi = cz0 + r;
+        int m = 0x7fffffff;
+        bool open = false;
+        if (ylo > 0)      { open = true; m = min(m, KInt::gap_dn_y(g, q.y, ylo - 1)); }
+        if (yhi < ny - 1) { open = true; m = min(m, KInt::gap_up_y(g, q.y, yhi + 1)); }
+        if (zlo > 0)      { open = true; m = min(m, KInt::gap_dn_z(g, q.z, zlo - 1)); }
+        if (zhi < nz - 1) { open = true; m = min(m, KInt::gap_up_z(g, q.z, zhi + 1)); }
+        const uint32_t gap2 = !open ? 0xFFFFFFFFu : (m > 65535 ? 0xFFFFFFFFu : (uint32_t)(m * m));
+        if (total >= (uint32_t)k) {
+            uint32_t cum = 0;
+            int b = 0;
+            for (; b < kHistBins; ++b) { const uint32_t c = H[b * kNrmThreads]; if (cum + c >= (uint32_t)k) break; cum += c; }
+            if (b < kHistBins) {
+                T = (uint32_t)b; nless = cum;
+                limit = T;                                    // later rings only need d2 <= T
+                if (T < gap2) { resolved = true; rfin = r; break; }
+            }
+        }
+        if (!open) { rfin = r; break; }                       // whole table visited: fewer than k points within range
+        if (gap2 > (uint32_t)(kHistBins - 1)) { rfin = r; break; }   // farther candidates cannot fall into the bins
+    }
+    if (!resolved) {                                          // sparse neighbourhood or n < k: generic kernel finishes it
+        P.normals_out[3 * (size_t)qidx] = __longlong_as_double(0x7ff8000000000001ll);
+        return;
+    }
+    // ---- pass 2: cumulants of d2 < T, smallest indices among d2 == T ----
+    const int mties = k - (int)nless;
+    int nt = 0;
+    unsigned long long sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    uint32_t sx = 0, sy = 0, sz = 0;
+    auto add = [&](const uint4& rec) {
+        const uint32_t x = rec.x & 0xffffu, y = rec.x >> 16, z = rec.y & 0xffffu;
+        sx += x; sy += y; sz += z;
+        sxx += (unsigned long long)(x * x); sxy += (unsigned long long)(x * y); sxz += (unsigned long long)(x * z);
+        syy += (unsigned long long)(y * y); syz += (unsigned long long)(y * z); szz += (unsigned long long)(z * z);
+    };
+    for (int r = 0; r <= rfin; ++r) {
+        int_window_walk(g, P.c.row_start, recs, q, qcy, qcz, cy0, cz0, r, T, [&](const uint4& rec, uint32_t pos, uint32_t d2) {
+            if (d2 < T) { add(rec); return; }
+            const uint32_t idx = rec.z;
+            int j;
+            if (nt < mties) j = nt++;
+            else { if (idx >= Tidx[(mties - 1) * kNrmThreads]) return; j = mties - 1; }
+            while (j > 0 && Tidx[(j - 1) * kNrmThreads] > idx) {
+                Tidx[j * kNrmThreads] = Tidx[(j - 1) * kNrmThreads];
+                Tpos[j * kNrmThreads] = Tpos[(j - 1) * kNrmThreads];
+                --j;
+            }
+            Tidx[j * kNrmThreads] = idx;
+            Tpos[j * kNrmThreads] = pos;
+        });
+    }
+    for (int j = 0; j < nt; ++j) add(__ldg(recs + Tpos[j * kNrmThreads]));
+    double cum[9] = {(double)sx, (double)sy, (double)sz, (double)sxx, (double)sxy, (double)sxz, (double)syy, (double)syz, (double)szz};
+    double nv[3];
+    normal_from_cumulants(cum, k, nv);
+    P.normals_out[3 * (size_t)qidx + 0] = nv[0];
+    P.normals_out[3 * (size_t)qidx + 1] = nv[1];
+    P.normals_out[3 * (size_t)qidx + 2] = nv[2];
 }
 
 __global__ void minmax_finalize_kernel(const double* in, uint32_t nb, double* out) {

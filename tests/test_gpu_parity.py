@@ -396,3 +396,45 @@ def test_cli_end_to_end(ctx, tmp_path):
     pair = CloudPair(read_point_cloud(pa), read_point_cloud(pb), ctx=ctx, peak="resolution", resolution_bits=7)
     want = MetricCalculator(pair).calculate(transform_options(CalculateOptions("ycc", True, True))).as_df().to_csv()
     assert out.stdout.strip() == want.strip()
+
+
+def test_counting_normals_equal_list_normals():
+    """Integer clouds: the counting-selection normal kernel selects exactly the (d2, index)-ordered
+    30-NN set of the list kernel -> bit-identical normals; including duplicates, ties at the k-th
+    distance, sparse outliers (flag -> generic kernel) and clouds with fewer than k points."""
+    import os
+    from open_pcc_metric_b200 import _native as N
+    from open_pcc_metric_b200.synth import synth_vox
+    rng = np.random.default_rng(21)
+    surf = synth_vox(9, 60000, 5, with_colors=False, with_normals=False, oversample=4).points
+    clouds = {
+        "surface": surf,
+        "dense_blob_with_duplicates": np.concatenate([rng.integers(0, 24, (20000, 3)), rng.integers(0, 24, (3000, 3))]).astype(np.float64),
+        "sparse": rng.integers(0, 3000, (5000, 3)).astype(np.float64),
+        "surface_plus_outliers": np.concatenate([surf[:20000], rng.integers(0, 30000, (200, 3)).astype(np.float64)]),
+        "tiny": rng.integers(0, 6, (17, 3)).astype(np.float64),
+    }
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["PCCM_NORMALS_COUNTING"] = flag
+        c = N.Context(0)
+        for name, pts in clouds.items():
+            cl = c.cloud(pts)
+            cl.build_index()
+            for k in (30, 7):
+                cl.estimate_normals(k)
+                out[(flag, name, k)] = cl.get_normals()
+            cl.close()
+        c.close()
+    os.environ.pop("PCCM_NORMALS_COUNTING")
+    for name in clouds:
+        for k in (30, 7):
+            a, b = out[("1", name, k)], out[("0", name, k)]
+            assert not np.isnan(a).any()
+            assert np.array_equal(a, b), (name, k, int((a != b).any(axis=1).sum()))
+    oi, _ = cnn.knn(clouds["surface"][:8000], clouds["surface"][:8000], 30)   # and against the oracle on a sub-cloud
+    c = N.Context(0)
+    cl = c.cloud(clouds["surface"][:8000]); cl.build_index(); cl.estimate_normals(30)
+    got, want = cl.get_normals(), cnn.normals(clouds["surface"][:8000], oi)
+    assert (np.abs(np.sum(got * want, axis=1)) > 1 - 1e-9).mean() > 0.998
+    c.close()
