@@ -175,21 +175,21 @@ def main():
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
-    from open_pcc_metric_b200 import _native as N
-    from open_pcc_metric_b200.calculator import MetricCalculator
-    from open_pcc_metric_b200.cloud_pair import CloudPair
-    from open_pcc_metric_b200.options import CalculateOptions, transform_options
-    from open_pcc_metric_b200.synth import Cloud
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: open_pcc_metric_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        dist.barrier()
+    if rank == 0:
+        ge.build()           # no-op when the in-tree libpccm.so is current
+    if world > 1:
+        dist.barrier()       # nobody loads the library while rank 0 may still be linking it
+    from open_pcc_metric_b200 import _native as N
+    from open_pcc_metric_b200.calculator import MetricCalculator
+    from open_pcc_metric_b200.cloud_pair import CloudPair
+    from open_pcc_metric_b200.options import CalculateOptions, transform_options
+    from open_pcc_metric_b200.synth import Cloud
 
     partition = args.mode == "partition" and world > 1
     A, B = make_pair(args, 0 if partition else rank)

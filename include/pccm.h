@@ -15,7 +15,9 @@
  *  - all device work is ordered on the context's CUDA stream; functions that
  *    fill HOST outputs synchronise that stream before returning;
  *  - a pccm_ctx is not thread safe: one context per (thread, device);
- *  - caller owns every buffer it passes; HOST inputs are copied before return;
+ *  - caller owns every buffer it passes; pageable HOST inputs are copied before return,
+ *    PINNED host inputs are copied asynchronously (cudaMemcpyAsync): keep them unchanged
+ *    until a call that returns results or pccm_ctx_synchronize;
  *    DEVICE coordinates / colours are read until the index is built; packed float64
  *    DEVICE normals given to pccm_cloud_create are used in place and must outlive
  *    the cloud;

@@ -268,8 +268,8 @@ class Cloud:
             pb.mem, C.byref(h)))
         self.h = h
         self.n = pb.n
-        self._keep = (pb, cb, nb) if pb.mem == DEVICE else None  # device inputs are read until build_index
-        self._keep_normals = nb if pb.mem == DEVICE else None    # packed f64 device normals are used in place
+        self._keep = (pb, cb, nb)  # inputs may still be read (device inputs; pinned host inputs in flight) until the index is built / first results
+        self._keep_normals = nb   # device normals are used in place; pinned host normals may be in flight on the copy stream
 
     def info(self) -> CloudInfo:
         out = CloudInfo()

@@ -30,6 +30,8 @@ struct pccm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // host->device copies of attributes that are only needed by the query epilogue
+    cudaEvent_t ev_fork = nullptr;
     std::string err;
     int profiling = 0;
     pccm_timings tm{};
@@ -148,6 +150,8 @@ struct pccm_cloud {
     double* rgb_f64 = nullptr;
     double* normals = nullptr;
     bool normals_borrowed = false;   // caller's packed float64 device array (pccm_cloud_create, DEVICE)
+    cudaEvent_t nrm_ready = nullptr; // normals still in flight on the copy stream
+    bool nrm_pending = false;
     bool has_colors = false, has_normals = false;
     // index
     int index_kind = -1;
@@ -197,6 +201,14 @@ static int ensure_stats(pccm_ctx* ctx, pccm_cloud* c) {
     c->rgb_u8_ok = !rgb_bad;
     c->stats_ready = true;
     return PCCM_OK;
+}
+
+// order the context stream after an in-flight normal upload (no-op when there is none)
+static void wait_normals(pccm_ctx* ctx, pccm_cloud* c) {
+    if (c->nrm_pending) {
+        cudaStreamWaitEvent(ctx->stream, c->nrm_ready, 0);
+        c->nrm_pending = false;
+    }
 }
 
 // colours: uchar4 when every channel is k/255, else packed float64
@@ -266,6 +278,8 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
         if (e != cudaSuccess) { delete ctx; return fail(nullptr, PCCM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         ctx->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->copy_stream = nullptr;
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { ctx->copy_stream = nullptr; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -301,6 +315,8 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->pinned);
     cudaFree(ctx->dscratch);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCCM_OK;
@@ -337,6 +353,8 @@ extern "C" int pccm_ctx_get_timings(pccm_ctx* ctx, pccm_timings* out) {
 extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     if (!ctx || !c) return PCCM_OK;
     cudaSetDevice(ctx->device);
+    wait_normals(ctx, c);
+    if (c->nrm_ready) cudaEventDestroy(c->nrm_ready);
     dfree(ctx, c->raw_owned);
     dfree(ctx, c->raw_rgb_owned);
     dfree(ctx, c->d_stats);
@@ -376,8 +394,22 @@ static int set_normals_impl(pccm_ctx* ctx, pccm_cloud* c, const void* normals, i
         return PCCM_OK;
     }
     if (!c->normals) CK(dalloc(ctx, &c->normals, (size_t)c->n * 3));
+    wait_normals(ctx, c);
     if (packed_f64) {   // already in the device format: one copy, no repack
-        if (c->n) CK(cudaMemcpyAsync(c->normals, normals, (size_t)c->n * 24, mem_kind == PCCM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+        if (c->n) {
+            if (mem_kind == PCCM_HOST && may_borrow && ctx->copy_stream) {
+                // at cloud creation: the normals are first read by the query epilogue, so their
+                // upload runs on the copy stream while statistics, sort and table build proceed
+                if (!c->nrm_ready) CK(cudaEventCreateWithFlags(&c->nrm_ready, cudaEventDisableTiming));
+                CK(cudaEventRecord(ctx->ev_fork, ctx->stream));            // after the allocation above
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+                CK(cudaMemcpyAsync(c->normals, normals, (size_t)c->n * 24, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CK(cudaEventRecord(c->nrm_ready, ctx->copy_stream));
+                c->nrm_pending = true;
+            } else {
+                CK(cudaMemcpyAsync(c->normals, normals, (size_t)c->n * 24, mem_kind == PCCM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
         c->has_normals = true;
         return PCCM_OK;
     }
@@ -482,6 +514,7 @@ extern "C" int pccm_cloud_get_normals(pccm_ctx* ctx, pccm_cloud* c, double* out,
     if (!ctx || !c || (!out && c->n)) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     if (!c->has_normals) return fail(ctx, PCCM_ERR_STATE, "cloud has no normals");
     CK(cudaSetDevice(ctx->device));
+    wait_normals(ctx, c);
     return copy_out(ctx, out, c->normals, (size_t)c->n * 3 * sizeof(double), mem_kind);
 }
 
@@ -992,6 +1025,8 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
     if (a->n == 0 || b->n == 0) return fail(ctx, PCCM_ERR_INDEX, "empty cloud (reference: IndexError at cloud_pair.py:23)");
     if (flags & PCCM_EVAL_D2) {
         if (!a->has_normals || !b->has_normals) return fail(ctx, PCCM_ERR_STATE, "D2 needs normals on both clouds (set or estimate them)");
+        wait_normals(ctx, a);
+        wait_normals(ctx, b);
     }
     if (flags & PCCM_EVAL_COLOR) {
         if (!a->has_colors || !b->has_colors) return fail(ctx, PCCM_ERR_STATE, "colour metrics need colours on both clouds");
@@ -1156,6 +1191,7 @@ extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_
     CK(cudaSetDevice(ctx->device));
     int rc = check_range(ctx, c, begin, end);
     if (rc) return rc;
+    wait_normals(ctx, c);
     if (c->normals_borrowed) { c->normals = nullptr; c->normals_borrowed = false; }
     if (!c->normals) {
         // zero-filled so that ranks estimating disjoint slices can combine buffers by summation
