@@ -305,7 +305,10 @@ def main():
             t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
+        _, _, tm3, _ = timed(step_e2e, 5, 1, 2)
+        e2e_stages = {k: round(v / 5, 5) for k, v in tm3.items() if k.endswith("_ms")}
         e2e = {"value": nq * n_e2e * (1 if partition else world) / (ms_e2e * 1e-3), "unit": UNIT,
+               "stage_ms_per_step": e2e_stages,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * 96 + 16),
                "ms_per_step": ms_e2e / n_e2e,
                "api": "CloudPair(host float64 arrays) + MetricCalculator.calculate(transform_options(color=yuv, point_to_plane))"}

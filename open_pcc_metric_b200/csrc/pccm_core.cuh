@@ -219,6 +219,22 @@ struct Best1 {
     }
 };
 
+// Two smallest squared distances, values only (registers).  Enough for Open3D's
+// ComputeNearestNeighborDistance = sqrt(second entry of the 2-NN result): ties and indices do
+// not influence the value.
+template <class K>
+struct Best2Val {
+    typename K::D m1, m2;
+    int count;
+    PCCM_HD void init() { m1 = K::inf(); m2 = K::inf(); count = 0; }
+    PCCM_HD typename K::D worst() const { return m2; }
+    PCCM_HD void offer(typename K::D d, uint32_t, uint32_t) {
+        ++count;
+        if (d < m1) { m2 = m1; m1 = d; }
+        else if (d < m2) m2 = d;
+    }
+};
+
 // Top-k accumulator over caller-provided strided storage (shared memory on the
 // device: element j of this thread lives at base[j * stride]).  Kept sorted
 // ascending by (d2, idx).

@@ -899,7 +899,16 @@ knn_self_kernel(const __grid_constant__ KnnParams P) {
     const uint32_t qidx = K::rec_idx(qr);
     if (active && P.mode == KNN_NORMALS_FLAGGED)     // only the points normals_int_kernel could not finish
         active = __double_as_longlong(P.normals_out[3 * (size_t)qidx]) == 0x7ff8000000000001ll;
-    if (active) {
+    if (active && P.mode == KNN_BOUNDARY) {
+        // ComputeNearestNeighborDistance: sqrt of the second entry of the 2-NN result, 0 when absent
+        const Q q = K::rec_q(qr);
+        Best2Val<K> b2;
+        b2.init();
+        search<K>(P.c.grid, P.c.row_start, recs, q, b2);
+        const double v = b2.count > 1 ? sqrt(K::d2_as_double(b2.m2)) : 0.0;
+        bmin = v; bmax = v;
+        if (P.d2_out) P.d2_out[qidx] = v;
+    } else if (active) {
         const Q q = K::rec_q(qr);
         TopK<K> acc;
         acc.init(d2s + threadIdx.x, idxs + threadIdx.x, poss + threadIdx.x, kKnnThreads, k);
@@ -910,11 +919,6 @@ knn_self_kernel(const __grid_constant__ KnnParams P) {
                 P.idx_out[(size_t)qidx * k + j] = have ? (int32_t)idxs[j * kKnnThreads + threadIdx.x] : -1;
                 P.d2_out[(size_t)qidx * k + j] = have ? K::d2_as_double(d2s[j * kKnnThreads + threadIdx.x]) : INFINITY;
             }
-        } else if (P.mode == KNN_BOUNDARY) {
-            // ComputeNearestNeighborDistance: sqrt of the second entry, 0 when it is absent
-            double v = acc.count > 1 ? sqrt(K::d2_as_double(d2s[1 * kKnnThreads + threadIdx.x])) : 0.0;
-            bmin = v; bmax = v;
-            if (P.d2_out) P.d2_out[qidx] = v;
         } else {
             double cum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int j = 0; j < acc.count; ++j) {
