@@ -179,6 +179,22 @@ int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint32_t flags,
  * which = PCCM_GET_IDX (int32[n]) or PCCM_GET_D2 (double[n]); direction 0 = left. */
 int pccm_pair_get(pccm_ctx* ctx, int which, int direction, void* out, int mem_kind);
 
+/* Facet sweep of Open3D's OrientedBoundingBox::CreateFromPointsMinimal (the PSNR peak,
+ * cloud_pair.py:111-112): for each of nf hull triangles (9 doubles: a, b, c) the extent and
+ * volume of the axis-aligned box of the nv hull vertices in the triangle's frame.  The convex
+ * hull itself is computed by the caller (Qhull on the host, as Open3D does).  HOST buffers. */
+int pccm_obb_sweep(pccm_ctx* ctx, const double* hull_vertices, int64_t nv, const double* triangles, int64_t nf,
+                   double* vol_out, double* ext_out);
+
+/* Convex-hull prefilter for that peak.  pccm_cloud_extremes: original index of the arg-max of
+ * dirs[d] . p for each of ndirs directions (row-major [ndirs][3]).  pccm_cloud_outside_hull:
+ * the points that are NOT strictly inside the convex polytope { p : n_f . p + d_f < -eps for all
+ * f } given as planes[nf][4] (e.g. the hull of the extremes) -- a superset of the hull vertices
+ * of the whole cloud.  count_out receives the number found; at most `capacity` are written. */
+int pccm_cloud_extremes(pccm_ctx* ctx, pccm_cloud* cloud, const double* dirs, int ndirs, int32_t* idx_out);
+int pccm_cloud_outside_hull(pccm_ctx* ctx, pccm_cloud* cloud, const double* planes, int nf, double eps,
+                            int64_t capacity, double* xyz_out, int64_t* count_out);
+
 #ifdef __cplusplus
 }
 #endif

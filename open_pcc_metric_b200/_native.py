@@ -28,7 +28,7 @@ EXPORTS = [
     "pccm_ctx_set_profiling", "pccm_ctx_reset_timings", "pccm_ctx_get_timings",
     "pccm_cloud_create", "pccm_cloud_destroy", "pccm_cloud_info_get", "pccm_cloud_build_index", "pccm_pair_build_index",
     "pccm_cloud_set_normals", "pccm_cloud_get_normals", "pccm_estimate_normals", "pccm_knn_self",
-    "pccm_self_nn_minmax", "pccm_nn", "pccm_pair_eval", "pccm_pair_get",
+    "pccm_self_nn_minmax", "pccm_nn", "pccm_pair_eval", "pccm_pair_get", "pccm_obb_sweep", "pccm_cloud_extremes", "pccm_cloud_outside_hull",
 ]
 
 
@@ -103,6 +103,9 @@ def lib():
         "pccm_nn": [vp, vp, vp, vp, vp, i32],
         "pccm_pair_eval": [vp, vp, vp, C.c_uint32, vp, dbl, i32, i32, i32, C.POINTER(PairResult)],
         "pccm_pair_get": [vp, i32, i32, vp, i32],
+        "pccm_obb_sweep": [vp, vp, i64, vp, i64, vp, vp],
+        "pccm_cloud_extremes": [vp, vp, vp, i32, vp],
+        "pccm_cloud_outside_hull": [vp, vp, vp, i32, dbl, i64, vp, C.POINTER(i64)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -242,6 +245,15 @@ class Context:
                                          float(color_scale), int(normals_mode), int(rank), int(world), C.byref(res)))
         return res
 
+    def obb_sweep(self, hull_vertices, triangles):
+        """(volume[nf], extent[nf, 3]) of the hull vertices' box in every hull triangle's frame."""
+        hv = np.ascontiguousarray(hull_vertices, dtype=np.float64)
+        tr = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 9)
+        vol = np.empty(len(tr), dtype=np.float64)
+        ext = np.empty((len(tr), 3), dtype=np.float64)
+        self.check(self.L.pccm_obb_sweep(self.h, hv.ctypes.data, len(hv), tr.ctypes.data, len(tr), vol.ctypes.data, ext.ctypes.data))
+        return vol, ext
+
     def pair_get(self, which, direction, n):
         out = np.empty(n, dtype=np.int32 if which == GET_IDX else np.float64)
         self.check(self.L.pccm_pair_get(self.h, which, direction, out.ctypes.data, HOST))
@@ -310,6 +322,23 @@ class Cloud:
         self.ctx.check(self.ctx.L.pccm_self_nn_minmax(self.ctx.h, self.h, int(begin), int(self.n if end is None else end),
                                                       C.byref(mn), C.byref(mx), pp.ctypes.data if per_point else None, HOST))
         return mn.value, mx.value, pp
+
+    def extremes(self, dirs):
+        """Original indices of the arg-max of dirs[d] . p."""
+        d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(d), dtype=np.int32)
+        self.ctx.check(self.ctx.L.pccm_cloud_extremes(self.ctx.h, self.h, d.ctypes.data, len(d), out.ctypes.data))
+        return out
+
+    def outside_hull(self, planes, eps: float, capacity: int | None = None):
+        """Points not strictly inside the polytope planes[f] = (n, d); returns an (M, 3) array."""
+        pl = np.ascontiguousarray(planes, dtype=np.float64).reshape(-1, 4)
+        cap = self.n if capacity is None else int(capacity)
+        out = np.empty((cap, 3), dtype=np.float64)
+        cnt = C.c_int64()
+        self.ctx.check(self.ctx.L.pccm_cloud_outside_hull(self.ctx.h, self.h, pl.ctypes.data, len(pl), float(eps), cap,
+                                                          out.ctypes.data, C.byref(cnt)))
+        return out[:min(cnt.value, cap)], cnt.value
 
     def close(self):
         if self.h is not None and self.ctx.h is not None:

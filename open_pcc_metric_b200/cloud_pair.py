@@ -132,7 +132,8 @@ class CloudPair:
         if self._extent is None:
             lo, hi = self._aabb[0]
             if self._peak == "obb":
-                self._extent = _obb.minimal_obb_extent(np.asarray(self.clouds[0].points, dtype=np.float64))
+                self._extent = _obb.minimal_obb_extent(np.asarray(self.clouds[0].points, dtype=np.float64), ctx=self._ctx,
+                                                       dev_cloud=self._dev[0])
             elif self._peak == "aabb_diag":
                 self._extent = np.full(3, _obb.aabb_diag(lo, hi))
             else:

@@ -1220,3 +1220,112 @@ extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_
     if (!rc) c->has_normals = true;
     return rc;
 }
+
+// --------------------------------------------------------------------------------------
+// minimal-OBB sweep
+// --------------------------------------------------------------------------------------
+extern "C" int pccm_obb_sweep(pccm_ctx* ctx, const double* hull_vertices, int64_t nv, const double* triangles, int64_t nf,
+                              double* vol_out, double* ext_out) {
+    if (!ctx || !hull_vertices || !triangles || !vol_out || !ext_out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    if (nv <= 0 || nf <= 0 || nv > 0x7fffffffLL || nf > 0x7fffffffLL) return fail(ctx, PCCM_ERR_INVALID, "bad sizes");
+    CK(cudaSetDevice(ctx->device));
+    double *dv = nullptr, *dt = nullptr, *dvol = nullptr, *dext = nullptr;
+    CK(dalloc(ctx, &dv, (size_t)nv * 3));
+    CK(dalloc(ctx, &dt, (size_t)nf * 9));
+    CK(dalloc(ctx, &dvol, (size_t)nf));
+    CK(dalloc(ctx, &dext, (size_t)nf * 3));
+    CK(cudaMemcpyAsync(dv, hull_vertices, (size_t)nv * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dt, triangles, (size_t)nf * 72, cudaMemcpyHostToDevice, ctx->stream));
+    obb_sweep_kernel<<<(unsigned)nf, kObbThreads, 0, ctx->stream>>>(dv, (uint32_t)nv, dt, (uint32_t)nf, dvol, dext);
+    ctx->tm.total_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(vol_out, dvol, (size_t)nf * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ext_out, dext, (size_t)nf * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, dv); dfree(ctx, dt); dfree(ctx, dvol); dfree(ctx, dext);
+    return PCCM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// convex-hull prefilter
+// --------------------------------------------------------------------------------------
+extern "C" int pccm_cloud_extremes(pccm_ctx* ctx, pccm_cloud* c, const double* dirs, int ndirs, int32_t* idx_out) {
+    if (!ctx || !c || !dirs || !idx_out || ndirs < 1) return fail(ctx, PCCM_ERR_INVALID, "bad argument");
+    if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
+    if (c->n == 0) return fail(ctx, PCCM_ERR_INVALID, "empty cloud");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = (uint32_t)c->n;
+    const uint32_t nchunks = (n + kExtChunk - 1) / kExtChunk;
+    double *ddirs = nullptr, *pval = nullptr;
+    uint32_t* pidx = nullptr;
+    CK(dalloc(ctx, &ddirs, (size_t)ndirs * 3));
+    CK(dalloc(ctx, &pval, (size_t)nchunks * ndirs));
+    CK(dalloc(ctx, &pidx, (size_t)nchunks * ndirs));
+    CK(cudaMemcpyAsync(ddirs, dirs, (size_t)ndirs * 24, cudaMemcpyHostToDevice, ctx->stream));
+    const dim3 grid(nchunks, (ndirs + kExtDirs - 1) / kExtDirs);
+    if (c->index_kind == PCCM_KIND_INT) extremes_kernel<KInt><<<grid, kExtThreads, 0, ctx->stream>>>(static_cast<const uint4*>(c->recs), c->base, n, ddirs, ndirs, pval, pidx);
+    else if (c->index_kind == PCCM_KIND_F32) extremes_kernel<KF32><<<grid, kExtThreads, 0, ctx->stream>>>(static_cast<const float4*>(c->recs), c->base, n, ddirs, ndirs, pval, pidx);
+    else extremes_kernel<KF64><<<grid, kExtThreads, 0, ctx->stream>>>(static_cast<const RecF64*>(c->recs), c->base, n, ddirs, ndirs, pval, pidx);
+    ctx->tm.total_launches++;
+    CK(cudaGetLastError());
+    std::vector<double> hv((size_t)nchunks * ndirs);
+    std::vector<uint32_t> hi((size_t)nchunks * ndirs);
+    CK(cudaMemcpyAsync(hv.data(), pval, hv.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hi.data(), pidx, hi.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < ndirs; ++d) {
+        double bv = -INFINITY;
+        uint32_t bi = 0xFFFFFFFFu;
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            const double v = hv[(size_t)k * ndirs + d];
+            const uint32_t i = hi[(size_t)k * ndirs + d];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        idx_out[d] = (int32_t)bi;
+    }
+    dfree(ctx, ddirs); dfree(ctx, pval); dfree(ctx, pidx);
+    return PCCM_OK;
+}
+
+extern "C" int pccm_cloud_outside_hull(pccm_ctx* ctx, pccm_cloud* c, const double* planes, int nf, double eps,
+                                       int64_t capacity, double* xyz_out, int64_t* count_out) {
+    if (!ctx || !c || !planes || !count_out || nf < 1 || capacity < 0 || (capacity && !xyz_out)) return fail(ctx, PCCM_ERR_INVALID, "bad argument");
+    if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
+    if (nf * 32 > 200 * 1024) return fail(ctx, PCCM_ERR_UNSUPPORTED, "too many facets (%d)", nf);
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = (uint32_t)c->n;
+    double *dpl = nullptr, *dout = nullptr;
+    unsigned long long* dcnt = nullptr;
+    CK(dalloc(ctx, &dpl, (size_t)nf * 4));
+    CK(dalloc(ctx, &dout, (size_t)std::max<int64_t>(capacity, 1) * 3));
+    CK(dalloc(ctx, &dcnt, 1));
+    CK(cudaMemcpyAsync(dpl, planes, (size_t)nf * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(dcnt, 0, 8, ctx->stream));
+    const size_t smem = (size_t)nf * 32;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    if (n) {
+        if (c->index_kind == PCCM_KIND_INT) {
+            CK(cudaFuncSetAttribute(outside_kernel<KInt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            outside_kernel<KInt><<<blocks, threads, smem, ctx->stream>>>(static_cast<const uint4*>(c->recs), c->base, n, dpl, nf, eps, dout, (unsigned long long)capacity, dcnt);
+        } else if (c->index_kind == PCCM_KIND_F32) {
+            CK(cudaFuncSetAttribute(outside_kernel<KF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            outside_kernel<KF32><<<blocks, threads, smem, ctx->stream>>>(static_cast<const float4*>(c->recs), c->base, n, dpl, nf, eps, dout, (unsigned long long)capacity, dcnt);
+        } else {
+            CK(cudaFuncSetAttribute(outside_kernel<KF64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            outside_kernel<KF64><<<blocks, threads, smem, ctx->stream>>>(static_cast<const RecF64*>(c->recs), c->base, n, dpl, nf, eps, dout, (unsigned long long)capacity, dcnt);
+        }
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, dcnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *count_out = (int64_t)cnt;
+    const int64_t take = std::min<int64_t>((int64_t)cnt, capacity);
+    if (take > 0) {
+        CK(cudaMemcpyAsync(xyz_out, dout, (size_t)take * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    dfree(ctx, dpl); dfree(ctx, dout); dfree(ctx, dcnt);
+    return PCCM_OK;
+}

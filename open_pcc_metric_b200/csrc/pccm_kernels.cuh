@@ -1099,4 +1099,128 @@ __global__ void minmax_finalize_kernel(const double* in, uint32_t nb, double* ou
     if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
+// ------------------------------------------------------------------------------------
+// minimal oriented bounding box sweep (the PSNR peak of the reference: cloud_pair.py:111-112 ->
+// Open3D OrientedBoundingBox::CreateFromPointsMinimal).  The convex hull comes from Qhull on the
+// host (as in Open3D); for EVERY hull triangle the hull vertices are expressed in the triangle's
+// frame (u = b - a, w = u x (c - a), v = w x u, normalised) and the axis-aligned extent / volume
+// of that box is reduced here: one block per triangle, F x V point rotations in total.
+// ------------------------------------------------------------------------------------
+constexpr int kObbThreads = 128;
+__global__ void __launch_bounds__(kObbThreads)
+obb_sweep_kernel(const double* __restrict__ verts, uint32_t nv, const double* __restrict__ tris, uint32_t nf,
+                 double* __restrict__ vol_out, double* __restrict__ ext_out) {
+    const uint32_t f = blockIdx.x;
+    if (f >= nf) return;
+    const double* t = tris + 9 * (size_t)f;
+    const double a[3] = {t[0], t[1], t[2]};
+    double u[3] = {dsub(t[3], a[0]), dsub(t[4], a[1]), dsub(t[5], a[2])};
+    double v[3] = {dsub(t[6], a[0]), dsub(t[7], a[1]), dsub(t[8], a[2])};
+    double w[3];
+    cross3(u, v, w);
+    cross3(w, u, v);
+    const double lu = sqrt(dot3(u, u)), lv = sqrt(dot3(v, v)), lw = sqrt(dot3(w, w));
+    for (int k = 0; k < 3; ++k) { u[k] /= lu; v[k] /= lv; w[k] /= lw; }
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = threadIdx.x; i < nv; i += kObbThreads) {
+        const double p[3] = {dsub(__ldg(verts + 3 * (size_t)i), a[0]), dsub(__ldg(verts + 3 * (size_t)i + 1), a[1]),
+                             dsub(__ldg(verts + 3 * (size_t)i + 2), a[2])};
+        const double l[3] = {dot3(u, p), dot3(v, p), dot3(w, p)};   // R^T (p - a): the frame is orthonormal
+        for (int k = 0; k < 3; ++k) { mn[k] = fmin(mn[k], l[k]); mx[k] = fmax(mx[k], l[k]); }
+    }
+    __shared__ double sm[kObbThreads / 32];
+    double ext[3];
+    for (int k = 0; k < 3; ++k) {
+        const double lo = block_min<kObbThreads>(mn[k], sm);
+        const double hi = block_max<kObbThreads>(mx[k], sm);
+        ext[k] = dsub(hi, lo);
+    }
+    if (threadIdx.x == 0) {
+        ext_out[3 * (size_t)f] = ext[0]; ext_out[3 * (size_t)f + 1] = ext[1]; ext_out[3 * (size_t)f + 2] = ext[2];
+        vol_out[f] = dmul(dmul(ext[0], ext[1]), ext[2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// convex-hull prefilter for the minimal-OBB peak
+//   extremes_kernel : arg-max of the projection on each of D directions (seed points);
+//   outside_kernel  : keep only the points that are NOT strictly inside the seed polytope
+//                     (n_f . p + d_f < -eps for every facet f) -- exact: a point strictly inside
+//                     a convex subset of the hull cannot be a hull vertex.
+// Qhull then runs on a few percent of the cloud.
+// ------------------------------------------------------------------------------------
+constexpr int kExtThreads = 128;
+constexpr int kExtDirs = 16;          // directions per block (registers)
+constexpr int kExtChunk = 16384;      // points per block
+
+template <class K>
+__global__ void __launch_bounds__(kExtThreads)
+extremes_kernel(const typename K::Rec* __restrict__ recs, uint32_t first, uint32_t n, const double* __restrict__ dirs, int ndirs,
+                double* __restrict__ pval, uint32_t* __restrict__ pidx) {
+    const int d0 = blockIdx.y * kExtDirs;
+    const uint32_t c0 = blockIdx.x * kExtChunk;
+    double dx[kExtDirs], dy[kExtDirs], dz[kExtDirs], best[kExtDirs];
+    uint32_t bi[kExtDirs];
+#pragma unroll
+    for (int j = 0; j < kExtDirs; ++j) {
+        const int d = d0 + j < ndirs ? d0 + j : ndirs - 1;
+        dx[j] = dirs[3 * d]; dy[j] = dirs[3 * d + 1]; dz[j] = dirs[3 * d + 2];
+        best[j] = -INFINITY; bi[j] = 0xFFFFFFFFu;
+    }
+    const uint32_t end = c0 + kExtChunk < n ? c0 + kExtChunk : n;
+    for (uint32_t i = c0 + threadIdx.x; i < end; i += kExtThreads) {
+        const typename K::Rec r = load_rec(recs + first + i);
+        const typename K::Q q = K::rec_q(r);
+        const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
+        const uint32_t idx = K::rec_idx(r);
+#pragma unroll
+        for (int j = 0; j < kExtDirs; ++j) {
+            const double v = dx[j] * x + dy[j] * y + dz[j] * z;
+            if (v > best[j] || (v == best[j] && idx < bi[j])) { best[j] = v; bi[j] = idx; }
+        }
+    }
+    __shared__ double sv[kExtThreads / 32][kExtDirs];
+    __shared__ uint32_t si[kExtThreads / 32][kExtDirs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kExtDirs; ++j) {
+        double v = best[j];
+        uint32_t id = bi[j];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, v, o);
+            const uint32_t oi = __shfl_down_sync(0xffffffffu, id, o);
+            if (ov > v || (ov == v && oi < id)) { v = ov; id = oi; }
+        }
+        if (lane == 0) { sv[warp][j] = v; si[warp][j] = id; }
+    }
+    __syncthreads();
+    if (threadIdx.x < kExtDirs && d0 + (int)threadIdx.x < ndirs) {
+        double v = sv[0][threadIdx.x];
+        uint32_t id = si[0][threadIdx.x];
+        for (int w = 1; w < kExtThreads / 32; ++w)
+            if (sv[w][threadIdx.x] > v || (sv[w][threadIdx.x] == v && si[w][threadIdx.x] < id)) { v = sv[w][threadIdx.x]; id = si[w][threadIdx.x]; }
+        pval[(size_t)blockIdx.x * ndirs + d0 + threadIdx.x] = v;
+        pidx[(size_t)blockIdx.x * ndirs + d0 + threadIdx.x] = id;
+    }
+}
+
+template <class K>
+__global__ void outside_kernel(const typename K::Rec* __restrict__ recs, uint32_t first, uint32_t n,
+                               const double* __restrict__ planes, int nf, double eps,
+                               double* __restrict__ out_xyz, unsigned long long capacity, unsigned long long* counter) {
+    extern __shared__ double sp[];   // planes
+    for (int i = threadIdx.x; i < nf * 4; i += blockDim.x) sp[i] = planes[i];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const typename K::Q q = K::rec_q(load_rec(recs + first + i));
+    const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
+    bool inside = true;
+    for (int f = 0; f < nf && inside; ++f)
+        inside = sp[4 * f] * x + sp[4 * f + 1] * y + sp[4 * f + 2] * z + sp[4 * f + 3] < -eps;
+    if (inside) return;
+    const unsigned long long slot = atomicAdd(counter, 1ull);
+    if (slot < capacity) { out_xyz[3 * slot] = x; out_xyz[3 * slot + 1] = y; out_xyz[3 * slot + 2] = z; }
+}
+
 }  // namespace pccm

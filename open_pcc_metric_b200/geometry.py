@@ -117,7 +117,7 @@ class PointCloud:
 
     def get_minimal_oriented_bounding_box(self, robust: bool = False):
         """cloud_pair.py:112 -- only ``.extent`` is consumed."""
-        return OrientedBoundingBox(_obb.minimal_obb_extent(np.asarray(self._points)))
+        return OrientedBoundingBox(_obb.minimal_obb_extent(np.asarray(self._points), default_context()))
 
     def get_axis_aligned_bounding_box_extent(self):
         p = np.asarray(self._points)
