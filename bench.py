@@ -215,6 +215,18 @@ def main():
     hB = Cloud(pinned(B.points), pinned(B.colors), pinned(B.normals))
     h2d = sum(x.nbytes for c in (hA, hB) for x in (c.points, c.colors, c.normals))
 
+    # the same clouds in the compact form a voxelised PLY file holds (uint16 coordinates, uchar colours,
+    # float32 normals): accepted by the same public API, 3.4x fewer bytes over PCIe (informational arm)
+    def pinned_as(a, dt):
+        import torch as _t
+        t = _t.empty(a.shape, dtype={np.uint16: _t.uint16, np.uint8: _t.uint8, np.float32: _t.float32}[dt], pin_memory=True)
+        out = t.numpy()
+        out[...] = a.astype(dt)
+        return out
+    cA = Cloud(pinned_as(A.points, np.uint16), pinned_as(np.rint(A.colors * 255), np.uint8), pinned_as(A.normals, np.float32))
+    cB = Cloud(pinned_as(B.points, np.uint16), pinned_as(np.rint(B.colors * 255), np.uint8), pinned_as(B.normals, np.float32))
+    h2d_compact = sum(x.nbytes for c in (cA, cB) for x in (c.points, c.colors, c.normals))
+
     sl = (rank, world) if partition else (0, 1)
 
     def step_device():
@@ -228,8 +240,8 @@ def main():
 
     opts = CalculateOptions(color="yuv", hausdorff=False, point_to_plane=True)
 
-    def step_e2e():
-        pair = CloudPair(hA, hB, ctx=ctx, peak="resolution", resolution_bits=args.bits,
+    def step_e2e(a=None, b=None):
+        pair = CloudPair(a or hA, b or hB, ctx=ctx, peak="resolution", resolution_bits=args.bits,
                          rank=sl[0], world=sl[1])
         out = MetricCalculator(pair).calculate(transform_options(opts)).as_dict()
         pair.close()
@@ -312,6 +324,12 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * 96 + 16),
                "ms_per_step": ms_e2e / n_e2e,
                "api": "CloudPair(host float64 arrays) + MetricCalculator.calculate(transform_options(color=yuv, point_to_plane))"}
+        ms_c, _, _, out_c = timed(lambda: step_e2e(cA, cB), max(3, args.steps // 4), 3, 0)
+        n_c = max(3, args.steps // 4)
+        same = all(np.array_equal(np.asarray(out[k]), np.asarray(out_c[k])) for k in out if k[0] in ("GeoMSE", "ColorMSE") and k[-1] is not True)
+        e2e["compact_inputs"] = {"value": nq * n_c / (ms_c * 1e-3), "ms_per_step": ms_c / n_c, "h2d_bytes_per_step": int(h2d_compact),
+                                 "what": "same API, clouds held as uint16 / uchar / float32 (float32 normals change D2 only)",
+                                 "d1_and_colour_identical_to_float64_inputs": bool(same)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

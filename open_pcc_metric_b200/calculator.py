@@ -67,5 +67,33 @@ class MetricCalculator:
         self._calculated_metrics[key] = metric
         return metric
 
+    def _prefetch(self, metrics_list) -> None:
+        """One fused GPU evaluation for everything the list will ask for (D2 and the first colour
+        scheme on top of D1) instead of one per kind of metric as the graph walk reaches them."""
+        p2p, schemes = False, []
+
+        def scan(m):
+            nonlocal p2p
+            if isinstance(m, SymmetricMetric):
+                for c in m.metrics:
+                    scan(c)
+                return
+            if not hasattr(m, "calculate_fused") and not hasattr(m, "_get_dependencies"):
+                return
+            if getattr(m, "point_to_plane", False):
+                p2p = True
+            cs = getattr(m, "color_scheme", None)
+            if cs is not None and cs not in schemes:
+                schemes.append(cs)
+        for m in metrics_list:
+            scan(m)
+        if p2p or schemes:
+            try:
+                self._cloud_pair.fused(True, point_to_plane=p2p, color_scheme=schemes[0] if schemes else None)
+            except (IndexError, ValueError, KeyError):
+                pass    # the individual metric raises the reference's error when it is reached
+
     def calculate(self, metrics_list: typing.List[AbstractMetric]) -> CalculateResult:
+        if self._use_fused:
+            self._prefetch(metrics_list)
         return CalculateResult([self._metric_recursive_calculate(m) for m in metrics_list])
