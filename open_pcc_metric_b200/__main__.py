@@ -1,4 +1,7 @@
-from . import handler
+"""``python -m open_pcc_metric_b200 --ocloud a.ply --pcloud b.ply [...]``: runs the click
+command of handler.py (same flags and table as the reference CLI, on a B200)."""
+import sys
 
-if __name__ == "__main__":
-    handler.cli()  # pylint: disable=no-value-for-parameter
+from .handler import cli
+
+sys.exit(cli())  # pylint: disable=no-value-for-parameter
