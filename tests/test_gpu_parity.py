@@ -488,3 +488,50 @@ def test_obb_prefilter_keeps_every_hull_vertex(ctx):
         assert np.isclose(np.prod(e_pre), np.prod(e_all), rtol=1e-3) and np.isclose(e_pre.max(), e_all.max(), rtol=1e-5)
         assert np.array_equal(e_pre, obb.minimal_obb_extent(pts, ctx, dev_cloud=c))     # deterministic
         c.close()
+
+
+def test_randomised_clouds_against_oracle(ctx):
+    """many small random cloud pairs of every coordinate kind, size (incl. 1 and 2
+    points), extent, duplicate rate and cell size; NN both ways, self k-NN and boundary distances
+    must equal the brute-force C oracle bit for bit; results do not depend on the query order."""
+    rng = np.random.default_rng(2026)
+    for case in range(60):
+        kind = case % 3
+        na, nb = int(rng.integers(1, 2500)), int(rng.integers(1, 2500))
+        span = int(rng.choice([3, 17, 200, 30000]))
+        if kind == 0:
+            A = rng.integers(0, span, (na, 3)).astype(np.float64)
+            B = rng.integers(0, span, (nb, 3)).astype(np.float64)
+        else:
+            A = rng.normal(0, span / 10.0, (na, 3))
+            B = rng.normal(0, span / 10.0, (nb, 3)) + rng.normal(0, 1, 3)
+            if kind == 1:
+                A, B = A.astype(np.float32).astype(np.float64), B.astype(np.float32).astype(np.float64)
+        if case % 4 == 0 and nb > 4:
+            B[nb // 2:] = B[:nb - nb // 2]          # duplicates
+        if case % 5 == 0:
+            A[:, 2] = A[0, 2]                        # flat cloud
+        cell = 0.0 if case % 2 else float(rng.choice([1.0, 4.0, 64.0])) * (1.0 if kind == 0 else span / 50.0)
+        a, b = ctx.cloud(A), ctx.cloud(B)
+        ctx.build_pair(a, b, cell)
+        for q, s_, Q, S in ((a, b, A, B), (b, a, B, A)):
+            idx, d2 = ctx.nn(q, s_)
+            oi, od = cnn.knn(S, Q, 1)
+            assert np.array_equal(d2, od[:, 0]) and np.array_equal(idx, oi[:, 0]), (case, kind, na, nb, span, cell)
+        k = int(rng.integers(1, 12))
+        ki, kd = a.knn_self(k)
+        oi, od = cnn.knn(A, A, k)
+        oi = np.where(np.isinf(od), -1, oi)
+        assert np.array_equal(kd, od) and np.array_equal(ki, oi), (case, "knn", k)
+        if na >= 2:
+            mn, mx, per = a.self_nn_minmax(per_point=True)
+            _, o2 = cnn.knn(A, A, 2)
+            assert np.array_equal(per, np.sqrt(o2[:, 1])), (case, "boundary")
+        # query order invariance: same cloud A permuted
+        perm = rng.permutation(na)
+        a2 = ctx.cloud(A[perm])
+        a2.build_index(cell, max(a.info().index_kind, 0))
+        i2, d2b = ctx.nn(a2, b)
+        i1, d1b = ctx.nn(a, b)
+        assert np.array_equal(d2b, d1b[perm]) and np.array_equal(i2, i1[perm]), (case, "order")
+        a.close(); b.close(); a2.close()
