@@ -2,7 +2,6 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared ...
 // There is no CPU path: every entry point needs a CUDA device.
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -540,13 +539,15 @@ static int sort_pairs(pccm_ctx* ctx, KeyT* keys_in, KeyT* keys_out, uint32_t* va
 }
 
 static int exclusive_scan(pccm_ctx* ctx, uint32_t* data, size_t count) {
-    size_t bytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, data, data, (int)count, ctx->stream));
-    unsigned char* tmp = nullptr;
-    CK(dalloc(ctx, &tmp, bytes));
-    CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, data, data, (int)count, ctx->stream));
-    dfree(ctx, tmp);
-    ctx->tm.library_launches += 2;
+    const uint32_t nblocks = (uint32_t)((count + kScanTile - 1) / kScanTile);
+    uint32_t* sums = nullptr;
+    CK(dalloc(ctx, &sums, (size_t)nblocks));
+    scan_tile_sums_kernel<<<nblocks, kScanThreads, 0, ctx->stream>>>(data, count, sums);
+    scan_sums_kernel<<<1, kScanThreads, 0, ctx->stream>>>(sums, nblocks);
+    scan_apply_kernel<<<nblocks, kScanThreads, 0, ctx->stream>>>(data, count, sums);
+    ctx->tm.total_launches += 3;
+    CK(cudaGetLastError());
+    dfree(ctx, sums);
     return PCCM_OK;
 }
 

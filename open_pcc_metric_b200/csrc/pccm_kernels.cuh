@@ -213,6 +213,71 @@ __global__ void reorder_kernel(const void* xyz, int dtype, int64_t stride, uint3
 }
 
 // ------------------------------------------------------------------------------------
+// exclusive prefix sum of the row histogram -> pencil table (hand-written, three launches:
+// per-tile sums, scan of the tile sums by one block, tile-local scan + offset).  In place.
+// ------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;                         // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;  // 2048 entries per block
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t ws[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) { if (w < warp) base += ws[w]; tot += ws[w]; }
+    if (total) *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ data, size_t n, uint32_t* __restrict__ sums) {
+    const size_t base = (size_t)blockIdx.x * kScanTile;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        const size_t i = base + (size_t)j * kScanThreads + threadIdx.x;
+        if (i < n) s += data[i];
+    }
+    uint32_t tot;
+    block_exclusive_scan_u32(s, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(uint32_t* sums, uint32_t nblocks) {
+    uint32_t carry = 0;                                // one block walks the tile sums (<= 32k of them)
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = i < nblocks ? sums[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan_u32(v, &tot);
+        if (i < nblocks) sums[i] = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ sums) {
+    // thread t owns kScanItems CONSECUTIVE entries of the tile: local serial scan + block scan of the per-thread sums
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) { v[j] = base + j < n ? data[base + j] : 0u; s += v[j]; }
+    uint32_t ex = block_exclusive_scan_u32(s, nullptr) + sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) { if (base + j < n) data[base + j] = ex; ex += v[j]; }
+}
+
+// ------------------------------------------------------------------------------------
 // joint index build of the two clouds of a pair: one key pass, ONE sort (cloud id in the top
 // key bit), one scan, one reorder -- half the launches of two separate builds
 // ------------------------------------------------------------------------------------
