@@ -329,8 +329,23 @@ PCCM_HD void visit_run(const typename K::Rec* __restrict__ recs, uint32_t lo, ui
 }
 
 // Exact search of query q in an indexed cloud whose rows are served by `rows`.
+// true when nothing outside the Chebyshev ring-r square around (cy0, cz0) can tie or beat `worst`
+template <class K>
+PCCM_HD bool ring_done(const RowGrid& g, const typename K::Q& q, int cy0, int cz0, int r, typename K::D worst) {
+    typedef typename K::C C;
+    const int ylo = cy0 - r, yhi = cy0 + r, zlo = cz0 - r, zhi = cz0 + r;
+    C m = K::gap_inf();
+    bool open = false;
+    if (ylo > 0)         { open = true; C t = K::gap_dn_y(g, q.y, ylo - 1); m = t < m ? t : m; }
+    if (yhi < g.ny - 1)  { open = true; C t = K::gap_up_y(g, q.y, yhi + 1); m = t < m ? t : m; }
+    if (zlo > 0)         { open = true; C t = K::gap_dn_z(g, q.z, zlo - 1); m = t < m ? t : m; }
+    if (zhi < g.nz - 1)  { open = true; C t = K::gap_up_z(g, q.z, zhi + 1); m = t < m ? t : m; }
+    return !open || K::gap_sq_gt(m, worst);
+}
+
+// r_begin > 0: rings 0 .. r_begin-1 were already visited by the caller (and ring_done was false).
 template <class K, class Rows, class Acc>
-PCCM_HD void search_rows(const RowGrid& g, const Rows& rows, const typename K::Q& q, Acc& acc) {
+PCCM_HD void search_rows(const RowGrid& g, const Rows& rows, const typename K::Q& q, Acc& acc, int r_begin = 0) {
     typedef typename K::C C;
     typedef typename K::D D;
     const int ny = g.ny, nz = g.nz;
@@ -349,7 +364,7 @@ PCCM_HD void search_rows(const RowGrid& g, const Rows& rows, const typename K::Q
         if (lo < hi) { PCCM_CNT(g_cnt.pencils_visited++); visit_run<K, Rows>(base, lo, hi, q, B2, acc, g.short_row); }
     };
 
-    for (int r = 0;; ++r) {
+    for (int r = r_begin;; ++r) {
         const int ylo = cy0 - r, yhi = cy0 + r, zlo = cz0 - r, zhi = cz0 + r;
         PCCM_CNT(g_cnt.rings++);
         if (r == 0) {
@@ -373,14 +388,7 @@ PCCM_HD void search_rows(const RowGrid& g, const Rows& rows, const typename K::Q
             }
         }
         // can the unvisited region still hold an equal or better point?
-        C m = K::gap_inf();
-        bool open = false;
-        if (ylo > 0)      { open = true; C t = K::gap_dn_y(g, q.y, ylo - 1); m = t < m ? t : m; }
-        if (yhi < ny - 1) { open = true; C t = K::gap_up_y(g, q.y, yhi + 1); m = t < m ? t : m; }
-        if (zlo > 0)      { open = true; C t = K::gap_dn_z(g, q.z, zlo - 1); m = t < m ? t : m; }
-        if (zhi < nz - 1) { open = true; C t = K::gap_up_z(g, q.z, zhi + 1); m = t < m ? t : m; }
-        if (!open) break;
-        if (K::gap_sq_gt(m, acc.worst())) break;
+        if (ring_done<K>(g, q, cy0, cz0, r, acc.worst())) break;
     }
 }
 
