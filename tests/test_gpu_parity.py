@@ -3,6 +3,8 @@ drop-in Python surface, against the oracle and the committed outputs of the unmo
 reference.  Integer / index / d2 quantities bit exact; D2 and colour rtol 1e-6
 (the tolerance BASELINE.json's north_star states); normals to 1e-9 away from
 degenerate neighbourhoods."""
+import os
+
 import numpy as np
 import pytest
 
@@ -535,3 +537,29 @@ def test_randomised_clouds_against_oracle(ctx):
         i1, d1b = ctx.nn(a, b)
         assert np.array_equal(d2b, d1b[perm]) and np.array_equal(i2, i1[perm]), (case, "order")
         a.close(); b.close(); a2.close()
+
+
+def test_integration_md_stub_runs(ctx):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would add) is
+    executed as written against the in-tree library and must reproduce the oracle's NN pass."""
+    import re
+    from conftest import ROOT
+    from open_pcc_metric_b200 import _native as N
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# open_pcc_metric/_pccm\.py.*?)```", text, re.S).group(1)
+    code = code.replace('C.CDLL("libpccm.so")', f'C.CDLL({N.LIB_PATH!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, 64, (3000, 3)).astype(np.float64)
+    B = rng.integers(0, 64, (2500, 3)).astype(np.float64)
+    gpu = ns["Pccm"](0)
+    ha, hb = gpu.cloud(A), gpu.cloud(B)
+    gpu.index(ha); gpu.index(hb)
+    (il, dl), (ir, dr) = gpu.neighbours(ha, hb, len(A), len(B))
+    oi, od = cnn.knn(B, A, 1)
+    assert np.array_equal(il, oi[:, 0]) and np.array_equal(dl, od[:, 0])
+    oi, od = cnn.knn(A, B, 1)
+    assert np.array_equal(ir, oi[:, 0]) and np.array_equal(dr, od[:, 0])
+    nrm = gpu.estimate_normals(ha, len(A))
+    assert nrm.shape == (3000, 3) and np.allclose(np.linalg.norm(nrm, axis=1), 1.0)
