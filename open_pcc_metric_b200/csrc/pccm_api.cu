@@ -1104,7 +1104,8 @@ extern "C" int pccm_pair_get(pccm_ctx* ctx, int which, int direction, void* out,
 static int launch_knn(pccm_ctx* ctx, pccm_cloud* c, KnnParams& P) {
     const uint32_t cnt = P.end - P.begin;
     if (cnt == 0) return PCCM_OK;
-    const uint32_t nblocks = (cnt + kKnnThreads - 1) / kKnnThreads;
+    uint32_t nblocks = (cnt + kKnnThreads - 1) / kKnnThreads;
+    if (P.mode == KNN_NORMALS_FLAGGED) nblocks = std::min(nblocks, (uint32_t)ctx->sm_count * 2u);   // walks the todo list
     const size_t dsz = c->index_kind == PCCM_KIND_INT ? sizeof(uint32_t) : sizeof(double);
     const size_t smem = (size_t)P.k * kKnnThreads * (dsz + 2 * sizeof(uint32_t));
     if (smem > 200 * 1024) return fail(ctx, PCCM_ERR_UNSUPPORTED, "k=%d too large", P.k);
@@ -1200,13 +1201,20 @@ extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_
         CK(cudaMemsetAsync(c->normals, 0, (size_t)c->n * 3 * sizeof(double), ctx->stream));
     }
     KnnParams P{};
+    uint32_t* todo_buf = nullptr;
     P.c = view_of(c); P.begin = c->base + (uint32_t)begin; P.end = c->base + (uint32_t)end; P.k = k; P.mode = KNN_NORMALS;
     P.normals_out = c->normals;
     if (c->index_kind == PCCM_KIND_INT && k <= 255 && ctx->normals_counting && end > begin) {
         // voxelised clouds: counting selection (no per-thread sorted list), then the generic
         // kernel only for the points it flagged (sparse neighbourhoods, fewer than k points)
         const uint32_t cnt = P.end - P.begin;
-        const size_t smem = (size_t)kHistBins * kNrmThreads + (size_t)k * kNrmThreads * 2 * sizeof(uint32_t);
+        const size_t smem = (size_t)kHistBins * kNrmThreads + (size_t)kTieCap * kNrmThreads * 2 * sizeof(uint32_t);
+        uint32_t* todo = nullptr;
+        CK(dalloc(ctx, &todo, (size_t)cnt + 1));           // [0] = count, [1..] = sorted positions
+        CK(cudaMemsetAsync(todo, 0, sizeof(uint32_t), ctx->stream));
+        P.todo = todo + 1;
+        P.todo_count = todo;
+        todo_buf = todo;
         {
             StageTimer t(ctx, &ctx->tm.knn_ms, 1);
             CK(cudaFuncSetAttribute(normals_int_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1218,6 +1226,7 @@ extern "C" int pccm_estimate_normals(pccm_ctx* ctx, pccm_cloud* c, int k, int64_
         P.mode = KNN_NORMALS_FLAGGED;
     }
     rc = launch_knn(ctx, c, P);
+    dfree(ctx, todo_buf);
     if (!rc) c->has_normals = true;
     return rc;
 }

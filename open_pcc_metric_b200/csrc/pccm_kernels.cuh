@@ -943,61 +943,73 @@ struct KnnParams {
     double* d2_out;        // KNN_LIST: [n][k];  KNN_BOUNDARY: optional per-point sqrt distance [n]
     double* normals_out;   // KNN_NORMALS: [n][3] original order
     double* minmax;        // KNN_BOUNDARY: per-block {min, max}
+    uint32_t* todo;        // KNN_NORMALS: sorted positions normals_int_kernel left to the list kernel
+    uint32_t* todo_count;
 };
 
+// one point of the self k-NN: search + the epilogue selected by P.mode
 template <class K>
-__global__ void __launch_bounds__(kKnnThreads)
-knn_self_kernel(const __grid_constant__ KnnParams P) {
+__device__ __forceinline__ void knn_point(const KnnParams& P, uint32_t t, typename K::D* d2s, uint32_t* idxs, uint32_t* poss,
+                                          double& bmin, double& bmax) {
     typedef typename K::Rec Rec;
     typedef typename K::Q Q;
-    typedef typename K::D D;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = P.k;
-    D* d2s = reinterpret_cast<D*>(smem_raw);
-    uint32_t* idxs = reinterpret_cast<uint32_t*>(d2s + (size_t)k * kKnnThreads);
-    uint32_t* poss = idxs + (size_t)k * kKnnThreads;
     const Rec* __restrict__ recs = static_cast<const Rec*>(P.c.recs);
-    const uint32_t t = P.begin + blockIdx.x * kKnnThreads + threadIdx.x;
-    bool active = t < P.end;
-    double bmin = INFINITY, bmax = -INFINITY;
-    const Rec qr = load_rec(recs + (active ? t : P.begin));
+    const Rec qr = load_rec(recs + t);
+    const Q q = K::rec_q(qr);
     const uint32_t qidx = K::rec_idx(qr);
-    if (active && P.mode == KNN_NORMALS_FLAGGED)     // only the points normals_int_kernel could not finish
-        active = __double_as_longlong(P.normals_out[3 * (size_t)qidx]) == 0x7ff8000000000001ll;
-    if (active && P.mode == KNN_BOUNDARY) {
+    if (P.mode == KNN_BOUNDARY) {
         // ComputeNearestNeighborDistance: sqrt of the second entry of the 2-NN result, 0 when absent
-        const Q q = K::rec_q(qr);
         Best2Val<K> b2;
         b2.init();
         search<K>(P.c.grid, P.c.row_start, recs, q, b2);
         const double v = b2.count > 1 ? sqrt(K::d2_as_double(b2.m2)) : 0.0;
         bmin = v; bmax = v;
         if (P.d2_out) P.d2_out[qidx] = v;
-    } else if (active) {
-        const Q q = K::rec_q(qr);
-        TopK<K> acc;
-        acc.init(d2s + threadIdx.x, idxs + threadIdx.x, poss + threadIdx.x, kKnnThreads, k);
-        search<K>(P.c.grid, P.c.row_start, recs, q, acc);
-        if (P.mode == KNN_LIST) {
-            for (int j = 0; j < k; ++j) {
-                const bool have = j < acc.count;
-                P.idx_out[(size_t)qidx * k + j] = have ? (int32_t)idxs[j * kKnnThreads + threadIdx.x] : -1;
-                P.d2_out[(size_t)qidx * k + j] = have ? K::d2_as_double(d2s[j * kKnnThreads + threadIdx.x]) : INFINITY;
-            }
-        } else {
-            double cum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int j = 0; j < acc.count; ++j) {
-                const Rec nr = load_rec(recs + poss[j * kKnnThreads + threadIdx.x]);
-                const Q nq = K::rec_q(nr);
-                cumulant_add(cum, (double)nq.x, (double)nq.y, (double)nq.z);
-            }
-            double nv[3];
-            normal_from_cumulants(cum, acc.count, nv);
-            P.normals_out[3 * (size_t)qidx + 0] = nv[0];
-            P.normals_out[3 * (size_t)qidx + 1] = nv[1];
-            P.normals_out[3 * (size_t)qidx + 2] = nv[2];
-        }
+        return;
     }
+    TopK<K> acc;
+    acc.init(d2s + threadIdx.x, idxs + threadIdx.x, poss + threadIdx.x, kKnnThreads, k);
+    search<K>(P.c.grid, P.c.row_start, recs, q, acc);
+    if (P.mode == KNN_LIST) {
+        for (int j = 0; j < k; ++j) {
+            const bool have = j < acc.count;
+            P.idx_out[(size_t)qidx * k + j] = have ? (int32_t)idxs[j * kKnnThreads + threadIdx.x] : -1;
+            P.d2_out[(size_t)qidx * k + j] = have ? K::d2_as_double(d2s[j * kKnnThreads + threadIdx.x]) : INFINITY;
+        }
+    } else {
+        double cum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < acc.count; ++j) {
+            const Rec nr = load_rec(recs + poss[j * kKnnThreads + threadIdx.x]);
+            const Q nq = K::rec_q(nr);
+            cumulant_add(cum, (double)nq.x, (double)nq.y, (double)nq.z);
+        }
+        double nv[3];
+        normal_from_cumulants(cum, acc.count, nv);
+        P.normals_out[3 * (size_t)qidx + 0] = nv[0];
+        P.normals_out[3 * (size_t)qidx + 1] = nv[1];
+        P.normals_out[3 * (size_t)qidx + 2] = nv[2];
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_self_kernel(const __grid_constant__ KnnParams P) {
+    typedef typename K::D D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    D* d2s = reinterpret_cast<D*>(smem_raw);
+    uint32_t* idxs = reinterpret_cast<uint32_t*>(d2s + (size_t)P.k * kKnnThreads);
+    uint32_t* poss = idxs + (size_t)P.k * kKnnThreads;
+    double bmin = INFINITY, bmax = -INFINITY;
+    if (P.mode == KNN_NORMALS_FLAGGED) {
+        // a small grid walks the positions normals_int_kernel left over (usually none)
+        const uint32_t nwork = *P.todo_count;
+        for (uint32_t w = blockIdx.x * kKnnThreads + threadIdx.x; w < nwork; w += gridDim.x * kKnnThreads)
+            knn_point<K>(P, P.todo[w], d2s, idxs, poss, bmin, bmax);
+        return;
+    }
+    const uint32_t t = P.begin + blockIdx.x * kKnnThreads + threadIdx.x;
+    if (t < P.end) knn_point<K>(P, t, d2s, idxs, poss, bmin, bmax);
     if (P.mode == KNN_BOUNDARY) {
         __shared__ double sm[kKnnThreads / 32];
         double mn = block_min<kKnnThreads>(bmin, sm);
@@ -1027,6 +1039,7 @@ knn_self_kernel(const __grid_constant__ KnnParams P) {
 // ------------------------------------------------------------------------------------
 constexpr int kHistBins = 64;
 constexpr int kNrmThreads = 64;
+constexpr int kTieCap = 16;           // ties kept at the k-th distance (more -> generic kernel)
 
 template <class F>
 __device__ __forceinline__ void int_window_walk(const RowGrid& g, const uint32_t* __restrict__ row_start,
@@ -1067,8 +1080,8 @@ normals_int_kernel(const __grid_constant__ KnnParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = P.k;
     uint8_t* H = smem_raw + threadIdx.x;                                                   // H[bin * T]
-    uint32_t* Tidx = reinterpret_cast<uint32_t*>(smem_raw + kHistBins * kNrmThreads) + threadIdx.x;   // [k][T]
-    uint32_t* Tpos = Tidx + (size_t)k * kNrmThreads;
+    uint32_t* Tidx = reinterpret_cast<uint32_t*>(smem_raw + kHistBins * kNrmThreads) + threadIdx.x;   // [kTieCap][T]
+    uint32_t* Tpos = Tidx + (size_t)kTieCap * kNrmThreads;
     const uint4* __restrict__ recs = static_cast<const uint4*>(P.c.recs);
     const RowGrid& g = P.c.grid;
     const uint32_t t = P.begin + blockIdx.x * kNrmThreads + threadIdx.x;
@@ -1115,8 +1128,9 @@ normals_int_kernel(const __grid_constant__ KnnParams P) {
         if (!open) { rfin = r; break; }                       // whole table visited: fewer than k points within range
         if (gap2 > (uint32_t)(kHistBins - 1)) { rfin = r; break; }   // farther candidates cannot fall into the bins
     }
-    if (!resolved) {                                          // sparse neighbourhood or n < k: generic kernel finishes it
-        P.normals_out[3 * (size_t)qidx] = __longlong_as_double(0x7ff8000000000001ll);
+    if (!resolved || k - (int)nless > kTieCap) {              // sparse neighbourhood, n < k, or a huge tie class:
+        P.normals_out[3 * (size_t)qidx] = __longlong_as_double(0x7ff8000000000001ll);   // the generic kernel finishes it
+        P.todo[atomicAdd(P.todo_count, 1u)] = t;
         return;
     }
     // ---- pass 2: cumulants of d2 < T, smallest indices among d2 == T ----
