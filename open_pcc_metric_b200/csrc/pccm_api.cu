@@ -842,8 +842,9 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
         scatter_pair_kernel<<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table, items);
         const uint32_t wblocks = (uint32_t)((nrows * 32 + kRowSortThreads - 1) / kRowSortThreads);
         rowsort_warp_kernel<<<wblocks, kRowSortThreads, 0, ctx->stream>>>(sh->table, (uint32_t)nrows, items, long_rows + 1, long_rows);
+        rowsort_medium_kernel<<<ctx->sm_count * 14, kRowSortThreads, 0, ctx->stream>>>(sh->table, items, long_rows + 1, long_rows);
         rowsort_block_kernel<<<ctx->sm_count * 2, kRowSortThreads, 0, ctx->stream>>>(sh->table, items, long_rows + 1, long_rows);
-        ctx->tm.total_launches += 3;
+        ctx->tm.total_launches += 4;
         CK(cudaGetLastError());
     }
     if (!rc) {

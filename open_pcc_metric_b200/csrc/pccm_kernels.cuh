@@ -379,43 +379,21 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-// pass 3: one warp per row.  <= 32 items: bitonic network over lanes (shuffles, registers);
-// <= kRowSortWarpSmem items: the same warp sorts in its private slice of shared memory
-// (no block barrier); longer rows are queued for the block kernel.
+// pass 3a: one warp per row, rows of <= 32 items: bitonic network over lanes (shuffles, registers
+// only, no shared memory -> full occupancy); longer rows are queued.
 constexpr int kRowSortThreads = 256;
 constexpr uint32_t kRowSortWarpSmem = 512;
 __global__ void __launch_bounds__(kRowSortThreads)
 rowsort_warp_kernel(const uint32_t* __restrict__ table, uint32_t nrows, unsigned long long* __restrict__ items,
                     uint32_t* __restrict__ long_rows, uint32_t* long_count) {
-    __shared__ unsigned long long smw[kRowSortThreads / 32][kRowSortWarpSmem];
     const uint32_t row = (blockIdx.x * kRowSortThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
     const uint32_t lo = table[row], hi = table[row + 1];
     const uint32_t len = hi - lo;
     if (len < 2) return;
-    if (len > kRowSortWarpSmem) {
-        if (lane == 0) long_rows[atomicAdd(long_count, 1u)] = row;
-        return;
-    }
     if (len > 32) {
-        unsigned long long* sm = smw[threadIdx.x >> 5];
-        uint32_t p2 = 64;
-        while (p2 < len) p2 <<= 1;
-        for (uint32_t i = lane; i < p2; i += 32) sm[i] = i < len ? items[lo + i] : ~0ull;
-        __syncwarp();
-        for (uint32_t k = 2; k <= p2; k <<= 1)
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t t = lane; t < (p2 >> 1); t += 32) {
-                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
-                    const uint32_t l = i | j;
-                    const unsigned long long a = sm[i], b = sm[l];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { sm[i] = b; sm[l] = a; }
-                }
-                __syncwarp();
-            }
-        for (uint32_t i = lane; i < len; i += 32) items[lo + i] = sm[i];
+        if (lane == 0) long_rows[atomicAdd(long_count, 1u)] = row;
         return;
     }
     unsigned long long v = lane < (int)len ? items[lo + lane] : ~0ull;
@@ -433,6 +411,40 @@ rowsort_warp_kernel(const uint32_t* __restrict__ table, uint32_t nrows, unsigned
     if (lane < (int)len) items[lo + lane] = v;
 }
 
+// pass 3b: queued rows of 33..kRowSortWarpSmem items: one warp each, network in the warp's
+// private slice of shared memory (no block barrier); a fixed grid walks the queue.
+__global__ void __launch_bounds__(kRowSortThreads)
+rowsort_medium_kernel(const uint32_t* __restrict__ table, unsigned long long* __restrict__ items,
+                      const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count) {
+    __shared__ unsigned long long smw[kRowSortThreads / 32][kRowSortWarpSmem];
+    const int lane = threadIdx.x & 31;
+    unsigned long long* sm = smw[threadIdx.x >> 5];
+    const uint32_t count = *long_count;
+    const uint32_t nwarps = gridDim.x * (kRowSortThreads / 32);
+    for (uint32_t w = (blockIdx.x * kRowSortThreads + threadIdx.x) >> 5; w < count; w += nwarps) {
+        const uint32_t row = long_rows[w];
+        const uint32_t lo = table[row], len = table[row + 1] - lo;
+        if (len > kRowSortWarpSmem) continue;              // block kernel
+        uint32_t p2 = 64;
+        while (p2 < len) p2 <<= 1;
+        for (uint32_t i = lane; i < p2; i += 32) sm[i] = i < len ? items[lo + i] : ~0ull;
+        __syncwarp();
+        for (uint32_t k = 2; k <= p2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = lane; t < (p2 >> 1); t += 32) {
+                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                    const uint32_t l = i | j;
+                    const unsigned long long a = sm[i], b = sm[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { sm[i] = b; sm[l] = a; }
+                }
+                __syncwarp();
+            }
+        for (uint32_t i = lane; i < len; i += 32) items[lo + i] = sm[i];
+        __syncwarp();
+    }
+}
+
 // pass 4: one block per long row: bitonic sort in shared memory (<= kRowSortSmem items) or,
 // for degenerate inputs (e.g. thousands of duplicates of one voxel column), in global memory
 constexpr uint32_t kRowSortSmem = 4096;
@@ -444,6 +456,7 @@ rowsort_block_kernel(const uint32_t* __restrict__ table, unsigned long long* __r
     for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
         const uint32_t row = long_rows[w];
         const uint32_t lo = table[row], len = table[row + 1] - lo;
+        if (len <= kRowSortWarpSmem) continue;             // done by rowsort_medium_kernel
         uint32_t p2 = 64;
         while (p2 < len) p2 <<= 1;
         if (p2 <= kRowSortSmem) {
