@@ -355,12 +355,13 @@ def main():
                        "peak": "resolution", "parallelism": ("query slices of one pair" if partition else "one pair per GPU"),
                        "l2": "flushed between iterations (256 MiB write)", "ms_per_1M_point_pair": ms_dev_max / args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "kernel": "pair_query_kernel<KInt>", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "vx_query_kernel" if tm2.get("vox_build_ms", 0) > 0 else "pair_query_kernel<KInt>", "peak_source": peak_src,
                          "alg_bytes_per_query": ALG_BYTES_PER_QUERY, "queries_per_launch": queries_per_launch,
                          "avg_launch_ms": q_ms_avg},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(tm["total_launches"]), "library_launches": int(tm["library_launches"]),
             "wall_s_timed_region": wall_dev, "stage_ms_per_step": stages,
+            "brick_path": {k: int(tm[k]) for k in ("vox_undecided", "vox_far", "vox_tail") if k in tm},
             "check": None if ps is None else {"d1_psnr_left": float(ps[0][0]), "d2_psnr_left": float(ps[0][1]),
                                               "y_psnr_left": float(ps[0][2][0])},
         }

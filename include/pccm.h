@@ -101,9 +101,14 @@ typedef struct pccm_pair_result {
 typedef struct pccm_timings {
     double upload_ms, stats_ms, keys_ms, sort_ms, table_ms, reorder_ms;
     double query_ms, finalize_ms, knn_ms;
+    double vox_build_ms;       /* occupancy-brick index of integer pairs */
+    double vox_tail_ms;        /* general search + epilogue of the queries the staged search left undecided */
     int64_t query_launches, knn_launches;
     int64_t total_launches;    /* kernels of this library (hand-written, sm_100a) */
     int64_t library_launches;  /* CUB device-wide calls (radix sort passes, scans) */
+    int64_t vox_undecided;     /* queries of the last brick-path evaluation that needed the general search */
+    int64_t vox_far;           /* ... of which the pencil search had to finish (nearest point tens of voxels away) */
+    int64_t vox_tail;          /* points sharing a voxel with a smaller index (duplicate tails), last evaluation */
 } pccm_timings;
 
 int pccm_version(void);

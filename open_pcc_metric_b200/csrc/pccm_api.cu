@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "pccm_kernels.cuh"
+#include "pccm_vox_kernels.cuh"
 
 using namespace pccm;
 
@@ -50,6 +51,8 @@ struct pccm_ctx {
     uint32_t short_row = 0;         // rows up to this length skip the binary search (PCCM_SHORT_ROW; measured: never a win)
     bool normals_counting = true;   // KInt normals by counting selection (PCCM_NORMALS_COUNTING=0: list-based kernel only)
     bool use_rowsort = true;        // KInt pair build: counting sort + per-row sort instead of CUB radix (PCCM_ROWSORT=0 disables)
+    bool use_vox = true;            // KInt pairs: occupancy-brick index + bit-scan query (PCCM_VOX=0: pencil path only)
+    bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
 };
 
 static thread_local std::string g_err;
@@ -159,6 +162,8 @@ struct pccm_cloud {
     uint32_t* row_start = nullptr; // pencil table; values are positions in `recs`
     uint32_t base = 0;             // position of this cloud's first record in `recs`
     struct SharedIndex* shared = nullptr;   // joint build: buffers owned by both clouds
+    struct SharedVox* vox = nullptr;        // occupancy-brick index of the pair this cloud was built with (KInt)
+    int vox_id = 0;                         // which of the pair's two views is this cloud
     bool rgb_in_rec = false;       // KInt records carry the 8-bit colour
     double cell_size = 0;
 };
@@ -168,6 +173,30 @@ struct SharedIndex {
     uint32_t* table = nullptr;
     int refs = 0;
 };
+
+struct SharedVox {
+    uint32_t *dirbits = nullptr, *dirpre = nullptr, *masks = nullptr, *base = nullptr, *gstart = nullptr;
+    uint4* pts = nullptr;
+    uint16_t* pre = nullptr;
+    uint4* recs = nullptr;
+    VoxView view[2];
+    struct pccm_cloud* owner[2] = {nullptr, nullptr};   // live clouds of the pair (the pencil index is built from recs on demand)
+    double cell_size = 0;                                // what pccm_pair_build_index was asked for
+    int refs = 0;
+};
+
+static void free_vox(pccm_ctx* ctx, SharedVox* v) {
+    dfree(ctx, v->dirbits); dfree(ctx, v->dirpre); dfree(ctx, v->masks); dfree(ctx, v->base); dfree(ctx, v->gstart);
+    dfree(ctx, v->pre); dfree(ctx, v->recs); dfree(ctx, v->pts);
+    delete v;
+}
+static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
+    SharedVox* v = c->vox;
+    c->vox = nullptr;
+    if (!v) return;
+    v->owner[c->vox_id] = nullptr;
+    if (--v->refs == 0) free_vox(ctx, v);
+}
 
 static size_t dtype_size(int dt) {
     switch (dt) {
@@ -298,6 +327,8 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
     if (const char* s = getenv("PCCM_SHORT_ROW")) ctx->short_row = (uint32_t)atoi(s);
     if (const char* s = getenv("PCCM_ROWSORT")) ctx->use_rowsort = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_VOX")) ctx->use_vox = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
     if (const char* s = getenv("PCCM_NORMALS_COUNTING")) ctx->normals_counting = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
@@ -360,6 +391,7 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     dfree(ctx, c->rgb_u8);
     dfree(ctx, c->rgb_f64);
     if (!c->normals_borrowed) dfree(ctx, c->normals);
+    release_vox(ctx, c);
     if (c->shared) {
         if (--c->shared->refs == 0) {
             dfree(ctx, c->shared->recs);
@@ -858,9 +890,11 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
     }
     dfree(ctx, rowof); dfree(ctx, rank); dfree(ctx, items); dfree(ctx, long_rows);
     if (rc) { dfree(ctx, sh->table); delete sh; return rc; }
-    sh->refs = 2;
+    sh->refs = 0;
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
+        if (!p) continue;           // pencil index built on demand from brick records: the partner may be gone
+        sh->refs++;
         p->shared = sh;
         p->recs = sh->recs;
         p->row_start = sh->table + R.table_off[c];
@@ -873,6 +907,153 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
         if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
     }
     return PCCM_OK;
+}
+
+// Occupancy-brick index of a KInt pair (pccm_vox.cuh): directory of occupied 32 x 8 x 8 bricks,
+// their 64 occupancy words, voxel ranks and one record per distinct voxel.  One host
+// synchronisation (the number of occupied bricks sizes the mask arrays).  Clouds whose brick grid
+// would not fit the directory budget keep the pencil path only.
+static constexpr size_t kVoxPinnedOffset = 12288;   // bytes into ctx->pinned
+static constexpr uint64_t kVoxMaxDirBits = 1ull << 30;
+
+static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double cell_size, bool* built) {
+    StageTimer t(ctx, &ctx->tm.vox_build_ms);
+    *built = false;
+    VoxBuild B{};
+    B.nclouds = 2;
+    uint32_t ndirw[2];
+    for (int c = 0; c < 2; ++c) {
+        const pccm_cloud* p = cl[c];
+        VoxCloudBuild& C = B.c[c];
+        C.xyz = R.xyz[c]; C.rgb = R.rgb[c]; C.stride = R.stride[c]; C.rgb_stride = R.rgb_stride[c];
+        C.dtype = R.dtype[c]; C.rgb_dtype = R.rgb_dtype[c]; C.rgb_in_rec = R.rgb_in_rec[c]; C.n = R.n[c];
+        C.g.obx = (int)p->mn[0] >> 5; C.g.oby = (int)p->mn[1] >> 3; C.g.obz = (int)p->mn[2] >> 3;
+        C.g.nbx = ((int)p->mx[0] >> 5) - C.g.obx + 1;
+        C.g.nby = ((int)p->mx[1] >> 3) - C.g.oby + 1;
+        C.g.nbz = ((int)p->mx[2] >> 3) - C.g.obz + 1;
+        const uint64_t bits = (uint64_t)C.g.nbx * (uint64_t)C.g.nby * (uint64_t)C.g.nbz;
+        if (bits > kVoxMaxDirBits) return PCCM_OK;      // pencil path only
+        ndirw[c] = (uint32_t)((bits + 31) / 32);
+    }
+    B.c[0].dir_off = 0; B.c[1].dir_off = ndirw[0];
+    B.ndirw_total = ndirw[0] + ndirw[1];
+    B.n_total = R.n[0] + R.n[1];
+    SharedVox* v = new SharedVox();
+    const int threads = 256, blocks = (int)((B.n_total + threads - 1) / threads);
+    auto bail = [&](int rc) { free_vox(ctx, v); return rc; };
+#define CKV(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return bail(fail(ctx, PCCM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_))); \
+    } while (0)
+    CKV(dalloc(ctx, &v->dirbits, (size_t)B.ndirw_total));
+    CKV(dalloc(ctx, &v->dirpre, (size_t)B.ndirw_total + 1));
+    CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)B.ndirw_total * sizeof(uint32_t), ctx->stream));
+    B.dirbits = v->dirbits; B.dirpre = v->dirpre;
+    vx_mark_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+    vx_dircount_kernel<<<(B.ndirw_total + 1 + threads - 1) / threads, threads, 0, ctx->stream>>>(v->dirbits, B.ndirw_total, v->dirpre);
+    ctx->tm.total_launches += 2;
+    CKV(cudaGetLastError());
+    int rc = exclusive_scan(ctx, v->dirpre, (size_t)B.ndirw_total + 1);
+    if (rc) return bail(rc);
+    uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
+    CKV(cudaMemcpyAsync(hcnt, v->dirpre + ndirw[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CKV(cudaMemcpyAsync(hcnt + 1, v->dirpre + B.ndirw_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CKV(cudaStreamSynchronize(ctx->stream));
+    const uint32_t nblk0 = hcnt[0];
+    B.nblk_total = hcnt[1];
+    uint2* counted = nullptr;
+    uint32_t* longq = nullptr;
+    CKV(dalloc(ctx, &v->masks, (size_t)B.nblk_total * kVxRows));
+    CKV(dalloc(ctx, &v->pre, (size_t)B.nblk_total * kVxRows));
+    CKV(dalloc(ctx, &v->base, (size_t)B.nblk_total + 1));
+    CKV(dalloc(ctx, &v->recs, (size_t)B.n_total));
+    CKV(dalloc(ctx, &v->gstart, (size_t)B.n_total + 1));
+    CKV(dalloc(ctx, &v->pts, (size_t)B.n_total));
+    CKV(dalloc(ctx, &counted, (size_t)B.n_total));
+    CKV(dalloc(ctx, &longq, (size_t)B.n_total / kVxGroupSmall + 2));
+    CKV(cudaMemsetAsync(v->masks, 0, (size_t)B.nblk_total * kVxRows * sizeof(uint32_t), ctx->stream));
+    CKV(cudaMemsetAsync(v->gstart, 0, ((size_t)B.n_total + 1) * sizeof(uint32_t), ctx->stream));
+    CKV(cudaMemsetAsync(longq, 0, sizeof(uint32_t), ctx->stream));
+    B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.gstart = v->gstart; B.pts = v->pts;
+    B.counted = counted; B.longq = longq;
+    vx_fill_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+    vx_brickpre_kernel<<<(B.nblk_total + 1 + 7) / 8, 256, 0, ctx->stream>>>(B);
+    ctx->tm.total_launches += 2;
+    CKV(cudaGetLastError());
+    rc = exclusive_scan(ctx, v->base, (size_t)B.nblk_total + 1);
+    if (!rc) {
+        vx_count_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+        ctx->tm.total_launches++;
+        rc = exclusive_scan(ctx, v->gstart, (size_t)B.n_total + 1);
+    }
+    if (!rc) {
+        vx_scatter_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+        vx_group_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+        vx_longgroup_kernel<<<64, 256, 0, ctx->stream>>>(B);
+        ctx->tm.total_launches += 3;
+    }
+    dfree(ctx, counted); dfree(ctx, longq);
+    if (rc) return bail(rc);
+    CKV(cudaGetLastError());
+#undef CKV
+    for (int c = 0; c < 2; ++c) {
+        VoxView& V = v->view[c];
+        V.g = B.c[c].g;
+        V.dirbits = v->dirbits + B.c[c].dir_off;
+        V.dirpre = v->dirpre + B.c[c].dir_off;
+        V.masks = v->masks; V.pre = v->pre; V.base = v->base; V.recs = v->recs;
+        V.gstart = v->gstart; V.pts = v->pts;
+        V.slot0 = c ? nblk0 : 0u;
+        V.nblk = c ? B.nblk_total - nblk0 : nblk0;
+        V.n = R.n[c];
+        V.nblk_total = B.nblk_total; V.n_total = B.n_total;
+        pccm_cloud* p = cl[c];
+        release_vox(ctx, p);
+        p->vox = v;
+        p->vox_id = c;
+        v->owner[c] = p;
+        p->index_kind = PCCM_KIND_INT;
+        p->rgb_in_rec = R.rgb_in_rec[c] != 0;
+        dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // the records hold every point
+        if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
+    }
+    v->refs = 2;
+    v->cell_size = cell_size;
+    *built = true;
+    return PCCM_OK;
+}
+
+// Pencil index of a brick-indexed cloud, built on first use (self k-NN, normals, hull prefilter,
+// far queries) for both clouds of the pair from the brick records.
+static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
+    if (c->recs || c->row_start || !c->vox) return PCCM_OK;
+    SharedVox* v = c->vox;
+    pccm_cloud* cl[2] = {v->owner[0], v->owner[1]};
+    PairRaw R{};
+    for (int k = 0; k < 2; ++k) {
+        RowGrid g{};
+        g.short_row = ctx->short_row;
+        if (cl[k] && cl[k]->recs) cl[k] = nullptr;    // (cannot happen: both are built together)
+        if (cl[k]) {
+            int xb = 0;
+            g.n = (uint32_t)cl[k]->n;
+            choose_grid(ctx, cl[k], PCCM_KIND_INT, v->cell_size, g, xb);
+            R.n[k] = (uint32_t)cl[k]->n;
+            R.rgb_in_rec[k] = cl[k]->rgb_in_rec;
+        } else {
+            g.ny = g.nz = 1; g.h = g.inv_h = 1;
+            R.n[k] = 0;
+        }
+        R.g[k] = g;
+        R.xyz[k] = v->recs; R.dtype[k] = kDtypeVRec; R.stride[k] = sizeof(uint4);
+    }
+    R.table_off[0] = 0;
+    R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
+    R.vpts = v->pts;
+    R.vpts_off[0] = 0; R.vpts_off[1] = v->view[0].n;
+    return build_pair_rowsort(ctx, cl, R);
 }
 
 extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind) {
@@ -917,6 +1098,12 @@ extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b
     R.table_off[0] = 0;
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
     if (kind == PCCM_KIND_INT) {
+        if (ctx->use_vox) {
+            bool built = false;
+            rc = build_vox(ctx, cl, R, cell_size, &built);
+            if (rc) return rc;
+            if (built) return ctx->eager_pencil ? ensure_pencil(ctx, a) : PCCM_OK;
+        }
         if (ctx->use_rowsort) return build_pair_rowsort(ctx, cl, R);
         if (rowbits + xbits + 1 <= 32) return build_pair_impl<uint32_t, KIND_INT>(ctx, cl, R, xbits, rowbits);
         return build_pair_impl<unsigned long long, KIND_INT>(ctx, cl, R, xbits, rowbits);
@@ -982,6 +1169,116 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
     return PCCM_OK;
 }
 
+// Brick path of a symmetric evaluation: staged bit-scan search (one warp per query brick), brick
+// ring search for what it leaves undecided, their epilogue in a fixed order, then the common
+// fold.  Voxels even the brick rings cannot certify (nearest point tens of voxels away) are
+// finished by the pencil search in a second round.  Synchronises; results land where
+// launch_query puts them.
+static constexpr int kVxPendBlocks = 256;
+static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cloud* sc[2], QueryParams& Q, int rank, int world) {
+    SharedVox* v = qc[0]->vox;
+    VxParams P{};
+    P.ndirs = ndirs;
+    P.normals_mode = Q.normals_mode;
+    P.rank = rank; P.world = world;
+    memcpy(P.T, Q.T, sizeof P.T);
+    P.color_scale = Q.color_scale;
+    const double* lut = reinterpret_cast<const double*>(static_cast<char*>(ctx->dscratch) + kLutOffset);
+    const uint32_t n_total = v->view[0].n_total;
+    uint32_t* todo = nullptr;      // [0..3] counters (undecided, far per direction), then the four lists
+    uint32_t* pendbits = nullptr;
+    uint2* res = nullptr;
+    BlockPartial* partials = nullptr;
+    const uint32_t npendw = (n_total + 31u) / 32u;
+    CK(dalloc(ctx, &todo, 2 * (size_t)n_total + 4));
+    CK(dalloc(ctx, &pendbits, (size_t)npendw + 1));
+    CK(dalloc(ctx, &res, (size_t)n_total));
+    CK(cudaMemsetAsync(todo, 0, 4 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
+    uint32_t rec_stride = 0, nwarps = 0;
+    for (int d = 0; d < ndirs; ++d) {
+        VxDir& D = P.dir[d];
+        D.q = v->view[qc[d]->vox_id];
+        D.s = v->view[sc[d]->vox_id];
+        D.qa = Q.dir[d].q; D.sa = Q.dir[d].s;
+        D.qa.lut255 = D.sa.lut255 = lut;
+        D.flags = Q.dir[d].flags;
+        D.idx_out = Q.dir[d].idx_out; D.d2_out = Q.dir[d].d2_out;
+        D.todo_count = todo + d;
+        D.todo = todo + 4 + (d ? (size_t)qc[0]->n : 0);
+        D.far_count = todo + 2 + d;
+        D.far = todo + 4 + n_total + (d ? (size_t)qc[0]->n : 0);
+        rec_stride = std::max(rec_stride, D.q.nblk + 2u * kVxPendBlocks);
+        nwarps += D.q.nblk;
+    }
+    for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
+    CK(dalloc(ctx, &partials, (size_t)rec_stride * 2 + 1));
+    P.partials = partials; P.pendbits = pendbits; P.res = res;
+    {
+        StageTimer t(ctx, &ctx->tm.query_ms, 1);
+        vx_query_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
+        ctx->tm.query_launches++;
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    {
+        StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
+        vx_general_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
+        vx_pending_kernel<<<dim3(kVxPendBlocks, ndirs), kVxPendThreads, 0, ctx->stream>>>(P);
+        ctx->tm.total_launches += 2;
+        CK(cudaGetLastError());
+    }
+    // common fold: same record layout as the pencil path
+    Q.rec_stride = rec_stride;
+    Q.partials = partials;
+    Q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->dscratch) + kTicketOffset);
+    Q.out = static_cast<BlockPartial*>(ctx->dscratch);
+    Q.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);
+    uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
+    auto fold = [&](uint32_t pend_rounds) -> int {
+        StageTimer t(ctx, &ctx->tm.finalize_ms);
+        for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = P.dir[d].q.nblk + pend_rounds * kVxPendBlocks;
+        finalize_kernel<<<Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream>>>(Q);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
+        return PCCM_OK;
+    };
+    int rc = fold(1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hcnt + 2, todo, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hcnt + 6, v->base + v->view[0].nblk_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tm.vox_undecided = (int64_t)hcnt[2] + hcnt[3];
+    ctx->tm.vox_far = (int64_t)hcnt[4] + hcnt[5];
+    ctx->tm.vox_tail = (int64_t)n_total - (int64_t)hcnt[6];
+    if (hcnt[4] + hcnt[5] > 0) {
+        // second round: pencil search for the far voxels, their epilogue, fold again
+        for (int d = 0; d < ndirs; ++d) {
+            rc = ensure_pencil(ctx, sc[d]);
+            if (rc) return rc;
+            VxDir& D = P.dir[d];
+            D.sgrid = sc[d]->grid;
+            D.srecs = static_cast<const uint4*>(sc[d]->recs);
+            D.srow_start = sc[d]->row_start;
+        }
+        P.pend_rec = kVxPendBlocks;
+        CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
+        {
+            StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
+            vx_far_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
+            vx_pending_kernel<<<dim3(kVxPendBlocks, ndirs), kVxPendThreads, 0, ctx->stream>>>(P);
+            ctx->tm.total_launches += 2;
+            CK(cudaGetLastError());
+        }
+        rc = fold(2);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    dfree(ctx, todo); dfree(ctx, pendbits); dfree(ctx, res); dfree(ctx, partials);
+    return PCCM_OK;
+}
+
 static int check_pair(pccm_ctx* ctx, pccm_cloud* q, pccm_cloud* s) {
     if (q->index_kind < 0 || s->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "both clouds must be indexed (pccm_cloud_build_index)");
     if (q->index_kind != s->index_kind)
@@ -1007,7 +1304,18 @@ extern "C" int pccm_nn(pccm_ctx* ctx, pccm_cloud* query, pccm_cloud* search, int
     P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq; P.dir[0].flags = 0;
     P.dir[0].idx_out = d_idx; P.dir[0].d2_out = d_d2;
     P.normals_mode = 0; P.color_scale = 1;
-    rc = launch_query(ctx, query->index_kind, P);
+    if (ctx->use_vox && query->vox && query->vox == search->vox && query != search && query->index_kind == PCCM_KIND_INT) {
+        pccm_cloud* qc[2] = {query, nullptr};
+        pccm_cloud* sc[2] = {search, nullptr};
+        rc = launch_vox_query(ctx, 1, qc, sc, P, 0, 1);
+    } else {
+        rc = ensure_pencil(ctx, query);
+        if (!rc) rc = ensure_pencil(ctx, search);
+        if (rc) return rc;
+        P.dir[0].q = view_of(query); P.dir[0].s = view_of(search);
+        P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq;
+        rc = launch_query(ctx, query->index_kind, P);
+    }
     if (!rc && mem_kind == PCCM_HOST) {
         if (idx_out) rc = copy_out(ctx, idx_out, d_idx, (size_t)nq * sizeof(int32_t), PCCM_HOST);
         if (!rc && d2_out) rc = copy_out(ctx, d2_out, d_d2, (size_t)nq * sizeof(double), PCCM_HOST);
@@ -1068,14 +1376,29 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
             D.d2_out = ctx->pp_d2[d];
         }
     }
-    rc = launch_query(ctx, a->index_kind, P);
+    const bool vox = ctx->use_vox && a->vox && a->vox == b->vox && a != b && a->index_kind == PCCM_KIND_INT;
+    pccm_cloud* sc[2] = {b, a};
+    if (vox) {
+        rc = launch_vox_query(ctx, 2, cl, sc, P, rank, world);
+    } else {
+        rc = ensure_pencil(ctx, a);
+        if (!rc) rc = ensure_pencil(ctx, b);
+        if (rc) return rc;
+        for (int d = 0; d < 2; ++d) {
+            const uint64_t n = (uint64_t)cl[d]->n;
+            P.dir[d].q = view_of(cl[d]); P.dir[d].s = view_of(cl[1 - d]);
+            P.dir[d].qbegin = cl[d]->base + (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
+            P.dir[d].qend = cl[d]->base + (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
+        }
+        rc = launch_query(ctx, a->index_kind, P);
+    }
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     const BlockPartial* r = static_cast<const BlockPartial*>(ctx->pinned);
     memset(out, 0, sizeof *out);
     for (int d = 0; d < 2; ++d) {
         pccm_dir_result& o = out->dir[d];
-        o.n = (int64_t)(P.dir[d].qend - P.dir[d].qbegin);
+        o.n = vox ? (int64_t)r[d].sum_d1 : (int64_t)(P.dir[d].qend - P.dir[d].qbegin);   // brick path: slices are cut by voxel, the kernels count the points
         o.n_total = cl[d]->n;
         o.d1_exact_int = a->index_kind == PCCM_KIND_INT;
         o.d2_valid = (dflags[d] & PCCM_EVAL_D2) != 0;
@@ -1130,7 +1453,7 @@ static int launch_knn(pccm_ctx* ctx, pccm_cloud* c, KnnParams& P) {
 static int check_range(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end) {
     if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
     if (begin < 0 || end < begin || end > c->n) return fail(ctx, PCCM_ERR_INVALID, "bad range [%lld, %lld)", (long long)begin, (long long)end);
-    return PCCM_OK;
+    return ensure_pencil(ctx, c);
 }
 
 extern "C" int pccm_knn_self(pccm_ctx* ctx, pccm_cloud* c, int k, int32_t* idx_out, double* d2_out, int mem_kind) {
@@ -1265,6 +1588,7 @@ extern "C" int pccm_cloud_extremes(pccm_ctx* ctx, pccm_cloud* c, const double* d
     if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
     if (c->n == 0) return fail(ctx, PCCM_ERR_INVALID, "empty cloud");
     CK(cudaSetDevice(ctx->device));
+    { const int rc = ensure_pencil(ctx, c); if (rc) return rc; }
     const uint32_t n = (uint32_t)c->n;
     const uint32_t nchunks = (n + kExtChunk - 1) / kExtChunk;
     double *ddirs = nullptr, *pval = nullptr;
@@ -1304,6 +1628,7 @@ extern "C" int pccm_cloud_outside_hull(pccm_ctx* ctx, pccm_cloud* c, const doubl
     if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
     if (nf * 32 > 200 * 1024) return fail(ctx, PCCM_ERR_UNSUPPORTED, "too many facets (%d)", nf);
     CK(cudaSetDevice(ctx->device));
+    { const int rc = ensure_pencil(ctx, c); if (rc) return rc; }
     const uint32_t n = (uint32_t)c->n;
     double *dpl = nullptr, *dout = nullptr;
     unsigned long long* dcnt = nullptr;

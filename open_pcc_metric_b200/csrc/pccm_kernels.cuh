@@ -21,9 +21,15 @@ constexpr int kKnnThreads = 64;
 // ------------------------------------------------------------------------------------
 // raw input access
 // ------------------------------------------------------------------------------------
+constexpr int kDtypeVRec = 100;   // internal source format: the brick index's point list pts[] = {rgb, idx, rank, -} + voxel records (pccm_vox.cuh)
+
 __device__ __forceinline__ double load_coord(const void* base, int dtype, int64_t stride, int64_t i, int axis) {
     const char* p = static_cast<const char*>(base) + i * stride;
     switch (dtype) {
+        case kDtypeVRec: {      // base = voxel records, i = the voxel's rank
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(p);
+            return axis == 0 ? (double)(u[0] & 0xffffu) : (axis == 1 ? (double)(u[0] >> 16) : (double)u[1]);
+        }
         case PCCM_F64: return reinterpret_cast<const double*>(p)[axis];
         case PCCM_F32: return (double)reinterpret_cast<const float*>(p)[axis];
         case PCCM_I32: return (double)reinterpret_cast<const int32_t*>(p)[axis];
@@ -290,7 +296,16 @@ struct PairRaw {
     uint32_t n[2];
     uint32_t table_off[2];     // offset of each cloud's row table inside the joint table
     RowGrid g[2];
+    const uint4* vpts;         // kDtypeVRec sources: the brick index's point list (cloud 1's points follow cloud 0's)
+    uint32_t vpts_off[2];      // first entry of each cloud in vpts
 };
+
+// Row of the coordinate source that holds point li of cloud c (brick-index sources: the record of
+// the point's voxel).
+__device__ __forceinline__ uint32_t pair_src(const PairRaw& R, int c, uint32_t li) {
+    if (R.dtype[c] != kDtypeVRec) return li;
+    return __ldg(reinterpret_cast<const uint32_t*>(R.vpts + R.vpts_off[c] + li) + 2);
+}
 
 __device__ __forceinline__ uint32_t int_row(const RowGrid& g, int y, int z) {
     uint32_t cy = (uint32_t)((y - g.iy0) >> g.shift), cz = (uint32_t)((z - g.iz0) >> g.shift);
@@ -356,7 +371,7 @@ __global__ void rowrank_pair_kernel(const __grid_constant__ PairRaw R, uint32_t*
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
-    const uint32_t li = i - (c ? R.n[0] : 0u);
+    const uint32_t li = pair_src(R, c, i - (c ? R.n[0] : 0u));
     const uint32_t row = R.table_off[c] + int_row(R.g[c], (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1),
                                                   (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
     rowof[i] = row;
@@ -371,7 +386,7 @@ __global__ void scatter_pair_kernel(const __grid_constant__ PairRaw R, const uin
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
     const uint32_t li = i - (c ? R.n[0] : 0u);
-    const uint32_t x = (uint32_t)(int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 0);
+    const uint32_t x = (uint32_t)(int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], pair_src(R, c, li), 0);
     items[table[rowof[i]] + rank[i]] = ((unsigned long long)x << 32) | li;
 }
 
@@ -506,7 +521,13 @@ __global__ void reorder_items_pair_kernel(const __grid_constant__ PairRaw R, con
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
-    const uint32_t src = (uint32_t)items[i];
+    uint32_t src = (uint32_t)items[i];
+    if (R.dtype[c] == kDtypeVRec) {          // point {rgb, idx, rank} + voxel {xy, z} -> {xy, z, idx, rgb}
+        const uint4 e = __ldg(R.vpts + R.vpts_off[c] + src);
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint4*>(R.xyz[c]) + e.z));
+        recs[i] = RecPack<K>::make((double)(v.x & 0xffffu), (double)(v.x >> 16), (double)v.y, e.y, R.rgb_in_rec[c] ? e.x : 0u);
+        return;
+    }
     uint32_t rgba = 0;
     if (R.rgb_in_rec[c]) {
         if (R.rgb_dtype[c] == PCCM_U8) {

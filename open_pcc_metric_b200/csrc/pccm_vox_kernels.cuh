@@ -1,0 +1,469 @@
+// pccm_vox_kernels.cuh -- sm_100a kernels of the occupancy-brick path for voxelised pairs:
+// index build (mark / fill / prefix / place / tail sort) and the symmetric query
+// (vx_query_kernel: one warp per query brick, search rows staged in shared memory;
+//  vx_general_kernel: the undecided queries and the duplicate tails; vx_pending_kernel: their
+//  epilogue in a fixed order).  Per-point / per-query logic: pccm_vox.cuh.
+#pragma once
+#include "pccm_kernels.cuh"
+#include "pccm_vox.cuh"
+
+namespace pccm {
+
+// ------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------
+struct VoxCloudBuild {
+    const void* xyz;
+    const void* rgb;
+    int64_t stride, rgb_stride;
+    int32_t dtype, rgb_dtype, rgb_in_rec;
+    uint32_t n;
+    VoxDims g;
+    uint32_t dir_off;          // word offset of this cloud's directory in the joint dirbits / dirpre
+};
+struct VoxBuild {
+    VoxCloudBuild c[2];
+    int32_t nclouds;
+    uint32_t n_total, ndirw_total, nblk_total;
+    uint32_t* dirbits;         // [ndirw_total]
+    uint32_t* dirpre;          // [ndirw_total + 1]
+    uint32_t* masks;           // [nblk_total][64]
+    uint16_t* pre;             // [nblk_total][64]
+    uint32_t* base;            // [nblk_total + 1]
+    uint4* recs;               // [n_total]
+    uint32_t* gstart;          // [n_total + 1]: multiplicities, then (scanned) group starts
+    uint4* pts;                // [n_total]
+    uint2* counted;            // [n_total] scratch: {rank, arrival order} of input point i
+    uint32_t* longq;           // [0] = count, [1..] = voxels whose group is longer than kVxGroupSmall
+};
+
+__device__ __forceinline__ void vx_point(const VoxBuild& B, uint32_t i, int& c, uint32_t& li, int& x, int& y, int& z) {
+    c = (B.nclouds > 1 && i >= B.c[0].n) ? 1 : 0;
+    li = i - (c ? B.c[0].n : 0u);
+    const VoxCloudBuild& C = B.c[c];
+    x = (int)load_coord(C.xyz, C.dtype, C.stride, li, 0);
+    y = (int)load_coord(C.xyz, C.dtype, C.stride, li, 1);
+    z = (int)load_coord(C.xyz, C.dtype, C.stride, li, 2);
+}
+
+__global__ void vx_mark_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_total) return;
+    int c, x, y, z; uint32_t li;
+    vx_point(B, i, c, li, x, y, z);
+    vx_mark_point(B.dirbits + B.c[c].dir_off, vx_key(B.c[c].g, x, y, z));
+}
+
+__global__ void vx_dircount_kernel(const uint32_t* __restrict__ dirbits, uint32_t nw, uint32_t* __restrict__ dirpre) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nw) dirpre[i] = i < nw ? (uint32_t)__popc(dirbits[i]) : 0u;
+}
+
+__global__ void vx_fill_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_total) return;
+    int c, x, y, z; uint32_t li;
+    vx_point(B, i, c, li, x, y, z);
+    const uint32_t off = B.c[c].dir_off;
+    vx_fill_point(B.masks, vx_slot_of_key(B.dirbits + off, B.dirpre + off, vx_key(B.c[c].g, x, y, z)), x, y, z);
+}
+
+// one warp per brick: exclusive prefix of the row popcounts, brick total -> base[slot] (scanned next)
+__global__ void __launch_bounds__(256) vx_brickpre_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t slot = (blockIdx.x * 256u + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slot > B.nblk_total) return;
+    if (slot == B.nblk_total) { if (lane == 0) B.base[slot] = 0u; return; }
+    const uint32_t* m = B.masks + (size_t)slot * kVxRows;
+    const uint32_t c0 = (uint32_t)__popc(m[2 * lane]), c1 = (uint32_t)__popc(m[2 * lane + 1]);
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t ex = incl - c0 - c1;
+    B.pre[(size_t)slot * kVxRows + 2 * lane] = (uint16_t)ex;
+    B.pre[(size_t)slot * kVxRows + 2 * lane + 1] = (uint16_t)(ex + c0);
+    if (lane == 31) B.base[slot] = incl;
+}
+
+__global__ void vx_count_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_total) return;
+    int c, x, y, z; uint32_t li;
+    vx_point(B, i, c, li, x, y, z);
+    const VoxCloudBuild& C = B.c[c];
+    const uint32_t slot = vx_slot_of_key(B.dirbits + C.dir_off, B.dirpre + C.dir_off, vx_key(C.g, x, y, z));
+    const VxCounted k = vx_count_point(B.masks, B.pre, B.base, B.recs, B.gstart, slot, x, y, z);
+    B.counted[i] = make_uint2(k.rank, k.ord);
+}
+
+__global__ void vx_scatter_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_total) return;
+    const int c = (B.nclouds > 1 && i >= B.c[0].n) ? 1 : 0;
+    const uint32_t li = i - (c ? B.c[0].n : 0u);
+    const VoxCloudBuild& C = B.c[c];
+    uint32_t rgba = 0;
+    if (C.rgb_in_rec) {
+        if (C.rgb_dtype == PCCM_U8) {
+            const uint8_t* p = static_cast<const uint8_t*>(C.rgb) + (int64_t)li * C.rgb_stride;
+            rgba = p[0] | (p[1] << 8) | (p[2] << 16);
+        } else {
+            rgba = (uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 0) * 255.0) |
+                   ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 1) * 255.0) << 8) |
+                   ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 2) * 255.0) << 16);
+        }
+    }
+    const uint2 k = B.counted[i];
+    VxCounted kc; kc.rank = k.x; kc.ord = k.y;
+    vx_scatter_point(B.gstart, B.pts, kc, rgba, li);
+}
+
+// one thread per voxel (gstart[nblk_total-th base] of them, a device value)
+__global__ void vx_group_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B.base[B.nblk_total]) return;
+    if (vx_group_finish(B.gstart, B.pts, B.recs, v)) B.longq[1 + atomicAdd(B.longq, 1u)] = v;
+}
+
+// Groups of more than kVxGroupSmall points in ONE voxel (heavily duplicated inputs): one block each,
+// bitonic network in global memory, all-ascending form (the virtual +inf padding never moves).
+__global__ void __launch_bounds__(256) vx_longgroup_kernel(const __grid_constant__ VoxBuild B) {
+    const uint32_t count = B.longq[0];
+    for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
+        const uint32_t v = B.longq[1 + w];
+        const uint32_t g0 = B.gstart[v], len = B.gstart[v + 1] - g0;
+        uint4* a = B.pts + g0;
+        uint32_t p2 = 2;
+        while (p2 < len) p2 <<= 1;
+        for (uint32_t k = 2; k <= p2; k <<= 1) {
+            for (uint32_t i = threadIdx.x; i < len; i += 256) {
+                const uint32_t l = i ^ (k - 1);
+                if (l > i && l < len) { const uint4 x = a[i], y = a[l]; if (x.y > y.y) { a[i] = y; a[l] = x; } }
+            }
+            __syncthreads();
+            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < len; i += 256) {
+                    const uint32_t l = i ^ j;
+                    if (l > i && l < len) { const uint4 x = a[i], y = a[l]; if (x.y > y.y) { a[i] = y; a[l] = x; } }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// query
+// ------------------------------------------------------------------------------------
+struct VxDir {
+    VoxView q, s;
+    CloudView qa, sa;          // attribute views (colours, normals) of the query / search cloud
+    uint32_t flags;
+    int32_t* idx_out;          // original query order, or null
+    double* d2_out;
+    uint32_t* todo;            // ranked positions of the voxels the staged search left undecided
+    uint32_t* todo_count;
+    uint32_t* far;             // ... and of those the brick rings left undecided (pencil search)
+    uint32_t* far_count;
+    RowGrid sgrid;             // pencil index of the search cloud (vx_far_kernel only)
+    const uint4* srecs;
+    const uint32_t* srow_start;
+    uint32_t rec_off;          // first reduction record of this direction
+};
+
+struct VxParams {
+    VxDir dir[2];
+    int32_t ndirs;
+    int32_t normals_mode;
+    int32_t rank, world;       // this call handles the rank-th of `world` equal slices of each cloud's voxels
+    double T[9];
+    double color_scale;
+    BlockPartial* partials;
+    uint32_t* pendbits;        // [n_total / 32 + 1] zero on entry: voxels whose result waits in res[]
+    uint2* res;                // [n_total] {d2, neighbour position} of pending voxels
+    uint32_t pend_rec;         // reduction records of vx_pending_kernel start at rec_off + q.nblk + pend_rec
+};
+
+struct VxAcc {
+    unsigned long long s1;
+    uint32_t m1, cnt;
+    double s2, m2, cs[3], cm[3];
+    __device__ __forceinline__ void init() {
+        s1 = 0; m1 = 0; cnt = 0; s2 = 0; m2 = -INFINITY;
+        for (int k = 0; k < 3; ++k) { cs[k] = 0; cm[k] = -INFINITY; }
+    }
+};
+
+// epilogue of ONE query point: D1 (+ per-point outputs), D2 with the other cloud's normals, colour
+__device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, uint32_t qidx, uint32_t qrgb, uint32_t d2,
+                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a) {
+    a.s1 += d2;
+    a.m1 = d2 > a.m1 ? d2 : a.m1;
+    a.cnt++;
+    if (D.idx_out) D.idx_out[qidx] = (int32_t)nidx;
+    if (D.d2_out) D.d2_out[qidx] = (double)d2;
+    if (D.flags & PCCM_EVAL_D2) {
+        const double e[3] = {(double)ex, (double)ey, (double)ez};
+        const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
+        double nv[3] = {__ldg(D.sa.normals + 3 * (size_t)ni), __ldg(D.sa.normals + 3 * (size_t)ni + 1),
+                        __ldg(D.sa.normals + 3 * (size_t)ni + 2)};
+        const double pe = plane_err2(e, nv);
+        a.s2 = dadd(a.s2, pe);
+        a.m2 = fmax(a.m2, pe);
+    }
+    if (D.flags & PCCM_EVAL_COLOR) {
+        double cq[3], cn[3], c2[3], c2s[3];
+        load_color(D.qa, qidx, qrgb, cq);
+        load_color(D.sa, nidx, nrgb, cn);
+        color_diff2(P.T, cq, cn, P.color_scale, c2, c2s);
+        for (int k = 0; k < 3; ++k) { a.cs[k] = dadd(a.cs[k], c2[k]); a.cm[k] = fmax(a.cm[k], c2s[k]); }
+    }
+}
+
+// sum_d1 (unused by integer pairs) carries the number of query POINTS reduced: slices are cut by
+// voxel, so the host cannot know it
+__device__ __forceinline__ void vx_warp_record(const VxAcc& a, uint32_t flags, BlockPartial& r) {
+    const unsigned full = 0xffffffffu;
+    r.sum_d1_u64 = warp_sum_u64(a.s1);
+    const uint32_t cnt = __reduce_add_sync(full, a.cnt);
+    r.sum_d1 = (double)cnt;
+    r.max_d1 = cnt ? (double)__reduce_max_sync(full, a.m1) : -INFINITY;
+    r.sum_d2 = 0; r.max_d2 = -INFINITY;
+    for (int k = 0; k < 3; ++k) { r.csum[k] = 0; r.cmax[k] = -INFINITY; }
+    if (flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
+        const double s = warp_reduce4<false>(a.s2, a.cs[0], a.cs[1], a.cs[2]);
+        const double m = warp_reduce4<true>(a.m2, a.cm[0], a.cm[1], a.cm[2]);
+        r.sum_d2 = __shfl_sync(full, s, 0);  r.csum[0] = __shfl_sync(full, s, 8);
+        r.csum[1] = __shfl_sync(full, s, 16); r.csum[2] = __shfl_sync(full, s, 24);
+        r.max_d2 = __shfl_sync(full, m, 0);  r.cmax[0] = __shfl_sync(full, m, 8);
+        r.cmax[1] = __shfl_sync(full, m, 16); r.cmax[2] = __shfl_sync(full, m, 24);
+    }
+}
+
+// this rank's slice [t_lo, t_hi) of the query cloud's ranked positions
+__device__ __forceinline__ void vx_slice(const VxParams& P, const VoxView& Q, uint32_t& t_lo, uint32_t& t_hi) {
+    const uint32_t r0 = vx_ranked_begin(Q), nd = vx_ndistinct(Q);
+    t_lo = r0 + (uint32_t)((unsigned long long)nd * (unsigned)P.rank / (unsigned)P.world);
+    t_hi = r0 + (uint32_t)((unsigned long long)nd * (unsigned)(P.rank + 1) / (unsigned)P.world);
+}
+
+// One warp = one brick of the query cloud.  The warp stages the search cloud's occupancy rows
+// around the brick (12 x 12 rows x 64 bits, 1.1 KB) in its private slice of shared memory, then
+// takes the brick's voxels 32 at a time.  Search phase, one lane per VOXEL: bit scans over the
+// 3 x 3 (5 x 5) rows, rank look-ups only for the voxels that tie at the minimum.  Epilogue phase,
+// one lane per POINT of those 32 voxels (contiguous in pts[]; duplicated points share their voxel's
+// answer through shared memory).  One reduction record per brick at a fixed position -> float
+// sums do not depend on scheduling.
+constexpr int kVxThreads = 128;
+constexpr int kVxWarps = kVxThreads / 32;
+
+__global__ void __launch_bounds__(kVxThreads)
+vx_query_kernel(const __grid_constant__ VxParams P) {
+    __shared__ uint2 s_win[kVxWarps][kVxRegRows];
+    __shared__ uint4 s_res[kVxWarps][32];
+    __shared__ int s_slot[kVxWarps][28];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * kVxWarps + warp;
+    const int d = (P.ndirs > 1 && gw >= P.dir[0].q.nblk) ? 1 : 0;
+    const VxDir& D = P.dir[d];
+    const uint32_t lb = gw - (d ? P.dir[0].q.nblk : 0u);
+    if (lb >= D.q.nblk) return;
+    const uint32_t slot = D.q.slot0 + lb;
+    const uint4* __restrict__ qrecs = D.q.recs;
+    const uint32_t b0 = __ldg(D.q.base + slot), b1 = __ldg(D.q.base + slot + 1);
+    uint32_t t_lo, t_hi;
+    vx_slice(P, D.q, t_lo, t_hi);
+    const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
+    VxAcc acc;
+    acc.init();
+    if (t0 < t1) {
+        uint2* win = s_win[warp];
+        uint4* vres = s_res[warp];
+        int* sslot = s_slot[warp];
+        const uint2 first = __ldg(reinterpret_cast<const uint2*>(qrecs + b0));
+        const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+        int myslot = -1;
+        if (lane < 27) {
+            myslot = vx_slot(D.s, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
+            sslot[lane] = myslot;
+        }
+        const bool any_brick = __any_sync(full, myslot >= 0);
+        __syncwarp();
+        if (any_brick) {
+            for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(D.s, sslot, i);
+            __syncwarp();
+        }
+        for (uint32_t tb = t0; tb < t1; tb += 32) {
+            // ---- search: lane = voxel ----
+            const uint32_t t = tb + lane;
+            const bool active = t < t1;
+            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(qrecs + (active ? t : t0)));
+            const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+            uint32_t bd2 = kVxNone, rows = 0;
+            bool done = false;
+            if (any_brick) {
+                const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
+                vx_rows_inner(win, lx, ly, lz, bd2, rows);
+                done = bd2 < 4u;
+                if (__any_sync(full, active && !done)) {
+                    vx_rows_outer(win, lx, ly, lz, bd2, rows);
+                    done = bd2 < 9u;
+                }
+            }
+            uint4 r = make_uint4(kVxNone, 0u, 0u, 0u);
+            if (active && done) {
+                VxPick pk;
+                vx_pick(D.s, sslot, win, bx, by, bz, qx, qy, qz, rows, pk);
+                r = make_uint4(bd2, (uint32_t)(pk.ex + 128) | ((uint32_t)(pk.ey + 128) << 8) | ((uint32_t)(pk.ez + 128) << 16), pk.idx, pk.rgb);
+            }
+            vres[lane] = r;
+            const unsigned und = __ballot_sync(full, active && !done);
+            if (und) {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(D.todo_count, (uint32_t)__popc(und));
+                pos = __shfl_sync(full, pos, 0);
+                if (active && !done) D.todo[pos + __popc(und & ((1u << lane) - 1u))] = t;
+            }
+            // ---- epilogue: lane = point of these voxels ----
+            const uint32_t g0 = __ldg(D.q.gstart + tb), g1 = __ldg(D.q.gstart + min(tb + 32u, t1));
+            __syncwarp();
+            for (uint32_t gb = g0; gb < g1; gb += 32) {
+                const uint32_t g = gb + lane;
+                if (g < g1) {
+                    const uint4 e = __ldg(D.q.pts + g);          // {rgb, idx, rank, -}
+                    const uint4 v = vres[e.z - tb];
+                    if (v.x != kVxNone)
+                        vx_epilogue(P, D, e.y, e.x, v.x, (int)(v.y & 0xffu) - 128, (int)((v.y >> 8) & 0xffu) - 128,
+                                    (int)((v.y >> 16) & 0xffu) - 128, v.z, v.w, acc);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    BlockPartial r;
+    vx_warp_record(acc, D.flags, r);
+    if (lane == 0) P.partials[D.rec_off + lb] = r;
+}
+
+// Undecided voxels: one WARP each.  The lanes share the 125 bricks of rings 0..2 around the query
+// (directory look-up + row scan), the best (d2, index) is reduced with shuffles; an answer closer
+// than 17 voxels is certified (everything unvisited is at least that far), the rest goes to the
+// pencil search.  Results land in res[] / pendbits[]; vx_pending_kernel reduces them in a fixed order.
+__global__ void __launch_bounds__(128)
+vx_general_kernel(const __grid_constant__ VxParams P) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int d = 0; d < P.ndirs; ++d) {
+        const VxDir& D = P.dir[d];
+        const uint32_t ntodo = *D.todo_count;
+        for (uint32_t w = gwarp; w < ntodo; w += nwarps) {
+            const uint32_t t = D.todo[w];
+            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(D.q.recs + t));
+            const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+            const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
+            VxHit h;
+            h.d2 = kVxNone; h.idx = kVxNone; h.rgb = 0; h.rank = kVxNone; h.cx = h.cy = h.cz = 0;
+            for (int b = lane; b < 125; b += 32) {
+                const int bx = qbx + b % 5 - 2, by = qby + (b / 5) % 5 - 2, bz = qbz + b / 25 - 2;
+                const int gx = vx_gap(qx, bx << 5, (bx << 5) + 31), gy = vx_gap(qy, by << 3, (by << 3) + 7), gz = vx_gap(qz, bz << 3, (bz << 3) + 7);
+                if ((uint32_t)(gx * gx + gy * gy + gz * gz) > h.d2) continue;
+                const int slot = vx_slot(D.s, bx, by, bz);
+                if (slot >= 0) vx_scan_brick(D.s, (uint32_t)slot, bx, by, bz, qx, qy, qz, h);
+            }
+            unsigned long long key = ((unsigned long long)h.d2 << 32) | h.idx;
+            unsigned long long best = key;
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(full, best, o);
+                best = other < best ? other : best;
+            }
+            const int src = __ffs((int)__ballot_sync(full, key == best)) - 1;
+            const uint32_t rank = __shfl_sync(full, h.rank, src);
+            const uint32_t bd2 = (uint32_t)(best >> 32);
+            if (lane == 0) {
+                if (bd2 < 289u) {
+                    P.res[t] = make_uint2(bd2, rank);
+                    atomicOr(P.pendbits + (t >> 5), 1u << (t & 31u));
+                } else {
+                    D.far[atomicAdd(D.far_count, 1u)] = t;
+                }
+            }
+        }
+    }
+}
+
+// What the brick rings could not certify (the nearest point is tens of voxels away: disjoint
+// clouds, isolated outliers): exact pencil search, which skips empty space by its row table.
+__global__ void __launch_bounds__(128)
+vx_far_kernel(const __grid_constant__ VxParams P) {
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int d = 0; d < P.ndirs; ++d) {
+        const VxDir& D = P.dir[d];
+        const uint32_t nfar = *D.far_count;
+        for (uint32_t w = gtid; w < nfar; w += stride) {
+            const uint32_t t = D.far[w];
+            const uint4 qr = __ldg(D.q.recs + t);
+            KInt::Q q;
+            q.x = (int)(qr.x & 0xffffu); q.y = (int)(qr.x >> 16); q.z = (int)qr.y;
+            Best1<KInt> best;
+            best.init();
+            search<KInt>(D.sgrid, D.srow_start, D.srecs, q, best);
+            P.res[t] = make_uint2(best.d2, best.pos | 0x80000000u);      // top bit: position in the pencil records
+            atomicOr(P.pendbits + (t >> 5), 1u << (t & 31u));
+        }
+    }
+}
+
+// Epilogue of the pending voxels.  gridDim = (G, ndirs): block (b, d) owns a fixed chunk of the
+// ranked positions and a fixed thread <-> position mapping, so its record is reproducible.
+constexpr int kVxPendThreads = 128;
+__global__ void __launch_bounds__(kVxPendThreads)
+vx_pending_kernel(const __grid_constant__ VxParams P) {
+    const int d = blockIdx.y;
+    const VxDir& D = P.dir[d];
+    const uint32_t nwords = (D.q.n_total + 31u) / 32u;
+    const uint32_t per = (nwords + gridDim.x - 1) / gridDim.x;
+    const uint32_t w0 = blockIdx.x * per, w1 = min(w0 + per, nwords);
+    const uint32_t r0 = vx_ranked_begin(D.q), nd = vx_ndistinct(D.q);
+    VxAcc acc;
+    acc.init();
+    for (uint32_t w = w0 + threadIdx.x; w < w1; w += kVxPendThreads) {
+        uint32_t bits = P.pendbits[w];
+        while (bits) {
+            const uint32_t t = w * 32u + (uint32_t)(__ffs((int)bits) - 1);
+            bits &= bits - 1u;
+            if (t - r0 >= nd) continue;               // a voxel of the other cloud
+            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(D.q.recs + t));
+            const uint2 res = P.res[t];
+            uint4 nr;
+            if (res.y & 0x80000000u) {                // pencil record {xy, z, idx, rgb}
+                nr = __ldg(D.srecs + (res.y & 0x7fffffffu));
+                const uint32_t i = nr.z; nr.z = nr.w; nr.w = i;
+            } else {
+                nr = __ldg(D.s.recs + res.y);
+            }
+            const int ex = (int)(qr.x & 0xffffu) - (int)(nr.x & 0xffffu), ey = (int)(qr.x >> 16) - (int)(nr.x >> 16), ez = (int)qr.y - (int)nr.y;
+            const uint32_t g0 = __ldg(D.q.gstart + t), g1 = __ldg(D.q.gstart + t + 1);
+            for (uint32_t g = g0; g < g1; ++g) {      // every point of the voxel
+                const uint4 e = __ldg(D.q.pts + g);
+                vx_epilogue(P, D, e.y, e.x, res.x, ex, ey, ez, nr.w, nr.z, acc);
+            }
+        }
+    }
+    BlockPartial r;
+    vx_warp_record(acc, D.flags, r);
+    __shared__ BlockPartial sm[kVxPendThreads / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockPartial o = sm[0];
+        for (int w = 1; w < kVxPendThreads / 32; ++w) partial_merge(o, sm[w]);
+        P.partials[D.rec_off + D.q.nblk + P.pend_rec + blockIdx.x] = o;
+    }
+}
+
+}  // namespace pccm

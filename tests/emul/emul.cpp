@@ -149,3 +149,183 @@ extern "C" int emul_knn_self(int kind, const double* pts, int64_t n, int k, doub
     else knn_impl<KF64>(pts, n, k, cell, idx, d2, normals);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// occupancy-brick path (pccm_vox.cuh): the same per-point build functions and per-query search
+// functions the sm_100a kernels call, stepped sequentially in kernel order.
+// ------------------------------------------------------------------------------------------
+#include "../../open_pcc_metric_b200/csrc/pccm_vox.cuh"
+
+struct VoxPair {
+    std::vector<uint32_t> dirbits, dirpre, masks, base, gstart;
+    std::vector<uint4> pts;
+    std::vector<uint16_t> pre;
+    std::vector<uint4> recs;
+    VoxView view[2];
+};
+
+static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
+    VoxDims g[2];
+    uint32_t ndirw[2], dir_off[2];
+    for (int c = 0; c < 2; ++c) {
+        int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {0, 0, 0};
+        for (int64_t i = 0; i < n[c]; ++i)
+            for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], (int)pts[c][3 * i + a]); mx[a] = std::max(mx[a], (int)pts[c][3 * i + a]); }
+        g[c].obx = mn[0] >> 5; g[c].oby = mn[1] >> 3; g[c].obz = mn[2] >> 3;
+        g[c].nbx = (mx[0] >> 5) - g[c].obx + 1; g[c].nby = (mx[1] >> 3) - g[c].oby + 1; g[c].nbz = (mx[2] >> 3) - g[c].obz + 1;
+        const uint64_t bits = (uint64_t)g[c].nbx * g[c].nby * g[c].nbz;
+        if (bits > (1ull << 30)) return false;       // the library keeps such pairs on the pencil path
+        ndirw[c] = (uint32_t)((bits + 31) / 32);
+    }
+    dir_off[0] = 0; dir_off[1] = ndirw[0];
+    const uint32_t nw = ndirw[0] + ndirw[1], n_total = (uint32_t)(n[0] + n[1]);
+    V.dirbits.assign(nw, 0); V.dirpre.assign(nw + 1, 0);
+    auto coords = [&](int c, int64_t i, int& x, int& y, int& z) { x = (int)pts[c][3 * i]; y = (int)pts[c][3 * i + 1]; z = (int)pts[c][3 * i + 2]; };
+    for (int c = 0; c < 2; ++c)                                   // vx_mark_kernel
+        for (int64_t i = 0; i < n[c]; ++i) { int x, y, z; coords(c, i, x, y, z); vx_mark_point(V.dirbits.data() + dir_off[c], vx_key(g[c], x, y, z)); }
+    uint32_t run = 0;                                             // vx_dircount_kernel + exclusive scan
+    for (uint32_t w = 0; w < nw; ++w) { V.dirpre[w] = run; run += (uint32_t)vx_popc(V.dirbits[w]); }
+    V.dirpre[nw] = run;
+    const uint32_t nblk0 = V.dirpre[ndirw[0]], nblk = run;
+    V.masks.assign((size_t)nblk * kVxRows, 0); V.pre.assign((size_t)nblk * kVxRows, 0); V.base.assign(nblk + 1, 0);
+    V.recs.resize(n_total);
+    memset(V.recs.data(), 0xff, (size_t)n_total * sizeof(uint4));   // (not needed: every word is written below)
+    V.gstart.assign((size_t)n_total + 1, 0); V.pts.resize(n_total);
+    for (int c = 0; c < 2; ++c)                                   // vx_fill_kernel
+        for (int64_t i = 0; i < n[c]; ++i) {
+            int x, y, z; coords(c, i, x, y, z);
+            vx_fill_point(V.masks.data(), vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z)), x, y, z);
+        }
+    run = 0;                                                      // vx_brickpre_kernel + exclusive scan
+    for (uint32_t s = 0; s < nblk; ++s) {
+        uint32_t in = 0;
+        for (int r = 0; r < kVxRows; ++r) { V.pre[(size_t)s * kVxRows + r] = (uint16_t)in; in += (uint32_t)vx_popc(V.masks[(size_t)s * kVxRows + r]); }
+        V.base[s] = run; run += in;
+    }
+    V.base[nblk] = run;
+    std::vector<VxCounted> counted[2];
+    std::vector<int64_t> order[2];                                 // arrival order of the atomics: odd indices downwards, then even ones upwards
+    for (int c = 0; c < 2; ++c) {
+        for (int64_t i = n[c]; i-- > 0;) if (i & 1) order[c].push_back(i);
+        for (int64_t i = 0; i < n[c]; ++i) if (!(i & 1)) order[c].push_back(i);
+        counted[c].resize(n[c]);
+        for (int64_t i : order[c]) {                               // vx_count_kernel
+            int x, y, z; coords(c, i, x, y, z);
+            const uint32_t slot = vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z));
+            counted[c][i] = vx_count_point(V.masks.data(), V.pre.data(), V.base.data(), V.recs.data(), V.gstart.data(), slot, x, y, z);
+        }
+    }
+    run = 0;                                                       // exclusive scan of the multiplicities
+    for (uint32_t v = 0; v <= n_total; ++v) { const uint32_t m = V.gstart[v]; V.gstart[v] = run; run += m; }
+    for (int c = 0; c < 2; ++c)                                    // vx_scatter_kernel
+        for (int64_t i = 0; i < n[c]; ++i) vx_scatter_point(V.gstart.data(), V.pts.data(), counted[c][i], 0u, (uint32_t)i);
+    for (uint32_t v = 0; v < V.base[nblk]; ++v)                    // vx_group_kernel + vx_longgroup_kernel
+        if (vx_group_finish(V.gstart.data(), V.pts.data(), V.recs.data(), v))
+            std::sort(V.pts.begin() + V.gstart[v], V.pts.begin() + V.gstart[v + 1], [](const uint4& p, const uint4& q) { return p.y < q.y; });
+    for (int c = 0; c < 2; ++c) {
+        VoxView& W = V.view[c];
+        W.g = g[c]; W.dirbits = V.dirbits.data() + dir_off[c]; W.dirpre = V.dirpre.data() + dir_off[c];
+        W.masks = V.masks.data(); W.pre = V.pre.data(); W.base = V.base.data(); W.recs = V.recs.data();
+        W.gstart = V.gstart.data(); W.pts = V.pts.data();
+        W.slot0 = c ? nblk0 : 0; W.nblk = c ? nblk - nblk0 : nblk0; W.n = (uint32_t)n[c];
+        W.nblk_total = nblk; W.n_total = n_total;
+    }
+    return true;
+}
+
+// stats: [0] staged-decided (inner rows only), [1] staged-decided (with outer rows), [2] undecided, [3] tail,
+// [4] left to the pencil search.  Returns 1 when the brick grid exceeds the directory budget.
+extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t ns, int max_ring, int32_t* idx, double* d2, int64_t* stats) {
+    const double* pts[2] = {q, s};
+    const int64_t n[2] = {nq, ns};
+    VoxPair V;
+    if (!vox_build(pts, n, V)) return 1;
+    Index<KInt> pencil;
+    pencil.build(s, ns, 2.0);
+    const VoxView& Q = V.view[0];
+    const VoxView& S = V.view[1];
+    for (int k = 0; k < 5; ++k) stats[k] = 0;
+    for (int64_t i = 0; i < nq; ++i) { idx[i] = -2; d2[i] = -1; }
+    std::vector<uint32_t> todo;
+    int order_errors = 0;
+    // every point of the voxel at ranked position t gets the voxel's answer
+    auto assign = [&](uint32_t t, uint32_t nidx, uint32_t nd2) {
+        const uint4 qr = Q.recs[t];
+        uint32_t last = 0;
+        for (uint32_t gi = Q.gstart[t]; gi < Q.gstart[t + 1]; ++gi) {
+            const uint4 e = Q.pts[gi];
+            if (e.z != t || (gi > Q.gstart[t] && e.y <= last) || (gi == Q.gstart[t] && e.y != qr.w) || idx[e.y] != -2) ++order_errors;
+            last = e.y;
+            idx[e.y] = (int32_t)nidx; d2[e.y] = (double)nd2;
+            if (gi > Q.gstart[t]) stats[3]++;
+        }
+    };
+    // vx_query_kernel: one "warp" per query brick
+    for (uint32_t lb = 0; lb < Q.nblk; ++lb) {
+        const uint32_t slot = Q.slot0 + lb, t0 = Q.base[slot], t1 = Q.base[slot + 1];
+        const uint4 first = Q.recs[t0];
+        const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+        int sslot[27];
+        bool any_brick = false;
+        for (int l = 0; l < 27; ++l) { sslot[l] = vx_slot(S, bx + l % 3 - 1, by + (l / 3) % 3 - 1, bz + l / 9 - 1); any_brick |= sslot[l] >= 0; }
+        uint2 win[kVxRegRows];
+        if (any_brick) for (int r = 0; r < kVxRegRows; ++r) win[r] = vx_stage_row(S, sslot, r);
+        for (uint32_t tb = t0; tb < t1; tb += 32) {
+            uint32_t bd2[32], rows[32];
+            bool done[32], need_outer = false;
+            const uint32_t cnt = std::min<uint32_t>(32, t1 - tb);
+            for (uint32_t l = 0; l < cnt; ++l) {
+                const uint4 qr = Q.recs[tb + l];
+                bd2[l] = kVxNone; rows[l] = 0; done[l] = false;
+                if (any_brick) {
+                    vx_rows_inner(win, (int)(qr.x & 0xffffu) & 31, (int)((qr.x >> 16) & 7) + 2, (int)(qr.y & 7) + 2, bd2[l], rows[l]);
+                    done[l] = bd2[l] < 4u;
+                    if (!done[l]) need_outer = true;
+                }
+            }
+            for (uint32_t l = 0; l < cnt; ++l) {
+                const uint4 qr = Q.recs[tb + l];
+                const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+                const bool inner = done[l];
+                if (any_brick && need_outer) {       // the whole warp runs the outer rows
+                    vx_rows_outer(win, qx & 31, (qy & 7) + 2, (qz & 7) + 2, bd2[l], rows[l]);
+                    done[l] = bd2[l] < 9u;
+                    if (inner && !done[l]) return -10;   // outer rows must never worsen a decided query
+                }
+                if (done[l]) {
+                    VxPick pk;
+                    vx_pick(S, sslot, win, bx, by, bz, qx, qy, qz, rows[l], pk);
+                    assign(tb + l, pk.idx, bd2[l]);
+                    if ((uint32_t)(pk.ex * pk.ex + pk.ey * pk.ey + pk.ez * pk.ez) != bd2[l]) return -11;
+                    const uint4 nr = S.recs[pk.rank];
+                    if (nr.w != pk.idx || qx - (int)(nr.x & 0xffffu) != pk.ex || qy - (int)(nr.x >> 16) != pk.ey || qz - (int)nr.y != pk.ez) return -12;
+                    stats[inner ? 0 : 1]++;
+                } else {
+                    todo.push_back(tb + l);
+                }
+            }
+        }
+    }
+    // vx_general_kernel: undecided voxels
+    stats[2] = (int64_t)todo.size();
+    for (uint32_t t : todo) {
+        const uint4 qr = Q.recs[t];
+        VxHit h;
+        if (vx_search_general(S, (int)(qr.x & 0xffffu), (int)(qr.x >> 16), (int)qr.y, h, max_ring)) {
+            const uint4 nr = S.recs[h.rank];
+            if (nr.w != h.idx) return -13;
+            assign(t, h.idx, h.d2);
+        } else {                                    // vx_far_kernel
+            KInt::Q qq; qq.x = (int)(qr.x & 0xffffu); qq.y = (int)(qr.x >> 16); qq.z = (int)qr.y;
+            Best1<KInt> best;
+            best.init();
+            search<KInt>(pencil.g, pencil.row_start.data(), pencil.recs.data(), qq, best);
+            assign(t, best.idx, best.d2);
+            stats[4]++;
+        }
+    }
+    if (order_errors) return -15;
+    if ((uint32_t)stats[3] != Q.n - vx_ndistinct(Q) || Q.gstart[Q.slot0 + vx_ndistinct(Q)] != Q.n) return -16;
+    for (int64_t i = 0; i < nq; ++i) if (idx[i] == -2) return -14;   // every query exactly once
+    return 0;
+}

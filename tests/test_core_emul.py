@@ -143,3 +143,93 @@ fcloud = st.lists(st.tuples(fl, fl, fl), min_size=1, max_size=40)
 @given(a=fcloud, b=fcloud, cell=st.sampled_from([0.05, 1.0, 30.0]), kind=st.sampled_from([KF32, KF64]))
 def test_property_float_nn(a, b, cell, kind):
     _check_nn(kind, np.array(a, dtype=float), np.array(b, dtype=float), cell)
+
+
+# ---- occupancy-brick path (pccm_vox.cuh): build functions + staged / general search ----------
+def emul_vox_nn(q, s, max_ring=2):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q))
+    stats = np.zeros(5, np.int64)
+    rc = _L.emul_vox_nn(_p(q), ctypes.c_int64(len(q)), _p(s), ctypes.c_int64(len(s)), ctypes.c_int(max_ring), _p(idx), _p(d2), _p(stats))
+    assert rc in (0, 1), f"internal consistency check {rc} failed"
+    return (idx, d2, stats) if rc == 0 else (None, None, None)
+
+
+def _check_vox(q, s, max_ring=2):
+    oi, od = cnn.knn(s, q, 1)
+    i, d, stats = emul_vox_nn(q, s, max_ring)
+    assert stats is not None, "brick grid over the directory budget"
+    assert np.array_equal(d, od[:, 0])
+    assert np.array_equal(i, oi[:, 0])
+    return stats
+
+
+def test_vox_dense_ties_duplicates_outliers():
+    rng = np.random.default_rng(1)
+    A = rng.integers(0, 64, (3000, 3)).astype(float)
+    B = rng.integers(0, 64, (2000, 3)).astype(float)
+    B[:5] += 300                      # isolated far points: the general search must reach them
+    B = np.concatenate([B, B[:50]])   # duplicates: smallest index wins, the others form the tail
+    sa = _check_vox(A, B)
+    sb = _check_vox(B, A)
+    assert sa[0] > 0 and sa[1] > 0 and sa[2] > 0      # every stage of the search is exercised
+    assert sb[3] >= 50                                 # the duplicate tail is queried too
+
+
+def test_vox_lattice_pair_is_decided_by_the_staged_rows():
+    rng = np.random.default_rng(5)
+    A = np.unique(rng.integers(100, 140, (4000, 3)), axis=0).astype(float)
+    J = rng.integers(-1, 2, A.shape) * (rng.random(A.shape) < 0.25)
+    B = np.unique((np.round(A / 2) * 2 + J).clip(0, 1023), axis=0)
+    rng.shuffle(A)
+    rng.shuffle(B)
+    for q, s in ((A, B), (B, A)):
+        stats = _check_vox(q, s)
+        assert stats[3] == 0 and stats[2] < 0.05 * len(q)     # (rounding + jitter can move a point 2 voxels per axis)
+
+
+def test_vox_extremes_and_far_apart():
+    A = np.array([[0, 0, 0], [4095, 4095, 4095], [0, 4095, 0], [2000, 1, 2]], dtype=float)
+    B = np.array([[4095, 0, 4095], [1, 1, 1], [4094, 4095, 4095]], dtype=float)
+    for ring in (0, 2, 1000):                 # 1000: the brick rings finish every query themselves
+        _check_vox(A, B, ring)
+        _check_vox(B, A, ring)
+    _check_vox(A, A[:1])
+    _check_vox(A[:1], A)
+    full = np.array([[0, 0, 0], [32767, 32767, 32767]], dtype=float)
+    assert emul_vox_nn(full, full)[2] is None  # 15-bit cube: over the directory budget -> pencil path only
+    thin = np.array([[0, 0, 0], [32767, 900, 900], [31000, 5, 7]], dtype=float)
+    _check_vox(thin, thin[::-1].copy())        # one long axis fits
+    rng = np.random.default_rng(6)
+    P = rng.integers(0, 200, (2000, 3)).astype(float)
+    s = _check_vox(P, P + [0, 250, 0])         # disjoint clouds: everything ends in the pencil search
+    assert s[4] > 0
+    s = _check_vox(P, P + [0, 250, 0], 1000)
+    assert s[4] == 0
+    _check_vox(P, P[::-1].copy())              # identical clouds: d2 = 0 everywhere
+    s = _check_vox(np.tile([[3.0, 3, 3]], (100, 1)), np.tile([[3.0, 4, 3]], (40, 1)))   # one voxel each, long groups
+    assert s[3] == 99
+    W = rng.integers(0, 4096, (2000, 3)).astype(float)
+    _check_vox(W, (W + rng.integers(-3, 4, W.shape)).clip(0, 4095))
+    _check_vox(W, rng.integers(0, 4096, (500, 3)).astype(float))   # sparse: rings, then pencils
+
+
+def test_vox_window_edges():
+    """neighbours exactly 15 / 16 / 17 voxels away along x and across brick borders in y, z"""
+    base = np.array([[31, 7, 7], [32, 8, 8], [0, 0, 0], [63, 15, 16]], dtype=float)
+    for dx in (-17, -16, -15, -2, -1, 1, 2, 15, 16, 17):
+        for dy, dz in ((0, 0), (1, 0), (0, -1), (2, 2), (-2, 1), (3, 0)):
+            S = (base + 40 + [dx, dy, dz])
+            Q = base + 40
+            _check_vox(Q, S)
+            _check_vox(S, Q)
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=list(__import__('hypothesis').HealthCheck))
+@given(a=cloud, b=cloud, off=st.tuples(st.integers(0, 3000), st.integers(0, 3000), st.integers(0, 3000)))
+def test_property_vox_nn(a, b, off):
+    A = np.array(a, dtype=float) + np.array(off, dtype=float)
+    B = np.array(b, dtype=float) + np.array(off, dtype=float)
+    _check_vox(A, B)

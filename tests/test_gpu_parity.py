@@ -177,14 +177,19 @@ def test_joint_build_equals_separate_builds(ctx, kind):
             k = max(a.info().data_kind, b.info().data_kind)
             a.build_index(0.0, k); b.build_index(0.0, k)
         r = ctx.pair_eval(a, b, N.EVAL_COLOR, np.eye(3), 255.0)
-        outs.append((ctx.nn(a, b), ctx.nn(b, a), b.knn_self(5), bytes(r)))
+        outs.append((ctx.nn(a, b), ctx.nn(b, a), b.knn_self(5), r))
         b.estimate_normals(12)
         outs[-1] += (b.get_normals(),)
         a.close(); b.close()
     s, j = outs
     for x, y in ((s[0], j[0]), (s[1], j[1]), (s[2], j[2])):
         assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
-    assert s[3] == j[3]
+    for d in range(2):      # integer pairs built jointly take the brick path: same values, another summation order
+        x, y = s[3].dir[d], j[3].dir[d]
+        assert (x.n, x.sum_d1_u64, x.sum_d1, x.max_d1) == (y.n, y.sum_d1_u64, y.sum_d1, y.max_d1)
+        for c in range(3):
+            assert x.color_max[c] == y.color_max[c]
+            assert x.color_sum[c] == y.color_sum[c] if kind != "int" else np.isclose(x.color_sum[c], y.color_sum[c], rtol=1e-13, atol=0)
     assert np.array_equal(s[4], j[4])
     oi, od = cnn.knn(B, A, 1)
     assert np.array_equal(j[0][0], oi[:, 0]) and np.array_equal(j[0][1], od[:, 0])

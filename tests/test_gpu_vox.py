@@ -1,0 +1,147 @@
+"""GPU tier: the occupancy-brick path (pccm_vox*.cuh) of integer pairs against the brute-force C
+oracle and against the pencil path of the same library (PCCM_VOX=0) -- staged bit-scan search,
+general search, pencil fallback for far queries, duplicate tails, rank slices, determinism."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cnn
+
+pytestmark = pytest.mark.gpu
+
+YUV = np.array([[0.25, 0.5, 0.25], [1, 0, -1], [-0.5, 1, -0.5]])
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    from open_pcc_metric_b200 import _native as N
+    vox = N.Context(0)
+    os.environ["PCCM_VOX"] = "0"
+    try:
+        pencil = N.Context(0)
+    finally:
+        del os.environ["PCCM_VOX"]
+    yield vox, pencil
+    vox.close()
+    pencil.close()
+
+
+def _attrs(rng, n):
+    col = rng.integers(0, 256, (n, 3)).astype(np.float64) / 255.0
+    nrm = rng.normal(0, 1, (n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    return col, nrm
+
+
+def _cases():
+    from open_pcc_metric_b200.synth import synth_pair
+    rng = np.random.default_rng(77)
+    out = {}
+    A, B = synth_pair(9, 60000, 11)
+    out["surface"] = (A.points, B.points)
+    P = rng.integers(0, 64, (5000, 3)).astype(np.float64)
+    Q = rng.integers(0, 64, (4000, 3)).astype(np.float64)
+    Q[:7] += 400
+    out["dense_dups_outliers"] = (np.concatenate([P, P[:300], P[:100]]), np.concatenate([Q, Q[-200:]]))
+    S = rng.integers(0, 300, (6000, 3)).astype(np.float64)
+    out["far_apart"] = (S, S + [0, 330, 40])
+    out["sparse"] = (rng.integers(0, 4096, (3000, 3)).astype(np.float64), rng.integers(0, 4096, (2500, 3)).astype(np.float64))
+    L = np.unique(rng.integers(200, 260, (20000, 3)), axis=0).astype(np.float64)
+    out["lattice"] = (L, np.unique(np.round(L / 4) * 4, axis=0))
+    out["one_point_each"] = (np.array([[5.0, 6, 7]]), np.array([[900.0, 2, 40]]))
+    out["same_voxel_only"] = (np.tile([[3.0, 3, 3]], (700, 1)), np.tile([[3.0, 4, 3]], (40, 1)))
+    return out
+
+
+CASES = None
+
+
+def _case(name):
+    global CASES
+    if CASES is None:
+        CASES = _cases()
+    return CASES[name]
+
+
+NAMES = ["surface", "dense_dups_outliers", "far_apart", "sparse", "lattice", "one_point_each", "same_voxel_only"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_vox_nn_equals_oracle(ctxs, name):
+    vox, _ = ctxs
+    A, B = _case(name)
+    a, b = vox.cloud(A), vox.cloud(B)
+    vox.build_pair(a, b)
+    for q, s, Q, S in ((a, b, A, B), (b, a, B, A)):
+        idx, d2 = vox.nn(q, s)
+        oi, od = cnn.knn(S, Q, 1)
+        assert np.array_equal(d2, od[:, 0]), name
+        assert np.array_equal(idx, oi[:, 0]), name
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_vox_pair_eval_equals_pencil_path(ctxs, name, mode):
+    """every fused quantity and the per-point products, both normal modes"""
+    from open_pcc_metric_b200 import _native as N
+    A, B = _case(name)
+    rng = np.random.default_rng(5)
+    n = min(len(A), len(B))          # reference normal indexing needs equal lengths (quirk Q1)
+    A, B = A[:n], B[:n]
+    ca, na = _attrs(rng, n)
+    cb, nb = _attrs(rng, n)
+    flags = N.EVAL_D2 | N.EVAL_COLOR | N.EVAL_PERPOINT
+    res = []
+    for ctx in ctxs:
+        a, b = ctx.cloud(A, ca, na), ctx.cloud(B, cb, nb)
+        ctx.build_pair(a, b)
+        r = ctx.pair_eval(a, b, flags, YUV, 1.0, mode)
+        pp = [(ctx.pair_get(N.GET_IDX, d, n), ctx.pair_get(N.GET_D2, d, n)) for d in range(2)]
+        res.append((r, pp, ctx.timings()))
+        a.close(); b.close()
+    (rv, pv, tv), (rp, pq, _) = res
+    for d in range(2):
+        assert np.array_equal(pv[d][0], pq[d][0]) and np.array_equal(pv[d][1], pq[d][1]), (name, d)
+        x, y = rv.dir[d], rp.dir[d]
+        assert (x.n, x.n_total, x.sum_d1_u64, x.max_d1, x.max_d2, x.d2_valid) == (y.n, y.n_total, y.sum_d1_u64, y.max_d1, y.max_d2, y.d2_valid)
+        assert x.sum_d1_u64 == int(pv[d][1].sum())
+        assert np.isclose(x.sum_d2, y.sum_d2, rtol=1e-12, atol=0)
+        for c in range(3):
+            assert np.isclose(x.color_sum[c], y.color_sum[c], rtol=1e-12, atol=0)
+            assert x.color_max[c] == y.color_max[c]
+    if name == "far_apart":
+        assert tv["vox_far"] > 0
+    if name == "dense_dups_outliers":
+        assert tv["vox_tail"] > 0 and tv["vox_undecided"] > 0
+
+
+def test_vox_rank_slices_add_up_and_are_deterministic(ctxs):
+    from open_pcc_metric_b200 import _native as N
+    vox, _ = ctxs
+    A, B = _case("dense_dups_outliers")
+    n = min(len(A), len(B))
+    A, B = A[:n], B[:n]
+    rng = np.random.default_rng(6)
+    ca, na = _attrs(rng, n)
+    cb, nb = _attrs(rng, n)
+    outs = []
+    for rep in range(3):
+        a, b = vox.cloud(A, ca, na), vox.cloud(B, cb, nb)
+        vox.build_pair(a, b)
+        full = vox.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV)
+        outs.append(bytes(full))
+        if rep == 0:
+            for world in (2, 3, 7):
+                parts = [vox.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV, rank=r, world=world) for r in range(world)]
+                for d in range(2):
+                    assert sum(p.dir[d].n for p in parts) == full.dir[d].n == n
+                    assert sum(p.dir[d].sum_d1_u64 for p in parts) == full.dir[d].sum_d1_u64
+                    assert max(p.dir[d].max_d1 for p in parts) == full.dir[d].max_d1
+                    assert max(p.dir[d].max_d2 for p in parts) == full.dir[d].max_d2
+                    assert np.isclose(sum(p.dir[d].sum_d2 for p in parts), full.dir[d].sum_d2, rtol=1e-12)
+                    for c in range(3):
+                        assert np.isclose(sum(p.dir[d].color_sum[c] for p in parts), full.dir[d].color_sum[c], rtol=1e-12)
+        a.close(); b.close()
+    assert outs[0] == outs[1] == outs[2]     # duplicate tails and undecided queries included
