@@ -102,7 +102,8 @@ typedef struct pccm_timings {
     double upload_ms, stats_ms, keys_ms, sort_ms, table_ms, reorder_ms;
     double query_ms, finalize_ms, knn_ms;
     double vox_build_ms;       /* occupancy-brick index of integer pairs */
-    double vox_tail_ms;        /* general search + epilogue of the queries the staged search left undecided */
+    double vox_tail_ms;        /* brick-ring (and pencil) search of the voxels the staged search left undecided */
+    double vox_epilogue_ms;    /* per-point epilogue kernel of the brick path (D1 / D2 / colour + reduction records) */
     int64_t query_launches, knn_launches;
     int64_t total_launches;    /* kernels of this library (hand-written, sm_100a) */
     int64_t library_launches;  /* CUB device-wide calls (radix sort passes, scans) */

@@ -53,7 +53,7 @@ class PairResult(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("upload_ms", "stats_ms", "keys_ms", "sort_ms", "table_ms",
                                            "reorder_ms", "query_ms", "finalize_ms", "knn_ms",
-                                           "vox_build_ms", "vox_tail_ms")] + \
+                                           "vox_build_ms", "vox_tail_ms", "vox_epilogue_ms")] + \
                [(k, C.c_int64) for k in ("query_launches", "knn_launches", "total_launches", "library_launches",
                                          "vox_undecided", "vox_far", "vox_tail")]
 

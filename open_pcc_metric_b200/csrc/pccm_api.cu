@@ -571,6 +571,12 @@ static int sort_pairs(pccm_ctx* ctx, KeyT* keys_in, KeyT* keys_out, uint32_t* va
 }
 
 static int exclusive_scan(pccm_ctx* ctx, uint32_t* data, size_t count) {
+    if (count <= kScanSmallMax) {
+        scan_small_kernel<<<1, kScanSmallThreads, 0, ctx->stream>>>(data, (uint32_t)count);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        return PCCM_OK;
+    }
     const uint32_t nblocks = (uint32_t)((count + kScanTile - 1) / kScanTile);
     uint32_t* sums = nullptr;
     CK(dalloc(ctx, &sums, (size_t)nblocks));
@@ -963,8 +969,8 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     CKV(cudaStreamSynchronize(ctx->stream));
     const uint32_t nblk0 = hcnt[0];
     B.nblk_total = hcnt[1];
-    uint2* counted = nullptr;
-    uint32_t* longq = nullptr;
+    uint2 *counted = nullptr, *packed = nullptr;
+    uint32_t *longq = nullptr, *pslot = nullptr;
     CKV(dalloc(ctx, &v->masks, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->pre, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->base, (size_t)B.nblk_total + 1));
@@ -972,12 +978,14 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     CKV(dalloc(ctx, &v->gstart, (size_t)B.n_total + 1));
     CKV(dalloc(ctx, &v->pts, (size_t)B.n_total));
     CKV(dalloc(ctx, &counted, (size_t)B.n_total));
+    CKV(dalloc(ctx, &packed, (size_t)B.n_total));
+    CKV(dalloc(ctx, &pslot, (size_t)B.n_total));
     CKV(dalloc(ctx, &longq, (size_t)B.n_total / kVxGroupSmall + 2));
     CKV(cudaMemsetAsync(v->masks, 0, (size_t)B.nblk_total * kVxRows * sizeof(uint32_t), ctx->stream));
     CKV(cudaMemsetAsync(v->gstart, 0, ((size_t)B.n_total + 1) * sizeof(uint32_t), ctx->stream));
     CKV(cudaMemsetAsync(longq, 0, sizeof(uint32_t), ctx->stream));
     B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.gstart = v->gstart; B.pts = v->pts;
-    B.counted = counted; B.longq = longq;
+    B.counted = counted; B.longq = longq; B.packed = packed; B.pslot = pslot;
     vx_fill_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
     vx_brickpre_kernel<<<(B.nblk_total + 1 + 7) / 8, 256, 0, ctx->stream>>>(B);
     ctx->tm.total_launches += 2;
@@ -994,7 +1002,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         vx_longgroup_kernel<<<64, 256, 0, ctx->stream>>>(B);
         ctx->tm.total_launches += 3;
     }
-    dfree(ctx, counted); dfree(ctx, longq);
+    dfree(ctx, counted); dfree(ctx, longq); dfree(ctx, packed); dfree(ctx, pslot);
     if (rc) return bail(rc);
     CKV(cudaGetLastError());
 #undef CKV
@@ -1195,7 +1203,9 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     CK(dalloc(ctx, &res, (size_t)n_total));
     CK(cudaMemsetAsync(todo, 0, 4 * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
-    uint32_t rec_stride = 0, nwarps = 0;
+    uint32_t rec_stride = 0, nwarps = 0, ntiles = 0;
+    uint4* vres = nullptr;
+    CK(dalloc(ctx, &vres, (size_t)n_total));
     for (int d = 0; d < ndirs; ++d) {
         VxDir& D = P.dir[d];
         D.q = v->view[qc[d]->vox_id];
@@ -1208,15 +1218,18 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         D.todo = todo + 4 + (d ? (size_t)qc[0]->n : 0);
         D.far_count = todo + 2 + d;
         D.far = todo + 4 + n_total + (d ? (size_t)qc[0]->n : 0);
-        rec_stride = std::max(rec_stride, D.q.nblk + 2u * kVxPendBlocks);
+        D.pts0 = qc[d]->vox_id ? v->view[0].n : 0u;
+        D.ntiles = (D.q.n + kVxEpiThreads - 1) / kVxEpiThreads;
+        rec_stride = std::max(rec_stride, D.ntiles + kVxPendBlocks);
         nwarps += D.q.nblk;
+        ntiles += D.ntiles;
     }
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
     CK(dalloc(ctx, &partials, (size_t)rec_stride * 2 + 1));
-    P.partials = partials; P.pendbits = pendbits; P.res = res;
+    P.partials = partials; P.pendbits = pendbits; P.res = res; P.vres = vres;
     {
         StageTimer t(ctx, &ctx->tm.query_ms, 1);
-        vx_query_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
+        vx_search_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
         ctx->tm.query_launches++;
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
@@ -1224,8 +1237,13 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     {
         StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
         vx_general_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
-        vx_pending_kernel<<<dim3(kVxPendBlocks, ndirs), kVxPendThreads, 0, ctx->stream>>>(P);
-        ctx->tm.total_launches += 2;
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+    }
+    {
+        StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 1);
+        vx_epilogue_kernel<<<ntiles, kVxEpiThreads, 0, ctx->stream>>>(P);
+        ctx->tm.total_launches++;
         CK(cudaGetLastError());
     }
     // common fold: same record layout as the pencil path
@@ -1237,14 +1255,14 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
     auto fold = [&](uint32_t pend_rounds) -> int {
         StageTimer t(ctx, &ctx->tm.finalize_ms);
-        for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = P.dir[d].q.nblk + pend_rounds * kVxPendBlocks;
+        for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = P.dir[d].ntiles + pend_rounds * kVxPendBlocks;
         finalize_kernel<<<Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream>>>(Q);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
         return PCCM_OK;
     };
-    int rc = fold(1);
+    int rc = fold(0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hcnt + 2, todo, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hcnt + 6, v->base + v->view[0].nblk_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1262,8 +1280,6 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
             D.srecs = static_cast<const uint4*>(sc[d]->recs);
             D.srow_start = sc[d]->row_start;
         }
-        P.pend_rec = kVxPendBlocks;
-        CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
         {
             StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
             vx_far_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
@@ -1271,11 +1287,11 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
             ctx->tm.total_launches += 2;
             CK(cudaGetLastError());
         }
-        rc = fold(2);
+        rc = fold(1);
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    dfree(ctx, todo); dfree(ctx, pendbits); dfree(ctx, res); dfree(ctx, partials);
+    dfree(ctx, todo); dfree(ctx, pendbits); dfree(ctx, res); dfree(ctx, partials); dfree(ctx, vres);
     return PCCM_OK;
 }
 

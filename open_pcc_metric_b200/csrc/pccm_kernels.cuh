@@ -283,6 +283,39 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t* __re
     for (int j = 0; j < kScanItems; ++j) { if (base + j < n) data[base + j] = ex; ex += v[j]; }
 }
 
+// short tables (brick directory, brick totals: <= kScanSmallMax entries): one block, one launch --
+// thread t sums its contiguous segment, the block scans the 1024 sums, thread t writes its prefixes
+constexpr int kScanSmallThreads = 1024;
+constexpr size_t kScanSmallMax = 64 * 1024;
+__global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t* __restrict__ data, uint32_t n) {
+    __shared__ uint32_t ws[kScanSmallThreads / 32];
+    const uint32_t per = (n + kScanSmallThreads - 1) / kScanSmallThreads;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += data[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = ws[lane], in = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, in, o);
+            if (lane >= o) in += u;
+        }
+        ws[lane] = in - v;
+    }
+    __syncthreads();
+    uint32_t ex = ws[warp] + incl - s;
+    for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = data[i]; data[i] = ex; ex += v; }
+}
+
 // ------------------------------------------------------------------------------------
 // joint index build of the two clouds of a pair: one key pass, ONE sort (cloud id in the top
 // key bit), one scan, one reorder -- half the launches of two separate builds

@@ -34,6 +34,8 @@ struct VoxBuild {
     uint32_t* gstart;          // [n_total + 1]: multiplicities, then (scanned) group starts
     uint4* pts;                // [n_total]
     uint2* counted;            // [n_total] scratch: {rank, arrival order} of input point i
+    uint2* packed;             // [n_total] scratch: {x | y << 16, z} of input point i (written by the fill pass)
+    uint32_t* pslot;           // [n_total] scratch: brick slot of input point i
     uint32_t* longq;           // [0] = count, [1..] = voxels whose group is longer than kVxGroupSmall
 };
 
@@ -65,7 +67,10 @@ __global__ void vx_fill_kernel(const __grid_constant__ VoxBuild B) {
     int c, x, y, z; uint32_t li;
     vx_point(B, i, c, li, x, y, z);
     const uint32_t off = B.c[c].dir_off;
-    vx_fill_point(B.masks, vx_slot_of_key(B.dirbits + off, B.dirpre + off, vx_key(B.c[c].g, x, y, z)), x, y, z);
+    const uint32_t slot = vx_slot_of_key(B.dirbits + off, B.dirpre + off, vx_key(B.c[c].g, x, y, z));
+    vx_fill_point(B.masks, slot, x, y, z);
+    B.packed[i] = make_uint2((uint32_t)x | ((uint32_t)y << 16), (uint32_t)z);   // later passes need not parse the input again
+    B.pslot[i] = slot;
 }
 
 // one warp per brick: exclusive prefix of the row popcounts, brick total -> base[slot] (scanned next)
@@ -91,11 +96,9 @@ __global__ void __launch_bounds__(256) vx_brickpre_kernel(const __grid_constant_
 __global__ void vx_count_kernel(const __grid_constant__ VoxBuild B) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n_total) return;
-    int c, x, y, z; uint32_t li;
-    vx_point(B, i, c, li, x, y, z);
-    const VoxCloudBuild& C = B.c[c];
-    const uint32_t slot = vx_slot_of_key(B.dirbits + C.dir_off, B.dirpre + C.dir_off, vx_key(C.g, x, y, z));
-    const VxCounted k = vx_count_point(B.masks, B.pre, B.base, B.recs, B.gstart, slot, x, y, z);
+    const uint2 pk = B.packed[i];
+    const VxCounted k = vx_count_point(B.masks, B.pre, B.base, B.recs, B.gstart, B.pslot[i],
+                                       (int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)pk.y);
     B.counted[i] = make_uint2(k.rank, k.ord);
 }
 
@@ -172,6 +175,8 @@ struct VxDir {
     const uint4* srecs;
     const uint32_t* srow_start;
     uint32_t rec_off;          // first reduction record of this direction
+    uint32_t pts0;             // first point of the query cloud in pts[]
+    uint32_t ntiles;           // ceil(q.n / kVxEpiThreads): reduction records of vx_epilogue_kernel
 };
 
 struct VxParams {
@@ -182,10 +187,15 @@ struct VxParams {
     double T[9];
     double color_scale;
     BlockPartial* partials;
-    uint32_t* pendbits;        // [n_total / 32 + 1] zero on entry: voxels whose result waits in res[]
-    uint2* res;                // [n_total] {d2, neighbour position} of pending voxels
-    uint32_t pend_rec;         // reduction records of vx_pending_kernel start at rec_off + q.nblk + pend_rec
+    uint4* vres;               // [n_total] by ranked position: {d2, packed (query - neighbour), neighbour idx, neighbour rgb};
+                               // d2 == kVxNone while the voxel is undecided
+    uint32_t* pendbits;        // [n_total / 32 + 1] zero on entry: voxels whose result waits in res[] (pencil round)
+    uint2* res;                // [n_total] {d2, neighbour position in the pencil records} of those voxels
 };
+
+__device__ __forceinline__ uint32_t vx_pack_e(int ex, int ey, int ez) {   // |e| <= 16 for every certified brick answer
+    return (uint32_t)(ex + 128) | ((uint32_t)(ey + 128) << 8) | ((uint32_t)(ez + 128) << 16);
+}
 
 struct VxAcc {
     unsigned long long s1;
@@ -250,20 +260,17 @@ __device__ __forceinline__ void vx_slice(const VxParams& P, const VoxView& Q, ui
     t_hi = r0 + (uint32_t)((unsigned long long)nd * (unsigned)(P.rank + 1) / (unsigned)P.world);
 }
 
-// One warp = one brick of the query cloud.  The warp stages the search cloud's occupancy rows
-// around the brick (12 x 12 rows x 64 bits, 1.1 KB) in its private slice of shared memory, then
-// takes the brick's voxels 32 at a time.  Search phase, one lane per VOXEL: bit scans over the
-// 3 x 3 (5 x 5) rows, rank look-ups only for the voxels that tie at the minimum.  Epilogue phase,
-// one lane per POINT of those 32 voxels (contiguous in pts[]; duplicated points share their voxel's
-// answer through shared memory).  One reduction record per brick at a fixed position -> float
-// sums do not depend on scheduling.
+// SEARCH.  One warp = one brick of the query cloud.  The warp stages the search cloud's occupancy
+// rows around the brick (12 x 12 rows x 64 bits, 1.1 KB) in its private slice of shared memory,
+// then takes the brick's voxels 32 at a time, one lane per voxel: bit scans over the 3 x 3 (5 x 5)
+// rows, rank look-ups only for the voxels that tie at the minimum.  Integer work only; the answer of
+// every voxel goes to vres[] (16 bytes), undecided voxels to the todo list.
 constexpr int kVxThreads = 128;
 constexpr int kVxWarps = kVxThreads / 32;
 
 __global__ void __launch_bounds__(kVxThreads)
-vx_query_kernel(const __grid_constant__ VxParams P) {
+vx_search_kernel(const __grid_constant__ VxParams P) {
     __shared__ uint2 s_win[kVxWarps][kVxRegRows];
-    __shared__ uint4 s_res[kVxWarps][32];
     __shared__ int s_slot[kVxWarps][28];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,85 +285,114 @@ vx_query_kernel(const __grid_constant__ VxParams P) {
     uint32_t t_lo, t_hi;
     vx_slice(P, D.q, t_lo, t_hi);
     const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
+    if (t0 >= t1) return;
+    uint2* win = s_win[warp];
+    int* sslot = s_slot[warp];
+    const uint2 first = __ldg(reinterpret_cast<const uint2*>(qrecs + b0));
+    const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+    int myslot = -1;
+    if (lane < 27) {
+        myslot = vx_slot(D.s, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
+        sslot[lane] = myslot;
+    }
+    const bool any_brick = __any_sync(full, myslot >= 0);
+    __syncwarp();
+    if (any_brick) {
+        for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(D.s, sslot, i);
+        __syncwarp();
+    }
+    for (uint32_t tb = t0; tb < t1; tb += 32) {
+        const uint32_t t = tb + lane;
+        const bool active = t < t1;
+        const uint2 qr = __ldg(reinterpret_cast<const uint2*>(qrecs + (active ? t : t0)));
+        const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+        uint32_t bd2 = kVxNone, rows = 0;
+        bool done = false;
+        if (any_brick) {
+            const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
+            vx_rows_inner(win, lx, ly, lz, bd2, rows);
+            done = bd2 < 4u;
+            if (__any_sync(full, active && !done)) {
+                vx_rows_outer(win, lx, ly, lz, bd2, rows);
+                done = bd2 < 9u;
+            }
+        }
+        uint4 r = make_uint4(kVxNone, 0u, 0u, 0u);
+        if (active && done) {
+            VxPick pk;
+            vx_pick(D.s, sslot, win, bx, by, bz, qx, qy, qz, rows, pk);
+            r = make_uint4(bd2, vx_pack_e(pk.ex, pk.ey, pk.ez), pk.idx, pk.rgb);
+        }
+        if (active) P.vres[t] = r;
+        const unsigned und = __ballot_sync(full, active && !done);
+        if (und) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(D.todo_count, (uint32_t)__popc(und));
+            pos = __shfl_sync(full, pos, 0);
+            if (active && !done) D.todo[pos + __popc(und & ((1u << lane) - 1u))] = t;
+        }
+    }
+}
+
+// EPILOGUE.  One thread = one query POINT, in pts[] order (grouped by voxel, so the 16-byte voxel
+// answers are read almost contiguously; duplicated points share their voxel's answer).  A block is
+// a fixed tile of kVxEpiThreads points and writes one reduction record -> float sums do not depend
+// on scheduling.  Points of voxels that are still undecided (pencil round) are skipped.
+constexpr int kVxEpiThreads = 256;
+__global__ void __launch_bounds__(kVxEpiThreads)
+vx_epilogue_kernel(const __grid_constant__ VxParams P) {
+    const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
+    const VxDir& D = P.dir[d];
+    const uint32_t tile = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
+    uint32_t t_lo, t_hi;
+    vx_slice(P, D.q, t_lo, t_hi);
+    const uint32_t g_lo = __ldg(D.q.gstart + t_lo), g_hi = __ldg(D.q.gstart + t_hi);
+    const uint32_t g = D.pts0 + tile * kVxEpiThreads + threadIdx.x;
     VxAcc acc;
     acc.init();
-    if (t0 < t1) {
-        uint2* win = s_win[warp];
-        uint4* vres = s_res[warp];
-        int* sslot = s_slot[warp];
-        const uint2 first = __ldg(reinterpret_cast<const uint2*>(qrecs + b0));
-        const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
-        int myslot = -1;
-        if (lane < 27) {
-            myslot = vx_slot(D.s, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
-            sslot[lane] = myslot;
-        }
-        const bool any_brick = __any_sync(full, myslot >= 0);
-        __syncwarp();
-        if (any_brick) {
-            for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(D.s, sslot, i);
-            __syncwarp();
-        }
-        for (uint32_t tb = t0; tb < t1; tb += 32) {
-            // ---- search: lane = voxel ----
-            const uint32_t t = tb + lane;
-            const bool active = t < t1;
-            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(qrecs + (active ? t : t0)));
-            const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
-            uint32_t bd2 = kVxNone, rows = 0;
-            bool done = false;
-            if (any_brick) {
-                const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
-                vx_rows_inner(win, lx, ly, lz, bd2, rows);
-                done = bd2 < 4u;
-                if (__any_sync(full, active && !done)) {
-                    vx_rows_outer(win, lx, ly, lz, bd2, rows);
-                    done = bd2 < 9u;
-                }
-            }
-            uint4 r = make_uint4(kVxNone, 0u, 0u, 0u);
-            if (active && done) {
-                VxPick pk;
-                vx_pick(D.s, sslot, win, bx, by, bz, qx, qy, qz, rows, pk);
-                r = make_uint4(bd2, (uint32_t)(pk.ex + 128) | ((uint32_t)(pk.ey + 128) << 8) | ((uint32_t)(pk.ez + 128) << 16), pk.idx, pk.rgb);
-            }
-            vres[lane] = r;
-            const unsigned und = __ballot_sync(full, active && !done);
-            if (und) {
-                uint32_t pos = 0;
-                if (lane == 0) pos = atomicAdd(D.todo_count, (uint32_t)__popc(und));
-                pos = __shfl_sync(full, pos, 0);
-                if (active && !done) D.todo[pos + __popc(und & ((1u << lane) - 1u))] = t;
-            }
-            // ---- epilogue: lane = point of these voxels ----
-            const uint32_t g0 = __ldg(D.q.gstart + tb), g1 = __ldg(D.q.gstart + min(tb + 32u, t1));
-            __syncwarp();
-            for (uint32_t gb = g0; gb < g1; gb += 32) {
-                const uint32_t g = gb + lane;
-                if (g < g1) {
-                    const uint4 e = __ldg(D.q.pts + g);          // {rgb, idx, rank, -}
-                    const uint4 v = vres[e.z - tb];
-                    if (v.x != kVxNone)
-                        vx_epilogue(P, D, e.y, e.x, v.x, (int)(v.y & 0xffu) - 128, (int)((v.y >> 8) & 0xffu) - 128,
-                                    (int)((v.y >> 16) & 0xffu) - 128, v.z, v.w, acc);
-                }
-            }
-            __syncwarp();
-        }
+    if (g >= g_lo && g < g_hi && g < D.pts0 + D.q.n) {
+        const uint4 e = __ldg(D.q.pts + g);            // {rgb, idx, rank, -}
+        const uint4 v = __ldg(P.vres + e.z);
+        if (v.x != kVxNone)
+            vx_epilogue(P, D, e.y, e.x, v.x, (int)(v.y & 0xffu) - 128, (int)((v.y >> 8) & 0xffu) - 128,
+                        (int)((v.y >> 16) & 0xffu) - 128, v.z, v.w, acc);
     }
     BlockPartial r;
     vx_warp_record(acc, D.flags, r);
-    if (lane == 0) P.partials[D.rec_off + lb] = r;
+    __shared__ BlockPartial sm[kVxEpiThreads / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockPartial o = sm[0];
+        for (int w = 1; w < kVxEpiThreads / 32; ++w) partial_merge(o, sm[w]);
+        P.partials[D.rec_off + tile] = o;
+    }
 }
 
-// Undecided voxels: one WARP each.  The lanes share the 125 bricks of rings 0..2 around the query
-// (directory look-up + row scan), the best (d2, index) is reduced with shuffles; an answer closer
-// than 17 voxels is certified (everything unvisited is at least that far), the rest goes to the
-// pencil search.  Results land in res[] / pendbits[]; vx_pending_kernel reduces them in a fixed order.
+// Undecided voxels: one WARP each, over the 125 bricks of rings 0..2 around the query.  Lanes look
+// the bricks up in the directory; every occupied brick is then scanned by the whole warp (lane l
+// owns rows 2l and 2l+1: one coalesced load of the 64 occupancy words), first for the minimal
+// distance only (bit scans, no record is touched), then again to fetch the index of the voxels
+// that tie at that distance.  An answer closer than 17 voxels is certified (everything unvisited is
+// at least that far) and written to vres[] before the epilogue kernel runs; the rest goes to the
+// pencil search (second round).
+__device__ __forceinline__ void vx_row_nearest(uint32_t m, int p, int& dlo, int& dhi) {
+    // distance from word coordinate p (any integer) to the nearest set bit at or below / above; 40000 when none
+    const uint32_t at_or_below = p >= 31 ? 0xFFFFFFFFu : (p < 0 ? 0u : ((2u << p) - 1u));
+    const uint32_t above = p < 0 ? 0xFFFFFFFFu : (p >= 31 ? 0u : ~((2u << p) - 1u));
+    const uint32_t ml = m & at_or_below, mh = m & above;
+    dlo = ml ? p - (31 - __clz((int)ml)) : 40000;
+    dhi = mh ? (__ffs((int)mh) - 1) - p : 40000;
+}
+
 __global__ void __launch_bounds__(128)
 vx_general_kernel(const __grid_constant__ VxParams P) {
+    __shared__ int s_slot[4][128];
+    __shared__ int s_occ[4][128];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    int* bslot = s_slot[threadIdx.x >> 5];
+    int* bocc = s_occ[threadIdx.x >> 5];
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int d = 0; d < P.ndirs; ++d) {
         const VxDir& D = P.dir[d];
@@ -366,31 +402,85 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
             const uint2 qr = __ldg(reinterpret_cast<const uint2*>(D.q.recs + t));
             const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
             const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
-            VxHit h;
-            h.d2 = kVxNone; h.idx = kVxNone; h.rgb = 0; h.rank = kVxNone; h.cx = h.cy = h.cz = 0;
-            for (int b = lane; b < 125; b += 32) {
-                const int bx = qbx + b % 5 - 2, by = qby + (b / 5) % 5 - 2, bz = qbz + b / 25 - 2;
-                const int gx = vx_gap(qx, bx << 5, (bx << 5) + 31), gy = vx_gap(qy, by << 3, (by << 3) + 7), gz = vx_gap(qz, bz << 3, (bz << 3) + 7);
-                if ((uint32_t)(gx * gx + gy * gy + gz * gz) > h.d2) continue;
-                const int slot = vx_slot(D.s, bx, by, bz);
-                if (slot >= 0) vx_scan_brick(D.s, (uint32_t)slot, bx, by, bz, qx, qy, qz, h);
-            }
-            unsigned long long key = ((unsigned long long)h.d2 << 32) | h.idx;
-            unsigned long long best = key;
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(full, best, o);
-                best = other < best ? other : best;
-            }
-            const int src = __ffs((int)__ballot_sync(full, key == best)) - 1;
-            const uint32_t rank = __shfl_sync(full, h.rank, src);
-            const uint32_t bd2 = (uint32_t)(best >> 32);
-            if (lane == 0) {
-                if (bd2 < 289u) {
-                    P.res[t] = make_uint2(bd2, rank);
-                    atomicOr(P.pendbits + (t >> 5), 1u << (t & 31u));
-                } else {
-                    D.far[atomicAdd(D.far_count, 1u)] = t;
+            __syncwarp();
+            // occupied bricks of the 5 x 5 x 5 neighbourhood, compacted: bocc[k] = brick number, bslot[k] = slot
+            int nocc = 0;
+            for (int b0 = 0; b0 < 125; b0 += 32) {
+                const int b = b0 + lane;
+                const int slot = b < 125 ? vx_slot(D.s, qbx + b % 5 - 2, qby + (b / 5) % 5 - 2, qbz + b / 25 - 2) : -1;
+                const unsigned has = __ballot_sync(full, slot >= 0);
+                if (slot >= 0) {
+                    const int k = nocc + __popc(has & ((1u << lane) - 1u));
+                    bslot[k] = slot;
+                    bocc[k] = b;
                 }
+                nocc += __popc(has);
+            }
+            __syncwarp();
+            // pass 1: minimal squared distance (four bricks in flight per step)
+            uint32_t best = kVxNone;
+            for (int k0 = 0; k0 < nocc; k0 += 4) {
+                uint2 m4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    m4[j] = k0 + j < nocc ? __ldg(reinterpret_cast<const uint2*>(D.s.masks + (size_t)bslot[k0 + j] * kVxRows) + lane) : make_uint2(0u, 0u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (k0 + j >= nocc) break;
+                    const int b = bocc[k0 + j];
+                    const int bx = qbx + b % 5 - 2, by = qby + (b / 5) % 5 - 2, bz = qbz + b / 25 - 2;
+                    const int p = qx - (bx << 5);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t m = k ? m4[j].y : m4[j].x;
+                        if (!m) continue;
+                        const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
+                        int dlo, dhi;
+                        vx_row_nearest(m, p, dlo, dhi);
+                        const int dx = dlo < dhi ? dlo : dhi;
+                        const uint32_t d2 = (uint32_t)(dx * dx + dy * dy + dz * dz);
+                        best = d2 < best ? d2 : best;
+                    }
+                }
+            }
+            best = __reduce_min_sync(full, best);
+            if (best >= 289u) {               // nothing certified within two brick rings
+                if (lane == 0) D.far[atomicAdd(D.far_count, 1u)] = t;
+                continue;
+            }
+            // pass 2: smallest original index among the voxels at that distance
+            uint32_t bidx = kVxNone, brank = kVxNone;
+            for (int k0 = 0; k0 < nocc; ++k0) {
+                const int slot = bslot[k0], b = bocc[k0];
+                const int bx = qbx + b % 5 - 2, by = qby + (b / 5) % 5 - 2, bz = qbz + b / 25 - 2;
+                const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(D.s.masks + (size_t)slot * kVxRows) + lane);
+                const int p = qx - (bx << 5);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t m = k ? m2.y : m2.x;
+                    if (!m) continue;
+                    const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
+                    int dlo, dhi;
+                    vx_row_nearest(m, p, dlo, dhi);
+                    const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
+                    if (byz + (uint32_t)(dlo * dlo) == best) {
+                        const uint32_t rank = vx_rank(D.s, (uint32_t)slot, r, (p - dlo) & 31);
+                        const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(D.s.recs + rank) + 3);
+                        if (i < bidx) { bidx = i; brank = rank; }
+                    }
+                    if (byz + (uint32_t)(dhi * dhi) == best) {
+                        const uint32_t rank = vx_rank(D.s, (uint32_t)slot, r, (p + dhi) & 31);
+                        const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(D.s.recs + rank) + 3);
+                        if (i < bidx) { bidx = i; brank = rank; }
+                    }
+                }
+            }
+            const uint32_t widx = __reduce_min_sync(full, bidx);
+            const int src = __ffs((int)__ballot_sync(full, bidx == widx)) - 1;
+            brank = __shfl_sync(full, brank, src);
+            if (lane == 0) {
+                const uint4 nr = __ldg(D.s.recs + brank);
+                P.vres[t] = make_uint4(best, vx_pack_e(qx - (int)(nr.x & 0xffffu), qy - (int)(nr.x >> 16), qz - (int)nr.y), nr.w, nr.z);
             }
         }
     }
@@ -418,7 +508,7 @@ vx_far_kernel(const __grid_constant__ VxParams P) {
     }
 }
 
-// Epilogue of the pending voxels.  gridDim = (G, ndirs): block (b, d) owns a fixed chunk of the
+// Epilogue of the voxels the pencil round answered.  gridDim = (G, ndirs): block (b, d) owns a fixed chunk of the
 // ranked positions and a fixed thread <-> position mapping, so its record is reproducible.
 constexpr int kVxPendThreads = 128;
 __global__ void __launch_bounds__(kVxPendThreads)
@@ -462,7 +552,7 @@ vx_pending_kernel(const __grid_constant__ VxParams P) {
     if (threadIdx.x == 0) {
         BlockPartial o = sm[0];
         for (int w = 1; w < kVxPendThreads / 32; ++w) partial_merge(o, sm[w]);
-        P.partials[D.rec_off + D.q.nblk + P.pend_rec + blockIdx.x] = o;
+        P.partials[D.rec_off + D.ntiles + blockIdx.x] = o;
     }
 }
 
