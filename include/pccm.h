@@ -103,6 +103,7 @@ typedef struct pccm_timings {
     double query_ms, finalize_ms, knn_ms;
     double vox_build_ms;       /* occupancy-brick index of integer pairs */
     double vox_tail_ms;        /* brick-ring (and pencil) search of the voxels the staged search left undecided */
+    double vox_search_ms;      /* staged bit-scan search kernel of the brick path (query_ms covers the whole query stage) */
     double vox_epilogue_ms;    /* per-point epilogue kernel of the brick path (D1 / D2 / colour + reduction records) */
     int64_t query_launches, knn_launches;
     int64_t total_launches;    /* kernels of this library (hand-written, sm_100a) */
@@ -131,6 +132,13 @@ int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, int64_t n, 
                       const void* rgb, int rgb_dtype, int64_t rgb_stride,
                       const void* normals, int nrm_dtype, int64_t nrm_stride,
                       int mem_kind, pccm_cloud** out);
+/* Colours and / or normals for a cloud created without them (NULL = leave as is); same formats and
+ * ownership rules as pccm_cloud_create.  Lets a caller submit the COORDINATES of both clouds of a pair
+ * first: the index build needs nothing else, and attributes uploaded afterwards travel on the copy
+ * stream beside it (they are first read by the epilogue).  Colours must be attached before
+ * pccm_cloud_build_index (a brick-indexed pair accepts them until its first colour evaluation). */
+int pccm_cloud_attach(pccm_ctx* ctx, pccm_cloud* cloud, const void* rgb, int rgb_dtype, int64_t rgb_stride,
+                      const void* normals, int nrm_dtype, int64_t nrm_stride, int mem_kind);
 int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* cloud);
 int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* cloud, pccm_cloud_info* out);
 

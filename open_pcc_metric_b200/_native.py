@@ -26,7 +26,7 @@ ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_NONFINITE, ERR_UNSUPPORTED = -1
 EXPORTS = [
     "pccm_version", "pccm_last_error", "pccm_ctx_create", "pccm_ctx_destroy", "pccm_ctx_synchronize",
     "pccm_ctx_set_profiling", "pccm_ctx_reset_timings", "pccm_ctx_get_timings",
-    "pccm_cloud_create", "pccm_cloud_destroy", "pccm_cloud_info_get", "pccm_cloud_build_index", "pccm_pair_build_index",
+    "pccm_cloud_create", "pccm_cloud_attach", "pccm_cloud_destroy", "pccm_cloud_info_get", "pccm_cloud_build_index", "pccm_pair_build_index",
     "pccm_cloud_set_normals", "pccm_cloud_get_normals", "pccm_estimate_normals", "pccm_knn_self",
     "pccm_self_nn_minmax", "pccm_nn", "pccm_pair_eval", "pccm_pair_get", "pccm_obb_sweep", "pccm_cloud_extremes", "pccm_cloud_outside_hull",
 ]
@@ -53,7 +53,7 @@ class PairResult(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("upload_ms", "stats_ms", "keys_ms", "sort_ms", "table_ms",
                                            "reorder_ms", "query_ms", "finalize_ms", "knn_ms",
-                                           "vox_build_ms", "vox_tail_ms", "vox_epilogue_ms")] + \
+                                           "vox_build_ms", "vox_tail_ms", "vox_search_ms", "vox_epilogue_ms")] + \
                [(k, C.c_int64) for k in ("query_launches", "knn_launches", "total_launches", "library_launches",
                                          "vox_undecided", "vox_far", "vox_tail")]
 
@@ -93,6 +93,7 @@ def lib():
         "pccm_ctx_reset_timings": [vp],
         "pccm_ctx_get_timings": [vp, C.POINTER(Timings)],
         "pccm_cloud_create": [vp, vp, i32, i64, i64, vp, i32, i64, vp, i32, i64, i32, C.POINTER(vp)],
+        "pccm_cloud_attach": [vp, vp, vp, i32, i64, vp, i32, i64, i32],
         "pccm_cloud_destroy": [vp, vp],
         "pccm_cloud_info_get": [vp, vp, C.POINTER(CloudInfo)],
         "pccm_cloud_build_index": [vp, vp, dbl, i32],
@@ -282,8 +283,25 @@ class Cloud:
             pb.mem, C.byref(h)))
         self.h = h
         self.n = pb.n
-        self._keep = (pb, cb, nb)  # inputs may still be read (device inputs; pinned host inputs in flight) until the index is built / first results
+        self._keep = pb            # coordinates are read until the index is built
+        self._keep_attr = (cb, nb)  # colours / normals travel on the copy stream (pinned host inputs) or are used in place (device normals)
         self._keep_normals = nb   # device normals are used in place; pinned host normals may be in flight on the copy stream
+
+    def attach(self, colors=None, normals=None):
+        """Colours and / or normals for a cloud created from coordinates only (uploaded on the copy
+        stream beside the index build; see pccm_cloud_attach)."""
+        cb = _Buf(colors, (F64, U8), "colors") if colors is not None and len(colors) else None
+        nb = _Buf(normals, (F64, F32), "normals") if normals is not None and len(normals) else None
+        if cb is None and nb is None:
+            return
+        mem = (cb or nb).mem
+        for b, what in ((cb, "colors"), (nb, "normals")):
+            if b is not None and (b.n != self.n or b.mem != mem):
+                raise ValueError(f"{what}: must match the cloud in length and share one memory kind")
+        self.ctx.check(self.ctx.L.pccm_cloud_attach(
+            self.ctx.h, self.h, cb.ptr if cb else None, cb.dtype if cb else F64, cb.stride if cb else 0,
+            nb.ptr if nb else None, nb.dtype if nb else F64, nb.stride if nb else 0, mem))
+        self._keep_attr = (cb, nb)     # pinned host inputs may be in flight, device normals are used in place
 
     def info(self) -> CloudInfo:
         out = CloudInfo()

@@ -70,10 +70,12 @@ class MetricCalculator:
     def _prefetch(self, metrics_list) -> None:
         """One fused GPU evaluation for everything the list will ask for (D2 and the first colour
         scheme on top of D1) instead of one per kind of metric as the graph walk reaches them."""
-        p2p, schemes = False, []
+        p2p, schemes, boundary = False, [], False
 
         def scan(m):
-            nonlocal p2p
+            nonlocal p2p, boundary
+            if type(m).__name__ in ("MinSqrtDistance", "MaxSqrtDistance", "BoundarySqrtDistances", "GeoHausdorffDistancePSNR"):
+                boundary = True
             if isinstance(m, SymmetricMetric):
                 for c in m.metrics:
                     scan(c)
@@ -87,6 +89,12 @@ class MetricCalculator:
                 schemes.append(cs)
         for m in metrics_list:
             scan(m)
+        if boundary and hasattr(self._cloud_pair, "boundary_minmax"):
+            # needs coordinates only: runs while colours / normals are still on their way to the device
+            try:
+                self._cloud_pair.boundary_minmax()
+            except (IndexError, ValueError, KeyError):
+                pass
         if p2p or schemes:
             try:
                 self._cloud_pair.fused(True, point_to_plane=p2p, color_scheme=schemes[0] if schemes else None)

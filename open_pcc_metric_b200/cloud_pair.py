@@ -79,10 +79,13 @@ class CloudPair:
         self._normals_host = {}
 
         # upload + index (replaces the two KDTreeFlann builds, cloud_pair.py:65)
+        # coordinates of BOTH clouds first: statistics and the index build need nothing else, colours and
+        # normals follow on the copy stream while the index is built (they are first read by the epilogue)
         self._dev = []
         for c in self.clouds:
-            self._dev.append(self._ctx.cloud(_attr(c, "points") if _attr(c, "points") is not None else np.zeros((0, 3)),
-                                             _attr(c, "colors"), _attr(c, "normals")))
+            self._dev.append(self._ctx.cloud(_attr(c, "points") if _attr(c, "points") is not None else np.zeros((0, 3))))
+        for c, d in zip(self.clouds, self._dev):
+            d.attach(_attr(c, "colors"), _attr(c, "normals"))
         self._ctx.build_pair(self._dev[0], self._dev[1], cell_size)
         infos = [d.info() for d in self._dev]
         kind = infos[0].index_kind

@@ -31,7 +31,12 @@ struct pccm_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // host->device copies of attributes that are only needed by the query epilogue
-    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // per-cloud pinned statistics buffers and events are recycled: cudaMallocHost / cudaFreeHost are
+    // synchronous OS-level calls (tens of microseconds) and a cloud lives for one evaluation
+    std::vector<void*> stats_pool;
+    std::vector<cudaEvent_t> cloud_events;
+    size_t stats_pool_bytes = 0;
     std::string err;
     int profiling = 0;
     pccm_timings tm{};
@@ -80,15 +85,16 @@ struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     double* dest;
     bool on;
-    StageTimer(pccm_ctx* c, double* d, int level = 2) : ctx(c), dest(d), on(c->profiling >= level) {
+    cudaStream_t st;
+    StageTimer(pccm_ctx* c, double* d, int level = 2, cudaStream_t s = nullptr) : ctx(c), dest(d), on(c->profiling >= level), st(s ? s : c->stream) {
         if (!on) return;
         a = get();
         b = get();
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, st);
     }
     ~StageTimer() {
         if (!on) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, st);
         ctx->pending.push_back({a, b, dest});
     }
     cudaEvent_t get() {
@@ -147,6 +153,12 @@ struct pccm_cloud {
     double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
     int data_kind = PCCM_KIND_F64;
     bool rgb_u8_ok = false;
+    // colours travel on the copy stream (upload + the k/255 classification) beside the index build
+    cudaEvent_t rgb_ready = nullptr;
+    bool rgb_pending = false;
+    uint32_t* d_rgbflag = nullptr;   // behind d_stats
+    uint32_t* h_rgbflag = nullptr;   // behind h_stats (pinned)
+    bool vox_rgb_done = false;       // brick index: colours copied into the point list / voxel records
     // attributes (original order)
     uchar4* rgb_u8 = nullptr;
     double* rgb_f64 = nullptr;
@@ -239,8 +251,65 @@ static void wait_normals(pccm_ctx* ctx, pccm_cloud* c) {
     }
 }
 
+// colours in flight on the copy stream: wait (host: the classification decides the device format;
+// context stream: later kernels read the uploaded rows)
+static int ensure_colors(pccm_ctx* ctx, pccm_cloud* c) {
+    if (!c->has_colors || !c->rgb_pending) return PCCM_OK;
+    CK(cudaEventSynchronize(c->rgb_ready));
+    CK(cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0));
+    c->rgb_u8_ok = c->raw_rgb_dtype == PCCM_U8 || c->n == 0 || (c->h_rgbflag && *c->h_rgbflag == 0u);
+    c->rgb_pending = false;
+    return PCCM_OK;
+}
+
+// Colours of a cloud: upload (HOST) and classify (every channel == k / 255 ?) on the copy stream,
+// so that the statistics pass, the index build and the search never wait for them.
+static int attach_colors(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, int dtype, int64_t stride, int mem_kind) {
+    if (dtype != PCCM_F64 && dtype != PCCM_U8) return fail(ctx, PCCM_ERR_INVALID, "rgb must be F64 or U8");
+    if (c->has_colors) return fail(ctx, PCCM_ERR_STATE, "cloud already has colours");
+    if (c->index_kind >= 0 && !(c->vox && !c->recs && !c->vox_rgb_done))
+        return fail(ctx, PCCM_ERR_STATE, "colours must be attached before the index is built");
+    const size_t es = dtype_size(dtype);
+    if (stride == 0) stride = (int64_t)(3 * es);
+    if (stride < (int64_t)(3 * es) || (stride % (int64_t)es) != 0) return fail(ctx, PCCM_ERR_INVALID, "bad row stride %lld", (long long)stride);
+    c->raw_rgb_dtype = dtype;
+    c->raw_rgb_stride = stride;
+    c->has_colors = true;
+    if (c->n == 0) { c->rgb_u8_ok = true; return PCCM_OK; }
+    cudaStream_t s = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
+    if (!c->rgb_ready) {
+        if (!ctx->cloud_events.empty()) { c->rgb_ready = ctx->cloud_events.back(); ctx->cloud_events.pop_back(); }
+        else CK(cudaEventCreateWithFlags(&c->rgb_ready, cudaEventDisableTiming));
+    }
+    unsigned char* d = nullptr;
+    const size_t bytes = (size_t)c->n * (size_t)stride;
+    if (mem_kind == PCCM_HOST) CK(dalloc(ctx, &d, bytes));
+    if (s != ctx->stream) {      // after the allocation above / after the caller's device data
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+    }
+    if (mem_kind == PCCM_HOST) {
+        CK(cudaMemcpyAsync(d, rgb, bytes, cudaMemcpyHostToDevice, s));
+        c->raw_rgb = d;
+        c->raw_rgb_owned = d;
+    } else {
+        c->raw_rgb = rgb;
+    }
+    if (dtype == PCCM_F64) {
+        CK(cudaMemsetAsync(c->d_rgbflag, 0, sizeof(uint32_t), s));
+        rgb_classify_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(c->raw_rgb, stride, c->n, c->d_rgbflag);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_rgbflag, c->d_rgbflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaEventRecord(c->rgb_ready, s));
+    c->rgb_pending = true;
+    return PCCM_OK;
+}
+
 // colours: uchar4 when every channel is k/255, else packed float64
 static int finish_colors(pccm_ctx* ctx, pccm_cloud* c) {
+    { const int rc0 = ensure_colors(ctx, c); if (rc0) return rc0; }
     if (!c->has_colors || c->rgb_u8 || c->rgb_f64 || c->n == 0) return PCCM_OK;
     const int threads = 256;
     const int blocks = (int)((c->n + threads - 1) / threads);
@@ -308,12 +377,14 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->copy_stream = nullptr;
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { ctx->copy_stream = nullptr; }
+    if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) ctx->ev_join = nullptr;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ctx->stats_pool_bytes = sizeof(StatsPartial) * (size_t)ctx->sm_count * 4;
     if (cudaMallocHost(&ctx->pinned, pccm_ctx::kScratch) != cudaSuccess || cudaMalloc(&ctx->dscratch, pccm_ctx::kScratch) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, PCCM_ERR_CUDA, "scratch allocation failed");
@@ -341,12 +412,15 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     resolve_timers(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto e : ctx->cloud_events) cudaEventDestroy(e);
+    for (auto p : ctx->stats_pool) cudaFreeHost(p);
     for (int d = 0; d < 2; ++d) { dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]); }
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->pinned);
     cudaFree(ctx->dscratch);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCCM_OK;
@@ -385,6 +459,8 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     cudaSetDevice(ctx->device);
     wait_normals(ctx, c);
     if (c->nrm_ready) cudaEventDestroy(c->nrm_ready);
+    if (c->rgb_pending) cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0);   // the frees below are ordered on the context stream
+    if (c->rgb_ready) ctx->cloud_events.push_back(c->rgb_ready);
     dfree(ctx, c->raw_owned);
     dfree(ctx, c->raw_rgb_owned);
     dfree(ctx, c->d_stats);
@@ -403,10 +479,10 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
         dfree(ctx, c->row_start);
     }
     if (c->h_stats) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFreeHost(c->h_stats);
+        if (c->stats_done) cudaEventSynchronize(c->stats_done);   // the copy into the buffer has landed
+        ctx->stats_pool.push_back(c->h_stats);
     }
-    if (c->stats_done) cudaEventDestroy(c->stats_done);
+    if (c->stats_done) ctx->cloud_events.push_back(c->stats_done);
     delete c;
     return PCCM_OK;
 }
@@ -477,38 +553,63 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
         c->raw_dtype = xyz_dtype;
         c->raw_stride = xyz_stride;
         if (n) rc = upload_rows(ctx, xyz, xyz_dtype, n, &c->raw_stride, mem_kind, &c->raw_xyz, &c->raw_owned);
-        if (!rc && rgb && n) {
-            c->raw_rgb_dtype = rgb_dtype;
-            c->raw_rgb_stride = rgb_stride;
-            rc = upload_rows(ctx, rgb, rgb_dtype, n, &c->raw_rgb_stride, mem_kind, &c->raw_rgb, &c->raw_rgb_owned);
-        }
-        c->has_colors = rgb != nullptr;
-        if (!rc && normals) rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind, true);
     }
     if (rc) { pccm_cloud_destroy(ctx, c); return rc; }
     if (n) {
         StageTimer t(ctx, &ctx->tm.stats_ms);
         c->stats_blocks = (int)std::min<int64_t>((n + kStatsThreads - 1) / kStatsThreads, (int64_t)ctx->sm_count * 4);
-        cudaError_t e = dalloc(ctx, &c->d_stats, (size_t)c->stats_blocks);
-        if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->h_stats), sizeof(StatsPartial) * c->stats_blocks);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->stats_done, cudaEventDisableTiming);
+        cudaError_t e = dalloc(ctx, &c->d_stats, (size_t)c->stats_blocks + 1);
+        if (e == cudaSuccess) {
+            if (!ctx->stats_pool.empty()) {
+                c->h_stats = static_cast<StatsPartial*>(ctx->stats_pool.back());
+                ctx->stats_pool.pop_back();
+            } else {
+                e = cudaMallocHost(reinterpret_cast<void**>(&c->h_stats), ctx->stats_pool_bytes + sizeof(StatsPartial));
+            }
+        }
+        if (e == cudaSuccess) {
+            c->d_rgbflag = reinterpret_cast<uint32_t*>(c->d_stats + c->stats_blocks);
+            c->h_rgbflag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_stats) + ctx->stats_pool_bytes);
+        }
+        if (e == cudaSuccess) {
+            if (!ctx->cloud_events.empty()) { c->stats_done = ctx->cloud_events.back(); ctx->cloud_events.pop_back(); }
+            else e = cudaEventCreateWithFlags(&c->stats_done, cudaEventDisableTiming);
+        }
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
         stats_kernel<<<c->stats_blocks, kStatsThreads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
-                                                                         c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->d_stats);
+                                                                         nullptr, PCCM_F64, 0, c->d_stats);   // colours are classified on the copy stream
         ctx->tm.total_launches++;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsPartial) * c->stats_blocks, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->stats_done, ctx->stream);
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats launch: %s", cudaGetErrorString(e)); }
     }
+    {   // attributes: needed by the epilogue only -> copy stream, behind the coordinates
+        StageTimer t(ctx, &ctx->tm.upload_ms);
+        if (rgb) rc = attach_colors(ctx, c, rgb, rgb_dtype, rgb_stride, mem_kind);
+        if (!rc && normals) rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind, true);
+    }
+    if (rc) { pccm_cloud_destroy(ctx, c); return rc; }
     *out = c;
     return PCCM_OK;
+}
+
+extern "C" int pccm_cloud_attach(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, int rgb_dtype, int64_t rgb_stride,
+                                 const void* normals, int nrm_dtype, int64_t nrm_stride, int mem_kind) {
+    if (!ctx || !c) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, &ctx->tm.upload_ms);
+    int rc = PCCM_OK;
+    if (rgb) rc = attach_colors(ctx, c, rgb, rgb_dtype, rgb_stride, mem_kind);
+    if (!rc && normals) rc = set_normals_impl(ctx, c, normals, nrm_dtype, nrm_stride, mem_kind, true);
+    return rc;
 }
 
 extern "C" int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* c, pccm_cloud_info* out) {
     if (!ctx || !c || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_stats(ctx, c);
+    if (!rc) rc = ensure_colors(ctx, c);
     if (rc) return rc;
     memset(out, 0, sizeof *out);
     out->n = c->n;
@@ -996,6 +1097,22 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         ctx->tm.total_launches++;
         rc = exclusive_scan(ctx, v->gstart, (size_t)B.n_total + 1);
     }
+    bool rgb_now[2] = {false, false};
+    if (!rc) {
+        // colours that have already arrived (device inputs, or a fast upload) ride along with the scatter pass
+        // in input order; colours still in flight are gathered later (vox_colors) -- the build never waits for them
+        for (int c = 0; c < 2; ++c) {
+            pccm_cloud* p = cl[c];
+            B.c[c].rgb_in_rec = 0;
+            if (!p->has_colors) continue;
+            if (p->rgb_pending && cudaEventQuery(p->rgb_ready) == cudaSuccess) { rc = ensure_colors(ctx, p); if (rc) break; }
+            if (!p->rgb_pending && p->rgb_u8_ok && p->raw_rgb) {
+                B.c[c].rgb = p->raw_rgb; B.c[c].rgb_dtype = p->raw_rgb_dtype; B.c[c].rgb_stride = p->raw_rgb_stride;
+                B.c[c].rgb_in_rec = 1;
+                rgb_now[c] = true;
+            }
+        }
+    }
     if (!rc) {
         vx_scatter_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
         vx_group_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
@@ -1023,13 +1140,38 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         p->vox_id = c;
         v->owner[c] = p;
         p->index_kind = PCCM_KIND_INT;
-        p->rgb_in_rec = R.rgb_in_rec[c] != 0;
+        p->rgb_in_rec = rgb_now[c];         // otherwise colours join the records on first use (vox_colors)
+        p->vox_rgb_done = rgb_now[c];
+        if (rgb_now[c]) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
         dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // the records hold every point
-        if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
     }
     v->refs = 2;
     v->cell_size = cell_size;
     *built = true;
+    return PCCM_OK;
+}
+
+// Colours of a brick-indexed cloud, on first use: 8-bit colours are copied into the point list and
+// the voxel records (one gather by original index), anything else becomes a float64 array.
+static int vox_colors(pccm_ctx* ctx, pccm_cloud* c) {
+    if (!c->vox || c->vox_rgb_done || !c->has_colors) return PCCM_OK;
+    int rc = ensure_colors(ctx, c);
+    if (rc) return rc;
+    if (c->n && c->rgb_u8_ok) {
+        const VoxView& V = c->vox->view[c->vox_id];
+        const uint32_t pts0 = c->vox_id ? c->vox->view[0].n : 0u;
+        vx_rgbfill_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(c->vox->pts, c->vox->recs, V.gstart, pts0, (uint32_t)c->n,
+                                                                                     c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        c->rgb_in_rec = true;
+        dfree(ctx, c->raw_rgb_owned); c->raw_rgb_owned = nullptr; c->raw_rgb = nullptr;
+    } else {
+        rc = finish_colors(ctx, c);
+        if (rc) return rc;
+        c->rgb_in_rec = false;
+    }
+    c->vox_rgb_done = true;
     return PCCM_OK;
 }
 
@@ -1044,6 +1186,7 @@ static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
         RowGrid g{};
         g.short_row = ctx->short_row;
         if (cl[k] && cl[k]->recs) cl[k] = nullptr;    // (cannot happen: both are built together)
+        if (cl[k]) { const int rc = vox_colors(ctx, cl[k]); if (rc) return rc; }   // the pencil records carry the colours
         if (cl[k]) {
             int xb = 0;
             g.n = (uint32_t)cl[k]->n;
@@ -1096,22 +1239,27 @@ extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b
         R.g[c] = g;
         R.n[c] = (uint32_t)p->n;
         R.xyz[c] = p->raw_xyz; R.dtype[c] = p->raw_dtype; R.stride[c] = p->raw_stride;
-        // 8-bit colours ride in the KInt record; every other combination keeps a colour array
-        R.rgb_in_rec[c] = kind == PCCM_KIND_INT && p->has_colors && (p->raw_rgb_dtype == PCCM_U8 || p->rgb_u8_ok);
-        R.rgb[c] = p->raw_rgb; R.rgb_dtype[c] = p->raw_rgb_dtype; R.rgb_stride[c] = p->raw_rgb_stride;
-        if (!R.rgb_in_rec[c]) { rc = finish_colors(ctx, p); if (rc) return rc; }
         xbits = std::max(xbits, xb);
         rowbits = std::max(rowbits, bits_for((uint64_t)g.ny * g.nz - 1));
     }
     R.table_off[0] = 0;
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
+    if (kind == PCCM_KIND_INT && ctx->use_vox) {       // the brick index needs coordinates only: colours may still be in flight
+        bool built = false;
+        rc = build_vox(ctx, cl, R, cell_size, &built);
+        if (rc) return rc;
+        if (built) return ctx->eager_pencil ? ensure_pencil(ctx, a) : PCCM_OK;
+    }
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = cl[c];
+        rc = ensure_colors(ctx, p);
+        if (rc) return rc;
+        // 8-bit colours ride in the KInt record; every other combination keeps a colour array
+        R.rgb_in_rec[c] = kind == PCCM_KIND_INT && p->has_colors && (p->raw_rgb_dtype == PCCM_U8 || p->rgb_u8_ok);
+        R.rgb[c] = p->raw_rgb; R.rgb_dtype[c] = p->raw_rgb_dtype; R.rgb_stride[c] = p->raw_rgb_stride;
+        if (!R.rgb_in_rec[c]) { rc = finish_colors(ctx, p); if (rc) return rc; }
+    }
     if (kind == PCCM_KIND_INT) {
-        if (ctx->use_vox) {
-            bool built = false;
-            rc = build_vox(ctx, cl, R, cell_size, &built);
-            if (rc) return rc;
-            if (built) return ctx->eager_pencil ? ensure_pencil(ctx, a) : PCCM_OK;
-        }
         if (ctx->use_rowsort) return build_pair_rowsort(ctx, cl, R);
         if (rowbits + xbits + 1 <= 32) return build_pair_impl<uint32_t, KIND_INT>(ctx, cl, R, xbits, rowbits);
         return build_pair_impl<unsigned long long, KIND_INT>(ctx, cl, R, xbits, rowbits);
@@ -1219,25 +1367,33 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         D.far_count = todo + 2 + d;
         D.far = todo + 4 + n_total + (d ? (size_t)qc[0]->n : 0);
         D.pts0 = qc[d]->vox_id ? v->view[0].n : 0u;
-        D.ntiles = (D.q.n + kVxEpiThreads - 1) / kVxEpiThreads;
-        rec_stride = std::max(rec_stride, D.ntiles + kVxPendBlocks);
+        D.ntiles = (D.q.n + kVxEpiTile - 1) / kVxEpiTile;
+        rec_stride = std::max(rec_stride, D.ntiles + 2u * kVxPendBlocks);
         nwarps += D.q.nblk;
         ntiles += D.ntiles;
     }
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
     CK(dalloc(ctx, &partials, (size_t)rec_stride * 2 + 1));
     P.partials = partials; P.pendbits = pendbits; P.res = res; P.vres = vres;
+    StageTimer* stage = new StageTimer(ctx, &ctx->tm.query_ms, 1);     // the whole query stage: search -> epilogue / brick rings joined
     {
-        StageTimer t(ctx, &ctx->tm.query_ms, 1);
+        StageTimer t(ctx, &ctx->tm.vox_search_ms, 1);
         vx_search_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
         ctx->tm.query_launches++;
         ctx->tm.total_launches++;
-        CK(cudaGetLastError());
+    }
+    // brick-ring search of the undecided voxels + their epilogue on the second stream, beside the
+    // per-point epilogue kernel of everything else
+    cudaStream_t side = ctx->copy_stream && ctx->ev_fork && ctx->ev_join ? ctx->copy_stream : ctx->stream;
+    if (side != ctx->stream) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
     }
     {
-        StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
-        vx_general_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
-        ctx->tm.total_launches++;
+        StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1, side);
+        vx_general_kernel<<<ctx->sm_count * 8, 128, 0, side>>>(P);
+        vx_pending_kernel<<<dim3(kVxPendBlocks, ndirs), kVxPendThreads, 0, side>>>(P);
+        ctx->tm.total_launches += 2;
         CK(cudaGetLastError());
     }
     {
@@ -1246,6 +1402,12 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
     }
+    if (side != ctx->stream) {
+        cudaEventRecord(ctx->ev_join, side);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    }
+    delete stage;
+    CK(cudaGetLastError());
     // common fold: same record layout as the pencil path
     Q.rec_stride = rec_stride;
     Q.partials = partials;
@@ -1262,7 +1424,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
         return PCCM_OK;
     };
-    int rc = fold(0);
+    int rc = fold(1);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hcnt + 2, todo, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hcnt + 6, v->base + v->view[0].nblk_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1280,6 +1442,8 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
             D.srecs = static_cast<const uint4*>(sc[d]->recs);
             D.srow_start = sc[d]->row_start;
         }
+        P.pend_rec = kVxPendBlocks;
+        CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
         {
             StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
             vx_far_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
@@ -1287,7 +1451,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
             ctx->tm.total_launches += 2;
             CK(cudaGetLastError());
         }
-        rc = fold(1);
+        rc = fold(2);
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -1359,6 +1523,8 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
         if (!color_matrix) return fail(ctx, PCCM_ERR_INVALID, "color_matrix is NULL");
     }
     pccm_cloud* cl[2] = {a, b};
+    if (flags & PCCM_EVAL_COLOR)
+        for (int d = 0; d < 2; ++d) { rc = vox_colors(ctx, cl[d]); if (rc) return rc; }
     // metric.py:148-152 indexes the OTHER cloud's normals with the query index: a direction
     // whose search cloud is shorter than its query cloud raises IndexError in the reference.
     uint32_t dflags[2] = {flags, flags};

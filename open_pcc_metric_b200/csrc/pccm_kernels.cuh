@@ -98,6 +98,20 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
     }
 }
 
+// are all colour channels k / 255 for an integer k in [0, 255]?  (flag = 1 when not)
+__global__ void rgb_classify_kernel(const void* rgb, int64_t stride, int64_t n, uint32_t* flag) {
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double c = load_coord(rgb, PCCM_F64, stride, i, a);
+            const double k = rint(c * 255.0);
+            if (!(k >= 0.0 && k <= 255.0 && k / 255.0 == c)) bad = true;
+        }
+    }
+    if (bad) *flag = 1u;
+}
+
 // colours -> uchar4 (original order).  F64 input must have passed the k/255 test.
 __global__ void pack_rgb_u8_kernel(const void* rgb, int rgb_dtype, int64_t stride, int64_t n, uchar4* out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -292,7 +306,8 @@ __global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t*
     const uint32_t per = (n + kScanSmallThreads - 1) / kScanSmallThreads;
     const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
     uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; ++i) s += data[i];
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; ++i) s += data[i];          // unrolled: the loads are independent, keep them in flight
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = s;
 #pragma unroll
@@ -313,6 +328,7 @@ __global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t*
     }
     __syncthreads();
     uint32_t ex = ws[warp] + incl - s;
+#pragma unroll 8
     for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = data[i]; data[i] = ex; ex += v; }
 }
 
@@ -665,9 +681,9 @@ __device__ __forceinline__ void load_color(const CloudView& c, uint32_t idx, uin
     }
     uint32_t p = packed;
     if (c.rgb_mode == 2) { uchar4 u = __ldg(c.rgb_u8 + idx); p = u.x | (u.y << 8) | (u.z << 16); }
-    out[0] = __ldg(c.lut255 + (p & 0xffu));
-    out[1] = __ldg(c.lut255 + ((p >> 8) & 0xffu));
-    out[2] = __ldg(c.lut255 + ((p >> 16) & 0xffu));
+    out[0] = c.lut255[p & 0xffu];             // generic loads: the table may sit in shared memory
+    out[1] = c.lut255[(p >> 8) & 0xffu];
+    out[2] = c.lut255[(p >> 16) & 0xffu];
 }
 
 template <class K> __device__ __forceinline__ uint32_t rec_rgba(const typename K::Rec&) { return 0; }

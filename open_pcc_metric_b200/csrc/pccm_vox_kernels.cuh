@@ -124,6 +124,27 @@ __global__ void vx_scatter_kernel(const __grid_constant__ VoxBuild B) {
     vx_scatter_point(B.gstart, B.pts, kc, rgba, li);
 }
 
+// 8-bit colours into the point list and (first point of a voxel = its representative) the voxel
+// record, once they have arrived: the build itself never reads them
+__global__ void vx_rgbfill_kernel(uint4* __restrict__ pts, uint4* __restrict__ recs, const uint32_t* __restrict__ gstart,
+                                  uint32_t pts0, uint32_t n, const void* rgb, int rgb_dtype, int64_t rgb_stride) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = pts0 + i;
+    const uint4 e = pts[g];
+    uint32_t rgba;
+    if (rgb_dtype == PCCM_U8) {
+        const uint8_t* p = static_cast<const uint8_t*>(rgb) + (int64_t)e.y * rgb_stride;
+        rgba = p[0] | (p[1] << 8) | (p[2] << 16);
+    } else {
+        rgba = (uint32_t)rint(load_coord(rgb, PCCM_F64, rgb_stride, e.y, 0) * 255.0) |
+               ((uint32_t)rint(load_coord(rgb, PCCM_F64, rgb_stride, e.y, 1) * 255.0) << 8) |
+               ((uint32_t)rint(load_coord(rgb, PCCM_F64, rgb_stride, e.y, 2) * 255.0) << 16);
+    }
+    pts[g].x = rgba;
+    if (gstart[e.z] == g) recs[e.z].z = rgba;
+}
+
 // one thread per voxel (gstart[nblk_total-th base] of them, a device value)
 __global__ void vx_group_kernel(const __grid_constant__ VoxBuild B) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +197,7 @@ struct VxDir {
     const uint32_t* srow_start;
     uint32_t rec_off;          // first reduction record of this direction
     uint32_t pts0;             // first point of the query cloud in pts[]
-    uint32_t ntiles;           // ceil(q.n / kVxEpiThreads): reduction records of vx_epilogue_kernel
+    uint32_t ntiles;           // ceil(q.n / kVxEpiTile): reduction records of vx_epilogue_kernel
 };
 
 struct VxParams {
@@ -189,8 +210,9 @@ struct VxParams {
     BlockPartial* partials;
     uint4* vres;               // [n_total] by ranked position: {d2, packed (query - neighbour), neighbour idx, neighbour rgb};
                                // d2 == kVxNone while the voxel is undecided
-    uint32_t* pendbits;        // [n_total / 32 + 1] zero on entry: voxels whose result waits in res[] (pencil round)
-    uint2* res;                // [n_total] {d2, neighbour position in the pencil records} of those voxels
+    uint32_t* pendbits;        // [n_total / 32 + 1] zero on entry: voxels whose result waits in res[]
+    uint2* res;                // [n_total] {d2, neighbour position (top bit: in the pencil records)} of those voxels
+    uint32_t pend_rec;         // reduction records of vx_pending_kernel start at rec_off + ntiles + pend_rec
 };
 
 __device__ __forceinline__ uint32_t vx_pack_e(int ex, int ey, int ez) {   // |e| <= 16 for every certified brick answer
@@ -208,7 +230,8 @@ struct VxAcc {
 };
 
 // epilogue of ONE query point: D1 (+ per-point outputs), D2 with the other cloud's normals, colour
-__device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, uint32_t qidx, uint32_t qrgb, uint32_t d2,
+__device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, const CloudView& qa, const CloudView& sa,
+                                            uint32_t qidx, uint32_t qrgb, uint32_t d2,
                                             int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a) {
     a.s1 += d2;
     a.m1 = d2 > a.m1 ? d2 : a.m1;
@@ -218,16 +241,16 @@ __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, u
     if (D.flags & PCCM_EVAL_D2) {
         const double e[3] = {(double)ex, (double)ey, (double)ez};
         const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
-        double nv[3] = {__ldg(D.sa.normals + 3 * (size_t)ni), __ldg(D.sa.normals + 3 * (size_t)ni + 1),
-                        __ldg(D.sa.normals + 3 * (size_t)ni + 2)};
+        double nv[3] = {__ldg(sa.normals + 3 * (size_t)ni), __ldg(sa.normals + 3 * (size_t)ni + 1),
+                        __ldg(sa.normals + 3 * (size_t)ni + 2)};
         const double pe = plane_err2(e, nv);
         a.s2 = dadd(a.s2, pe);
         a.m2 = fmax(a.m2, pe);
     }
     if (D.flags & PCCM_EVAL_COLOR) {
         double cq[3], cn[3], c2[3], c2s[3];
-        load_color(D.qa, qidx, qrgb, cq);
-        load_color(D.sa, nidx, nrgb, cn);
+        load_color(qa, qidx, qrgb, cq);
+        load_color(sa, nidx, nrgb, cn);
         color_diff2(P.T, cq, cn, P.color_scale, c2, c2s);
         for (int k = 0; k < 3; ++k) { a.cs[k] = dadd(a.cs[k], c2[k]); a.cm[k] = fmax(a.cm[k], c2s[k]); }
     }
@@ -256,8 +279,90 @@ __device__ __forceinline__ void vx_warp_record(const VxAcc& a, uint32_t flags, B
 // this rank's slice [t_lo, t_hi) of the query cloud's ranked positions
 __device__ __forceinline__ void vx_slice(const VxParams& P, const VoxView& Q, uint32_t& t_lo, uint32_t& t_hi) {
     const uint32_t r0 = vx_ranked_begin(Q), nd = vx_ndistinct(Q);
+    if (P.world == 1) { t_lo = r0; t_hi = r0 + nd; return; }      // (no 64-bit division on the common path)
     t_lo = r0 + (uint32_t)((unsigned long long)nd * (unsigned)P.rank / (unsigned)P.world);
     t_hi = r0 + (uint32_t)((unsigned long long)nd * (unsigned)(P.rank + 1) / (unsigned)P.world);
+}
+
+__device__ __forceinline__ void vx_row_nearest(uint32_t m, int p, int& dlo, int& dhi) {
+    // distance from word coordinate p (any integer) to the nearest set bit at or below / above; 40000 when none
+    const uint32_t at_or_below = p >= 31 ? 0xFFFFFFFFu : (p < 0 ? 0u : ((2u << p) - 1u));
+    const uint32_t above = p < 0 ? 0xFFFFFFFFu : (p >= 31 ? 0u : ~((2u << p) - 1u));
+    const uint32_t ml = m & at_or_below, mh = m & above;
+    dlo = ml ? p - (31 - __clz((int)ml)) : 40000;
+    dhi = mh ? (__ffs((int)mh) - 1) - p : 40000;
+}
+
+
+// Warp-cooperative exact search of one query over a list of occupied bricks (slots[k], ids[k]; id
+// = position in a DIM^3 neighbourhood centred on the query's brick).  Lane l owns rows 2l and
+// 2l+1 of every brick (one coalesced load of the 64 occupancy words).  Pass 1: minimal squared
+// distance by bit scans only.  Pass 2 (when that distance is below `limit`, i.e. certified): the
+// smallest original index among the voxels at that distance.  Returns the distance; rank is valid
+// when it is below `limit`.
+template <int DIM>
+__device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* slots, const int* ids, int n,
+                                                   int qx, int qy, int qz, uint32_t limit, uint32_t& rank_out) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
+    uint32_t best = kVxNone;
+    for (int k0 = 0; k0 < n; k0 += 4) {            // four bricks in flight per step
+        uint2 m4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            m4[j] = k0 + j < n ? __ldg(reinterpret_cast<const uint2*>(S.masks + (size_t)slots[k0 + j] * kVxRows) + lane) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k0 + j >= n) break;
+            const int b = ids[k0 + j];
+            const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
+            const int p = qx - (bx << 5);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t m = k ? m4[j].y : m4[j].x;
+                if (!m) continue;
+                const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
+                int dlo, dhi;
+                vx_row_nearest(m, p, dlo, dhi);
+                const int dx = dlo < dhi ? dlo : dhi;
+                const uint32_t d2 = (uint32_t)(dx * dx + dy * dy + dz * dz);
+                best = d2 < best ? d2 : best;
+            }
+        }
+    }
+    best = __reduce_min_sync(full, best);
+    if (best >= limit) return best;
+    uint32_t bidx = kVxNone, brank = kVxNone;
+    for (int k0 = 0; k0 < n; ++k0) {
+        const int slot = slots[k0], b = ids[k0];
+        const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
+        const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(S.masks + (size_t)slot * kVxRows) + lane);
+        const int p = qx - (bx << 5);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t m = k ? m2.y : m2.x;
+            if (!m) continue;
+            const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
+            int dlo, dhi;
+            vx_row_nearest(m, p, dlo, dhi);
+            const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
+            if (byz + (uint32_t)(dlo * dlo) == best) {
+                const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p - dlo) & 31);
+                const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(S.recs + rank) + 3);
+                if (i < bidx) { bidx = i; brank = rank; }
+            }
+            if (byz + (uint32_t)(dhi * dhi) == best) {
+                const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p + dhi) & 31);
+                const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(S.recs + rank) + 3);
+                if (i < bidx) { bidx = i; brank = rank; }
+            }
+        }
+    }
+    const uint32_t widx = __reduce_min_sync(full, bidx);
+    const int src = __ffs((int)__ballot_sync(full, bidx == widx)) - 1;
+    rank_out = __shfl_sync(full, brank, src);
+    return best;
 }
 
 // SEARCH.  One warp = one brick of the query cloud.  The warp stages the search cloud's occupancy
@@ -268,10 +373,14 @@ __device__ __forceinline__ void vx_slice(const VxParams& P, const VoxView& Q, ui
 constexpr int kVxThreads = 128;
 constexpr int kVxWarps = kVxThreads / 32;
 
-__global__ void __launch_bounds__(kVxThreads)
+#ifndef PCCM_VX_MINBLOCKS
+#define PCCM_VX_MINBLOCKS 10      // <= 48 registers: the rare whole-brick scan may spill, the staged search must not lose occupancy
+#endif
+__global__ void __launch_bounds__(kVxThreads, PCCM_VX_MINBLOCKS)
 vx_search_kernel(const __grid_constant__ VxParams P) {
     __shared__ uint2 s_win[kVxWarps][kVxRegRows];
     __shared__ int s_slot[kVxWarps][28];
+    __shared__ int s_occ[kVxWarps][2][28];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t gw = blockIdx.x * kVxWarps + warp;
@@ -288,6 +397,8 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
     if (t0 >= t1) return;
     uint2* win = s_win[warp];
     int* sslot = s_slot[warp];
+    int* occ_slot = s_occ[warp][0];
+    int* occ_id = s_occ[warp][1];
     const uint2 first = __ldg(reinterpret_cast<const uint2*>(qrecs + b0));
     const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
     int myslot = -1;
@@ -295,7 +406,14 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
         myslot = vx_slot(D.s, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
         sslot[lane] = myslot;
     }
-    const bool any_brick = __any_sync(full, myslot >= 0);
+    const unsigned occ = __ballot_sync(full, myslot >= 0);
+    const bool any_brick = occ != 0u;
+    const int nocc = __popc(occ);
+    if (myslot >= 0) {                       // compacted list of the occupied neighbour bricks (undecided voxels scan them whole)
+        const int k = __popc(occ & ((1u << lane) - 1u));
+        occ_slot[k] = myslot;
+        occ_id[k] = lane;
+    }
     __syncwarp();
     if (any_brick) {
         for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(D.s, sslot, i);
@@ -323,6 +441,21 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
             vx_pick(D.s, sslot, win, bx, by, bz, qx, qy, qz, rows, pk);
             r = make_uint4(bd2, vx_pack_e(pk.ex, pk.ey, pk.ez), pk.idx, pk.rgb);
         }
+        // voxels the 5 x 5 rows left undecided (nearest point 3+ voxels away; rare): the whole warp scans the
+        // 27 neighbour bricks for one voxel at a time -- anything outside them is at least 9 voxels away
+        unsigned pend = any_brick ? __ballot_sync(full, active && !done) : 0u;
+        while (pend) {
+            const int src = __ffs((int)pend) - 1;
+            pend &= pend - 1u;
+            const int sx = __shfl_sync(full, qx, src), sy = __shfl_sync(full, qy, src), sz = __shfl_sync(full, qz, src);
+            uint32_t nrank = kVxNone;
+            const uint32_t nd2 = vx_warp_bricks<3>(D.s, occ_slot, occ_id, nocc, sx, sy, sz, 81u, nrank);
+            if (nd2 < 81u && lane == src) {
+                const uint4 nr = __ldg(D.s.recs + nrank);
+                r = make_uint4(nd2, vx_pack_e(qx - (int)(nr.x & 0xffffu), qy - (int)(nr.x >> 16), qz - (int)nr.y), nr.w, nr.z);
+                done = true;
+            }
+        }
         if (active) P.vres[t] = r;
         const unsigned und = __ballot_sync(full, active && !done);
         if (und) {
@@ -334,29 +467,45 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
     }
 }
 
-// EPILOGUE.  One thread = one query POINT, in pts[] order (grouped by voxel, so the 16-byte voxel
+// EPILOGUE.  Threads walk the query POINTS in pts[] order (grouped by voxel, so the 16-byte voxel
 // answers are read almost contiguously; duplicated points share their voxel's answer).  A block is
-// a fixed tile of kVxEpiThreads points and writes one reduction record -> float sums do not depend
-// on scheduling.  Points of voxels that are still undecided (pencil round) are skipped.
+// a fixed tile of kVxEpiTile points (kVxEpiPer per thread, strided so that every load is
+// coalesced) and writes one reduction record -> float sums do not depend on scheduling.  Points
+// of voxels that are still undecided are skipped (vx_pending_kernel reduces them).
 constexpr int kVxEpiThreads = 256;
+constexpr int kVxEpiPer = 4;
+constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
 __global__ void __launch_bounds__(kVxEpiThreads)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
+    __shared__ double s_lut[256];
     const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
     const VxDir& D = P.dir[d];
     const uint32_t tile = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
+    s_lut[threadIdx.x] = D.qa.lut255[threadIdx.x];       // k / 255.0 table: shared memory instead of six global loads per point
+    __syncthreads();
+    CloudView qa = D.qa, sa = D.sa;
+    qa.lut255 = s_lut; sa.lut255 = s_lut;
     uint32_t t_lo, t_hi;
     vx_slice(P, D.q, t_lo, t_hi);
-    const uint32_t g_lo = __ldg(D.q.gstart + t_lo), g_hi = __ldg(D.q.gstart + t_hi);
-    const uint32_t g = D.pts0 + tile * kVxEpiThreads + threadIdx.x;
+    const uint32_t g_lo = __ldg(D.q.gstart + t_lo), g_hi = min(__ldg(D.q.gstart + t_hi), D.pts0 + D.q.n);
+    const uint32_t g0 = D.pts0 + tile * kVxEpiTile + threadIdx.x;
+    uint4 e[kVxEpiPer], v[kVxEpiPer];
+    bool on[kVxEpiPer];
+#pragma unroll
+    for (int j = 0; j < kVxEpiPer; ++j) {
+        const uint32_t g = g0 + j * kVxEpiThreads;
+        on[j] = g >= g_lo && g < g_hi;
+        e[j] = on[j] ? __ldg(D.q.pts + g) : make_uint4(0u, 0u, 0u, 0u);      // {rgb, idx, rank, -}
+    }
+#pragma unroll
+    for (int j = 0; j < kVxEpiPer; ++j) v[j] = on[j] ? __ldg(P.vres + e[j].z) : make_uint4(kVxNone, 0u, 0u, 0u);
     VxAcc acc;
     acc.init();
-    if (g >= g_lo && g < g_hi && g < D.pts0 + D.q.n) {
-        const uint4 e = __ldg(D.q.pts + g);            // {rgb, idx, rank, -}
-        const uint4 v = __ldg(P.vres + e.z);
-        if (v.x != kVxNone)
-            vx_epilogue(P, D, e.y, e.x, v.x, (int)(v.y & 0xffu) - 128, (int)((v.y >> 8) & 0xffu) - 128,
-                        (int)((v.y >> 16) & 0xffu) - 128, v.z, v.w, acc);
-    }
+#pragma unroll
+    for (int j = 0; j < kVxEpiPer; ++j)
+        if (v[j].x != kVxNone)
+            vx_epilogue(P, D, qa, sa, e[j].y, e[j].x, v[j].x, (int)(v[j].y & 0xffu) - 128, (int)((v[j].y >> 8) & 0xffu) - 128,
+                        (int)((v[j].y >> 16) & 0xffu) - 128, v[j].z, v[j].w, acc);
     BlockPartial r;
     vx_warp_record(acc, D.flags, r);
     __shared__ BlockPartial sm[kVxEpiThreads / 32];
@@ -374,17 +523,9 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
 // owns rows 2l and 2l+1: one coalesced load of the 64 occupancy words), first for the minimal
 // distance only (bit scans, no record is touched), then again to fetch the index of the voxels
 // that tie at that distance.  An answer closer than 17 voxels is certified (everything unvisited is
-// at least that far) and written to vres[] before the epilogue kernel runs; the rest goes to the
-// pencil search (second round).
-__device__ __forceinline__ void vx_row_nearest(uint32_t m, int p, int& dlo, int& dhi) {
-    // distance from word coordinate p (any integer) to the nearest set bit at or below / above; 40000 when none
-    const uint32_t at_or_below = p >= 31 ? 0xFFFFFFFFu : (p < 0 ? 0u : ((2u << p) - 1u));
-    const uint32_t above = p < 0 ? 0xFFFFFFFFu : (p >= 31 ? 0u : ~((2u << p) - 1u));
-    const uint32_t ml = m & at_or_below, mh = m & above;
-    dlo = ml ? p - (31 - __clz((int)ml)) : 40000;
-    dhi = mh ? (__ffs((int)mh) - 1) - p : 40000;
-}
-
+// at least that far); the rest goes to the pencil search (second round).  Results land in res[] /
+// pendbits[] and vx_pending_kernel reduces them in a fixed order -- both run on a second stream
+// beside vx_epilogue_kernel.
 __global__ void __launch_bounds__(128)
 vx_general_kernel(const __grid_constant__ VxParams P) {
     __shared__ int s_slot[4][128];
@@ -417,70 +558,15 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
                 nocc += __popc(has);
             }
             __syncwarp();
-            // pass 1: minimal squared distance (four bricks in flight per step)
-            uint32_t best = kVxNone;
-            for (int k0 = 0; k0 < nocc; k0 += 4) {
-                uint2 m4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    m4[j] = k0 + j < nocc ? __ldg(reinterpret_cast<const uint2*>(D.s.masks + (size_t)bslot[k0 + j] * kVxRows) + lane) : make_uint2(0u, 0u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (k0 + j >= nocc) break;
-                    const int b = bocc[k0 + j];
-                    const int bx = qbx + b % 5 - 2, by = qby + (b / 5) % 5 - 2, bz = qbz + b / 25 - 2;
-                    const int p = qx - (bx << 5);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint32_t m = k ? m4[j].y : m4[j].x;
-                        if (!m) continue;
-                        const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
-                        int dlo, dhi;
-                        vx_row_nearest(m, p, dlo, dhi);
-                        const int dx = dlo < dhi ? dlo : dhi;
-                        const uint32_t d2 = (uint32_t)(dx * dx + dy * dy + dz * dz);
-                        best = d2 < best ? d2 : best;
-                    }
-                }
-            }
-            best = __reduce_min_sync(full, best);
+            uint32_t brank = kVxNone;
+            const uint32_t best = vx_warp_bricks<5>(D.s, bslot, bocc, nocc, qx, qy, qz, 289u, brank);
             if (best >= 289u) {               // nothing certified within two brick rings
                 if (lane == 0) D.far[atomicAdd(D.far_count, 1u)] = t;
                 continue;
             }
-            // pass 2: smallest original index among the voxels at that distance
-            uint32_t bidx = kVxNone, brank = kVxNone;
-            for (int k0 = 0; k0 < nocc; ++k0) {
-                const int slot = bslot[k0], b = bocc[k0];
-                const int bx = qbx + b % 5 - 2, by = qby + (b / 5) % 5 - 2, bz = qbz + b / 25 - 2;
-                const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(D.s.masks + (size_t)slot * kVxRows) + lane);
-                const int p = qx - (bx << 5);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const uint32_t m = k ? m2.y : m2.x;
-                    if (!m) continue;
-                    const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
-                    int dlo, dhi;
-                    vx_row_nearest(m, p, dlo, dhi);
-                    const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
-                    if (byz + (uint32_t)(dlo * dlo) == best) {
-                        const uint32_t rank = vx_rank(D.s, (uint32_t)slot, r, (p - dlo) & 31);
-                        const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(D.s.recs + rank) + 3);
-                        if (i < bidx) { bidx = i; brank = rank; }
-                    }
-                    if (byz + (uint32_t)(dhi * dhi) == best) {
-                        const uint32_t rank = vx_rank(D.s, (uint32_t)slot, r, (p + dhi) & 31);
-                        const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(D.s.recs + rank) + 3);
-                        if (i < bidx) { bidx = i; brank = rank; }
-                    }
-                }
-            }
-            const uint32_t widx = __reduce_min_sync(full, bidx);
-            const int src = __ffs((int)__ballot_sync(full, bidx == widx)) - 1;
-            brank = __shfl_sync(full, brank, src);
             if (lane == 0) {
-                const uint4 nr = __ldg(D.s.recs + brank);
-                P.vres[t] = make_uint4(best, vx_pack_e(qx - (int)(nr.x & 0xffffu), qy - (int)(nr.x >> 16), qz - (int)nr.y), nr.w, nr.z);
+                P.res[t] = make_uint2(best, brank);
+                atomicOr(P.pendbits + (t >> 5), 1u << (t & 31u));
             }
         }
     }
@@ -508,7 +594,7 @@ vx_far_kernel(const __grid_constant__ VxParams P) {
     }
 }
 
-// Epilogue of the voxels the pencil round answered.  gridDim = (G, ndirs): block (b, d) owns a fixed chunk of the
+// Epilogue of the voxels answered by the brick rings / the pencil round.  gridDim = (G, ndirs): block (b, d) owns a fixed chunk of the
 // ranked positions and a fixed thread <-> position mapping, so its record is reproducible.
 constexpr int kVxPendThreads = 128;
 __global__ void __launch_bounds__(kVxPendThreads)
@@ -540,7 +626,7 @@ vx_pending_kernel(const __grid_constant__ VxParams P) {
             const uint32_t g0 = __ldg(D.q.gstart + t), g1 = __ldg(D.q.gstart + t + 1);
             for (uint32_t g = g0; g < g1; ++g) {      // every point of the voxel
                 const uint4 e = __ldg(D.q.pts + g);
-                vx_epilogue(P, D, e.y, e.x, res.x, ex, ey, ez, nr.w, nr.z, acc);
+                vx_epilogue(P, D, D.qa, D.sa, e.y, e.x, res.x, ex, ey, ez, nr.w, nr.z, acc);
             }
         }
     }
@@ -552,7 +638,7 @@ vx_pending_kernel(const __grid_constant__ VxParams P) {
     if (threadIdx.x == 0) {
         BlockPartial o = sm[0];
         for (int w = 1; w < kVxPendThreads / 32; ++w) partial_merge(o, sm[w]);
-        P.partials[D.rec_off + D.ntiles + blockIdx.x] = o;
+        P.partials[D.rec_off + D.ntiles + P.pend_rec + blockIdx.x] = o;
     }
 }
 

@@ -311,7 +311,9 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
     for (uint32_t t : todo) {
         const uint4 qr = Q.recs[t];
         VxHit h;
-        if (vx_search_general(S, (int)(qr.x & 0xffffu), (int)(qr.x >> 16), (int)qr.y, h, max_ring)) {
+        // the search kernel first scans the 27 neighbour bricks (ring 1), vx_general_kernel rings 0..2
+        if (vx_search_general(S, (int)(qr.x & 0xffffu), (int)(qr.x >> 16), (int)qr.y, h, max_ring < 1 ? max_ring : 1) ||
+            vx_search_general(S, (int)(qr.x & 0xffffu), (int)(qr.x >> 16), (int)qr.y, h, max_ring)) {
             const uint4 nr = S.recs[h.rank];
             if (nr.w != h.idx) return -13;
             assign(t, h.idx, h.d2);

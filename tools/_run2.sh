@@ -1,5 +1,8 @@
-set -x
 cd $GRAFT_REPO_ROOT
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_vox.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_vox.log 2>&1
-echo rc=$?
-tail -3 gpurun_out/ncu_vox.log
+for v in mb8 mb10 mb12; do
+echo "== $v"
+PCCM_LIB=$PWD/build/libpccm_$v.so timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('ms_per_step',round(d['ms_per_step'],4), {k:round(v,4) for k,v in d['stage_ms_per_step'].items() if v}, d['roofline']['launch_ms_by_kernel'])"
+done
