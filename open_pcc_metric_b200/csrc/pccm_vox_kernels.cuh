@@ -307,20 +307,21 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
     const int lane = threadIdx.x & 31;
     const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
     uint32_t best = kVxNone;
-    for (int k0 = 0; k0 < n; k0 += 4) {            // four bricks in flight per step
-        uint2 m4[4];
+    constexpr int kBatch = 4;                      // bricks in flight per step (independent coalesced loads; 8 spills)
+    for (int k0 = 0; k0 < n; k0 += kBatch) {
+        uint2 mb[kBatch];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            m4[j] = k0 + j < n ? __ldg(reinterpret_cast<const uint2*>(S.masks + (size_t)slots[k0 + j] * kVxRows) + lane) : make_uint2(0u, 0u);
+        for (int j = 0; j < kBatch; ++j)
+            mb[j] = k0 + j < n ? __ldg(reinterpret_cast<const uint2*>(S.masks + (size_t)slots[k0 + j] * kVxRows) + lane) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kBatch; ++j) {
             if (k0 + j >= n) break;
             const int b = ids[k0 + j];
             const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
             const int p = qx - (bx << 5);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const uint32_t m = k ? m4[j].y : m4[j].x;
+                const uint32_t m = k ? mb[j].y : mb[j].x;
                 if (!m) continue;
                 const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
                 int dlo, dhi;
