@@ -158,7 +158,8 @@ struct pccm_cloud {
     bool rgb_pending = false;
     uint32_t* d_rgbflag = nullptr;   // behind d_stats
     uint32_t* h_rgbflag = nullptr;   // behind h_stats (pinned)
-    bool vox_rgb_done = false;       // brick index: colours copied into the point list / voxel records
+    bool vox_rgb_done = false;       // brick index: colours packed into their original-order array
+    bool vox_rgb_in_recs = false;    // brick index: the voxel records carry the representative's colour
     // attributes (original order)
     uchar4* rgb_u8 = nullptr;
     double* rgb_f64 = nullptr;
@@ -187,8 +188,7 @@ struct SharedIndex {
 };
 
 struct SharedVox {
-    uint32_t *dirbits = nullptr, *dirpre = nullptr, *masks = nullptr, *base = nullptr, *gstart = nullptr;
-    uint4* pts = nullptr;
+    uint32_t *dirbits = nullptr, *dirpre = nullptr, *masks = nullptr, *base = nullptr, *prank = nullptr;
     uint16_t* pre = nullptr;
     uint4* recs = nullptr;
     VoxView view[2];
@@ -198,8 +198,8 @@ struct SharedVox {
 };
 
 static void free_vox(pccm_ctx* ctx, SharedVox* v) {
-    dfree(ctx, v->dirbits); dfree(ctx, v->dirpre); dfree(ctx, v->masks); dfree(ctx, v->base); dfree(ctx, v->gstart);
-    dfree(ctx, v->pre); dfree(ctx, v->recs); dfree(ctx, v->pts);
+    dfree(ctx, v->dirbits); dfree(ctx, v->dirpre); dfree(ctx, v->masks); dfree(ctx, v->base); dfree(ctx, v->prank);
+    dfree(ctx, v->pre); dfree(ctx, v->recs);
     delete v;
 }
 static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
@@ -1070,37 +1070,28 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     CKV(cudaStreamSynchronize(ctx->stream));
     const uint32_t nblk0 = hcnt[0];
     B.nblk_total = hcnt[1];
-    uint2 *counted = nullptr, *packed = nullptr;
-    uint32_t *longq = nullptr, *pslot = nullptr;
+    uint2* packed = nullptr;
+    uint32_t* pslot = nullptr;
     CKV(dalloc(ctx, &v->masks, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->pre, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->base, (size_t)B.nblk_total + 1));
     CKV(dalloc(ctx, &v->recs, (size_t)B.n_total));
-    CKV(dalloc(ctx, &v->gstart, (size_t)B.n_total + 1));
-    CKV(dalloc(ctx, &v->pts, (size_t)B.n_total));
-    CKV(dalloc(ctx, &counted, (size_t)B.n_total));
+    CKV(dalloc(ctx, &v->prank, (size_t)B.n_total));
     CKV(dalloc(ctx, &packed, (size_t)B.n_total));
     CKV(dalloc(ctx, &pslot, (size_t)B.n_total));
-    CKV(dalloc(ctx, &longq, (size_t)B.n_total / kVxGroupSmall + 2));
     CKV(cudaMemsetAsync(v->masks, 0, (size_t)B.nblk_total * kVxRows * sizeof(uint32_t), ctx->stream));
-    CKV(cudaMemsetAsync(v->gstart, 0, ((size_t)B.n_total + 1) * sizeof(uint32_t), ctx->stream));
-    CKV(cudaMemsetAsync(longq, 0, sizeof(uint32_t), ctx->stream));
-    B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.gstart = v->gstart; B.pts = v->pts;
-    B.counted = counted; B.longq = longq; B.packed = packed; B.pslot = pslot;
+    CKV(cudaMemsetAsync(v->recs, 0xff, (size_t)B.n_total * sizeof(uint4), ctx->stream));
+    B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.prank = v->prank;
+    B.packed = packed; B.pslot = pslot;
     vx_fill_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
     vx_brickpre_kernel<<<(B.nblk_total + 1 + 7) / 8, 256, 0, ctx->stream>>>(B);
     ctx->tm.total_launches += 2;
     CKV(cudaGetLastError());
     rc = exclusive_scan(ctx, v->base, (size_t)B.nblk_total + 1);
-    if (!rc) {
-        vx_count_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
-        ctx->tm.total_launches++;
-        rc = exclusive_scan(ctx, v->gstart, (size_t)B.n_total + 1);
-    }
     bool rgb_now[2] = {false, false};
     if (!rc) {
-        // colours that have already arrived (device inputs, or a fast upload) ride along with the scatter pass
-        // in input order; colours still in flight are gathered later (vox_colors) -- the build never waits for them
+        // colours that have already arrived (device inputs, or a fast upload) ride in the voxel records; colours
+        // still in flight are read from the colour arrays by the epilogue -- the build never waits for them
         for (int c = 0; c < 2; ++c) {
             pccm_cloud* p = cl[c];
             B.c[c].rgb_in_rec = 0;
@@ -1114,12 +1105,10 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         }
     }
     if (!rc) {
-        vx_scatter_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
-        vx_group_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
-        vx_longgroup_kernel<<<64, 256, 0, ctx->stream>>>(B);
-        ctx->tm.total_launches += 3;
+        vx_place_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+        ctx->tm.total_launches++;
     }
-    dfree(ctx, counted); dfree(ctx, longq); dfree(ctx, packed); dfree(ctx, pslot);
+    dfree(ctx, packed); dfree(ctx, pslot);
     if (rc) return bail(rc);
     CKV(cudaGetLastError());
 #undef CKV
@@ -1129,7 +1118,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         V.dirbits = v->dirbits + B.c[c].dir_off;
         V.dirpre = v->dirpre + B.c[c].dir_off;
         V.masks = v->masks; V.pre = v->pre; V.base = v->base; V.recs = v->recs;
-        V.gstart = v->gstart; V.pts = v->pts;
+        V.prank = v->prank + (c ? R.n[0] : 0u);
         V.slot0 = c ? nblk0 : 0u;
         V.nblk = c ? B.nblk_total - nblk0 : nblk0;
         V.n = R.n[c];
@@ -1140,9 +1129,9 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         p->vox_id = c;
         v->owner[c] = p;
         p->index_kind = PCCM_KIND_INT;
-        p->rgb_in_rec = rgb_now[c];         // otherwise colours join the records on first use (vox_colors)
-        p->vox_rgb_done = rgb_now[c];
-        if (rgb_now[c]) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
+        p->rgb_in_rec = false;              // (pencil records; decided when that index is built)
+        p->vox_rgb_in_recs = rgb_now[c];    // the voxel records carry the representative's colour
+        p->vox_rgb_done = false;            // own colours: packed into an array on first use (vox_colors)
         dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // the records hold every point
     }
     v->refs = 2;
@@ -1151,26 +1140,14 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     return PCCM_OK;
 }
 
-// Colours of a brick-indexed cloud, on first use: 8-bit colours are copied into the point list and
-// the voxel records (one gather by original index), anything else becomes a float64 array.
+// Colours of a brick-indexed cloud, on first use: one packed array in original order (uchar4 when every
+// channel is k / 255, float64 otherwise) -- the epilogue streams through it for the query's own colour
+// and, when the voxel records do not carry colours (they were still uploading at build time), gathers
+// the neighbour's colour from it.
 static int vox_colors(pccm_ctx* ctx, pccm_cloud* c) {
     if (!c->vox || c->vox_rgb_done || !c->has_colors) return PCCM_OK;
-    int rc = ensure_colors(ctx, c);
+    const int rc = finish_colors(ctx, c);
     if (rc) return rc;
-    if (c->n && c->rgb_u8_ok) {
-        const VoxView& V = c->vox->view[c->vox_id];
-        const uint32_t pts0 = c->vox_id ? c->vox->view[0].n : 0u;
-        vx_rgbfill_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(c->vox->pts, c->vox->recs, V.gstart, pts0, (uint32_t)c->n,
-                                                                                     c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride);
-        ctx->tm.total_launches++;
-        CK(cudaGetLastError());
-        c->rgb_in_rec = true;
-        dfree(ctx, c->raw_rgb_owned); c->raw_rgb_owned = nullptr; c->raw_rgb = nullptr;
-    } else {
-        rc = finish_colors(ctx, c);
-        if (rc) return rc;
-        c->rgb_in_rec = false;
-    }
     c->vox_rgb_done = true;
     return PCCM_OK;
 }
@@ -1192,7 +1169,9 @@ static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
             g.n = (uint32_t)cl[k]->n;
             choose_grid(ctx, cl[k], PCCM_KIND_INT, v->cell_size, g, xb);
             R.n[k] = (uint32_t)cl[k]->n;
-            R.rgb_in_rec[k] = cl[k]->rgb_in_rec;
+            // 8-bit colours ride in the pencil records: read from the packed colour array vox_colors made
+            R.rgb_in_rec[k] = cl[k]->has_colors && cl[k]->rgb_u8 != nullptr;
+            R.rgb[k] = cl[k]->rgb_u8; R.rgb_dtype[k] = PCCM_U8; R.rgb_stride[k] = sizeof(uchar4);
         } else {
             g.ny = g.nz = 1; g.h = g.inv_h = 1;
             R.n[k] = 0;
@@ -1202,8 +1181,8 @@ static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
     }
     R.table_off[0] = 0;
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
-    R.vpts = v->pts;
-    R.vpts_off[0] = 0; R.vpts_off[1] = v->view[0].n;
+    R.vprank = v->prank;
+    R.vprank_off[0] = 0; R.vprank_off[1] = v->view[0].n;
     return build_pair_rowsort(ctx, cl, R);
 }
 
@@ -1325,12 +1304,11 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
     return PCCM_OK;
 }
 
-// Brick path of a symmetric evaluation: staged bit-scan search (one warp per query brick), brick
-// ring search for what it leaves undecided, their epilogue in a fixed order, then the common
-// fold.  Voxels even the brick rings cannot certify (nearest point tens of voxels away) are
-// finished by the pencil search in a second round.  Synchronises; results land where
-// launch_query puts them.
-static constexpr int kVxPendBlocks = 256;
+// Brick path of a symmetric evaluation: staged bit-scan search (one warp per query brick; it also
+// finishes most undecided voxels itself), brick-ring search for the rest, per-point epilogue in
+// the original order, common fold.  Voxels even the brick rings cannot certify (nearest point tens
+// of voxels away) are finished by the pencil search in a second round.  Synchronises; results
+// land where launch_query puts them.
 static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cloud* sc[2], QueryParams& Q, int rank, int world) {
     SharedVox* v = qc[0]->vox;
     VxParams P{};
@@ -1342,23 +1320,20 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     const double* lut = reinterpret_cast<const double*>(static_cast<char*>(ctx->dscratch) + kLutOffset);
     const uint32_t n_total = v->view[0].n_total;
     uint32_t* todo = nullptr;      // [0..3] counters (undecided, far per direction), then the four lists
-    uint32_t* pendbits = nullptr;
-    uint2* res = nullptr;
-    BlockPartial* partials = nullptr;
-    const uint32_t npendw = (n_total + 31u) / 32u;
-    CK(dalloc(ctx, &todo, 2 * (size_t)n_total + 4));
-    CK(dalloc(ctx, &pendbits, (size_t)npendw + 1));
-    CK(dalloc(ctx, &res, (size_t)n_total));
-    CK(cudaMemsetAsync(todo, 0, 4 * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
-    uint32_t rec_stride = 0, nwarps = 0, ntiles = 0;
     uint4* vres = nullptr;
+    BlockPartial* partials = nullptr;
+    CK(dalloc(ctx, &todo, 2 * (size_t)n_total + 4));
     CK(dalloc(ctx, &vres, (size_t)n_total));
+    CK(cudaMemsetAsync(todo, 0, 4 * sizeof(uint32_t), ctx->stream));
+    uint32_t rec_stride = 0, nwarps = 0, ntiles = 0;
     for (int d = 0; d < ndirs; ++d) {
         VxDir& D = P.dir[d];
         D.q = v->view[qc[d]->vox_id];
         D.s = v->view[sc[d]->vox_id];
         D.qa = Q.dir[d].q; D.sa = Q.dir[d].s;
+        // own colour: streamed from the packed array; neighbour colour: in the voxel answer when the records carry it
+        D.qa.rgb_mode = !qc[d]->has_colors ? 0 : (qc[d]->rgb_u8 ? 2 : 3);
+        D.sa.rgb_mode = !sc[d]->has_colors ? 0 : (sc[d]->vox_rgb_in_recs ? 1 : (sc[d]->rgb_u8 ? 2 : 3));
         D.qa.lut255 = D.sa.lut255 = lut;
         D.flags = Q.dir[d].flags;
         D.idx_out = Q.dir[d].idx_out; D.d2_out = Q.dir[d].d2_out;
@@ -1366,47 +1341,31 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         D.todo = todo + 4 + (d ? (size_t)qc[0]->n : 0);
         D.far_count = todo + 2 + d;
         D.far = todo + 4 + n_total + (d ? (size_t)qc[0]->n : 0);
-        D.pts0 = qc[d]->vox_id ? v->view[0].n : 0u;
         D.ntiles = (D.q.n + kVxEpiTile - 1) / kVxEpiTile;
-        rec_stride = std::max(rec_stride, D.ntiles + 2u * kVxPendBlocks);
+        rec_stride = std::max(rec_stride, 2u * D.ntiles);
         nwarps += D.q.nblk;
         ntiles += D.ntiles;
     }
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
     CK(dalloc(ctx, &partials, (size_t)rec_stride * 2 + 1));
-    P.partials = partials; P.pendbits = pendbits; P.res = res; P.vres = vres;
-    StageTimer* stage = new StageTimer(ctx, &ctx->tm.query_ms, 1);     // the whole query stage: search -> epilogue / brick rings joined
+    P.partials = partials; P.vres = vres;
     {
-        StageTimer t(ctx, &ctx->tm.vox_search_ms, 1);
-        vx_search_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
-        ctx->tm.query_launches++;
-        ctx->tm.total_launches++;
+        StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage
+        {
+            StageTimer t(ctx, &ctx->tm.vox_search_ms, 1);
+            vx_search_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
+            ctx->tm.query_launches++;
+        }
+        {
+            StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
+            vx_general_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(P);
+        }
+        {
+            StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 1);
+            vx_epilogue_kernel<<<ntiles, kVxEpiThreads, 0, ctx->stream>>>(P);
+        }
+        ctx->tm.total_launches += 3;
     }
-    // brick-ring search of the undecided voxels + their epilogue on the second stream, beside the
-    // per-point epilogue kernel of everything else
-    cudaStream_t side = ctx->copy_stream && ctx->ev_fork && ctx->ev_join ? ctx->copy_stream : ctx->stream;
-    if (side != ctx->stream) {
-        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CK(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
-    }
-    {
-        StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1, side);
-        vx_general_kernel<<<ctx->sm_count * 8, 128, 0, side>>>(P);
-        vx_pending_kernel<<<dim3(kVxPendBlocks, ndirs), kVxPendThreads, 0, side>>>(P);
-        ctx->tm.total_launches += 2;
-        CK(cudaGetLastError());
-    }
-    {
-        StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 1);
-        vx_epilogue_kernel<<<ntiles, kVxEpiThreads, 0, ctx->stream>>>(P);
-        ctx->tm.total_launches++;
-        CK(cudaGetLastError());
-    }
-    if (side != ctx->stream) {
-        cudaEventRecord(ctx->ev_join, side);
-        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-    }
-    delete stage;
     CK(cudaGetLastError());
     // common fold: same record layout as the pencil path
     Q.rec_stride = rec_stride;
@@ -1415,9 +1374,9 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     Q.out = static_cast<BlockPartial*>(ctx->dscratch);
     Q.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);
     uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
-    auto fold = [&](uint32_t pend_rounds) -> int {
+    auto fold = [&](uint32_t passes) -> int {
         StageTimer t(ctx, &ctx->tm.finalize_ms);
-        for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = P.dir[d].ntiles + pend_rounds * kVxPendBlocks;
+        for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = passes * P.dir[d].ntiles;
         finalize_kernel<<<Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream>>>(Q);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
@@ -1433,7 +1392,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     ctx->tm.vox_far = (int64_t)hcnt[4] + hcnt[5];
     ctx->tm.vox_tail = (int64_t)n_total - (int64_t)hcnt[6];
     if (hcnt[4] + hcnt[5] > 0) {
-        // second round: pencil search for the far voxels, their epilogue, fold again
+        // second round: pencil search for the far voxels, the epilogue of their points, fold again
         for (int d = 0; d < ndirs; ++d) {
             rc = ensure_pencil(ctx, sc[d]);
             if (rc) return rc;
@@ -1442,12 +1401,11 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
             D.srecs = static_cast<const uint4*>(sc[d]->recs);
             D.srow_start = sc[d]->row_start;
         }
-        P.pend_rec = kVxPendBlocks;
-        CK(cudaMemsetAsync(pendbits, 0, ((size_t)npendw + 1) * sizeof(uint32_t), ctx->stream));
+        P.pass = 1;
         {
             StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
             vx_far_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
-            vx_pending_kernel<<<dim3(kVxPendBlocks, ndirs), kVxPendThreads, 0, ctx->stream>>>(P);
+            vx_epilogue_kernel<<<ntiles, kVxEpiThreads, 0, ctx->stream>>>(P);
             ctx->tm.total_launches += 2;
             CK(cudaGetLastError());
         }
@@ -1455,7 +1413,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    dfree(ctx, todo); dfree(ctx, pendbits); dfree(ctx, res); dfree(ctx, partials); dfree(ctx, vres);
+    dfree(ctx, todo); dfree(ctx, partials); dfree(ctx, vres);
     return PCCM_OK;
 }
 

@@ -21,7 +21,7 @@ constexpr int kKnnThreads = 64;
 // ------------------------------------------------------------------------------------
 // raw input access
 // ------------------------------------------------------------------------------------
-constexpr int kDtypeVRec = 100;   // internal source format: the brick index's point list pts[] = {rgb, idx, rank, -} + voxel records (pccm_vox.cuh)
+constexpr int kDtypeVRec = 100;   // internal source format: the brick index's voxel records, addressed through prank[] (pccm_vox.cuh)
 
 __device__ __forceinline__ double load_coord(const void* base, int dtype, int64_t stride, int64_t i, int axis) {
     const char* p = static_cast<const char*>(base) + i * stride;
@@ -345,15 +345,15 @@ struct PairRaw {
     uint32_t n[2];
     uint32_t table_off[2];     // offset of each cloud's row table inside the joint table
     RowGrid g[2];
-    const uint4* vpts;         // kDtypeVRec sources: the brick index's point list (cloud 1's points follow cloud 0's)
-    uint32_t vpts_off[2];      // first entry of each cloud in vpts
+    const uint32_t* vprank;    // kDtypeVRec sources: rank of the voxel of every point (cloud 1's points follow cloud 0's)
+    uint32_t vprank_off[2];    // first entry of each cloud in vprank
 };
 
 // Row of the coordinate source that holds point li of cloud c (brick-index sources: the record of
 // the point's voxel).
 __device__ __forceinline__ uint32_t pair_src(const PairRaw& R, int c, uint32_t li) {
     if (R.dtype[c] != kDtypeVRec) return li;
-    return __ldg(reinterpret_cast<const uint32_t*>(R.vpts + R.vpts_off[c] + li) + 2);
+    return __ldg(R.vprank + R.vprank_off[c] + li);
 }
 
 __device__ __forceinline__ uint32_t int_row(const RowGrid& g, int y, int z) {
@@ -570,13 +570,7 @@ __global__ void reorder_items_pair_kernel(const __grid_constant__ PairRaw R, con
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
-    uint32_t src = (uint32_t)items[i];
-    if (R.dtype[c] == kDtypeVRec) {          // point {rgb, idx, rank} + voxel {xy, z} -> {xy, z, idx, rgb}
-        const uint4 e = __ldg(R.vpts + R.vpts_off[c] + src);
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint4*>(R.xyz[c]) + e.z));
-        recs[i] = RecPack<K>::make((double)(v.x & 0xffffu), (double)(v.x >> 16), (double)v.y, e.y, R.rgb_in_rec[c] ? e.x : 0u);
-        return;
-    }
+    const uint32_t src = (uint32_t)items[i];
     uint32_t rgba = 0;
     if (R.rgb_in_rec[c]) {
         if (R.rgb_dtype[c] == PCCM_U8) {
@@ -588,8 +582,9 @@ __global__ void reorder_items_pair_kernel(const __grid_constant__ PairRaw R, con
                    ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 2) * 255.0) << 16);
         }
     }
-    recs[i] = RecPack<K>::make(load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 0), load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 1),
-                               load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 2), src, rgba);
+    const uint32_t row = pair_src(R, c, src);       // where the coordinates of point src live
+    recs[i] = RecPack<K>::make(load_coord(R.xyz[c], R.dtype[c], R.stride[c], row, 0), load_coord(R.xyz[c], R.dtype[c], R.stride[c], row, 1),
+                               load_coord(R.xyz[c], R.dtype[c], R.stride[c], row, 2), src, rgba);
 }
 
 // ------------------------------------------------------------------------------------

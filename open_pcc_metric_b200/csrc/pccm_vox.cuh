@@ -14,11 +14,11 @@
 //   pre[slot][64]    : number of occupied voxels of the brick before row r
 //   base[slot]       : rank of the brick's first voxel; rank = base + pre + popc(bits below)
 //   recs[rank]       : {x | y << 16, z, rgb, idx} of the voxel's point with the SMALLEST original
-//                      index (only that one can win under the tie rule)
-//   gstart[rank]     : first entry of the voxel's points in pts[] (exclusive scan of the multiplicities)
-//   pts[g]           : {rgb, idx, rank, -} of every point, grouped by voxel, ascending idx inside a
-//                      voxel.  As queries the points of a voxel share one search and only repeat
-//                      the epilogue.
+//                      index (only that one can win under the tie rule; atomicMin on the 64-bit
+//                      {idx, rgb} half of the record)
+//   prank[i]         : rank of the voxel of input point i.  As queries the points of a voxel
+//                      share ONE search (one lane per voxel); the per-point epilogue runs in the
+//                      original order of the input and fetches its voxel's answer through prank.
 // Two clouds of a pair share the arrays (cloud 1's slots, ranks and points continue cloud 0's).
 //
 // Search.  The nearest occupied voxel of a row to the query's x is two bit scans (CLZ on the
@@ -93,6 +93,13 @@ PCCM_HD uint32_t vx_atomic_add(uint32_t* p, uint32_t v) {
     const uint32_t o = *p; *p = o + v; return o;
 #endif
 }
+PCCM_HD unsigned long long vx_atomic_min64(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return atomicMin(p, v);
+#else
+    const unsigned long long o = *p; if (v < o) *p = v; return o;
+#endif
+}
 PCCM_HD uint32_t vx_ld32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
@@ -141,8 +148,7 @@ struct VoxView {
     const uint16_t* pre;
     const uint32_t* base;            // [nblk_total + 1]
     const uint4* recs;               // [n_total]
-    const uint32_t* gstart;          // [n_total + 1] by rank (entries past the last voxel repeat n_total)
-    const uint4* pts;                // [n_total]
+    const uint32_t* prank;           // [n] this cloud's points, original order -> rank of their voxel
     uint32_t slot0, nblk;            // this cloud's bricks are slots [slot0, slot0 + nblk)
     uint32_t n;                      // points of this cloud
     uint32_t nblk_total, n_total;
@@ -179,46 +185,18 @@ PCCM_HD void vx_fill_point(uint32_t* masks, uint32_t slot, int x, int y, int z) 
     const uint32_t bit = 1u << (x & 31);
     if (!(*w & bit)) vx_atomic_or(w, bit);
 }
-// pass 3 (after the brick prefixes): rank of the point's voxel, its arrival order inside the voxel
-// (the multiplicity counter's atomicAdd), voxel coordinates into the record
-struct VxCounted { uint32_t rank, ord; };
-PCCM_HD VxCounted vx_count_point(const uint32_t* masks, const uint16_t* pre, const uint32_t* base, uint4* recs, uint32_t* gcount,
-                                 uint32_t slot, int x, int y, int z) {
+// pass 3 (after the brick prefixes): rank of the point's voxel; voxel coordinates into the record;
+// the smallest original index (with its colour) wins the record's {rgb, idx} half.  Records must
+// be pre-filled with 0xFF.
+PCCM_HD uint32_t vx_place_point(const uint32_t* masks, const uint16_t* pre, const uint32_t* base, uint4* recs,
+                                uint32_t slot, int x, int y, int z, uint32_t rgb, uint32_t idx) {
     const int r = vx_row(y, z);
     const uint32_t m = masks[(size_t)slot * kVxRows + r];
-    VxCounted c;
-    c.rank = base[slot] + pre[(size_t)slot * kVxRows + r] + (uint32_t)vx_popc(m & ((1u << (x & 31)) - 1u));
-    recs[c.rank].x = (uint32_t)x | ((uint32_t)y << 16);      // every point of the voxel writes the same two words
-    recs[c.rank].y = (uint32_t)z;
-    c.ord = vx_atomic_add(gcount + c.rank, 1u);
-    return c;
-}
-// pass 4 (after the scan of the multiplicities): the point's entry
-PCCM_HD void vx_scatter_point(const uint32_t* gstart, uint4* pts, VxCounted c, uint32_t rgb, uint32_t idx) {
-    uint4 e; e.x = rgb; e.y = idx; e.z = c.rank; e.w = 0u;
-    pts[gstart[c.rank] + c.ord] = e;
-}
-// pass 5, per voxel: order its points by original index (arrival order is arbitrary: later passes must
-// see a fixed order) and copy the first into the voxel's record.  Groups longer than kVxGroupSmall
-// are left to a cooperative sort (returns true); their representative is still found here.
-constexpr uint32_t kVxGroupSmall = 32;
-PCCM_HD bool vx_group_finish(const uint32_t* gstart, uint4* pts, uint4* recs, uint32_t v) {
-    const uint32_t g0 = gstart[v], m = gstart[v + 1] - g0;
-    uint4* p = pts + g0;
-    if (m <= kVxGroupSmall) {
-        for (uint32_t i = 1; i < m; ++i) {
-            const uint4 e = p[i];
-            uint32_t j = i;
-            while (j > 0 && p[j - 1].y > e.y) { p[j] = p[j - 1]; --j; }
-            p[j] = e;
-        }
-        recs[v].z = p[0].x; recs[v].w = p[0].y;
-        return false;
-    }
-    uint4 best = p[0];
-    for (uint32_t i = 1; i < m; ++i) if (p[i].y < best.y) best = p[i];
-    recs[v].z = best.x; recs[v].w = best.y;
-    return true;
+    const uint32_t rank = base[slot] + pre[(size_t)slot * kVxRows + r] + (uint32_t)vx_popc(m & ((1u << (x & 31)) - 1u));
+    recs[rank].x = (uint32_t)x | ((uint32_t)y << 16);      // every point of the voxel writes the same two words
+    recs[rank].y = (uint32_t)z;
+    vx_atomic_min64(reinterpret_cast<unsigned long long*>(&recs[rank].z), ((unsigned long long)idx << 32) | rgb);
+    return rank;
 }
 
 // ---- staged search (rows within 2 of the query, x within 16) ---------------------------------

@@ -30,13 +30,10 @@ struct VoxBuild {
     uint32_t* masks;           // [nblk_total][64]
     uint16_t* pre;             // [nblk_total][64]
     uint32_t* base;            // [nblk_total + 1]
-    uint4* recs;               // [n_total]
-    uint32_t* gstart;          // [n_total + 1]: multiplicities, then (scanned) group starts
-    uint4* pts;                // [n_total]
-    uint2* counted;            // [n_total] scratch: {rank, arrival order} of input point i
+    uint4* recs;               // [n_total] 0xFF-filled
+    uint32_t* prank;           // [n_total] rank of the voxel of input point i (cloud 1's points follow cloud 0's)
     uint2* packed;             // [n_total] scratch: {x | y << 16, z} of input point i (written by the fill pass)
     uint32_t* pslot;           // [n_total] scratch: brick slot of input point i
-    uint32_t* longq;           // [0] = count, [1..] = voxels whose group is longer than kVxGroupSmall
 };
 
 __device__ __forceinline__ void vx_point(const VoxBuild& B, uint32_t i, int& c, uint32_t& li, int& x, int& y, int& z) {
@@ -93,23 +90,14 @@ __global__ void __launch_bounds__(256) vx_brickpre_kernel(const __grid_constant_
     if (lane == 31) B.base[slot] = incl;
 }
 
-__global__ void vx_count_kernel(const __grid_constant__ VoxBuild B) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.n_total) return;
-    const uint2 pk = B.packed[i];
-    const VxCounted k = vx_count_point(B.masks, B.pre, B.base, B.recs, B.gstart, B.pslot[i],
-                                       (int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)pk.y);
-    B.counted[i] = make_uint2(k.rank, k.ord);
-}
-
-__global__ void vx_scatter_kernel(const __grid_constant__ VoxBuild B) {
+__global__ void vx_place_kernel(const __grid_constant__ VoxBuild B) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n_total) return;
     const int c = (B.nclouds > 1 && i >= B.c[0].n) ? 1 : 0;
     const uint32_t li = i - (c ? B.c[0].n : 0u);
     const VoxCloudBuild& C = B.c[c];
     uint32_t rgba = 0;
-    if (C.rgb_in_rec) {
+    if (C.rgb_in_rec) {       // colours that have already arrived ride in the record of the voxel's representative
         if (C.rgb_dtype == PCCM_U8) {
             const uint8_t* p = static_cast<const uint8_t*>(C.rgb) + (int64_t)li * C.rgb_stride;
             rgba = p[0] | (p[1] << 8) | (p[2] << 16);
@@ -119,64 +107,8 @@ __global__ void vx_scatter_kernel(const __grid_constant__ VoxBuild B) {
                    ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 2) * 255.0) << 16);
         }
     }
-    const uint2 k = B.counted[i];
-    VxCounted kc; kc.rank = k.x; kc.ord = k.y;
-    vx_scatter_point(B.gstart, B.pts, kc, rgba, li);
-}
-
-// 8-bit colours into the point list and (first point of a voxel = its representative) the voxel
-// record, once they have arrived: the build itself never reads them
-__global__ void vx_rgbfill_kernel(uint4* __restrict__ pts, uint4* __restrict__ recs, const uint32_t* __restrict__ gstart,
-                                  uint32_t pts0, uint32_t n, const void* rgb, int rgb_dtype, int64_t rgb_stride) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t g = pts0 + i;
-    const uint4 e = pts[g];
-    uint32_t rgba;
-    if (rgb_dtype == PCCM_U8) {
-        const uint8_t* p = static_cast<const uint8_t*>(rgb) + (int64_t)e.y * rgb_stride;
-        rgba = p[0] | (p[1] << 8) | (p[2] << 16);
-    } else {
-        rgba = (uint32_t)rint(load_coord(rgb, PCCM_F64, rgb_stride, e.y, 0) * 255.0) |
-               ((uint32_t)rint(load_coord(rgb, PCCM_F64, rgb_stride, e.y, 1) * 255.0) << 8) |
-               ((uint32_t)rint(load_coord(rgb, PCCM_F64, rgb_stride, e.y, 2) * 255.0) << 16);
-    }
-    pts[g].x = rgba;
-    if (gstart[e.z] == g) recs[e.z].z = rgba;
-}
-
-// one thread per voxel (gstart[nblk_total-th base] of them, a device value)
-__global__ void vx_group_kernel(const __grid_constant__ VoxBuild B) {
-    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= B.base[B.nblk_total]) return;
-    if (vx_group_finish(B.gstart, B.pts, B.recs, v)) B.longq[1 + atomicAdd(B.longq, 1u)] = v;
-}
-
-// Groups of more than kVxGroupSmall points in ONE voxel (heavily duplicated inputs): one block each,
-// bitonic network in global memory, all-ascending form (the virtual +inf padding never moves).
-__global__ void __launch_bounds__(256) vx_longgroup_kernel(const __grid_constant__ VoxBuild B) {
-    const uint32_t count = B.longq[0];
-    for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
-        const uint32_t v = B.longq[1 + w];
-        const uint32_t g0 = B.gstart[v], len = B.gstart[v + 1] - g0;
-        uint4* a = B.pts + g0;
-        uint32_t p2 = 2;
-        while (p2 < len) p2 <<= 1;
-        for (uint32_t k = 2; k <= p2; k <<= 1) {
-            for (uint32_t i = threadIdx.x; i < len; i += 256) {
-                const uint32_t l = i ^ (k - 1);
-                if (l > i && l < len) { const uint4 x = a[i], y = a[l]; if (x.y > y.y) { a[i] = y; a[l] = x; } }
-            }
-            __syncthreads();
-            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-                for (uint32_t i = threadIdx.x; i < len; i += 256) {
-                    const uint32_t l = i ^ j;
-                    if (l > i && l < len) { const uint4 x = a[i], y = a[l]; if (x.y > y.y) { a[i] = y; a[l] = x; } }
-                }
-                __syncthreads();
-            }
-        }
-    }
+    const uint2 pk = B.packed[i];
+    B.prank[i] = vx_place_point(B.masks, B.pre, B.base, B.recs, B.pslot[i], (int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)pk.y, rgba, li);
 }
 
 // ------------------------------------------------------------------------------------
@@ -196,8 +128,7 @@ struct VxDir {
     const uint4* srecs;
     const uint32_t* srow_start;
     uint32_t rec_off;          // first reduction record of this direction
-    uint32_t pts0;             // first point of the query cloud in pts[]
-    uint32_t ntiles;           // ceil(q.n / kVxEpiTile): reduction records of vx_epilogue_kernel
+    uint32_t ntiles;           // ceil(q.n / kVxEpiTile): reduction records of one vx_epilogue_kernel pass
 };
 
 struct VxParams {
@@ -209,11 +140,11 @@ struct VxParams {
     double color_scale;
     BlockPartial* partials;
     uint4* vres;               // [n_total] by ranked position: {d2, packed (query - neighbour), neighbour idx, neighbour rgb};
-                               // d2 == kVxNone while the voxel is undecided
-    uint32_t* pendbits;        // [n_total / 32 + 1] zero on entry: voxels whose result waits in res[]
-    uint2* res;                // [n_total] {d2, neighbour position (top bit: in the pencil records)} of those voxels
-    uint32_t pend_rec;         // reduction records of vx_pending_kernel start at rec_off + ntiles + pend_rec
+                               // d2 == kVxNone while the voxel is undecided.  Pencil-round answers set the top bit of
+                               // the neighbour idx and put the neighbour's position in the pencil records into .y
+    int32_t pass;              // vx_epilogue_kernel: 0 = brick answers, 1 = pencil-round answers only
 };
+constexpr uint32_t kVxFarBit = 0x80000000u;
 
 __device__ __forceinline__ uint32_t vx_pack_e(int ex, int ey, int ez) {   // |e| <= 16 for every certified brick answer
     return (uint32_t)(ex + 128) | ((uint32_t)(ey + 128) << 8) | ((uint32_t)(ez + 128) << 16);
@@ -444,7 +375,10 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
         }
         // voxels the 5 x 5 rows left undecided (nearest point 3+ voxels away; rare): the whole warp scans the
         // 27 neighbour bricks for one voxel at a time -- anything outside them is at least 9 voxels away
-        unsigned pend = any_brick ? __ballot_sync(full, active && !done) : 0u;
+#ifndef PCCM_VX_INKERNEL
+#define PCCM_VX_INKERNEL 1
+#endif
+        unsigned pend = (PCCM_VX_INKERNEL && any_brick) ? __ballot_sync(full, active && !done) : 0u;
         while (pend) {
             const int src = __ffs((int)pend) - 1;
             pend &= pend - 1u;
@@ -468,11 +402,12 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
     }
 }
 
-// EPILOGUE.  Threads walk the query POINTS in pts[] order (grouped by voxel, so the 16-byte voxel
-// answers are read almost contiguously; duplicated points share their voxel's answer).  A block is
-// a fixed tile of kVxEpiTile points (kVxEpiPer per thread, strided so that every load is
-// coalesced) and writes one reduction record -> float sums do not depend on scheduling.  Points
-// of voxels that are still undecided are skipped (vx_pending_kernel reduces them).
+// EPILOGUE.  Threads walk the query POINTS in the ORIGINAL order of the input (4 per thread, strided so
+// that every load is coalesced): own colour, the other cloud's normal at the query index (quirk Q1)
+// and the per-point outputs stream; only the voxel's 16-byte answer is a gather (through prank).
+// Points that share a voxel share its answer.  A block is a fixed tile of kVxEpiTile points and
+// writes one reduction record -> float sums do not depend on scheduling.  Multi-GPU slices are cut
+// by voxel: a rank skips the points of voxels it did not search.
 constexpr int kVxEpiThreads = 256;
 constexpr int kVxEpiPer = 4;
 constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
@@ -488,25 +423,37 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     qa.lut255 = s_lut; sa.lut255 = s_lut;
     uint32_t t_lo, t_hi;
     vx_slice(P, D.q, t_lo, t_hi);
-    const uint32_t g_lo = __ldg(D.q.gstart + t_lo), g_hi = min(__ldg(D.q.gstart + t_hi), D.pts0 + D.q.n);
-    const uint32_t g0 = D.pts0 + tile * kVxEpiTile + threadIdx.x;
-    uint4 e[kVxEpiPer], v[kVxEpiPer];
-    bool on[kVxEpiPer];
+    const uint32_t i0 = tile * kVxEpiTile + threadIdx.x;
+    uint32_t rk[kVxEpiPer];
+    uint4 v[kVxEpiPer];
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
-        const uint32_t g = g0 + j * kVxEpiThreads;
-        on[j] = g >= g_lo && g < g_hi;
-        e[j] = on[j] ? __ldg(D.q.pts + g) : make_uint4(0u, 0u, 0u, 0u);      // {rgb, idx, rank, -}
+        const uint32_t i = i0 + j * kVxEpiThreads;
+        rk[j] = i < D.q.n ? __ldg(D.q.prank + i) : kVxNone;
     }
 #pragma unroll
-    for (int j = 0; j < kVxEpiPer; ++j) v[j] = on[j] ? __ldg(P.vres + e[j].z) : make_uint4(kVxNone, 0u, 0u, 0u);
+    for (int j = 0; j < kVxEpiPer; ++j)
+        v[j] = (rk[j] >= t_lo && rk[j] < t_hi) ? __ldg(P.vres + rk[j]) : make_uint4(kVxNone, 0u, 0u, 0u);
     VxAcc acc;
     acc.init();
 #pragma unroll
-    for (int j = 0; j < kVxEpiPer; ++j)
-        if (v[j].x != kVxNone)
-            vx_epilogue(P, D, qa, sa, e[j].y, e[j].x, v[j].x, (int)(v[j].y & 0xffu) - 128, (int)((v[j].y >> 8) & 0xffu) - 128,
-                        (int)((v[j].y >> 16) & 0xffu) - 128, v[j].z, v[j].w, acc);
+    for (int j = 0; j < kVxEpiPer; ++j) {
+        if (v[j].x == kVxNone) continue;
+        const uint32_t i = i0 + j * kVxEpiThreads;
+        const bool far = (v[j].z & kVxFarBit) != 0u;
+        if (far != (P.pass == 1)) continue;
+        int ex, ey, ez;
+        uint32_t nrgb = v[j].w;
+        if (!far) {
+            ex = (int)(v[j].y & 0xffu) - 128; ey = (int)((v[j].y >> 8) & 0xffu) - 128; ez = (int)((v[j].y >> 16) & 0xffu) - 128;
+        } else {                                  // pencil-round answer: any distance, coordinates from the records
+            const uint2 qv = __ldg(reinterpret_cast<const uint2*>(D.q.recs + rk[j]));
+            const uint4 nr = __ldg(D.srecs + v[j].y);               // {xy, z, idx, rgb}
+            ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
+            nrgb = nr.w;
+        }
+        vx_epilogue(P, D, qa, sa, i, 0u, v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc);
+    }
     BlockPartial r;
     vx_warp_record(acc, D.flags, r);
     __shared__ BlockPartial sm[kVxEpiThreads / 32];
@@ -515,7 +462,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     if (threadIdx.x == 0) {
         BlockPartial o = sm[0];
         for (int w = 1; w < kVxEpiThreads / 32; ++w) partial_merge(o, sm[w]);
-        P.partials[D.rec_off + tile] = o;
+        P.partials[D.rec_off + (uint32_t)P.pass * D.ntiles + tile] = o;
     }
 }
 
@@ -524,9 +471,8 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
 // owns rows 2l and 2l+1: one coalesced load of the 64 occupancy words), first for the minimal
 // distance only (bit scans, no record is touched), then again to fetch the index of the voxels
 // that tie at that distance.  An answer closer than 17 voxels is certified (everything unvisited is
-// at least that far); the rest goes to the pencil search (second round).  Results land in res[] /
-// pendbits[] and vx_pending_kernel reduces them in a fixed order -- both run on a second stream
-// beside vx_epilogue_kernel.
+// at least that far) and written to vres[] before the epilogue kernel runs; the rest goes to the
+// pencil search (second round).
 __global__ void __launch_bounds__(128)
 vx_general_kernel(const __grid_constant__ VxParams P) {
     __shared__ int s_slot[4][128];
@@ -566,8 +512,8 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
                 continue;
             }
             if (lane == 0) {
-                P.res[t] = make_uint2(best, brank);
-                atomicOr(P.pendbits + (t >> 5), 1u << (t & 31u));
+                const uint4 nr = __ldg(D.s.recs + brank);
+                P.vres[t] = make_uint4(best, vx_pack_e(qx - (int)(nr.x & 0xffffu), qy - (int)(nr.x >> 16), qz - (int)nr.y), nr.w, nr.z);
             }
         }
     }
@@ -589,57 +535,8 @@ vx_far_kernel(const __grid_constant__ VxParams P) {
             Best1<KInt> best;
             best.init();
             search<KInt>(D.sgrid, D.srow_start, D.srecs, q, best);
-            P.res[t] = make_uint2(best.d2, best.pos | 0x80000000u);      // top bit: position in the pencil records
-            atomicOr(P.pendbits + (t >> 5), 1u << (t & 31u));
+            P.vres[t] = make_uint4(best.d2, best.pos, best.idx | kVxFarBit, 0u);   // .y: position in the pencil records
         }
-    }
-}
-
-// Epilogue of the voxels answered by the brick rings / the pencil round.  gridDim = (G, ndirs): block (b, d) owns a fixed chunk of the
-// ranked positions and a fixed thread <-> position mapping, so its record is reproducible.
-constexpr int kVxPendThreads = 128;
-__global__ void __launch_bounds__(kVxPendThreads)
-vx_pending_kernel(const __grid_constant__ VxParams P) {
-    const int d = blockIdx.y;
-    const VxDir& D = P.dir[d];
-    const uint32_t nwords = (D.q.n_total + 31u) / 32u;
-    const uint32_t per = (nwords + gridDim.x - 1) / gridDim.x;
-    const uint32_t w0 = blockIdx.x * per, w1 = min(w0 + per, nwords);
-    const uint32_t r0 = vx_ranked_begin(D.q), nd = vx_ndistinct(D.q);
-    VxAcc acc;
-    acc.init();
-    for (uint32_t w = w0 + threadIdx.x; w < w1; w += kVxPendThreads) {
-        uint32_t bits = P.pendbits[w];
-        while (bits) {
-            const uint32_t t = w * 32u + (uint32_t)(__ffs((int)bits) - 1);
-            bits &= bits - 1u;
-            if (t - r0 >= nd) continue;               // a voxel of the other cloud
-            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(D.q.recs + t));
-            const uint2 res = P.res[t];
-            uint4 nr;
-            if (res.y & 0x80000000u) {                // pencil record {xy, z, idx, rgb}
-                nr = __ldg(D.srecs + (res.y & 0x7fffffffu));
-                const uint32_t i = nr.z; nr.z = nr.w; nr.w = i;
-            } else {
-                nr = __ldg(D.s.recs + res.y);
-            }
-            const int ex = (int)(qr.x & 0xffffu) - (int)(nr.x & 0xffffu), ey = (int)(qr.x >> 16) - (int)(nr.x >> 16), ez = (int)qr.y - (int)nr.y;
-            const uint32_t g0 = __ldg(D.q.gstart + t), g1 = __ldg(D.q.gstart + t + 1);
-            for (uint32_t g = g0; g < g1; ++g) {      // every point of the voxel
-                const uint4 e = __ldg(D.q.pts + g);
-                vx_epilogue(P, D, D.qa, D.sa, e.y, e.x, res.x, ex, ey, ez, nr.w, nr.z, acc);
-            }
-        }
-    }
-    BlockPartial r;
-    vx_warp_record(acc, D.flags, r);
-    __shared__ BlockPartial sm[kVxPendThreads / 32];
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        BlockPartial o = sm[0];
-        for (int w = 1; w < kVxPendThreads / 32; ++w) partial_merge(o, sm[w]);
-        P.partials[D.rec_off + D.ntiles + P.pend_rec + blockIdx.x] = o;
     }
 }
 

@@ -157,8 +157,7 @@ extern "C" int emul_knn_self(int kind, const double* pts, int64_t n, int k, doub
 #include "../../open_pcc_metric_b200/csrc/pccm_vox.cuh"
 
 struct VoxPair {
-    std::vector<uint32_t> dirbits, dirpre, masks, base, gstart;
-    std::vector<uint4> pts;
+    std::vector<uint32_t> dirbits, dirpre, masks, base, prank;
     std::vector<uint16_t> pre;
     std::vector<uint4> recs;
     VoxView view[2];
@@ -189,8 +188,8 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
     const uint32_t nblk0 = V.dirpre[ndirw[0]], nblk = run;
     V.masks.assign((size_t)nblk * kVxRows, 0); V.pre.assign((size_t)nblk * kVxRows, 0); V.base.assign(nblk + 1, 0);
     V.recs.resize(n_total);
-    memset(V.recs.data(), 0xff, (size_t)n_total * sizeof(uint4));   // (not needed: every word is written below)
-    V.gstart.assign((size_t)n_total + 1, 0); V.pts.resize(n_total);
+    memset(V.recs.data(), 0xff, (size_t)n_total * sizeof(uint4));
+    V.prank.assign(n_total, kVxNone);
     for (int c = 0; c < 2; ++c)                                   // vx_fill_kernel
         for (int64_t i = 0; i < n[c]; ++i) {
             int x, y, z; coords(c, i, x, y, z);
@@ -203,30 +202,21 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
         V.base[s] = run; run += in;
     }
     V.base[nblk] = run;
-    std::vector<VxCounted> counted[2];
-    std::vector<int64_t> order[2];                                 // arrival order of the atomics: odd indices downwards, then even ones upwards
-    for (int c = 0; c < 2; ++c) {
-        for (int64_t i = n[c]; i-- > 0;) if (i & 1) order[c].push_back(i);
-        for (int64_t i = 0; i < n[c]; ++i) if (!(i & 1)) order[c].push_back(i);
-        counted[c].resize(n[c]);
-        for (int64_t i : order[c]) {                               // vx_count_kernel
+    for (int c = 0; c < 2; ++c) {                                  // vx_place_kernel; arrival order of the atomics: odd indices
+        std::vector<int64_t> order;                                 // downwards, then even ones upwards
+        for (int64_t i = n[c]; i-- > 0;) if (i & 1) order.push_back(i);
+        for (int64_t i = 0; i < n[c]; ++i) if (!(i & 1)) order.push_back(i);
+        for (int64_t i : order) {
             int x, y, z; coords(c, i, x, y, z);
             const uint32_t slot = vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z));
-            counted[c][i] = vx_count_point(V.masks.data(), V.pre.data(), V.base.data(), V.recs.data(), V.gstart.data(), slot, x, y, z);
+            V.prank[(c ? n[0] : 0) + i] = vx_place_point(V.masks.data(), V.pre.data(), V.base.data(), V.recs.data(), slot, x, y, z, 0u, (uint32_t)i);
         }
     }
-    run = 0;                                                       // exclusive scan of the multiplicities
-    for (uint32_t v = 0; v <= n_total; ++v) { const uint32_t m = V.gstart[v]; V.gstart[v] = run; run += m; }
-    for (int c = 0; c < 2; ++c)                                    // vx_scatter_kernel
-        for (int64_t i = 0; i < n[c]; ++i) vx_scatter_point(V.gstart.data(), V.pts.data(), counted[c][i], 0u, (uint32_t)i);
-    for (uint32_t v = 0; v < V.base[nblk]; ++v)                    // vx_group_kernel + vx_longgroup_kernel
-        if (vx_group_finish(V.gstart.data(), V.pts.data(), V.recs.data(), v))
-            std::sort(V.pts.begin() + V.gstart[v], V.pts.begin() + V.gstart[v + 1], [](const uint4& p, const uint4& q) { return p.y < q.y; });
     for (int c = 0; c < 2; ++c) {
         VoxView& W = V.view[c];
         W.g = g[c]; W.dirbits = V.dirbits.data() + dir_off[c]; W.dirpre = V.dirpre.data() + dir_off[c];
         W.masks = V.masks.data(); W.pre = V.pre.data(); W.base = V.base.data(); W.recs = V.recs.data();
-        W.gstart = V.gstart.data(); W.pts = V.pts.data();
+        W.prank = V.prank.data() + (c ? n[0] : 0);
         W.slot0 = c ? nblk0 : 0; W.nblk = c ? nblk - nblk0 : nblk0; W.n = (uint32_t)n[c];
         W.nblk_total = nblk; W.n_total = n_total;
     }
@@ -247,19 +237,9 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
     for (int k = 0; k < 5; ++k) stats[k] = 0;
     for (int64_t i = 0; i < nq; ++i) { idx[i] = -2; d2[i] = -1; }
     std::vector<uint32_t> todo;
-    int order_errors = 0;
-    // every point of the voxel at ranked position t gets the voxel's answer
-    auto assign = [&](uint32_t t, uint32_t nidx, uint32_t nd2) {
-        const uint4 qr = Q.recs[t];
-        uint32_t last = 0;
-        for (uint32_t gi = Q.gstart[t]; gi < Q.gstart[t + 1]; ++gi) {
-            const uint4 e = Q.pts[gi];
-            if (e.z != t || (gi > Q.gstart[t] && e.y <= last) || (gi == Q.gstart[t] && e.y != qr.w) || idx[e.y] != -2) ++order_errors;
-            last = e.y;
-            idx[e.y] = (int32_t)nidx; d2[e.y] = (double)nd2;
-            if (gi > Q.gstart[t]) stats[3]++;
-        }
-    };
+    // answer of the voxel at ranked position t (vres[]); every point of the voxel reads it through prank (epilogue)
+    std::vector<int64_t> res_idx(V.recs.size(), -2), res_d2(V.recs.size(), -1);
+    auto assign = [&](uint32_t t, uint32_t nidx, uint32_t nd2) { res_idx[t] = nidx; res_d2[t] = nd2; };
     // vx_query_kernel: one "warp" per query brick
     for (uint32_t lb = 0; lb < Q.nblk; ++lb) {
         const uint32_t slot = Q.slot0 + lb, t0 = Q.base[slot], t1 = Q.base[slot + 1];
@@ -326,8 +306,16 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
             stats[4]++;
         }
     }
-    if (order_errors) return -15;
-    if ((uint32_t)stats[3] != Q.n - vx_ndistinct(Q) || Q.gstart[Q.slot0 + vx_ndistinct(Q)] != Q.n) return -16;
+    // vx_epilogue_kernel: original order
+    for (int64_t i = 0; i < nq; ++i) {
+        const uint32_t t = Q.prank[i];
+        const uint4 qr = Q.recs[t];
+        if ((int)(qr.x & 0xffffu) != (int)q[3 * i] || (int)(qr.x >> 16) != (int)q[3 * i + 1] || (int)qr.y != (int)q[3 * i + 2]) return -15;
+        if (qr.w > (uint32_t)i) return -16;               // the record holds the smallest index of its voxel
+        if (qr.w != (uint32_t)i) stats[3]++;
+        idx[i] = (int32_t)res_idx[t]; d2[i] = (double)res_d2[t];
+    }
+    if ((uint32_t)stats[3] != Q.n - vx_ndistinct(Q)) return -17;
     for (int64_t i = 0; i < nq; ++i) if (idx[i] == -2) return -14;   // every query exactly once
     return 0;
 }
