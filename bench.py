@@ -293,11 +293,11 @@ def main():
     # query-kernel roofline (one launch per step covers A->B and B->A), measured live with CUDA events
     q_launches = max(1, tm["query_launches"])
     brick = tm.get("vox_epilogue_ms", 0) > 0
-    # brick path: the query stage is several launches (search; brick-ring search of the undecided voxels and
-    # per-point epilogue beside it on a second stream); query_ms brackets the whole stage, the split is reported beside it
+    # brick path: the query stage is three launches (search of one lane per voxel; brick-ring search of the voxels
+    # it left undecided; per-point epilogue); query_ms brackets the whole stage, the split is reported beside it
     q_ms_avg = tm["query_ms"] / q_launches
     q_split = {"vx_search_kernel": tm["vox_search_ms"] / q_launches,
-               "vx_general_kernel + vx_pending_kernel (side stream)": tm.get("vox_tail_ms", 0) / q_launches,
+               "vx_general_kernel": tm.get("vox_tail_ms", 0) / q_launches,
                "vx_epilogue_kernel": tm.get("vox_epilogue_ms", 0) / q_launches} if brick else None
     queries_per_launch = nq / (world if partition else 1)
     achieved = ALG_BYTES_PER_QUERY * queries_per_launch / (q_ms_avg * 1e-3) / 1e9
@@ -361,7 +361,7 @@ def main():
                        "peak": "resolution", "parallelism": ("query slices of one pair" if partition else "one pair per GPU"),
                        "l2": "flushed between iterations (256 MiB write)", "ms_per_1M_point_pair": ms_dev_max / args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "kernel": "query stage = vx_search_kernel -> vx_epilogue_kernel || (vx_general_kernel, vx_pending_kernel)" if brick else "pair_query_kernel<KInt>",
+                         "traffic": traffic, "kernel": "query stage = vx_search_kernel + vx_general_kernel + vx_epilogue_kernel" if brick else "pair_query_kernel<KInt>",
                          "launch_ms_by_kernel": q_split, "peak_source": peak_src,
                          "alg_bytes_per_query": ALG_BYTES_PER_QUERY, "queries_per_launch": queries_per_launch,
                          "avg_launch_ms": q_ms_avg},

@@ -1058,7 +1058,8 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     CKV(dalloc(ctx, &v->dirpre, (size_t)B.ndirw_total + 1));
     CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)B.ndirw_total * sizeof(uint32_t), ctx->stream));
     B.dirbits = v->dirbits; B.dirpre = v->dirpre;
-    vx_mark_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+    const int blocks_ilp = (int)(((B.n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
+    vx_mark_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
     vx_dircount_kernel<<<(B.ndirw_total + 1 + threads - 1) / threads, threads, 0, ctx->stream>>>(v->dirbits, B.ndirw_total, v->dirpre);
     ctx->tm.total_launches += 2;
     CKV(cudaGetLastError());
@@ -1083,7 +1084,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     CKV(cudaMemsetAsync(v->recs, 0xff, (size_t)B.n_total * sizeof(uint4), ctx->stream));
     B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.prank = v->prank;
     B.packed = packed; B.pslot = pslot;
-    vx_fill_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+    vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
     vx_brickpre_kernel<<<(B.nblk_total + 1 + 7) / 8, 256, 0, ctx->stream>>>(B);
     ctx->tm.total_launches += 2;
     CKV(cudaGetLastError());
@@ -1105,7 +1106,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         }
     }
     if (!rc) {
-        vx_place_kernel<<<blocks, threads, 0, ctx->stream>>>(B);
+        vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
         ctx->tm.total_launches++;
     }
     dfree(ctx, packed); dfree(ctx, pslot);

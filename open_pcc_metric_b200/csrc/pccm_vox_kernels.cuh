@@ -45,12 +45,28 @@ __device__ __forceinline__ void vx_point(const VoxBuild& B, uint32_t i, int& c, 
     z = (int)load_coord(C.xyz, C.dtype, C.stride, li, 2);
 }
 
+// The per-point passes are chains of dependent loads (coordinates -> directory -> masks -> atomic):
+// every thread carries kVxIlp points, stage by stage, so that their loads are in flight together.
+constexpr int kVxIlp = 2;
+__device__ __forceinline__ uint32_t vx_ilp_index(const VoxBuild& B, int k) {     // point k of this thread (>= n_total: none)
+    const uint32_t per = (B.n_total + kVxIlp - 1) / kVxIlp;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    return t < per ? t + (uint32_t)k * per : 0xFFFFFFFFu;
+}
+
 __global__ void vx_mark_kernel(const __grid_constant__ VoxBuild B) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.n_total) return;
-    int c, x, y, z; uint32_t li;
-    vx_point(B, i, c, li, x, y, z);
-    vx_mark_point(B.dirbits + B.c[c].dir_off, vx_key(B.c[c].g, x, y, z));
+    int c[kVxIlp], x[kVxIlp], y[kVxIlp], z[kVxIlp];
+    bool on[kVxIlp];
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k) {
+        const uint32_t i = vx_ilp_index(B, k);
+        on[k] = i < B.n_total;
+        uint32_t li;
+        if (on[k]) vx_point(B, i, c[k], li, x[k], y[k], z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k)
+        if (on[k]) vx_mark_point(B.dirbits + B.c[c[k]].dir_off, vx_key(B.c[c[k]].g, x[k], y[k], z[k]));
 }
 
 __global__ void vx_dircount_kernel(const uint32_t* __restrict__ dirbits, uint32_t nw, uint32_t* __restrict__ dirpre) {
@@ -59,56 +75,90 @@ __global__ void vx_dircount_kernel(const uint32_t* __restrict__ dirbits, uint32_
 }
 
 __global__ void vx_fill_kernel(const __grid_constant__ VoxBuild B) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.n_total) return;
-    int c, x, y, z; uint32_t li;
-    vx_point(B, i, c, li, x, y, z);
-    const uint32_t off = B.c[c].dir_off;
-    const uint32_t slot = vx_slot_of_key(B.dirbits + off, B.dirpre + off, vx_key(B.c[c].g, x, y, z));
-    vx_fill_point(B.masks, slot, x, y, z);
-    B.packed[i] = make_uint2((uint32_t)x | ((uint32_t)y << 16), (uint32_t)z);   // later passes need not parse the input again
-    B.pslot[i] = slot;
+    int c[kVxIlp], x[kVxIlp], y[kVxIlp], z[kVxIlp];
+    uint32_t idx[kVxIlp], slot[kVxIlp];
+    bool on[kVxIlp];
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k) {
+        idx[k] = vx_ilp_index(B, k);
+        on[k] = idx[k] < B.n_total;
+        uint32_t li;
+        if (on[k]) vx_point(B, idx[k], c[k], li, x[k], y[k], z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k)
+        if (on[k]) {
+            const uint32_t off = B.c[c[k]].dir_off;
+            slot[k] = vx_slot_of_key(B.dirbits + off, B.dirpre + off, vx_key(B.c[c[k]].g, x[k], y[k], z[k]));
+        }
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k)
+        if (on[k]) {
+            vx_fill_point(B.masks, slot[k], x[k], y[k], z[k]);
+            B.packed[idx[k]] = make_uint2((uint32_t)x[k] | ((uint32_t)y[k] << 16), (uint32_t)z[k]);   // later passes need not parse the input again
+            B.pslot[idx[k]] = slot[k];
+        }
 }
 
 // one warp per brick: exclusive prefix of the row popcounts, brick total -> base[slot] (scanned next)
 __global__ void __launch_bounds__(256) vx_brickpre_kernel(const __grid_constant__ VoxBuild B) {
+    __shared__ uint32_t s_tot[8];
     const uint32_t slot = (blockIdx.x * 256u + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (slot > B.nblk_total) return;
-    if (slot == B.nblk_total) { if (lane == 0) B.base[slot] = 0u; return; }
-    const uint32_t* m = B.masks + (size_t)slot * kVxRows;
-    const uint32_t c0 = (uint32_t)__popc(m[2 * lane]), c1 = (uint32_t)__popc(m[2 * lane + 1]);
-    uint32_t incl = c0 + c1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = 0;
+    if (slot < B.nblk_total) {
+        const uint32_t* m = B.masks + (size_t)slot * kVxRows;
+        const uint32_t c0 = (uint32_t)__popc(m[2 * lane]), c1 = (uint32_t)__popc(m[2 * lane + 1]);
+        incl = c0 + c1;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t ex = incl - c0 - c1;
+        B.pre[(size_t)slot * kVxRows + 2 * lane] = (uint16_t)ex;
+        B.pre[(size_t)slot * kVxRows + 2 * lane + 1] = (uint16_t)(ex + c0);
     }
-    const uint32_t ex = incl - c0 - c1;
-    B.pre[(size_t)slot * kVxRows + 2 * lane] = (uint16_t)ex;
-    B.pre[(size_t)slot * kVxRows + 2 * lane + 1] = (uint16_t)(ex + c0);
-    if (lane == 31) B.base[slot] = incl;
+    if (lane == 31) s_tot[warp] = incl;
+    __syncthreads();
+    // the block's eight brick totals leave as one full 32-byte sector (the entry past the last brick is zero)
+    if (threadIdx.x < 8) {
+        const uint32_t sl = blockIdx.x * 8u + threadIdx.x;
+        if (sl <= B.nblk_total) B.base[sl] = s_tot[threadIdx.x];
+    }
+}
+
+__device__ __forceinline__ uint32_t vx_point_rgb(const VoxCloudBuild& C, uint32_t li) {
+    if (!C.rgb_in_rec) return 0u;   // colours that have already arrived ride in the record of the voxel's representative
+    if (C.rgb_dtype == PCCM_U8) {
+        const uint8_t* p = static_cast<const uint8_t*>(C.rgb) + (int64_t)li * C.rgb_stride;
+        return p[0] | (p[1] << 8) | (p[2] << 16);
+    }
+    return (uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 0) * 255.0) |
+           ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 1) * 255.0) << 8) |
+           ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 2) * 255.0) << 16);
 }
 
 __global__ void vx_place_kernel(const __grid_constant__ VoxBuild B) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.n_total) return;
-    const int c = (B.nclouds > 1 && i >= B.c[0].n) ? 1 : 0;
-    const uint32_t li = i - (c ? B.c[0].n : 0u);
-    const VoxCloudBuild& C = B.c[c];
-    uint32_t rgba = 0;
-    if (C.rgb_in_rec) {       // colours that have already arrived ride in the record of the voxel's representative
-        if (C.rgb_dtype == PCCM_U8) {
-            const uint8_t* p = static_cast<const uint8_t*>(C.rgb) + (int64_t)li * C.rgb_stride;
-            rgba = p[0] | (p[1] << 8) | (p[2] << 16);
-        } else {
-            rgba = (uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 0) * 255.0) |
-                   ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 1) * 255.0) << 8) |
-                   ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 2) * 255.0) << 16);
+    uint32_t idx[kVxIlp], li[kVxIlp], slot[kVxIlp], rgba[kVxIlp];
+    uint2 pk[kVxIlp];
+    bool on[kVxIlp];
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k) {
+        idx[k] = vx_ilp_index(B, k);
+        on[k] = idx[k] < B.n_total;
+        if (on[k]) {
+            const int c = (B.nclouds > 1 && idx[k] >= B.c[0].n) ? 1 : 0;
+            li[k] = idx[k] - (c ? B.c[0].n : 0u);
+            pk[k] = B.packed[idx[k]];
+            slot[k] = B.pslot[idx[k]];
+            rgba[k] = vx_point_rgb(B.c[c], li[k]);
         }
     }
-    const uint2 pk = B.packed[i];
-    B.prank[i] = vx_place_point(B.masks, B.pre, B.base, B.recs, B.pslot[i], (int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)pk.y, rgba, li);
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k)
+        if (on[k])
+            B.prank[idx[k]] = vx_place_point(B.masks, B.pre, B.base, B.recs, slot[k], (int)(pk[k].x & 0xffffu), (int)(pk[k].x >> 16), (int)pk[k].y, rgba[k], li[k]);
 }
 
 // ------------------------------------------------------------------------------------
