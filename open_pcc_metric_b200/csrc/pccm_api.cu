@@ -1046,7 +1046,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     B.ndirw_total = ndirw[0] + ndirw[1];
     B.n_total = R.n[0] + R.n[1];
     SharedVox* v = new SharedVox();
-    const int threads = 256, blocks = (int)((B.n_total + threads - 1) / threads);
+    const int threads = 256;
     auto bail = [&](int rc) { free_vox(ctx, v); return rc; };
 #define CKV(call)                                                                                    \
     do {                                                                                             \
