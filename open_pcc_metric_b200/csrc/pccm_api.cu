@@ -1591,6 +1591,56 @@ static int launch_knn(pccm_ctx* ctx, pccm_cloud* c, KnnParams& P) {
     return PCCM_OK;
 }
 
+// pccm_self_nn_minmax on the brick index.  *ok = false when a voxel could not be decided within its 27
+// neighbour bricks (the caller then takes the pencil path).
+static int vox_self_nn(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end, double* min_out, double* max_out,
+                       double* per_point, int mem_kind, bool* ok) {
+    *ok = false;
+    SharedVox* v = c->vox;
+    VxSelfParams P{};
+    P.c = v->view[c->vox_id];
+    P.n = (uint32_t)c->n;
+    P.begin = (uint32_t)begin; P.end = (uint32_t)end;
+    const uint32_t n_total = P.c.n_total, nwords = (n_total + 31u) / 32u;
+    uint32_t* scratch = nullptr;      // [0] undecided counter, then dupbits
+    uint32_t* vself = nullptr;
+    double *mm = nullptr, *d_pp = nullptr;
+    CK(dalloc(ctx, &scratch, (size_t)nwords + 2));
+    CK(dalloc(ctx, &vself, (size_t)n_total));
+    CK(dalloc(ctx, &mm, (size_t)P.c.nblk * 2));
+    if (per_point) { if (mem_kind == PCCM_DEVICE) d_pp = per_point; else CK(dalloc(ctx, &d_pp, (size_t)c->n)); }
+    CK(cudaMemsetAsync(scratch, 0, ((size_t)nwords + 2) * sizeof(uint32_t), ctx->stream));
+    P.undecided = scratch; P.dupbits = scratch + 1; P.vself = vself; P.minmax = mm; P.per_point = d_pp;
+    {
+        StageTimer t(ctx, &ctx->tm.knn_ms, 1);
+        vx_dupflag_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(P);
+        vx_selfnn_kernel<<<(P.c.nblk + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
+        minmax_finalize_kernel<<<1, 256, 0, ctx->stream>>>(mm, P.c.nblk, static_cast<double*>(ctx->dscratch) + 1024);
+        ctx->tm.knn_launches++;
+        ctx->tm.total_launches += 3;
+        if (per_point) {
+            vx_selfout_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(P);
+            ctx->tm.total_launches++;
+        }
+        CK(cudaGetLastError());
+    }
+    double* hmm = static_cast<double*>(ctx->pinned) + 1024;
+    uint32_t* hund = reinterpret_cast<uint32_t*>(hmm + 2);
+    CK(cudaMemcpyAsync(hmm, static_cast<double*>(ctx->dscratch) + 1024, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hund, scratch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = PCCM_OK;
+    if (*hund == 0u) {
+        *ok = true;
+        *min_out = hmm[0];
+        *max_out = hmm[1];
+        if (per_point && mem_kind == PCCM_HOST) rc = copy_out(ctx, per_point, d_pp, (size_t)c->n * sizeof(double), PCCM_HOST);
+    }
+    if (per_point && mem_kind == PCCM_HOST) dfree(ctx, d_pp);
+    dfree(ctx, scratch); dfree(ctx, vself); dfree(ctx, mm);
+    return rc;
+}
+
 static int check_range(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end) {
     if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
     if (begin < 0 || end < begin || end > c->n) return fail(ctx, PCCM_ERR_INVALID, "bad range [%lld, %lld)", (long long)begin, (long long)end);
@@ -1624,9 +1674,18 @@ extern "C" int pccm_self_nn_minmax(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, 
                                    double* min_out, double* max_out, double* per_point, int mem_kind) {
     if (!ctx || !c || !min_out || !max_out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
+    if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
+    if (begin < 0 || end < begin || end > c->n) return fail(ctx, PCCM_ERR_INVALID, "bad range [%lld, %lld)", (long long)begin, (long long)end);
+    if (end == begin) { *min_out = INFINITY; *max_out = -INFINITY; return PCCM_OK; }
+    if (ctx->use_vox && c->vox && c->n >= 2 && (!per_point || (begin == 0 && end == c->n))) {
+        // brick index: the pair search's row scans with the voxel's own bit cleared; no pencil index needed
+        bool ok = false;
+        const int rcv = vox_self_nn(ctx, c, begin, end, min_out, max_out, per_point, mem_kind, &ok);
+        if (rcv) return rcv;
+        if (ok) return PCCM_OK;      // else: some point is isolated by more than 8 voxels -> pencil path below
+    }
     int rc = check_range(ctx, c, begin, end);
     if (rc) return rc;
-    if (end == begin) { *min_out = INFINITY; *max_out = -INFINITY; return PCCM_OK; }
     const uint32_t nblocks = (uint32_t)((end - begin + kKnnThreads - 1) / kKnnThreads);
     double* mm = nullptr;
     double* d_pp = nullptr;

@@ -240,6 +240,11 @@ PCCM_HD void vx_rows_inner(const uint2* win, int lx, int ly, int lz, uint32_t& b
     VX_ROW(-1, 0) VX_ROW(1, 0) VX_ROW(0, -1) VX_ROW(0, 1)
     VX_ROW(-1, -1) VX_ROW(1, -1) VX_ROW(-1, 1) VX_ROW(1, 1)
 }
+// the eight rows around the query's own row (self nearest neighbour: the own row is handled apart)
+PCCM_HD void vx_rows_ring1(const uint2* win, int lx, int ly, int lz, uint32_t& bd2, uint32_t& rows) {
+    VX_ROW(-1, 0) VX_ROW(1, 0) VX_ROW(0, -1) VX_ROW(0, 1)
+    VX_ROW(-1, -1) VX_ROW(1, -1) VX_ROW(-1, 1) VX_ROW(1, 1)
+}
 // the 16 rows of the 5 x 5 border: with them, every query with best d2 < 9.
 PCCM_HD void vx_rows_outer(const uint2* win, int lx, int ly, int lz, uint32_t& bd2, uint32_t& rows) {
     VX_ROW(-2, 0) VX_ROW(2, 0) VX_ROW(0, -2) VX_ROW(0, 2)

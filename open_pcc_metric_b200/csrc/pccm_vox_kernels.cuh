@@ -281,9 +281,10 @@ __device__ __forceinline__ void vx_row_nearest(uint32_t m, int p, int& dlo, int&
 // distance by bit scans only.  Pass 2 (when that distance is below `limit`, i.e. certified): the
 // smallest original index among the voxels at that distance.  Returns the distance; rank is valid
 // when it is below `limit`.
-template <int DIM>
+template <int DIM, bool SELF = false>
 __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* slots, const int* ids, int n,
                                                    int qx, int qy, int qz, uint32_t limit, uint32_t& rank_out) {
+    // SELF: the query is a voxel of S itself -- its own bit is cleared and only the distance is wanted
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
@@ -302,9 +303,10 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
             const int p = qx - (bx << 5);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const uint32_t m = k ? mb[j].y : mb[j].x;
-                if (!m) continue;
+                uint32_t m = k ? mb[j].y : mb[j].x;
                 const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
+                if (SELF && dy == 0 && dz == 0 && (unsigned)p < 32u) m &= ~(1u << p);
+                if (!m) continue;
                 int dlo, dhi;
                 vx_row_nearest(m, p, dlo, dhi);
                 const int dx = dlo < dhi ? dlo : dhi;
@@ -314,7 +316,7 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
         }
     }
     best = __reduce_min_sync(full, best);
-    if (best >= limit) return best;
+    if (SELF || best >= limit) return best;
     uint32_t bidx = kVxNone, brank = kVxNone;
     for (int k0 = 0; k0 < n; ++k0) {
         const int slot = slots[k0], b = ids[k0];
@@ -352,7 +354,10 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
 // then takes the brick's voxels 32 at a time, one lane per voxel: bit scans over the 3 x 3 (5 x 5)
 // rows, rank look-ups only for the voxels that tie at the minimum.  Integer work only; the answer of
 // every voxel goes to vres[] (16 bytes), undecided voxels to the todo list.
-constexpr int kVxThreads = 128;
+#ifndef PCCM_VX_THREADS
+#define PCCM_VX_THREADS 128
+#endif
+constexpr int kVxThreads = PCCM_VX_THREADS;
 constexpr int kVxWarps = kVxThreads / 32;
 
 #ifndef PCCM_VX_MINBLOCKS
@@ -588,6 +593,128 @@ vx_far_kernel(const __grid_constant__ VxParams P) {
             P.vres[t] = make_uint4(best.d2, best.pos, best.idx | kVxFarBit, 0u);   // .y: position in the pencil records
         }
     }
+}
+
+// ------------------------------------------------------------------------------------
+// distance of every point to its nearest OTHER point (compute_nearest_neighbor_distance,
+// cloud_pair.py:108-109) on the brick index: the same row scans with the voxel's own bit cleared;
+// a voxel that holds more than one point answers 0
+// ------------------------------------------------------------------------------------
+struct VxSelfParams {
+    VoxView c;
+    uint32_t n;                // points of the cloud
+    uint32_t begin, end;       // slice of the cloud's points [begin, end) -> the same share of its voxels
+    uint32_t* dupbits;         // [n_total / 32 + 1] by rank: voxel holds more than one point
+    uint32_t* vself;           // [n_total] by rank: squared distance to the nearest other point (kVxNone: not decided here)
+    double* minmax;            // per brick {min, max} of the distances (sqrt)
+    uint32_t* undecided;       // voxels farther than 8 voxels from every other one (caller falls back to the pencil path)
+    double* per_point;         // optional, original order
+};
+
+__global__ void vx_dupflag_kernel(const __grid_constant__ VxSelfParams P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t rank = __ldg(P.c.prank + i);
+    if (__ldg(reinterpret_cast<const uint32_t*>(P.c.recs + rank) + 3) != i) atomicOr(P.dupbits + (rank >> 5), 1u << (rank & 31u));
+}
+
+__global__ void __launch_bounds__(kVxThreads)
+vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
+    __shared__ uint2 s_win[kVxWarps][kVxRegRows];
+    __shared__ int s_slot[kVxWarps][28];
+    __shared__ int s_occ[kVxWarps][2][28];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lb = blockIdx.x * kVxWarps + warp;
+    if (lb >= P.c.nblk) return;
+    const uint32_t slot = P.c.slot0 + lb;
+    const uint32_t b0 = __ldg(P.c.base + slot), b1 = __ldg(P.c.base + slot + 1);
+    const uint32_t r0 = vx_ranked_begin(P.c), nd = vx_ndistinct(P.c);
+    const uint32_t t_lo = r0 + (uint32_t)((unsigned long long)nd * P.begin / (P.n ? P.n : 1u));
+    const uint32_t t_hi = r0 + (uint32_t)((unsigned long long)nd * P.end / (P.n ? P.n : 1u));
+    const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
+    uint32_t mn = kVxNone, mx = 0u;
+    bool any = false;
+    if (t0 < t1) {
+        uint2* win = s_win[warp];
+        int* sslot = s_slot[warp];
+        int* occ_slot = s_occ[warp][0];
+        int* occ_id = s_occ[warp][1];
+        const uint2 first = __ldg(reinterpret_cast<const uint2*>(P.c.recs + b0));
+        const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+        int myslot = -1;
+        if (lane < 27) {
+            myslot = vx_slot(P.c, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
+            sslot[lane] = myslot;
+        }
+        const unsigned occ = __ballot_sync(full, myslot >= 0);
+        const int nocc = __popc(occ);
+        if (myslot >= 0) {
+            const int k = __popc(occ & ((1u << lane) - 1u));
+            occ_slot[k] = myslot;
+            occ_id[k] = lane;
+        }
+        __syncwarp();
+        for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(P.c, sslot, i);
+        __syncwarp();
+        for (uint32_t tb = t0; tb < t1; tb += 32) {
+            const uint32_t t = tb + lane;
+            const bool active = t < t1;
+            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(P.c.recs + (active ? t : t0)));
+            const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+            const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
+            // the voxel's own bit sits at bit 16 + lx of its row window: clear it in a private copy of that row
+            const bool dup = active && ((__ldg(P.dupbits + (t >> 5)) >> (t & 31u)) & 1u);
+            uint32_t bd2 = kVxNone, rows = 0;
+            {
+                uint2 own = win[lz * kVxRegY + ly];
+                const int bit = 16 + lx;
+                if (bit < 32) own.x &= ~(1u << bit); else own.y &= ~(1u << (bit - 32));
+                int dd, du;
+                vx_row_dists(own, lx, dd, du);
+                const int dx = dd < du ? dd : du;
+                bd2 = (uint32_t)(dx * dx);
+            }
+            uint32_t nb = kVxNone, nrows = 0;
+            vx_rows_ring1(win, lx, ly, lz, nb, nrows);
+            bd2 = nb < bd2 ? nb : bd2;
+            bool done = bd2 < 4u;
+            if (__any_sync(full, active && !done && !dup)) {
+                vx_rows_outer(win, lx, ly, lz, bd2, rows);
+                done = bd2 < 9u;
+            }
+            unsigned pend = __ballot_sync(full, active && !done && !dup);
+            while (pend) {
+                const int src = __ffs((int)pend) - 1;
+                pend &= pend - 1u;
+                const int sx = __shfl_sync(full, qx, src), sy = __shfl_sync(full, qy, src), sz = __shfl_sync(full, qz, src);
+                uint32_t dummy = kVxNone;
+                const uint32_t nd2 = vx_warp_bricks<3, true>(P.c, occ_slot, occ_id, nocc, sx, sy, sz, 81u, dummy);
+                if (nd2 < 81u && lane == src) { bd2 = nd2; done = true; }
+            }
+            if (active) {
+                const uint32_t v = dup ? 0u : (done ? bd2 : kVxNone);
+                P.vself[t] = v;
+                if (v != kVxNone) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; any = true; }
+            }
+            const unsigned und = __ballot_sync(full, active && !dup && !done);
+            if (und && lane == 0) atomicAdd(P.undecided, (uint32_t)__popc(und));
+        }
+    }
+    mn = __reduce_min_sync(full, mn);
+    mx = __reduce_max_sync(full, mx);
+    const bool wany = __any_sync(full, any);
+    if (lane == 0) {
+        P.minmax[2 * lb] = wany ? sqrt((double)mn) : INFINITY;
+        P.minmax[2 * lb + 1] = wany ? sqrt((double)mx) : -INFINITY;
+    }
+}
+
+__global__ void vx_selfout_kernel(const __grid_constant__ VxSelfParams P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t v = P.vself[__ldg(P.c.prank + i)];
+    P.per_point[i] = sqrt((double)v);
 }
 
 }  // namespace pccm

@@ -145,3 +145,27 @@ def test_vox_rank_slices_add_up_and_are_deterministic(ctxs):
                         assert np.isclose(sum(p.dir[d].color_sum[c] for p in parts), full.dir[d].color_sum[c], rtol=1e-12)
         a.close(); b.close()
     assert outs[0] == outs[1] == outs[2]     # duplicate tails and undecided queries included
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_vox_boundary_distances_equal_oracle_and_pencil_path(ctxs, name):
+    """compute_nearest_neighbor_distance (cloud_pair.py:108-109) on the brick index: the pair search's
+    row scans with the voxel's own bit cleared; isolated points make the call fall back to the pencil path"""
+    vox, pencil = ctxs
+    A, B = _case(name)
+    if len(A) < 2:
+        pytest.skip("needs two points")
+    res = []
+    for ctx in (vox, pencil):
+        a, b = ctx.cloud(A), ctx.cloud(B)
+        ctx.build_pair(a, b)
+        mn, mx, per = a.self_nn_minmax(per_point=True)
+        parts = [a.self_nn_minmax(len(A) * r // 3, len(A) * (r + 1) // 3)[:2] for r in range(3)]
+        res.append((mn, mx, per, parts))
+        a.close(); b.close()
+    _, o2 = cnn.knn(A, A, 2)
+    want = np.sqrt(o2[:, 1])
+    for mn, mx, per, parts in res:
+        assert np.array_equal(per, want), name
+        assert mn == want.min() and mx == want.max()
+        assert min(p[0] for p in parts) == mn and max(p[1] for p in parts) == mx
