@@ -102,7 +102,7 @@ typedef struct pccm_timings {
     double upload_ms, stats_ms, keys_ms, sort_ms, table_ms, reorder_ms;
     double query_ms, finalize_ms, knn_ms;
     double vox_build_ms;       /* occupancy-brick index of integer pairs */
-    double vox_tail_ms;        /* brick-ring (and pencil) search of the voxels the staged search left undecided */
+    double vox_tail_ms;        /* brick-ring search of the voxels the search kernel left undecided (+ the pencil round, when one is needed) */
     double vox_search_ms;      /* staged bit-scan search kernel of the brick path (query_ms covers the whole query stage) */
     double vox_epilogue_ms;    /* per-point epilogue kernel of the brick path (D1 / D2 / colour + reduction records) */
     int64_t query_launches, knn_launches;
@@ -110,7 +110,7 @@ typedef struct pccm_timings {
     int64_t library_launches;  /* CUB device-wide calls (radix sort passes, scans) */
     int64_t vox_undecided;     /* queries of the last brick-path evaluation that needed the general search */
     int64_t vox_far;           /* ... of which the pencil search had to finish (nearest point tens of voxels away) */
-    int64_t vox_tail;          /* points sharing a voxel with a smaller index (duplicate tails), last evaluation */
+    int64_t vox_tail;          /* points that share a voxel with a smaller index (they reuse that voxel's search), last evaluation */
 } pccm_timings;
 
 int pccm_version(void);

@@ -31,7 +31,7 @@ struct pccm_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // host->device copies of attributes that are only needed by the query epilogue
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr;
     // per-cloud pinned statistics buffers and events are recycled: cudaMallocHost / cudaFreeHost are
     // synchronous OS-level calls (tens of microseconds) and a cloud lives for one evaluation
     std::vector<void*> stats_pool;
@@ -377,7 +377,6 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->copy_stream = nullptr;
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { ctx->copy_stream = nullptr; }
-    if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) ctx->ev_join = nullptr;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -420,7 +419,6 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     cudaFree(ctx->dscratch);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCCM_OK;

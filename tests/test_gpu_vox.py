@@ -169,3 +169,37 @@ def test_vox_boundary_distances_equal_oracle_and_pencil_path(ctxs, name):
         assert np.array_equal(per, want), name
         assert mn == want.min() and mx == want.max()
         assert min(p[0] for p in parts) == mn and max(p[1] for p in parts) == mx
+
+
+def test_attach_equals_create_with_attributes(ctxs):
+    """pccm_cloud_attach (coordinates of both clouds first, colours / normals afterwards on the copy
+    stream) gives the same evaluation as pccm_cloud_create with everything; float colours that are
+    not k/255 take the float64 colour array."""
+    from open_pcc_metric_b200 import _native as N
+    vox, _ = ctxs
+    A, B = _case("surface")
+    n = min(len(A), len(B))
+    A, B = A[:n], B[:n]
+    rng = np.random.default_rng(8)
+    for exact_u8 in (True, False):
+        ca, na = _attrs(rng, n)
+        cb, nb = _attrs(rng, n)
+        if not exact_u8:
+            ca, cb = rng.random((n, 3)), rng.random((n, 3))
+        outs = []
+        for late in (False, True):
+            if late:
+                a, b = vox.cloud(A), vox.cloud(B)
+                a.attach(ca, na); b.attach(cb, nb)
+            else:
+                a, b = vox.cloud(A, ca, na), vox.cloud(B, cb, nb)
+            vox.build_pair(a, b)
+            assert bool(a.info().colors_u8) == exact_u8
+            outs.append(bytes(vox.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV)))
+            a.close(); b.close()
+        assert outs[0] == outs[1]
+    a = vox.cloud(A)
+    a.build_index()
+    with pytest.raises(N.PccmError):
+        a.attach(ca, None)          # pencil records bake the colours in at build time
+    a.close()
