@@ -319,3 +319,53 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
     for (int64_t i = 0; i < nq; ++i) if (idx[i] == -2) return -14;   // every query exactly once
     return 0;
 }
+
+// Boundary distances on the brick index (vx_selfnn_kernel): distance of every point to its nearest OTHER
+// point by the staged row scans with the voxel's own bit cleared; voxels that hold several points answer 0.
+// out[i] = squared distance, -1 where the staged rows cannot decide (the kernel scans whole bricks there,
+// the library falls back to the pencil k-NN beyond 8 voxels).  Returns the number of undecided points.
+extern "C" int64_t emul_vox_self(const double* pts_in, int64_t n_in, double* out) {
+    const double* pts[2] = {pts_in, pts_in};
+    const int64_t n[2] = {n_in, 1};          // second cloud: one point, unused
+    VoxPair V;
+    if (!vox_build(pts, n, V)) return -1;
+    const VoxView& Q = V.view[0];
+    const uint32_t nd = vx_ndistinct(Q);
+    std::vector<uint8_t> dup(nd, 0);
+    for (int64_t i = 0; i < n_in; ++i)       // vx_dupflag_kernel
+        if (Q.recs[Q.prank[i]].w != (uint32_t)i) dup[Q.prank[i]] = 1;
+    std::vector<int64_t> vself(nd, -1);
+    for (uint32_t lb = 0; lb < Q.nblk; ++lb) {
+        const uint32_t slot = Q.slot0 + lb, t0 = Q.base[slot], t1 = Q.base[slot + 1];
+        const uint4 first = Q.recs[t0];
+        const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+        int sslot[27];
+        for (int l = 0; l < 27; ++l) sslot[l] = vx_slot(Q, bx + l % 3 - 1, by + (l / 3) % 3 - 1, bz + l / 9 - 1);
+        uint2 win[kVxRegRows];
+        for (int r = 0; r < kVxRegRows; ++r) win[r] = vx_stage_row(Q, sslot, r);
+        for (uint32_t t = t0; t < t1; ++t) {
+            if (dup[t]) { vself[t] = 0; continue; }
+            const uint4 qr = Q.recs[t];
+            const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+            const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
+            uint2 own = win[lz * kVxRegY + ly];
+            const int bit = 16 + lx;
+            if (bit < 32) own.x &= ~(1u << bit); else own.y &= ~(1u << (bit - 32));
+            int dd, du;
+            vx_row_dists(own, lx, dd, du);
+            const int dx = dd < du ? dd : du;
+            uint32_t bd2 = (uint32_t)(dx * dx), nb = kVxNone, rows = 0;
+            vx_rows_ring1(win, lx, ly, lz, nb, rows);
+            bd2 = nb < bd2 ? nb : bd2;
+            bool done = bd2 < 4u;
+            if (!done) { vx_rows_outer(win, lx, ly, lz, bd2, rows); done = bd2 < 9u; }
+            if (done) vself[t] = bd2;
+        }
+    }
+    int64_t undecided = 0;
+    for (int64_t i = 0; i < n_in; ++i) {     // vx_selfout_kernel
+        out[i] = (double)vself[Q.prank[i]];
+        if (out[i] < 0) ++undecided;
+    }
+    return undecided;
+}

@@ -233,3 +233,23 @@ def test_property_vox_nn(a, b, off):
     A = np.array(a, dtype=float) + np.array(off, dtype=float)
     B = np.array(b, dtype=float) + np.array(off, dtype=float)
     _check_vox(A, B)
+
+
+def test_vox_boundary_distances():
+    """nearest OTHER point by the staged row scans with the own bit cleared (vx_selfnn_kernel's logic)"""
+    _L.emul_vox_self.restype = ctypes.c_int64
+    rng = np.random.default_rng(9)
+    surf = np.unique(rng.integers(0, 48, (6000, 3)), axis=0).astype(float)        # dense: everything decided by the rows
+    sparse = rng.integers(0, 600, (400, 3)).astype(float)                          # mostly isolated points
+    edges = np.array([[31, 7, 7], [32, 7, 7], [47, 8, 8], [0, 0, 0], [16, 0, 0], [17, 0, 0], [63, 15, 16], [63, 15, 18]], dtype=float)
+    for P in (surf, np.concatenate([surf, surf[:200]]), sparse, edges):
+        P = np.ascontiguousarray(P)
+        out = np.empty(len(P))
+        und = _L.emul_vox_self(_p(P), ctypes.c_int64(len(P)), _p(out))
+        assert und >= 0
+        _, o2 = cnn.knn(P, P, 2)
+        decided = out >= 0
+        assert np.array_equal(out[decided], o2[decided, 1])
+        assert (o2[~decided, 1] >= 9).all()              # only answers 3+ voxels away are left to the brick scans
+        assert und == (~decided).sum()
+    assert decided.sum() >= 5
