@@ -203,3 +203,29 @@ def test_attach_equals_create_with_attributes(ctxs):
     with pytest.raises(N.PccmError):
         a.attach(ca, None)          # pencil records bake the colours in at build time
     a.close()
+
+
+def test_brick_indexed_cloud_outlives_its_partner_and_joins_other_pairs(ctxs):
+    """the pencil index of a brick-indexed cloud is built on demand from the pair's records: also after
+    the partner is gone, and for evaluations against a cloud of another pair"""
+    from open_pcc_metric_b200 import _native as N
+    vox, _ = ctxs
+    A, B = _case("dense_dups_outliers")
+    C = _case("lattice")[0][:3000] - 150
+    a, b = vox.cloud(A), vox.cloud(B)
+    vox.build_pair(a, b)
+    a.close()                                   # b keeps the shared brick arrays alive
+    ki, kd = b.knn_self(4)
+    oi, od = cnn.knn(B, B, 4)
+    assert np.array_equal(kd, od) and np.array_equal(ki, oi)
+    mn, mx, per = b.self_nn_minmax(per_point=True)
+    assert np.array_equal(per, np.sqrt(od[:, 1]))
+    c = vox.cloud(C)
+    vox.build_pair(b, c)                        # b is indexed already: c gets its own (pencil) index
+    for q, s_, Q, S in ((b, c, B, C), (c, b, C, B)):
+        idx, d2 = vox.nn(q, s_)
+        oi, od = cnn.knn(S, Q, 1)
+        assert np.array_equal(d2, od[:, 0]) and np.array_equal(idx, oi[:, 0])
+    r = vox.pair_eval(b, c, 0)
+    assert r.dir[0].n == len(B) and r.dir[1].n == len(C)
+    b.close(); c.close()
