@@ -285,6 +285,8 @@ PCCM_HD void vx_pick(const VoxView& S, const int* sslot, const uint2* win, int b
 }
 
 // ---- general search: brick rings, any distance (exact) --------------------------------------
+// Sequential statement of what the kernels do warp-cooperatively (vx_warp_bricks in pccm_vox_kernels.cuh:
+// ring 1 inside vx_search_kernel, rings 0..2 in vx_general_kernel); the CPU stepping harness runs this one.
 struct VxHit {
     uint32_t d2, idx, rgb, rank;
     int cx, cy, cz;

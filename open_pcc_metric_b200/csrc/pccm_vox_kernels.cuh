@@ -1,8 +1,12 @@
 // pccm_vox_kernels.cuh -- sm_100a kernels of the occupancy-brick path for voxelised pairs:
-// index build (mark / fill / prefix / place / tail sort) and the symmetric query
-// (vx_query_kernel: one warp per query brick, search rows staged in shared memory;
-//  vx_general_kernel: the undecided queries and the duplicate tails; vx_pending_kernel: their
-//  epilogue in a fixed order).  Per-point / per-query logic: pccm_vox.cuh.
+//   index build   vx_mark / vx_dircount / vx_fill / vx_brickpre / vx_place (+ the scans of pccm_kernels.cuh)
+//   query stage   vx_search_kernel   one warp per query brick, one lane per VOXEL, search rows staged in shared
+//                                    memory, tie look-ups, whole-brick scan for the rare undecided voxel
+//                 vx_general_kernel  what is still undecided: one warp per voxel over 125 bricks
+//                 vx_far_kernel      beyond 16 voxels: the pencil search (second round)
+//                 vx_epilogue_kernel one lane per query POINT in input order: D1 / D2 / colour + reduction records
+//   boundary      vx_dupflag / vx_selfnn / vx_selfout: distance to the nearest OTHER point of the same cloud
+// Per-point / per-query logic shared with the CPU stepping harness: pccm_vox.cuh.
 #pragma once
 #include "pccm_kernels.cuh"
 #include "pccm_vox.cuh"
