@@ -1863,3 +1863,15 @@ extern "C" int pccm_cloud_outside_hull(pccm_ctx* ctx, pccm_cloud* c, const doubl
     dfree(ctx, dpl); dfree(ctx, dout); dfree(ctx, dcnt);
     return PCCM_OK;
 }
+
+// debug builds (-DPCCM_VX_DEBUG): number of range-check violations the brick kernels have counted so far
+extern "C" int pccm_debug_errors(void) {
+#if defined(PCCM_VX_DEBUG)
+    unsigned int v = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(&v, pccm::g_vx_errors, sizeof v) != cudaSuccess) return -1;
+    return (int)v;
+#else
+    return -1;
+#endif
+}

@@ -36,6 +36,17 @@
 struct uint2 { uint32_t x, y; };
 #endif
 
+// Debug builds (-DPCCM_VX_DEBUG): every index the brick path computes is range-checked; violations are
+// counted (pccm_debug_errors) instead of trapping, so one run reports all of them.
+#if defined(PCCM_VX_DEBUG) && defined(__CUDACC__)
+namespace pccm { __device__ unsigned int g_vx_errors = 0; }      // (the library is one translation unit)
+#endif
+#if defined(PCCM_VX_DEBUG) && defined(__CUDA_ARCH__)
+#define VX_CHECK(cond) do { if (!(cond)) atomicAdd(&pccm::g_vx_errors, 1u); } while (0)
+#else
+#define VX_CHECK(cond) ((void)0)
+#endif
+
 namespace pccm {
 
 // ---- bit helpers ---------------------------------------------------------------------------
@@ -164,7 +175,9 @@ PCCM_HD int vx_slot(const VoxView& G, int bx, int by, int bz) {
     return (int)(vx_ld32(G.dirpre + (key >> 5)) + (uint32_t)vx_popc(w & ((1u << bit) - 1u)));
 }
 PCCM_HD uint32_t vx_rank(const VoxView& G, uint32_t slot, int r, int xbit) {
+    VX_CHECK(slot < G.nblk_total && (unsigned)r < (unsigned)kVxRows && (unsigned)xbit < 32u);
     const uint32_t m = vx_ld32(G.masks + (size_t)slot * kVxRows + r);
+    VX_CHECK((m >> xbit) & 1u);                       // the voxel we rank must be occupied
     return vx_ld32(G.base + slot) + vx_ld16(G.pre + (size_t)slot * kVxRows + r) + (uint32_t)vx_popc(m & ((1u << xbit) - 1u));
 }
 // positions of the cloud's records in the joint array
@@ -193,6 +206,7 @@ PCCM_HD uint32_t vx_place_point(const uint32_t* masks, const uint16_t* pre, cons
     const int r = vx_row(y, z);
     const uint32_t m = masks[(size_t)slot * kVxRows + r];
     const uint32_t rank = base[slot] + pre[(size_t)slot * kVxRows + r] + (uint32_t)vx_popc(m & ((1u << (x & 31)) - 1u));
+    VX_CHECK((m >> (x & 31)) & 1u);
     recs[rank].x = (uint32_t)x | ((uint32_t)y << 16);      // every point of the voxel writes the same two words
     recs[rank].y = (uint32_t)z;
     vx_atomic_min64(reinterpret_cast<unsigned long long*>(&recs[rank].z), ((unsigned long long)idx << 32) | rgb);
@@ -261,7 +275,9 @@ struct VxPick {           // the chosen neighbour
 PCCM_HD void vx_cand(const VoxView& S, const int* sslot, int bx, int by, int bz, int cx, int cy, int cz,
                      int qx, int qy, int qz, VxPick& pk) {
     const int nb = ((cz >> 3) - bz + 1) * 9 + ((cy >> 3) - by + 1) * 3 + ((cx >> 5) - bx + 1);
+    VX_CHECK((unsigned)nb < 27u && sslot[nb] >= 0);
     const uint32_t rank = vx_rank(S, (uint32_t)sslot[nb], vx_row(cy, cz), cx & 31);
+    VX_CHECK(rank < S.n_total);
     const uint2 a = vx_ld64(reinterpret_cast<const uint2*>(S.recs + rank) + 1);   // {rgb, idx}
     if (a.y < pk.idx) { pk.idx = a.y; pk.rgb = a.x; pk.rank = rank; pk.ex = qx - cx; pk.ey = qy - cy; pk.ez = qz - cz; }
 }

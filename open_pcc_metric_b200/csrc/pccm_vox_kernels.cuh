@@ -161,8 +161,12 @@ __global__ void vx_place_kernel(const __grid_constant__ VoxBuild B) {
     }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
-        if (on[k])
-            B.prank[idx[k]] = vx_place_point(B.masks, B.pre, B.base, B.recs, slot[k], (int)(pk[k].x & 0xffffu), (int)(pk[k].x >> 16), (int)pk[k].y, rgba[k], li[k]);
+        if (on[k]) {
+            VX_CHECK(slot[k] < B.nblk_total);
+            const uint32_t rank = vx_place_point(B.masks, B.pre, B.base, B.recs, slot[k], (int)(pk[k].x & 0xffffu), (int)(pk[k].x >> 16), (int)pk[k].y, rgba[k], li[k]);
+            VX_CHECK(rank < B.n_total && rank >= B.base[slot[k]] && rank < B.base[slot[k] + 1]);
+            B.prank[idx[k]] = rank;
+        }
 }
 
 // ------------------------------------------------------------------------------------
@@ -456,6 +460,7 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
             uint32_t pos = 0;
             if (lane == 0) pos = atomicAdd(D.todo_count, (uint32_t)__popc(und));
             pos = __shfl_sync(full, pos, 0);
+            VX_CHECK(pos + (uint32_t)__popc(und) <= D.q.n);
             if (active && !done) D.todo[pos + __popc(und & ((1u << lane) - 1u))] = t;
         }
     }
@@ -489,6 +494,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     for (int j = 0; j < kVxEpiPer; ++j) {
         const uint32_t i = i0 + j * kVxEpiThreads;
         rk[j] = i < D.q.n ? __ldg(D.q.prank + i) : kVxNone;
+        VX_CHECK(i >= D.q.n || rk[j] < D.q.n_total);
     }
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j)
@@ -511,6 +517,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
             ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
             nrgb = nr.w;
         }
+        VX_CHECK((v[j].z & ~kVxFarBit) < D.s.n);
         vx_epilogue(P, D, qa, sa, i, 0u, v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc);
     }
     BlockPartial r;
