@@ -187,17 +187,22 @@ def test_attach_equals_create_with_attributes(ctxs):
         if not exact_u8:
             ca, cb = rng.random((n, 3)), rng.random((n, 3))
         outs = []
-        for late in (False, True):
-            if late:
+        for late in (0, 1, 2):
+            if late == 0:
+                a, b = vox.cloud(A, ca, na), vox.cloud(B, cb, nb)
+                vox.build_pair(a, b)
+            elif late == 1:
                 a, b = vox.cloud(A), vox.cloud(B)
                 a.attach(ca, na); b.attach(cb, nb)
-            else:
-                a, b = vox.cloud(A, ca, na), vox.cloud(B, cb, nb)
-            vox.build_pair(a, b)
+                vox.build_pair(a, b)
+            else:                                   # a brick-indexed pair accepts colours until its first colour evaluation
+                a, b = vox.cloud(A), vox.cloud(B)
+                vox.build_pair(a, b)
+                a.attach(ca, na); b.attach(cb, nb)
             assert bool(a.info().colors_u8) == exact_u8
             outs.append(bytes(vox.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV)))
             a.close(); b.close()
-        assert outs[0] == outs[1]
+        assert outs[0] == outs[1] == outs[2]
     a = vox.cloud(A)
     a.build_index()
     with pytest.raises(N.PccmError):
