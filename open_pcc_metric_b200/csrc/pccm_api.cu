@@ -457,7 +457,10 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     cudaSetDevice(ctx->device);
     wait_normals(ctx, c);
     if (c->nrm_ready) cudaEventDestroy(c->nrm_ready);
-    if (c->rgb_pending) cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0);   // the frees below are ordered on the context stream
+    if (c->rgb_pending) {
+        cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0);   // the frees below are ordered on the context stream
+        cudaEventSynchronize(c->rgb_ready);                  // ... and the pinned flag behind h_stats goes back to the pool
+    }
     if (c->rgb_ready) ctx->cloud_events.push_back(c->rgb_ready);
     dfree(ctx, c->raw_owned);
     dfree(ctx, c->raw_rgb_owned);
