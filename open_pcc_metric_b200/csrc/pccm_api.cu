@@ -167,6 +167,7 @@ struct pccm_cloud {
     bool normals_borrowed = false;   // caller's packed float64 device array (pccm_cloud_create, DEVICE)
     cudaEvent_t nrm_ready = nullptr; // normals still in flight on the copy stream
     bool nrm_pending = false;
+    void* nrm_stage = nullptr;       // raw float32 / strided rows being converted on the copy stream
     bool has_colors = false, has_normals = false;
     // index
     int index_kind = -1;
@@ -248,6 +249,10 @@ static void wait_normals(pccm_ctx* ctx, pccm_cloud* c) {
     if (c->nrm_pending) {
         cudaStreamWaitEvent(ctx->stream, c->nrm_ready, 0);
         c->nrm_pending = false;
+    }
+    if (c->nrm_stage) {              // (after the wait: the free is ordered behind the conversion)
+        cudaFreeAsync(c->nrm_stage, ctx->stream);
+        c->nrm_stage = nullptr;
     }
 }
 
@@ -518,6 +523,28 @@ static int set_normals_impl(pccm_ctx* ctx, pccm_cloud* c, const void* normals, i
                 CK(cudaMemcpyAsync(c->normals, normals, (size_t)c->n * 24, mem_kind == PCCM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
             }
         }
+        c->has_normals = true;
+        return PCCM_OK;
+    }
+    if (c->n && mem_kind == PCCM_HOST && may_borrow && ctx->copy_stream) {
+        // float32 / strided host normals at cloud creation: upload and conversion on the copy stream as well
+        const size_t es = dtype_size(dtype);
+        if (stride == 0) stride = (int64_t)(3 * es);
+        if (stride < (int64_t)(3 * es) || (stride % (int64_t)es) != 0) return fail(ctx, PCCM_ERR_INVALID, "bad row stride %lld", (long long)stride);
+        unsigned char* d = nullptr;
+        CK(dalloc(ctx, &d, (size_t)c->n * (size_t)stride));
+        if (!c->nrm_ready) CK(cudaEventCreateWithFlags(&c->nrm_ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));            // after the allocations
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+        CK(cudaMemcpyAsync(d, normals, (size_t)c->n * (size_t)stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        pack_f64x3_kernel<<<(int)((c->n + 255) / 256), 256, 0, ctx->copy_stream>>>(d, dtype, stride, c->n, c->normals);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->nrm_ready, ctx->copy_stream));
+        c->nrm_pending = true;
+        // the staging buffer is freed on the context stream: order that free after the conversion without
+        // making the context stream wait now -- keep it until the normals are first used
+        c->nrm_stage = d;
         c->has_normals = true;
         return PCCM_OK;
     }
