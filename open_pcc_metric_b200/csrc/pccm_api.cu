@@ -1051,7 +1051,7 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
 static constexpr size_t kVoxPinnedOffset = 12288;   // bytes into ctx->pinned
 static constexpr uint64_t kVoxMaxDirBits = 1ull << 30;
 
-static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double cell_size, bool* built) {
+static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double cell_size, uint4* recs_ready, bool* built) {
     StageTimer t(ctx, &ctx->tm.vox_build_ms);
     *built = false;
     VoxBuild B{};
@@ -1074,6 +1074,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     B.ndirw_total = ndirw[0] + ndirw[1];
     B.n_total = R.n[0] + R.n[1];
     SharedVox* v = new SharedVox();
+    v->recs = recs_ready;          // (allocated and 0xFF-filled while the statistics were still running, or null) -- owned from here
     const int threads = 256;
     auto bail = [&](int rc) { free_vox(ctx, v); return rc; };
 #define CKV(call)                                                                                    \
@@ -1104,12 +1105,12 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     CKV(dalloc(ctx, &v->masks, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->pre, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->base, (size_t)B.nblk_total + 1));
-    CKV(dalloc(ctx, &v->recs, (size_t)B.n_total));
+    if (!v->recs) CKV(dalloc(ctx, &v->recs, (size_t)B.n_total));
     CKV(dalloc(ctx, &v->prank, (size_t)B.n_total));
     CKV(dalloc(ctx, &packed, (size_t)B.n_total));
     CKV(dalloc(ctx, &pslot, (size_t)B.n_total));
     CKV(cudaMemsetAsync(v->masks, 0, (size_t)B.nblk_total * kVxRows * sizeof(uint32_t), ctx->stream));
-    CKV(cudaMemsetAsync(v->recs, 0xff, (size_t)B.n_total * sizeof(uint4), ctx->stream));
+    if (!recs_ready) CKV(cudaMemsetAsync(v->recs, 0xff, (size_t)B.n_total * sizeof(uint4), ctx->stream));
     B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.prank = v->prank;
     B.packed = packed; B.pslot = pslot;
     vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
@@ -1218,6 +1219,22 @@ static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
 extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind) {
     if (!ctx || !a || !b) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
+    // The voxel records of the brick index (16 B per point, 0xFF-filled) do not depend on the statistics:
+    // allocate and fill them BEFORE waiting for those, so that the fill runs while the host is busy with
+    // the wait and the launches that follow it (speculative: dropped again when the pair is not integer).
+    uint4* recs_ready = nullptr;
+    const uint64_t n_pair = (uint64_t)a->n + (uint64_t)b->n;
+    if (ctx->use_vox && a != b && a->n && b->n && a->index_kind < 0 && b->index_kind < 0 && n_pair <= (1ull << 24) &&
+        (force_kind == PCCM_KIND_AUTO || force_kind == PCCM_KIND_INT)) {
+        if (dalloc(ctx, &recs_ready, (size_t)n_pair) == cudaSuccess)
+            cudaMemsetAsync(recs_ready, 0xff, (size_t)n_pair * sizeof(uint4), ctx->stream);
+        else
+            recs_ready = nullptr;
+    }
+    struct DropRecs {              // whatever path is taken below: the buffer is either adopted by the brick index or freed
+        pccm_ctx* ctx; uint4** p;
+        ~DropRecs() { if (*p) dfree(ctx, *p); }
+    } drop{ctx, &recs_ready};
     int rc = ensure_stats(ctx, a);
     if (!rc) rc = ensure_stats(ctx, b);
     if (rc) return rc;
@@ -1254,8 +1271,11 @@ extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
     if (kind == PCCM_KIND_INT && ctx->use_vox) {       // the brick index needs coordinates only: colours may still be in flight
         bool built = false;
-        rc = build_vox(ctx, cl, R, cell_size, &built);
+        uint4* adopt = recs_ready;
+        recs_ready = nullptr;                            // build_vox owns it from here (its error paths free the index)
+        rc = build_vox(ctx, cl, R, cell_size, adopt, &built);
         if (rc) return rc;
+        if (!built && adopt) dfree(ctx, adopt);          // brick grid over the directory budget: pencil path
         if (built) return ctx->eager_pencil ? ensure_pencil(ctx, a) : PCCM_OK;
     }
     for (int c = 0; c < 2; ++c) {
