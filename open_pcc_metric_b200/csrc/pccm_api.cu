@@ -32,6 +32,7 @@ struct pccm_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // host->device copies of attributes that are only needed by the query epilogue
     cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_sync = nullptr;         // host waits that must not cover work enqueued after them
     // per-cloud pinned statistics buffers and events are recycled: cudaMallocHost / cudaFreeHost are
     // synchronous OS-level calls (tens of microseconds) and a cloud lives for one evaluation
     std::vector<void*> stats_pool;
@@ -382,6 +383,10 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->copy_stream = nullptr;
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { ctx->copy_stream = nullptr; }
+    if (cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, PCCM_ERR_CUDA, "event creation failed");
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -424,6 +429,7 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     cudaFree(ctx->dscratch);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCCM_OK;
@@ -1097,18 +1103,28 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
     CKV(cudaMemcpyAsync(hcnt, v->dirpre + ndirw[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CKV(cudaMemcpyAsync(hcnt + 1, v->dirpre + B.ndirw_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CKV(cudaStreamSynchronize(ctx->stream));
-    const uint32_t nblk0 = hcnt[0];
-    B.nblk_total = hcnt[1];
+    CKV(cudaEventRecord(ctx->ev_sync, ctx->stream));       // the wait below is for the brick count only
+    // in the shadow of the wait below: everything that does not depend on the brick count -- the per-point
+    // scratch arrays and, for colours that have already arrived and been classified, their packed array
     uint2* packed = nullptr;
     uint32_t* pslot = nullptr;
+    CKV(dalloc(ctx, &v->prank, (size_t)B.n_total));
+    CKV(dalloc(ctx, &packed, (size_t)B.n_total));
+    CKV(dalloc(ctx, &pslot, (size_t)B.n_total));
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = cl[c];
+        if (!p->has_colors) continue;
+        if (p->rgb_pending && cudaEventQuery(p->rgb_ready) != cudaSuccess) continue;     // still uploading: the epilogue will gather
+        const int rcc = finish_colors(ctx, p);
+        if (rcc) { dfree(ctx, packed); dfree(ctx, pslot); return bail(rcc); }
+    }
+    CKV(cudaEventSynchronize(ctx->ev_sync));
+    const uint32_t nblk0 = hcnt[0];
+    B.nblk_total = hcnt[1];
     CKV(dalloc(ctx, &v->masks, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->pre, (size_t)B.nblk_total * kVxRows));
     CKV(dalloc(ctx, &v->base, (size_t)B.nblk_total + 1));
     if (!v->recs) CKV(dalloc(ctx, &v->recs, (size_t)B.n_total));
-    CKV(dalloc(ctx, &v->prank, (size_t)B.n_total));
-    CKV(dalloc(ctx, &packed, (size_t)B.n_total));
-    CKV(dalloc(ctx, &pslot, (size_t)B.n_total));
     CKV(cudaMemsetAsync(v->masks, 0, (size_t)B.nblk_total * kVxRows * sizeof(uint32_t), ctx->stream));
     if (!recs_ready) CKV(cudaMemsetAsync(v->recs, 0xff, (size_t)B.n_total * sizeof(uint4), ctx->stream));
     B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.prank = v->prank;
@@ -1126,9 +1142,8 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
             pccm_cloud* p = cl[c];
             B.c[c].rgb_in_rec = 0;
             if (!p->has_colors) continue;
-            if (p->rgb_pending && cudaEventQuery(p->rgb_ready) == cudaSuccess) { rc = ensure_colors(ctx, p); if (rc) break; }
-            if (!p->rgb_pending && p->rgb_u8_ok && p->raw_rgb) {
-                B.c[c].rgb = p->raw_rgb; B.c[c].rgb_dtype = p->raw_rgb_dtype; B.c[c].rgb_stride = p->raw_rgb_stride;
+            if (p->rgb_u8) {                       // packed before the brick-count wait: 4 bytes per point, in input order
+                B.c[c].rgb = p->rgb_u8; B.c[c].rgb_dtype = PCCM_U8; B.c[c].rgb_stride = (int64_t)sizeof(uchar4);
                 B.c[c].rgb_in_rec = 1;
                 rgb_now[c] = true;
             }
