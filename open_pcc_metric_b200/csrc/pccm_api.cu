@@ -707,7 +707,7 @@ static int sort_pairs(pccm_ctx* ctx, KeyT* keys_in, KeyT* keys_out, uint32_t* va
 
 static int exclusive_scan(pccm_ctx* ctx, uint32_t* data, size_t count) {
     if (count <= kScanSmallMax) {
-        scan_small_kernel<<<1, kScanSmallThreads, 0, ctx->stream>>>(data, (uint32_t)count);
+        scan_small_kernel<false><<<1, kScanSmallThreads, 0, ctx->stream>>>(data, (uint32_t)count, nullptr);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
         return PCCM_OK;
@@ -1095,11 +1095,18 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
     B.dirbits = v->dirbits; B.dirpre = v->dirpre;
     const int blocks_ilp = (int)(((B.n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
     vx_mark_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
-    vx_dircount_kernel<<<(B.ndirw_total + 1 + threads - 1) / threads, threads, 0, ctx->stream>>>(v->dirbits, B.ndirw_total, v->dirpre);
-    ctx->tm.total_launches += 2;
-    CKV(cudaGetLastError());
-    int rc = exclusive_scan(ctx, v->dirpre, (size_t)B.ndirw_total + 1);
-    if (rc) return bail(rc);
+    int rc = PCCM_OK;
+    if ((size_t)B.ndirw_total + 1 <= kScanSmallMax) {      // popcount + scan of the directory in one launch
+        scan_small_kernel<true><<<1, kScanSmallThreads, 0, ctx->stream>>>(v->dirpre, B.ndirw_total + 1, v->dirbits);
+        ctx->tm.total_launches += 2;
+        CKV(cudaGetLastError());
+    } else {
+        vx_dircount_kernel<<<(B.ndirw_total + 1 + threads - 1) / threads, threads, 0, ctx->stream>>>(v->dirbits, B.ndirw_total, v->dirpre);
+        ctx->tm.total_launches += 2;
+        CKV(cudaGetLastError());
+        rc = exclusive_scan(ctx, v->dirpre, (size_t)B.ndirw_total + 1);
+        if (rc) return bail(rc);
+    }
     uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
     CKV(cudaMemcpyAsync(hcnt, v->dirpre + ndirw[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CKV(cudaMemcpyAsync(hcnt + 1, v->dirpre + B.ndirw_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -301,7 +301,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t* __re
 // thread t sums its contiguous segment, the block scans the 1024 sums, thread t writes its prefixes
 constexpr int kScanSmallThreads = 1024;
 constexpr size_t kScanSmallMax = 64 * 1024;
-__global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t* __restrict__ data, uint32_t n) {
+// POPC: the input is a bitmap (`bits`, n - 1 words) and entry i of the output is the number of set bits before
+// word i (the brick directory: occupancy bits -> slot prefix, entry n - 1 = number of bricks); else in place.
+template <bool POPC>
+__global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restrict__ bits) {
     __shared__ uint32_t ws[kScanSmallThreads / 32];
     const uint32_t per = (n + kScanSmallThreads - 1) / kScanSmallThreads;
     const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t*
     for (uint32_t c = lo; c < hi; c += 8) {
         uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = c + j < hi ? data[c + j] : 0u;
+        for (int j = 0; j < 8; ++j) v[j] = c + j < hi ? (POPC ? (c + j < n - 1 ? (uint32_t)__popc(bits[c + j]) : 0u) : data[c + j]) : 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[j];
     }
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint32_t*
     for (uint32_t c = lo; c < hi; c += 8) {
         uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = c + j < hi ? data[c + j] : 0u;
+        for (int j = 0; j < 8; ++j) v[j] = c + j < hi ? (POPC ? (c + j < n - 1 ? (uint32_t)__popc(bits[c + j]) : 0u) : data[c + j]) : 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (c + j < hi) data[c + j] = ex;
