@@ -362,7 +362,14 @@ def main():
                        "l2": "flushed between iterations (256 MiB write)", "ms_per_1M_point_pair": ms_dev_max / args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "kernel": "query stage = vx_search_kernel + vx_general_kernel + vx_epilogue_kernel" if brick else "pair_query_kernel<KInt>",
-                         "launch_ms_by_kernel": q_split, "peak_source": peak_src,
+                         "launch_ms_by_kernel": q_split,
+                         # the two kernels of the stage against their own share of the algorithmic traffic (SURVEY 8(d):
+                         # 24 B/query for the search -- query + search coordinates; 20 B/query for the epilogue -- normal + two colours)
+                         "by_kernel": None if not brick else {
+                             k: {"alg_bytes_per_query": ab, "achieved": ab * queries_per_launch / (q_split[k] * 1e-3) / 1e9,
+                                 "frac": ab * queries_per_launch / (q_split[k] * 1e-3) / 1e9 / peak_gbs}
+                             for k, ab in (("vx_search_kernel", 24), ("vx_epilogue_kernel", 20)) if q_split[k] > 0},
+                         "peak_source": peak_src,
                          "alg_bytes_per_query": ALG_BYTES_PER_QUERY, "queries_per_launch": queries_per_launch,
                          "avg_launch_ms": q_ms_avg},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
