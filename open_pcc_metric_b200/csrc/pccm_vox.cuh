@@ -315,11 +315,20 @@ PCCM_HD void vx_offer(const VoxView& S, uint32_t slot, int r, uint32_t d2, int c
     if (d2 < h.d2 || a.y < h.idx) { h.d2 = d2; h.idx = a.y; h.rgb = a.x; h.rank = rank; h.cx = cx; h.cy = cy; h.cz = cz; }
 }
 
+// distance from word coordinate p (the query's x relative to the brick: ANY integer) to the nearest set bit
+// of a row at or below / strictly above it; 40000 when there is none.  Shared by the sequential brick scan
+// below and the warp-cooperative one of the kernels (vx_warp_bricks).
+PCCM_HD void vx_row_nearest(uint32_t m, int p, int& dlo, int& dhi) {
+    const uint32_t at_or_below = p >= 31 ? 0xFFFFFFFFu : (p < 0 ? 0u : ((2u << p) - 1u));
+    const uint32_t above = p < 0 ? 0xFFFFFFFFu : (p >= 31 ? 0u : ~((2u << p) - 1u));
+    const uint32_t ml = m & at_or_below, mh = m & above;
+    dlo = ml ? p - (31 - vx_clz(ml)) : 40000;
+    dhi = mh ? (vx_ffs(mh) - 1) - p : 40000;
+}
+
 PCCM_HD void vx_scan_brick(const VoxView& S, uint32_t slot, int bx, int by, int bz, int qx, int qy, int qz, VxHit& h) {
     const int X0 = bx << 5, Y0 = by << 3, Z0 = bz << 3;
-    const int p = qx - X0;                                  // the query's x in word coordinates (any integer)
-    const uint32_t at_or_below = p >= 31 ? 0xFFFFFFFFu : (p < 0 ? 0u : ((2u << p) - 1u));
-    const uint32_t at_or_above = p <= 0 ? 0xFFFFFFFFu : (p > 31 ? 0u : ~((1u << p) - 1u));
+    const int p = qx - X0;
     for (int zi = 0; zi < 8; ++zi) {
         const int dz = qz - (Z0 + zi);
         const uint32_t dz2 = (uint32_t)(dz * dz);
@@ -331,15 +340,10 @@ PCCM_HD void vx_scan_brick(const VoxView& S, uint32_t slot, int bx, int by, int 
             const int r = (zi << 3) | yi;
             const uint32_t m = vx_ld32(S.masks + (size_t)slot * kVxRows + r);
             if (!m) continue;
-            const uint32_t ml = m & at_or_below, mh = m & at_or_above;
-            if (ml) {
-                const int hb = 31 - vx_clz(ml), dx = p - hb;
-                vx_offer(S, slot, r, byz + (uint32_t)(dx * dx), X0 + hb, Y0 + yi, Z0 + zi, h);
-            }
-            if (mh) {
-                const int lb = vx_ffs(mh) - 1, dx = lb - p;
-                if (dx != 0) vx_offer(S, slot, r, byz + (uint32_t)(dx * dx), X0 + lb, Y0 + yi, Z0 + zi, h);
-            }
+            int dlo, dhi;
+            vx_row_nearest(m, p, dlo, dhi);
+            if (dlo < 40000) vx_offer(S, slot, r, byz + (uint32_t)(dlo * dlo), qx - dlo, Y0 + yi, Z0 + zi, h);
+            if (dhi < 40000) vx_offer(S, slot, r, byz + (uint32_t)(dhi * dhi), qx + dhi, Y0 + yi, Z0 + zi, h);
         }
     }
 }

@@ -273,16 +273,6 @@ __device__ __forceinline__ void vx_slice(const VxParams& P, const VoxView& Q, ui
     t_hi = r0 + (uint32_t)((unsigned long long)nd * (unsigned)(P.rank + 1) / (unsigned)P.world);
 }
 
-__device__ __forceinline__ void vx_row_nearest(uint32_t m, int p, int& dlo, int& dhi) {
-    // distance from word coordinate p (any integer) to the nearest set bit at or below / above; 40000 when none
-    const uint32_t at_or_below = p >= 31 ? 0xFFFFFFFFu : (p < 0 ? 0u : ((2u << p) - 1u));
-    const uint32_t above = p < 0 ? 0xFFFFFFFFu : (p >= 31 ? 0u : ~((2u << p) - 1u));
-    const uint32_t ml = m & at_or_below, mh = m & above;
-    dlo = ml ? p - (31 - __clz((int)ml)) : 40000;
-    dhi = mh ? (__ffs((int)mh) - 1) - p : 40000;
-}
-
-
 // Warp-cooperative exact search of one query over a list of occupied bricks (slots[k], ids[k]; id
 // = position in a DIM^3 neighbourhood centred on the query's brick).  Lane l owns rows 2l and
 // 2l+1 of every brick (one coalesced load of the 64 occupancy words).  Pass 1: minimal squared
