@@ -169,7 +169,8 @@ int pccm_knn_self(pccm_ctx* ctx, pccm_cloud* cloud, int k, int32_t* idx_out, dou
 
 /* Replaces PointCloud.compute_nearest_neighbor_distance() + np.min/np.max
  * (cloud_pair.py:108-109, metric.py:182-188): distance of each point to its nearest
- * OTHER point.  per_point may be NULL.  [begin, end) as above. */
+ * OTHER point.  per_point may be NULL.  [begin, end) as above (on the brick index: the same
+ * share of the cloud's occupied voxels; any partition of [0, n) into ranges covers every point once). */
 int pccm_self_nn_minmax(pccm_ctx* ctx, pccm_cloud* cloud, int64_t begin, int64_t end,
                         double* min_out, double* max_out, double* per_point, int mem_kind);
 
@@ -183,8 +184,10 @@ int pccm_nn(pccm_ctx* ctx, pccm_cloud* query, pccm_cloud* search, int32_t* idx_o
  * color_matrix: row-major 3x3 applied to both colours (identity for "rgb");
  * color_scale: factor inside color_max (255 for rgb, quirk Q6; else 1).
  * rank/world: this call reduces the rank-th of `world` equal contiguous slices of
- * each query cloud's sorted order (0, 1 = everything); partial results from all
- * ranks add up (sums) / max (maxima). */
+ * each query cloud's sorted order (0, 1 = everything; integer pairs on the brick index:
+ * of its occupied voxels -- points that share a voxel stay together, pccm_dir_result.n
+ * counts the points actually reduced); partial results from all ranks add up (sums) /
+ * max (maxima). */
 int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint32_t flags,
                    const double* color_matrix, double color_scale, int normals_mode,
                    int rank, int world, pccm_pair_result* out);
