@@ -463,7 +463,10 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
 // writes one reduction record -> float sums do not depend on scheduling.  Multi-GPU slices are cut
 // by voxel: a rank skips the points of voxels it did not search.
 constexpr int kVxEpiThreads = 256;
-constexpr int kVxEpiPer = 4;
+#ifndef PCCM_VX_EPIPER
+#define PCCM_VX_EPIPER 4
+#endif
+constexpr int kVxEpiPer = PCCM_VX_EPIPER;
 constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
 __global__ void __launch_bounds__(kVxEpiThreads)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
