@@ -63,10 +63,12 @@ def knn(points, queries, k, threads=None):
 
 
 def normals(points, nn_idx, threads=None):
+    """Normal of every ROW of nn_idx (neighbour lists into ``points``; one row per point of the cloud,
+    or the rows of a sample of it)."""
     pts = np.ascontiguousarray(points, dtype=np.float64)
     nn = np.ascontiguousarray(nn_idx, dtype=np.int64)
-    out = np.empty((len(pts), 3), dtype=np.float64)
+    out = np.empty((len(nn), 3), dtype=np.float64)
     L = lib()
-    _fan(len(pts), threads, lambda b, e: L.oracle_normals(_p(pts), ctypes.c_int64(b), ctypes.c_int64(e), _p(nn),
+    _fan(len(nn), threads, lambda b, e: L.oracle_normals(_p(pts), ctypes.c_int64(b), ctypes.c_int64(e), _p(nn),
                                                           ctypes.c_int(nn.shape[1]), _p(out)))
     return out

@@ -41,14 +41,22 @@ def _normals_close(got, want, pts, tol=1e-9):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_nn_matches_reference_outputs(golden, ctx, name):
-    """pccm_nn through the C ABI == cloud_pair.py:10-42 run by the unmodified reference."""
+@pytest.mark.parametrize("pair_build", [False, True])
+def test_nn_matches_reference_outputs(golden, ctx, name, pair_build):
+    """pccm_nn through the C ABI == cloud_pair.py:10-42 run by the unmodified reference; with one
+    index per cloud (pencil path) and with the joint build CloudPair and bench.py use (integer
+    pairs: occupancy-brick path)."""
     g = golden(name)
     i = g.inputs()
     a, b = ctx.cloud(i["pts_a"]), ctx.cloud(i["pts_b"])
     kind = max(a.info().data_kind, b.info().data_kind)
-    a.build_index(0.0, kind)
-    b.build_index(0.0, kind)
+    if pair_build:
+        if min(len(i["pts_a"]), len(i["pts_b"])) == 0:
+            pytest.skip("joint build needs two non-empty clouds")
+        ctx.build_pair(a, b)
+    else:
+        a.build_index(0.0, kind)
+        b.build_index(0.0, kind)
     for q, s, sfx in ((a, b, "l"), (b, a, "r")):
         idx, d2 = ctx.nn(q, s)
         assert np.array_equal(d2, g.arr["d2_" + sfx].astype(np.float64)), name
