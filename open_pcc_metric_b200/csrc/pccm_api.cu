@@ -47,6 +47,7 @@ struct pccm_ctx {
     int32_t* pp_idx[2] = {nullptr, nullptr};
     double* pp_d2[2] = {nullptr, nullptr};
     int64_t pp_n[2] = {0, 0};
+    const struct pccm_cloud* pp_owner[2] = {nullptr, nullptr};   // the pair those outputs belong to (dropped when either cloud goes)
     // small pinned + device scratch for result structs
     void* pinned = nullptr;
     void* dscratch = nullptr;
@@ -59,6 +60,7 @@ struct pccm_ctx {
     bool use_rowsort = true;        // KInt pair build: counting sort + per-row sort instead of CUB radix (PCCM_ROWSORT=0 disables)
     bool use_vox = true;            // KInt pairs: occupancy-brick index + bit-scan query (PCCM_VOX=0: pencil path only)
     bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
+    int vx_search_blocks = 10;      // resident blocks per SM of the persistent brick search kernel (PCCM_VX_BLOCKS)
 };
 
 static thread_local std::string g_err;
@@ -148,6 +150,8 @@ struct pccm_cloud {
     // statistics
     StatsPartial* d_stats = nullptr;
     StatsPartial* h_stats = nullptr;  // pinned
+    DevStats* d_dev = nullptr;        // behind d_stats: the same statistics as one device record (brick-index planning)
+    uint2* packed = nullptr;          // {x | y << 16, z} per point, written by the statistics pass (integer-valued clouds)
     int stats_blocks = 0;
     cudaEvent_t stats_done = nullptr;
     bool stats_ready = false;
@@ -160,6 +164,7 @@ struct pccm_cloud {
     uint32_t* d_rgbflag = nullptr;   // behind d_stats
     uint32_t* h_rgbflag = nullptr;   // behind h_stats (pinned)
     bool vox_rgb_done = false;       // brick index: colours packed into their original-order array
+    bool rgb_spec = false;           // rgb_u8 was packed before the k/255 classification was known (d_rgbflag is read at the next settle point)
     bool vox_rgb_in_recs = false;    // brick index: the voxel records carry the representative's colour
     // attributes (original order)
     uchar4* rgb_u8 = nullptr;
@@ -190,18 +195,24 @@ struct SharedIndex {
 };
 
 struct SharedVox {
-    uint32_t *dirbits = nullptr, *dirpre = nullptr, *masks = nullptr, *base = nullptr, *prank = nullptr;
-    uint16_t* pre = nullptr;
-    uint4* recs = nullptr;
-    VoxView view[2];
-    struct pccm_cloud* owner[2] = {nullptr, nullptr};   // live clouds of the pair (the pencil index is built from recs on demand)
+    uint32_t *dirbits = nullptr, *dirpre = nullptr, *dirsums = nullptr, *masks = nullptr, *rowbase = nullptr, *bricksums = nullptr,
+             *prank = nullptr;
+    uint2 *vxyz = nullptr, *vkey = nullptr;
+    VoxPlan* dplan = nullptr;        // device: written by the build kernels, read by every brick kernel
+    VoxPlan hplan{};                 // host copy, valid once the build has been settled
+    bool pending = false;            // the build is enqueued but the host has not looked at its outcome yet
+    uint32_t cap_dirw = 0, cap_blk = 0;
+    uint32_t n[2] = {0, 0};
+    VoxView view[2];                 // = hplan.view
+    struct pccm_cloud* owner[2] = {nullptr, nullptr};   // live clouds of the pair (the pencil index is built from vxyz on demand)
     double cell_size = 0;                                // what pccm_pair_build_index was asked for
+    int force_kind = PCCM_KIND_AUTO;
     int refs = 0;
 };
 
 static void free_vox(pccm_ctx* ctx, SharedVox* v) {
-    dfree(ctx, v->dirbits); dfree(ctx, v->dirpre); dfree(ctx, v->masks); dfree(ctx, v->base); dfree(ctx, v->prank);
-    dfree(ctx, v->pre); dfree(ctx, v->recs);
+    dfree(ctx, v->dirbits); dfree(ctx, v->dirpre); dfree(ctx, v->dirsums); dfree(ctx, v->masks); dfree(ctx, v->rowbase);
+    dfree(ctx, v->bricksums); dfree(ctx, v->prank); dfree(ctx, v->vxyz); dfree(ctx, v->vkey); dfree(ctx, v->dplan);
     delete v;
 }
 static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
@@ -211,6 +222,10 @@ static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
     v->owner[c->vox_id] = nullptr;
     if (--v->refs == 0) free_vox(ctx, v);
 }
+
+static int vox_settle(pccm_ctx* ctx, pccm_cloud* c);
+static int vox_fetch(pccm_ctx* ctx, SharedVox* v);
+static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo);
 
 static size_t dtype_size(int dt) {
     switch (dt) {
@@ -409,6 +424,7 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_ROWSORT")) ctx->use_rowsort = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VOX")) ctx->use_vox = atoi(s) != 0;
     if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
     if (const char* s = getenv("PCCM_NORMALS_COUNTING")) ctx->normals_counting = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
@@ -466,6 +482,7 @@ extern "C" int pccm_ctx_get_timings(pccm_ctx* ctx, pccm_timings* out) {
 extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     if (!ctx || !c) return PCCM_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->pp_owner[0] == c || ctx->pp_owner[1] == c) ctx->pp_owner[0] = ctx->pp_owner[1] = nullptr;   // per-point outputs of this pair are void
     wait_normals(ctx, c);
     if (c->nrm_ready) cudaEventDestroy(c->nrm_ready);
     if (c->rgb_pending) {
@@ -476,6 +493,7 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     dfree(ctx, c->raw_owned);
     dfree(ctx, c->raw_rgb_owned);
     dfree(ctx, c->d_stats);
+    dfree(ctx, c->packed);
     dfree(ctx, c->rgb_u8);
     dfree(ctx, c->rgb_f64);
     if (!c->normals_borrowed) dfree(ctx, c->normals);
@@ -592,7 +610,10 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
     if (n) {
         StageTimer t(ctx, &ctx->tm.stats_ms);
         c->stats_blocks = (int)std::min<int64_t>((n + kStatsThreads - 1) / kStatsThreads, (int64_t)ctx->sm_count * 4);
-        cudaError_t e = dalloc(ctx, &c->d_stats, (size_t)c->stats_blocks + 1);
+        cudaError_t e = dalloc(ctx, &c->d_stats, (size_t)c->stats_blocks + 2);
+        // integer-capable inputs also get their packed 8-byte coordinates (what the brick index is built from)
+        const bool want_packed = ctx->use_vox && xyz_dtype != PCCM_F32 && n <= 0x7fffffffLL;
+        if (e == cudaSuccess && want_packed) e = dalloc(ctx, &c->packed, (size_t)n);
         if (e == cudaSuccess) {
             if (!ctx->stats_pool.empty()) {
                 c->h_stats = static_cast<StatsPartial*>(ctx->stats_pool.back());
@@ -603,7 +624,9 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
         }
         if (e == cudaSuccess) {
             c->d_rgbflag = reinterpret_cast<uint32_t*>(c->d_stats + c->stats_blocks);
+            c->d_dev = reinterpret_cast<DevStats*>(c->d_stats + c->stats_blocks + 1);
             c->h_rgbflag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_stats) + ctx->stats_pool_bytes);
+            e = cudaMemsetAsync(c->d_stats + c->stats_blocks, 0, 2 * sizeof(StatsPartial), ctx->stream);
         }
         if (e == cudaSuccess) {
             if (!ctx->cloud_events.empty()) { c->stats_done = ctx->cloud_events.back(); ctx->cloud_events.pop_back(); }
@@ -611,7 +634,7 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
         }
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
         stats_kernel<<<c->stats_blocks, kStatsThreads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
-                                                                         nullptr, PCCM_F64, 0, c->d_stats);   // colours are classified on the copy stream
+                                                                         nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev);   // colours are classified on the copy stream
         ctx->tm.total_launches++;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsPartial) * c->stats_blocks, cudaMemcpyDeviceToHost, ctx->stream);
@@ -642,8 +665,13 @@ extern "C" int pccm_cloud_attach(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, 
 extern "C" int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* c, pccm_cloud_info* out) {
     if (!ctx || !c || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
-    int rc = ensure_stats(ctx, c);
-    if (!rc) rc = ensure_colors(ctx, c);
+    int rc = vox_settle(ctx, c);
+    if (!rc) rc = ensure_stats(ctx, c);
+    if (!rc && !c->rgb_spec) rc = ensure_colors(ctx, c);
+    if (!rc && c->rgb_spec && c->vox) {      // 8-bit colours were assumed: find out
+        rc = vox_fetch(ctx, c->vox);
+        if (!rc) { CK(cudaStreamSynchronize(ctx->stream)); bool redo = false; rc = vox_adopt(ctx, c->vox, &redo); }
+    }
     if (rc) return rc;
     memset(out, 0, sizeof *out);
     out->n = c->n;
@@ -769,7 +797,8 @@ static void choose_grid(pccm_ctx* ctx, const pccm_cloud* c, int kind, double cel
 extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_size, int force_kind) {
     if (!ctx || !c) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
-    int rc = ensure_stats(ctx, c);
+    int rc = vox_settle(ctx, c);
+    if (!rc) rc = ensure_stats(ctx, c);
     if (rc) return rc;
     rc = finish_colors(ctx, c);
     if (rc) return rc;
@@ -906,6 +935,8 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
     dfree(ctx, c->raw_owned);
     c->raw_owned = nullptr;
     c->raw_xyz = nullptr;
+    dfree(ctx, c->packed);
+    c->packed = nullptr;
     c->grid = g;
     c->index_kind = kind;
     return PCCM_OK;
@@ -1050,38 +1081,47 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
     return PCCM_OK;
 }
 
-// Occupancy-brick index of a KInt pair (pccm_vox.cuh): directory of occupied 32 x 8 x 8 bricks,
-// their 64 occupancy words, voxel ranks and one record per distinct voxel.  One host
-// synchronisation (the number of occupied bricks sizes the mask arrays).  Clouds whose brick grid
-// would not fit the directory budget keep the pencil path only.
-static constexpr size_t kVoxPinnedOffset = 12288;   // bytes into ctx->pinned
+// Occupancy-brick index of a KInt pair (pccm_vox.cuh), enqueued WITHOUT waiting for anything: the bounding
+// boxes, the number of occupied bricks and the number of distinct voxels stay on the device (VoxPlan); arrays are
+// sized by capacities.  Whether the assumptions held (integer coordinates, capacities) is looked at when the host
+// synchronises anyway -- the result read-back of pccm_pair_eval, or the first call that needs host-side knowledge
+// of the index (vox_settle) -- and only then is the build repeated with exact capacities or handed to the pencil path.
+static constexpr size_t kVoxPinnedOffset = 12288;   // bytes into ctx->pinned: VoxPlan + colour flags + counters
 static constexpr uint64_t kVoxMaxDirBits = 1ull << 30;
+static constexpr uint32_t kVoxDefaultDirWords = 1u << 20;
 
-static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double cell_size, uint4* recs_ready, bool* built) {
+static uint32_t pow2_ceil(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+static int finish_colors(pccm_ctx* ctx, pccm_cloud* c);
+
+// 8-bit colour array of a cloud without a host wait: float64 colours still being classified on the copy stream are
+// packed speculatively (the kernel re-checks every channel and raises the cloud's colour flag, read back at the
+// next settle point).  Returns with c->rgb_u8 set when the colours are (assumed) 8-bit.
+static int colors_u8_async(pccm_ctx* ctx, pccm_cloud* c) {
+    if (!c->has_colors || c->rgb_u8 || c->rgb_f64 || c->n == 0) return PCCM_OK;
+    if (c->rgb_pending && cudaEventQuery(c->rgb_ready) == cudaSuccess) { const int rc = ensure_colors(ctx, c); if (rc) return rc; }
+    if (!c->rgb_pending) return finish_colors(ctx, c);        // classification known: the ordinary path
+    CK(cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0));    // device-side wait for the upload + classification
+    CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n));
+    const int threads = 256, blocks = (int)((c->n + threads - 1) / threads);
+    if (c->raw_rgb_dtype == PCCM_U8) pack_rgb_u8_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, PCCM_U8, c->raw_rgb_stride, c->n, c->rgb_u8);
+    else pack_rgb_u8_check_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_stride, c->n, c->rgb_u8, c->d_rgbflag);
+    ctx->tm.total_launches++;
+    CK(cudaGetLastError());
+    c->rgb_spec = true;                                        // the raw colours stay until the flag has been read
+    return PCCM_OK;
+}
+
+static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int force_kind, uint32_t cap_dirw, uint32_t cap_blk) {
     StageTimer t(ctx, &ctx->tm.vox_build_ms);
-    *built = false;
-    VoxBuild B{};
-    B.nclouds = 2;
-    uint32_t ndirw[2];
-    for (int c = 0; c < 2; ++c) {
-        const pccm_cloud* p = cl[c];
-        VoxCloudBuild& C = B.c[c];
-        C.xyz = R.xyz[c]; C.rgb = R.rgb[c]; C.stride = R.stride[c]; C.rgb_stride = R.rgb_stride[c];
-        C.dtype = R.dtype[c]; C.rgb_dtype = R.rgb_dtype[c]; C.rgb_in_rec = R.rgb_in_rec[c]; C.n = R.n[c];
-        C.g.obx = (int)p->mn[0] >> 5; C.g.oby = (int)p->mn[1] >> 3; C.g.obz = (int)p->mn[2] >> 3;
-        C.g.nbx = ((int)p->mx[0] >> 5) - C.g.obx + 1;
-        C.g.nby = ((int)p->mx[1] >> 3) - C.g.oby + 1;
-        C.g.nbz = ((int)p->mx[2] >> 3) - C.g.obz + 1;
-        const uint64_t bits = (uint64_t)C.g.nbx * (uint64_t)C.g.nby * (uint64_t)C.g.nbz;
-        if (bits > kVoxMaxDirBits) return PCCM_OK;      // pencil path only
-        ndirw[c] = (uint32_t)((bits + 31) / 32);
-    }
-    B.c[0].dir_off = 0; B.c[1].dir_off = ndirw[0];
-    B.ndirw_total = ndirw[0] + ndirw[1];
-    B.n_total = R.n[0] + R.n[1];
+    const uint32_t n_total = (uint32_t)(cl[0]->n + cl[1]->n);
     SharedVox* v = new SharedVox();
-    v->recs = recs_ready;          // (allocated and 0xFF-filled while the statistics were still running, or null) -- owned from here
-    const int threads = 256;
+    v->cap_dirw = cap_dirw; v->cap_blk = cap_blk;
+    v->cell_size = cell_size; v->force_kind = force_kind;
     auto bail = [&](int rc) { free_vox(ctx, v); return rc; };
 #define CKV(call)                                                                                    \
     do {                                                                                             \
@@ -1089,107 +1129,176 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
         if (e_ != cudaSuccess)                                                                       \
             return bail(fail(ctx, PCCM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_))); \
     } while (0)
-    CKV(dalloc(ctx, &v->dirbits, (size_t)B.ndirw_total));
-    CKV(dalloc(ctx, &v->dirpre, (size_t)B.ndirw_total + 1));
-    CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)B.ndirw_total * sizeof(uint32_t), ctx->stream));
-    B.dirbits = v->dirbits; B.dirpre = v->dirpre;
-    const int blocks_ilp = (int)(((B.n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
-    vx_mark_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
-    int rc = PCCM_OK;
-    if ((size_t)B.ndirw_total + 1 <= kScanSmallMax) {      // popcount + scan of the directory in one launch
-        scan_small_kernel<true><<<1, kScanSmallThreads, 0, ctx->stream>>>(v->dirpre, B.ndirw_total + 1, v->dirbits);
-        ctx->tm.total_launches += 2;
-        CKV(cudaGetLastError());
-    } else {
-        vx_dircount_kernel<<<(B.ndirw_total + 1 + threads - 1) / threads, threads, 0, ctx->stream>>>(v->dirbits, B.ndirw_total, v->dirpre);
-        ctx->tm.total_launches += 2;
-        CKV(cudaGetLastError());
-        rc = exclusive_scan(ctx, v->dirpre, (size_t)B.ndirw_total + 1);
-        if (rc) return bail(rc);
-    }
-    uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
-    CKV(cudaMemcpyAsync(hcnt, v->dirpre + ndirw[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CKV(cudaMemcpyAsync(hcnt + 1, v->dirpre + B.ndirw_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CKV(cudaEventRecord(ctx->ev_sync, ctx->stream));       // the wait below is for the brick count only
-    // in the shadow of the wait below: everything that does not depend on the brick count -- the per-point
-    // scratch arrays and, for colours that have already arrived and been classified, their packed array
-    uint2* packed = nullptr;
+    const uint32_t ndirblocks = cap_dirw / kVxDirChunk + 1;
+    const uint32_t nbrickchunks = cap_blk / kVxBrickChunk + 2;
     uint32_t* pslot = nullptr;
-    CKV(dalloc(ctx, &v->prank, (size_t)B.n_total));
-    CKV(dalloc(ctx, &packed, (size_t)B.n_total));
-    CKV(dalloc(ctx, &pslot, (size_t)B.n_total));
+    CKV(dalloc(ctx, &v->dirbits, (size_t)cap_dirw));
+    CKV(dalloc(ctx, &v->dirpre, (size_t)cap_dirw + 1));
+    CKV(dalloc(ctx, &v->dirsums, (size_t)ndirblocks));
+    CKV(dalloc(ctx, &v->masks, (size_t)cap_blk * kVxRows));
+    CKV(dalloc(ctx, &v->rowbase, (size_t)cap_blk * kVxRows));
+    CKV(dalloc(ctx, &v->bricksums, (size_t)nbrickchunks));
+    CKV(dalloc(ctx, &v->vxyz, (size_t)n_total));
+    CKV(dalloc(ctx, &v->vkey, (size_t)n_total));
+    CKV(dalloc(ctx, &v->prank, (size_t)n_total));
+    CKV(dalloc(ctx, &v->dplan, 1));
+    CKV(dalloc(ctx, &pslot, (size_t)n_total));
+    CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
+    CKV(cudaMemsetAsync(v->vkey, 0xff, (size_t)n_total * sizeof(uint2), ctx->stream));
+    VoxBuildArgs A{};
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
-        if (!p->has_colors) continue;
-        if (p->rgb_pending && cudaEventQuery(p->rgb_ready) != cudaSuccess) continue;     // still uploading: the epilogue will gather
-        const int rcc = finish_colors(ctx, p);
-        if (rcc) { dfree(ctx, packed); dfree(ctx, pslot); return bail(rcc); }
-    }
-    CKV(cudaEventSynchronize(ctx->ev_sync));
-    const uint32_t nblk0 = hcnt[0];
-    B.nblk_total = hcnt[1];
-    CKV(dalloc(ctx, &v->masks, (size_t)B.nblk_total * kVxRows));
-    CKV(dalloc(ctx, &v->pre, (size_t)B.nblk_total * kVxRows));
-    CKV(dalloc(ctx, &v->base, (size_t)B.nblk_total + 1));
-    if (!v->recs) CKV(dalloc(ctx, &v->recs, (size_t)B.n_total));
-    CKV(cudaMemsetAsync(v->masks, 0, (size_t)B.nblk_total * kVxRows * sizeof(uint32_t), ctx->stream));
-    if (!recs_ready) CKV(cudaMemsetAsync(v->recs, 0xff, (size_t)B.n_total * sizeof(uint4), ctx->stream));
-    B.masks = v->masks; B.pre = v->pre; B.base = v->base; B.recs = v->recs; B.prank = v->prank;
-    B.packed = packed; B.pslot = pslot;
-    vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
-    vx_brickpre_kernel<<<(B.nblk_total + 1 + 7) / 8, 256, 0, ctx->stream>>>(B);
-    ctx->tm.total_launches += 2;
-    CKV(cudaGetLastError());
-    rc = exclusive_scan(ctx, v->base, (size_t)B.nblk_total + 1);
-    bool rgb_now[2] = {false, false};
-    if (!rc) {
-        // colours that have already arrived (device inputs, or a fast upload) ride in the voxel records; colours
-        // still in flight are read from the colour arrays by the epilogue -- the build never waits for them
-        for (int c = 0; c < 2; ++c) {
-            pccm_cloud* p = cl[c];
-            B.c[c].rgb_in_rec = 0;
-            if (!p->has_colors) continue;
-            if (p->rgb_u8) {                       // packed before the brick-count wait: 4 bytes per point, in input order
-                B.c[c].rgb = p->rgb_u8; B.c[c].rgb_dtype = PCCM_U8; B.c[c].rgb_stride = (int64_t)sizeof(uchar4);
-                B.c[c].rgb_in_rec = 1;
-                rgb_now[c] = true;
-            }
+        A.stats[c] = p->d_dev;
+        A.packed[c] = p->packed;
+        A.n[c] = v->n[c] = (uint32_t)p->n;
+        // colours that are already on the device ride in the voxel records; colours still in flight are read
+        // from the colour arrays by the epilogue -- the build never waits for them
+        A.rgb[c] = nullptr;
+        p->vox_rgb_in_recs = false;
+        if (p->has_colors && !p->rgb_f64 && (!p->rgb_pending || cudaEventQuery(p->rgb_ready) == cudaSuccess || p->raw_rgb_owned == nullptr)) {
+            const int rcc = colors_u8_async(ctx, p);
+            if (rcc) { dfree(ctx, pslot); return bail(rcc); }
+            if (p->rgb_u8) { A.rgb[c] = p->rgb_u8; p->vox_rgb_in_recs = true; }
         }
     }
-    if (!rc) {
-        vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(B);
-        ctx->tm.total_launches++;
-    }
-    dfree(ctx, packed); dfree(ctx, pslot);
-    if (rc) return bail(rc);
+    A.cap_dirw = cap_dirw; A.cap_blk = cap_blk;
+    A.dirbits = v->dirbits; A.dirpre = v->dirpre; A.dirsums = v->dirsums; A.masks = v->masks; A.rowbase = v->rowbase;
+    A.bricksums = v->bricksums; A.vxyz = v->vxyz; A.vkey = v->vkey; A.prank = v->prank; A.pslot = pslot; A.plan = v->dplan;
+    const int threads = 256;
+    const int blocks_ilp = (int)(((n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
+    const int brick_grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count * 4u, nbrickchunks);
+    vx_mark_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    vx_dirsum_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
+    vx_dirscan_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
+    vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    vx_bricksum_kernel<<<brick_grid, threads, 0, ctx->stream>>>(A);
+    vx_rowbase_kernel<<<brick_grid, threads, 0, ctx->stream>>>(A);
+    vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    ctx->tm.total_launches += 7;
     CKV(cudaGetLastError());
+    dfree(ctx, pslot);
 #undef CKV
+    v->pending = true;
+    v->refs = 2;
     for (int c = 0; c < 2; ++c) {
-        VoxView& V = v->view[c];
-        V.g = B.c[c].g;
-        V.dirbits = v->dirbits + B.c[c].dir_off;
-        V.dirpre = v->dirpre + B.c[c].dir_off;
-        V.masks = v->masks; V.pre = v->pre; V.base = v->base; V.recs = v->recs;
-        V.prank = v->prank + (c ? R.n[0] : 0u);
-        V.slot0 = c ? nblk0 : 0u;
-        V.nblk = c ? B.nblk_total - nblk0 : nblk0;
-        V.n = R.n[c];
-        V.nblk_total = B.nblk_total; V.n_total = B.n_total;
         pccm_cloud* p = cl[c];
         release_vox(ctx, p);
         p->vox = v;
         p->vox_id = c;
         v->owner[c] = p;
-        p->index_kind = PCCM_KIND_INT;
+        p->index_kind = PCCM_KIND_INT;      // assumed; vox_settle corrects it when the coordinates turn out not to be integers
         p->rgb_in_rec = false;              // (pencil records; decided when that index is built)
-        p->vox_rgb_in_recs = rgb_now[c];    // the voxel records carry the representative's colour
-        p->vox_rgb_done = false;            // own colours: packed into an array on first use (vox_colors)
-        dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // the records hold every point
+        p->vox_rgb_done = false;
     }
-    v->refs = 2;
-    v->cell_size = cell_size;
-    *built = true;
     return PCCM_OK;
+}
+
+// enqueue the read-back of everything the host needs to judge a pending build (the caller synchronises)
+static int vox_fetch(pccm_ctx* ctx, SharedVox* v) {
+    char* pin = static_cast<char*>(ctx->pinned) + kVoxPinnedOffset;
+    CK(cudaMemcpyAsync(pin, v->dplan, sizeof(VoxPlan), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = v->owner[c];
+        uint32_t* flag = reinterpret_cast<uint32_t*>(pin + sizeof(VoxPlan)) + c;
+        *flag = 0;
+        if (p && p->rgb_spec) CK(cudaMemcpyAsync(flag, p->d_rgbflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return PCCM_OK;
+}
+
+static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind, bool allow_vox);
+
+// After the stream has been synchronised behind vox_fetch: adopt the plan.  *redo is set when the evaluation that
+// was enqueued together with the build must be repeated (the index was rebuilt or the colour format changed).
+static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo) {
+    *redo = false;
+    const char* pin = static_cast<const char*>(ctx->pinned) + kVoxPinnedOffset;
+    const bool was_pending = v->pending;
+    if (was_pending) {
+        memcpy(&v->hplan, pin, sizeof(VoxPlan));
+        v->pending = false;
+        v->view[0] = v->hplan.view[0]; v->view[1] = v->hplan.view[1];
+    }
+    pccm_cloud* cl[2] = {v->owner[0], v->owner[1]};
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(pin + sizeof(VoxPlan));
+    int rc = PCCM_OK;
+    for (int c = 0; c < 2 && !rc; ++c) {
+        pccm_cloud* p = cl[c];
+        if (!p) continue;
+        if (p->rgb_spec) {                   // speculative 8-bit colours: keep or replace by the float64 array
+            p->rgb_spec = false;
+            p->rgb_pending = false;
+            p->rgb_u8_ok = flags[c] == 0u;
+            if (!p->rgb_u8_ok) {
+                dfree(ctx, p->rgb_u8); p->rgb_u8 = nullptr;
+                p->vox_rgb_in_recs = false;
+                rc = finish_colors(ctx, p);
+                *redo = true;
+            } else {
+                dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr;
+            }
+        }
+    }
+    if (rc || !was_pending) return rc;
+    for (int c = 0; c < 2 && !rc; ++c) if (cl[c]) rc = ensure_stats(ctx, cl[c]);
+    if (rc) return rc;
+    const uint32_t st = v->hplan.status;
+    if (st == 0) {
+        for (int c = 0; c < 2; ++c) {
+            pccm_cloud* p = cl[c];
+            if (!p) continue;
+            dfree(ctx, p->packed); p->packed = nullptr;
+            dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // vxyz holds every voxel, prank every point
+        }
+        return PCCM_OK;
+    }
+    // the assumptions did not hold: detach the index and rebuild
+    *redo = true;
+    const double cell = v->cell_size;
+    const int fk = v->force_kind;
+    uint32_t cap_dirw = v->cap_dirw, cap_blk = v->cap_blk;
+    bool retry_vox = !(st & kVxStNotInt) && cl[0] && cl[1];
+    if (retry_vox && (st & kVxStDirOverflow)) {
+        uint64_t words = 0;
+        for (int c = 0; c < 2; ++c) {
+            const pccm_cloud* p = cl[c];
+            const uint64_t bits = (uint64_t)(((int)p->mx[0] >> 5) - ((int)p->mn[0] >> 5) + 1) * (uint64_t)(((int)p->mx[1] >> 3) - ((int)p->mn[1] >> 3) + 1) *
+                                  (uint64_t)(((int)p->mx[2] >> 3) - ((int)p->mn[2] >> 3) + 1);
+            if (bits > kVoxMaxDirBits) retry_vox = false;
+            words += (bits + 31) / 32;
+            if (c == 0) words = (words + kVxDirChunk - 1) / kVxDirChunk * kVxDirChunk;
+        }
+        cap_dirw = (uint32_t)std::min<uint64_t>(words + kVxDirChunk, 0xffffffffull);
+        cap_blk = (uint32_t)std::min<uint64_t>((uint64_t)cl[0]->n + (uint64_t)cl[1]->n + 2, 0xffffffffull);      // (the brick count is not known yet)
+    } else if (retry_vox && (st & kVxStBrickOverflow)) {
+        cap_blk = v->hplan.view[0].nblk_total + 2;
+    }
+    for (int c = 0; c < 2; ++c)
+        if (cl[c]) { release_vox(ctx, cl[c]); cl[c]->index_kind = -1; }
+    if (retry_vox) {
+        rc = vox_enqueue(ctx, cl, cell, fk, cap_dirw, cap_blk);
+        if (rc) return rc;
+        SharedVox* nv = cl[0]->vox;
+        rc = vox_fetch(ctx, nv);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool again = false;
+        return vox_adopt(ctx, nv, &again);       // exact capacities: cannot overflow again
+    }
+    if (cl[0] && cl[1]) return pair_build_classic(ctx, cl[0], cl[1], cell, fk, false);
+    pccm_cloud* only = cl[0] ? cl[0] : cl[1];
+    return only ? pccm_cloud_build_index(ctx, only, cell, fk) : PCCM_OK;
+}
+
+// Make the host's knowledge of a cloud's index current (no-op unless a brick build is pending).
+static int vox_settle(pccm_ctx* ctx, pccm_cloud* c) {
+    if (!c->vox || !c->vox->pending) return PCCM_OK;
+    SharedVox* v = c->vox;
+    int rc = vox_fetch(ctx, v);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    bool redo = false;
+    return vox_adopt(ctx, v, &redo);
 }
 
 // Colours of a brick-indexed cloud, on first use: one packed array in original order (uchar4 when every
@@ -1198,7 +1307,7 @@ static int build_vox(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, double 
 // the neighbour's colour from it.
 static int vox_colors(pccm_ctx* ctx, pccm_cloud* c) {
     if (!c->vox || c->vox_rgb_done || !c->has_colors) return PCCM_OK;
-    const int rc = finish_colors(ctx, c);
+    const int rc = colors_u8_async(ctx, c);
     if (rc) return rc;
     c->vox_rgb_done = true;
     return PCCM_OK;
@@ -1207,6 +1316,7 @@ static int vox_colors(pccm_ctx* ctx, pccm_cloud* c) {
 // Pencil index of a brick-indexed cloud, built on first use (self k-NN, normals, hull prefilter,
 // far queries) for both clouds of the pair from the brick records.
 static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
+    { const int rc = vox_settle(ctx, c); if (rc) return rc; }
     if (c->recs || c->row_start || !c->vox) return PCCM_OK;
     SharedVox* v = c->vox;
     pccm_cloud* cl[2] = {v->owner[0], v->owner[1]};
@@ -1215,7 +1325,14 @@ static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
         RowGrid g{};
         g.short_row = ctx->short_row;
         if (cl[k] && cl[k]->recs) cl[k] = nullptr;    // (cannot happen: both are built together)
-        if (cl[k]) { const int rc = vox_colors(ctx, cl[k]); if (rc) return rc; }   // the pencil records carry the colours
+        if (cl[k]) {                                   // the pencil records carry the colours: their format must be final
+            int rc = vox_colors(ctx, cl[k]);
+            if (!rc && cl[k]->rgb_spec) {
+                rc = vox_fetch(ctx, v);
+                if (!rc) { CK(cudaStreamSynchronize(ctx->stream)); bool redo = false; rc = vox_adopt(ctx, v, &redo); }
+            }
+            if (rc) return rc;
+        }
         if (cl[k]) {
             int xb = 0;
             g.n = (uint32_t)cl[k]->n;
@@ -1229,34 +1346,43 @@ static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
             R.n[k] = 0;
         }
         R.g[k] = g;
-        R.xyz[k] = v->recs; R.dtype[k] = kDtypeVRec; R.stride[k] = sizeof(uint4);
+        R.xyz[k] = v->vxyz; R.dtype[k] = kDtypeVRec; R.stride[k] = sizeof(uint2);
     }
     R.table_off[0] = 0;
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
     R.vprank = v->prank;
-    R.vprank_off[0] = 0; R.vprank_off[1] = v->view[0].n;
+    R.vprank_off[0] = 0; R.vprank_off[1] = v->n[0];
     return build_pair_rowsort(ctx, cl, R);
 }
 
 extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind) {
     if (!ctx || !a || !b) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(ctx->device));
-    // The voxel records of the brick index (16 B per point, 0xFF-filled) do not depend on the statistics:
-    // allocate and fill them BEFORE waiting for those, so that the fill runs while the host is busy with
-    // the wait and the launches that follow it (speculative: dropped again when the pair is not integer).
-    uint4* recs_ready = nullptr;
+    { int rc = vox_settle(ctx, a); if (!rc) rc = vox_settle(ctx, b); if (rc) return rc; }
     const uint64_t n_pair = (uint64_t)a->n + (uint64_t)b->n;
-    if (ctx->use_vox && a != b && a->n && b->n && a->index_kind < 0 && b->index_kind < 0 && n_pair <= (1ull << 24) &&
-        (force_kind == PCCM_KIND_AUTO || force_kind == PCCM_KIND_INT)) {
-        if (dalloc(ctx, &recs_ready, (size_t)n_pair) == cudaSuccess)
-            cudaMemsetAsync(recs_ready, 0xff, (size_t)n_pair * sizeof(uint4), ctx->stream);
-        else
-            recs_ready = nullptr;
+    bool spec = ctx->use_vox && a != b && a->n && b->n && a->index_kind < 0 && b->index_kind < 0 && a->packed && b->packed &&
+                n_pair <= 0x7fffffffull && (force_kind == PCCM_KIND_AUTO || force_kind == PCCM_KIND_INT);
+    if (spec && a->stats_ready && b->stats_ready && std::max(a->data_kind, b->data_kind) != PCCM_KIND_INT) spec = false;
+    if (spec) {
+        // statistics that have already landed decide at once (no wait); otherwise the build is enqueued on the
+        // assumption that both clouds are voxelised -- the stream's statistics kernels say so on the device
+        for (pccm_cloud* c : {a, b})
+            if (!c->stats_ready && cudaEventQuery(c->stats_done) == cudaSuccess) { const int rc = ensure_stats(ctx, c); if (rc) return rc; }
+        if (a->stats_ready && b->stats_ready && std::max(a->data_kind, b->data_kind) != PCCM_KIND_INT) spec = false;
     }
-    struct DropRecs {              // whatever path is taken below: the buffer is either adopted by the brick index or freed
-        pccm_ctx* ctx; uint4** p;
-        ~DropRecs() { if (*p) dfree(ctx, *p); }
-    } drop{ctx, &recs_ready};
+    if (spec) {
+        pccm_cloud* cl[2] = {a, b};
+        const uint32_t n_total = (uint32_t)n_pair;
+        const uint32_t cap_dirw = std::min(kVoxDefaultDirWords, std::max(1u << 12, pow2_ceil(n_total / 2)));
+        const uint32_t cap_blk = n_total <= (1u << 16) ? n_total + 2 : std::max(1u << 16, n_total / 8) + 2;
+        return vox_enqueue(ctx, cl, cell_size, force_kind, cap_dirw, cap_blk);
+    }
+    return pair_build_classic(ctx, a, b, cell_size, force_kind, true);
+}
+
+// The synchronous build: waits for the statistics, then the pencil index of both clouds in joint launches (integer
+// pairs whose statistics were known before the brick build could be enqueued still get the brick index).
+static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind, bool allow_vox) {
     int rc = ensure_stats(ctx, a);
     if (!rc) rc = ensure_stats(ctx, b);
     if (rc) return rc;
@@ -1273,6 +1399,7 @@ extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b
         if (!rc && a != b) rc = pccm_cloud_build_index(ctx, b, cell_size, kind);
         return rc;
     }
+    (void)allow_vox;
     PairRaw R{};
     int xbits = 1, rowbits = 1;
     for (int c = 0; c < 2; ++c) {
@@ -1291,24 +1418,16 @@ extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b
     }
     R.table_off[0] = 0;
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
-    if (kind == PCCM_KIND_INT && ctx->use_vox) {       // the brick index needs coordinates only: colours may still be in flight
-        bool built = false;
-        uint4* adopt = recs_ready;
-        recs_ready = nullptr;                            // build_vox owns it from here (its error paths free the index)
-        rc = build_vox(ctx, cl, R, cell_size, adopt, &built);
-        if (rc) return rc;
-        if (!built && adopt) dfree(ctx, adopt);          // brick grid over the directory budget: pencil path
-        if (built) return ctx->eager_pencil ? ensure_pencil(ctx, a) : PCCM_OK;
-    }
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
         rc = ensure_colors(ctx, p);
         if (rc) return rc;
         // 8-bit colours ride in the KInt record; every other combination keeps a colour array
-        R.rgb_in_rec[c] = kind == PCCM_KIND_INT && p->has_colors && (p->raw_rgb_dtype == PCCM_U8 || p->rgb_u8_ok);
+        R.rgb_in_rec[c] = kind == PCCM_KIND_INT && p->has_colors && (p->raw_rgb_dtype == PCCM_U8 || p->rgb_u8_ok) && p->raw_rgb != nullptr;
         R.rgb[c] = p->raw_rgb; R.rgb_dtype[c] = p->raw_rgb_dtype; R.rgb_stride[c] = p->raw_rgb_stride;
         if (!R.rgb_in_rec[c]) { rc = finish_colors(ctx, p); if (rc) return rc; }
     }
+    for (int c = 0; c < 2; ++c) { dfree(ctx, cl[c]->packed); cl[c]->packed = nullptr; }
     if (kind == PCCM_KIND_INT) {
         if (ctx->use_rowsort) return build_pair_rowsort(ctx, cl, R);
         if (rowbits + xbits + 1 <= 32) return build_pair_impl<uint32_t, KIND_INT>(ctx, cl, R, xbits, rowbits);
@@ -1377,54 +1496,64 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
 
 // Brick path of a symmetric evaluation: staged bit-scan search (one warp per query brick; it also
 // finishes most undecided voxels itself), brick-ring search for the rest, per-point epilogue in
-// the original order, common fold.  Voxels even the brick rings cannot certify (nearest point tens
-// of voxels away) are finished by the pencil search in a second round.  Synchronises; results
-// land where launch_query puts them.
-static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cloud* sc[2], QueryParams& Q, int rank, int world) {
+// the original order, common fold.  Works on a build that is still pending: nothing here needs to know
+// the outcome of the build, the ONE synchronisation is the result read-back, and the build is judged
+// there (*redo = the evaluation must be repeated: the index was rebuilt or the colour format changed).
+// Voxels even the brick rings cannot certify (nearest point tens of voxels away) are finished by the
+// pencil search in a second round.  Results land where launch_query puts them.
+struct VoxScratch {           // freed on every exit path
+    pccm_ctx* ctx;
+    uint32_t* todo = nullptr;
+    uint4* vres = nullptr;
+    BlockPartial* partials = nullptr;
+    ~VoxScratch() { dfree(ctx, todo); dfree(ctx, vres); dfree(ctx, partials); }
+};
+
+static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cloud* sc[2], QueryParams& Q, int rank, int world, bool* redo) {
+    *redo = false;
     SharedVox* v = qc[0]->vox;
     VxParams P{};
+    P.plan = v->dplan;
     P.ndirs = ndirs;
     P.normals_mode = Q.normals_mode;
     P.rank = rank; P.world = world;
     memcpy(P.T, Q.T, sizeof P.T);
     P.color_scale = Q.color_scale;
     const double* lut = reinterpret_cast<const double*>(static_cast<char*>(ctx->dscratch) + kLutOffset);
-    const uint32_t n_total = v->view[0].n_total;
-    uint32_t* todo = nullptr;      // [0..3] counters (undecided, far per direction), then the four lists
-    uint4* vres = nullptr;
-    BlockPartial* partials = nullptr;
-    CK(dalloc(ctx, &todo, 2 * (size_t)n_total + 4));
-    CK(dalloc(ctx, &vres, (size_t)n_total));
-    CK(cudaMemsetAsync(todo, 0, 4 * sizeof(uint32_t), ctx->stream));
-    uint32_t rec_stride = 0, nwarps = 0, ntiles = 0;
+    const uint32_t n_total = v->n[0] + v->n[1];
+    VoxScratch sx{ctx};             // todo: [0..7] counters (undecided, far per direction, brick ticket), then the four lists
+    CK(dalloc(ctx, &sx.todo, 2 * (size_t)n_total + 8));
+    CK(dalloc(ctx, &sx.vres, (size_t)n_total));
+    CK(cudaMemsetAsync(sx.todo, 0, 8 * sizeof(uint32_t), ctx->stream));
+    uint32_t rec_stride = 0, ntiles = 0;
     for (int d = 0; d < ndirs; ++d) {
         VxDir& D = P.dir[d];
-        D.q = v->view[qc[d]->vox_id];
-        D.s = v->view[sc[d]->vox_id];
+        D.qc = qc[d]->vox_id; D.sc = sc[d]->vox_id;
+        D.nq = v->n[D.qc];
+        D.qprank = v->prank + (D.qc ? v->n[0] : 0u);
         D.qa = Q.dir[d].q; D.sa = Q.dir[d].s;
         // own colour: streamed from the packed array; neighbour colour: in the voxel answer when the records carry it
         D.qa.rgb_mode = !qc[d]->has_colors ? 0 : (qc[d]->rgb_u8 ? 2 : 3);
         D.sa.rgb_mode = !sc[d]->has_colors ? 0 : (sc[d]->vox_rgb_in_recs ? 1 : (sc[d]->rgb_u8 ? 2 : 3));
+        D.qa.rgb_u8 = qc[d]->rgb_u8; D.qa.rgb_f64 = qc[d]->rgb_f64;
+        D.sa.rgb_u8 = sc[d]->rgb_u8; D.sa.rgb_f64 = sc[d]->rgb_f64;
         D.qa.lut255 = D.sa.lut255 = lut;
         D.flags = Q.dir[d].flags;
         D.idx_out = Q.dir[d].idx_out; D.d2_out = Q.dir[d].d2_out;
-        D.todo_count = todo + d;
-        D.todo = todo + 4 + (d ? (size_t)qc[0]->n : 0);
-        D.far_count = todo + 2 + d;
-        D.far = todo + 4 + n_total + (d ? (size_t)qc[0]->n : 0);
-        D.ntiles = (D.q.n + kVxEpiTile - 1) / kVxEpiTile;
+        D.todo = sx.todo + 8 + (d ? (size_t)v->n[P.dir[0].qc] : 0);
+        D.far = sx.todo + 8 + n_total + (d ? (size_t)v->n[P.dir[0].qc] : 0);
+        D.ntiles = (D.nq + kVxEpiTile - 1) / kVxEpiTile;
         rec_stride = std::max(rec_stride, 2u * D.ntiles);
-        nwarps += D.q.nblk;
         ntiles += D.ntiles;
     }
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
-    CK(dalloc(ctx, &partials, (size_t)rec_stride * 2 + 1));
-    P.partials = partials; P.vres = vres;
+    CK(dalloc(ctx, &sx.partials, (size_t)rec_stride * 2 + 1));
+    P.partials = sx.partials; P.vres = sx.vres; P.counters = sx.todo;
     {
         StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage
         {
             StageTimer t(ctx, &ctx->tm.vox_search_ms, 1);
-            vx_search_kernel<<<(nwarps + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
+            vx_search_kernel<<<ctx->sm_count * ctx->vx_search_blocks, kVxThreads, 0, ctx->stream>>>(P);
             ctx->tm.query_launches++;
         }
         {
@@ -1440,11 +1569,11 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     CK(cudaGetLastError());
     // common fold: same record layout as the pencil path
     Q.rec_stride = rec_stride;
-    Q.partials = partials;
+    Q.partials = sx.partials;
     Q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->dscratch) + kTicketOffset);
     Q.out = static_cast<BlockPartial*>(ctx->dscratch);
     Q.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);
-    uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset);
+    uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset + sizeof(VoxPlan) + 16);
     auto fold = [&](uint32_t passes) -> int {
         StageTimer t(ctx, &ctx->tm.finalize_ms);
         for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = passes * P.dir[d].ntiles;
@@ -1456,13 +1585,16 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     };
     int rc = fold(1);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(hcnt + 2, todo, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hcnt + 6, v->base + v->view[0].nblk_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->tm.vox_undecided = (int64_t)hcnt[2] + hcnt[3];
-    ctx->tm.vox_far = (int64_t)hcnt[4] + hcnt[5];
-    ctx->tm.vox_tail = (int64_t)n_total - (int64_t)hcnt[6];
-    if (hcnt[4] + hcnt[5] > 0) {
+    CK(cudaMemcpyAsync(hcnt, sx.todo, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = vox_fetch(ctx, v);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));          // the one host wait of build + evaluation
+    rc = vox_adopt(ctx, v, redo);
+    if (rc || *redo) return rc;
+    ctx->tm.vox_undecided = (int64_t)hcnt[0] + hcnt[1];
+    ctx->tm.vox_far = (int64_t)hcnt[2] + hcnt[3];
+    ctx->tm.vox_tail = (int64_t)n_total - (int64_t)v->hplan.nvox_total;
+    if (hcnt[2] + hcnt[3] > 0) {
         // second round: pencil search for the far voxels, the epilogue of their points, fold again
         for (int d = 0; d < ndirs; ++d) {
             rc = ensure_pencil(ctx, sc[d]);
@@ -1484,7 +1616,6 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    dfree(ctx, todo); dfree(ctx, partials); dfree(ctx, vres);
     return PCCM_OK;
 }
 
@@ -1508,25 +1639,33 @@ extern "C" int pccm_nn(pccm_ctx* ctx, pccm_cloud* query, pccm_cloud* search, int
     if (idx_out) { if (mem_kind == PCCM_DEVICE) d_idx = idx_out; else CK(dalloc(ctx, &d_idx, (size_t)nq)); }
     if (d2_out) { if (mem_kind == PCCM_DEVICE) d_d2 = d2_out; else CK(dalloc(ctx, &d_d2, (size_t)nq)); }
     QueryParams P{};
-    P.ndirs = 1;
-    P.dir[0].q = view_of(query); P.dir[0].s = view_of(search);
-    P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq; P.dir[0].flags = 0;
-    P.dir[0].idx_out = d_idx; P.dir[0].d2_out = d_d2;
-    P.normals_mode = 0; P.color_scale = 1;
-    if (ctx->use_vox && query->vox && query->vox == search->vox && query != search && query->index_kind == PCCM_KIND_INT) {
-        pccm_cloud* qc[2] = {query, nullptr};
-        pccm_cloud* sc[2] = {search, nullptr};
-        rc = launch_vox_query(ctx, 1, qc, sc, P, 0, 1);
-    } else {
-        rc = ensure_pencil(ctx, query);
-        if (!rc) rc = ensure_pencil(ctx, search);
-        if (rc) return rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        P = QueryParams{};
+        P.ndirs = 1;
         P.dir[0].q = view_of(query); P.dir[0].s = view_of(search);
-        P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq;
-        rc = launch_query(ctx, query->index_kind, P);
+        P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq; P.dir[0].flags = 0;
+        P.dir[0].idx_out = d_idx; P.dir[0].d2_out = d_d2;
+        P.normals_mode = 0; P.color_scale = 1;
+        if (ctx->use_vox && query->vox && query->vox == search->vox && query != search && query->index_kind == PCCM_KIND_INT) {
+            pccm_cloud* qc[2] = {query, nullptr};
+            pccm_cloud* sc[2] = {search, nullptr};
+            bool redo = false;
+            rc = launch_vox_query(ctx, 1, qc, sc, P, 0, 1, &redo);
+            if (!rc && redo) continue;               // the pending build was replaced: evaluate on what it became
+        } else {
+            rc = ensure_pencil(ctx, query);
+            if (!rc) rc = ensure_pencil(ctx, search);
+            if (!rc) rc = check_pair(ctx, query, search);
+            if (!rc) {
+                P.dir[0].q = view_of(query); P.dir[0].s = view_of(search);
+                P.dir[0].qbegin = query->base; P.dir[0].qend = query->base + nq;
+                rc = launch_query(ctx, query->index_kind, P);
+            }
+        }
+        break;
     }
-    if (!rc && mem_kind == PCCM_HOST) {
-        if (idx_out) rc = copy_out(ctx, idx_out, d_idx, (size_t)nq * sizeof(int32_t), PCCM_HOST);
+    if (mem_kind == PCCM_HOST) {
+        if (!rc && idx_out) rc = copy_out(ctx, idx_out, d_idx, (size_t)nq * sizeof(int32_t), PCCM_HOST);
         if (!rc && d2_out) rc = copy_out(ctx, d2_out, d_d2, (size_t)nq * sizeof(double), PCCM_HOST);
         dfree(ctx, d_idx); dfree(ctx, d_d2);
     }
@@ -1552,29 +1691,18 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
         if (!color_matrix) return fail(ctx, PCCM_ERR_INVALID, "color_matrix is NULL");
     }
     pccm_cloud* cl[2] = {a, b};
-    if (flags & PCCM_EVAL_COLOR)
-        for (int d = 0; d < 2; ++d) { rc = vox_colors(ctx, cl[d]); if (rc) return rc; }
     // metric.py:148-152 indexes the OTHER cloud's normals with the query index: a direction
     // whose search cloud is shorter than its query cloud raises IndexError in the reference.
     uint32_t dflags[2] = {flags, flags};
     for (int d = 0; d < 2; ++d)
         if ((flags & PCCM_EVAL_D2) && normals_mode == PCCM_NORMALS_BY_QUERY_INDEX && cl[1 - d]->n < cl[d]->n)
             dflags[d] &= ~(uint32_t)PCCM_EVAL_D2;
-    QueryParams P{};
-    P.ndirs = 2;
-    P.normals_mode = normals_mode;
-    if (color_matrix) memcpy(P.T, color_matrix, sizeof P.T);
-    P.color_scale = color_scale;
-    for (int d = 0; d < 2; ++d) {
-        const uint64_t n = (uint64_t)cl[d]->n;
-        DirParams& D = P.dir[d];
-        D.q = view_of(cl[d]); D.s = view_of(cl[1 - d]);
-        D.qbegin = cl[d]->base + (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
-        D.qend = cl[d]->base + (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
-        D.flags = dflags[d];
-        if (flags & PCCM_EVAL_PERPOINT) {
+    if (flags & PCCM_EVAL_PERPOINT) {
+        for (int d = 0; d < 2; ++d) {
+            const uint64_t n = (uint64_t)cl[d]->n;
             if (ctx->pp_n[d] != cl[d]->n) {
                 dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]);
+                ctx->pp_idx[d] = nullptr; ctx->pp_d2[d] = nullptr; ctx->pp_n[d] = 0;
                 CK(dalloc(ctx, &ctx->pp_idx[d], (size_t)n));
                 CK(dalloc(ctx, &ctx->pp_d2[d], (size_t)n));
                 ctx->pp_n[d] = cl[d]->n;
@@ -1583,25 +1711,44 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
                 CK(cudaMemsetAsync(ctx->pp_idx[d], 0xff, n * sizeof(int32_t), ctx->stream));
                 CK(cudaMemsetAsync(ctx->pp_d2[d], 0xff, n * sizeof(double), ctx->stream));
             }
-            D.idx_out = ctx->pp_idx[d];
-            D.d2_out = ctx->pp_d2[d];
         }
+        ctx->pp_owner[0] = a; ctx->pp_owner[1] = b;
     }
-    const bool vox = ctx->use_vox && a->vox && a->vox == b->vox && a != b && a->index_kind == PCCM_KIND_INT;
+    QueryParams P{};
+    bool vox = false;
     pccm_cloud* sc[2] = {b, a};
-    if (vox) {
-        rc = launch_vox_query(ctx, 2, cl, sc, P, rank, world);
-    } else {
-        rc = ensure_pencil(ctx, a);
-        if (!rc) rc = ensure_pencil(ctx, b);
-        if (rc) return rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        vox = ctx->use_vox && a->vox && a->vox == b->vox && a != b && a->index_kind == PCCM_KIND_INT;
+        if (vox && (flags & PCCM_EVAL_COLOR))
+            for (int d = 0; d < 2; ++d) { rc = vox_colors(ctx, cl[d]); if (rc) return rc; }
+        if (!vox) {
+            rc = ensure_pencil(ctx, a);
+            if (!rc) rc = ensure_pencil(ctx, b);
+            if (!rc) rc = check_pair(ctx, a, b);
+            if (rc) return rc;
+        }
+        P = QueryParams{};
+        P.ndirs = 2;
+        P.normals_mode = normals_mode;
+        if (color_matrix) memcpy(P.T, color_matrix, sizeof P.T);
+        P.color_scale = color_scale;
         for (int d = 0; d < 2; ++d) {
             const uint64_t n = (uint64_t)cl[d]->n;
-            P.dir[d].q = view_of(cl[d]); P.dir[d].s = view_of(cl[1 - d]);
-            P.dir[d].qbegin = cl[d]->base + (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
-            P.dir[d].qend = cl[d]->base + (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
+            DirParams& D = P.dir[d];
+            D.q = view_of(cl[d]); D.s = view_of(cl[1 - d]);
+            D.qbegin = cl[d]->base + (uint32_t)(n * (uint64_t)rank / (uint64_t)world);
+            D.qend = cl[d]->base + (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)world);
+            D.flags = dflags[d];
+            if (flags & PCCM_EVAL_PERPOINT) { D.idx_out = ctx->pp_idx[d]; D.d2_out = ctx->pp_d2[d]; }
         }
-        rc = launch_query(ctx, a->index_kind, P);
+        if (vox) {
+            bool redo = false;
+            rc = launch_vox_query(ctx, 2, cl, sc, P, rank, world, &redo);
+            if (!rc && redo) continue;               // the pending build was replaced: evaluate on what it became
+        } else {
+            rc = launch_query(ctx, a->index_kind, P);
+        }
+        break;
     }
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1625,7 +1772,8 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
 extern "C" int pccm_pair_get(pccm_ctx* ctx, int which, int direction, void* out, int mem_kind) {
     if (!ctx || !out) return fail(ctx, PCCM_ERR_INVALID, "NULL argument");
     if (direction < 0 || direction > 1) return fail(ctx, PCCM_ERR_INVALID, "direction must be 0 or 1");
-    if (!ctx->pp_idx[direction]) return fail(ctx, PCCM_ERR_STATE, "no per-point results: call pccm_pair_eval with PCCM_EVAL_PERPOINT");
+    if (!ctx->pp_idx[direction] || !ctx->pp_owner[0] || !ctx->pp_owner[1])
+        return fail(ctx, PCCM_ERR_STATE, "no per-point results: call pccm_pair_eval with PCCM_EVAL_PERPOINT (and keep both clouds alive)");
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->pp_n[direction];
     if (which == PCCM_GET_IDX) return copy_out(ctx, out, ctx->pp_idx[direction], n * sizeof(int32_t), mem_kind);
@@ -1661,53 +1809,77 @@ static int launch_knn(pccm_ctx* ctx, pccm_cloud* c, KnnParams& P) {
     return PCCM_OK;
 }
 
-// pccm_self_nn_minmax on the brick index.  *ok = false when a voxel could not be decided within its 27
-// neighbour bricks (the caller then takes the pencil path).
+// pccm_self_nn_minmax on the brick index.  Voxels that have no other voxel within their 27 neighbour bricks (isolated
+// by more than 8 voxels) are finished one by one with the pencil search -- the slice keeps its share of the voxels
+// whatever path its voxels take, so the slices of several ranks always cover every point exactly once.
+struct SelfScratch {
+    pccm_ctx* ctx;
+    uint32_t *scratch = nullptr, *vself = nullptr, *und = nullptr;
+    double *mm = nullptr, *d_pp = nullptr;
+    bool own_pp = false;
+    ~SelfScratch() { dfree(ctx, scratch); dfree(ctx, vself); dfree(ctx, und); dfree(ctx, mm); if (own_pp) dfree(ctx, d_pp); }
+};
+
 static int vox_self_nn(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end, double* min_out, double* max_out,
-                       double* per_point, int mem_kind, bool* ok) {
-    *ok = false;
+                       double* per_point, int mem_kind) {
     SharedVox* v = c->vox;
     VxSelfParams P{};
     P.c = v->view[c->vox_id];
     P.n = (uint32_t)c->n;
     P.begin = (uint32_t)begin; P.end = (uint32_t)end;
     const uint32_t n_total = P.c.n_total, nwords = (n_total + 31u) / 32u;
-    uint32_t* scratch = nullptr;      // [0] undecided counter, then dupbits
-    uint32_t* vself = nullptr;
-    double *mm = nullptr, *d_pp = nullptr;
-    CK(dalloc(ctx, &scratch, (size_t)nwords + 2));
-    CK(dalloc(ctx, &vself, (size_t)n_total));
-    CK(dalloc(ctx, &mm, (size_t)P.c.nblk * 2));
-    if (per_point) { if (mem_kind == PCCM_DEVICE) d_pp = per_point; else CK(dalloc(ctx, &d_pp, (size_t)c->n)); }
-    CK(cudaMemsetAsync(scratch, 0, ((size_t)nwords + 2) * sizeof(uint32_t), ctx->stream));
-    P.undecided = scratch; P.dupbits = scratch + 1; P.vself = vself; P.minmax = mm; P.per_point = d_pp;
+    const uint32_t far_blocks = (uint32_t)ctx->sm_count * 2u;
+    SelfScratch sx{ctx};
+    CK(dalloc(ctx, &sx.scratch, (size_t)nwords + 1));       // dupbits
+    CK(dalloc(ctx, &sx.vself, (size_t)n_total));
+    CK(dalloc(ctx, &sx.und, (size_t)P.c.n + 1));             // [0] count, then the ranks of the undecided voxels
+    CK(dalloc(ctx, &sx.mm, ((size_t)P.c.nblk + far_blocks) * 2));
+    if (per_point) {
+        if (mem_kind == PCCM_DEVICE) sx.d_pp = per_point;
+        else { CK(dalloc(ctx, &sx.d_pp, (size_t)c->n)); sx.own_pp = true; }
+    }
+    CK(cudaMemsetAsync(sx.scratch, 0, ((size_t)nwords + 1) * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(sx.und, 0, sizeof(uint32_t), ctx->stream));
+    P.undecided = sx.und; P.dupbits = sx.scratch; P.vself = sx.vself; P.minmax = sx.mm; P.per_point = sx.d_pp;
+    uint32_t* hund = reinterpret_cast<uint32_t*>(static_cast<double*>(ctx->pinned) + 1024 + 2);
     {
         StageTimer t(ctx, &ctx->tm.knn_ms, 1);
         vx_dupflag_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(P);
         vx_selfnn_kernel<<<(P.c.nblk + kVxWarps - 1) / kVxWarps, kVxThreads, 0, ctx->stream>>>(P);
-        minmax_finalize_kernel<<<1, 256, 0, ctx->stream>>>(mm, P.c.nblk, static_cast<double*>(ctx->dscratch) + 1024);
         ctx->tm.knn_launches++;
-        ctx->tm.total_launches += 3;
-        if (per_point) {
-            vx_selfout_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(P);
-            ctx->tm.total_launches++;
-        }
+        ctx->tm.total_launches += 2;
         CK(cudaGetLastError());
     }
-    double* hmm = static_cast<double*>(ctx->pinned) + 1024;
-    uint32_t* hund = reinterpret_cast<uint32_t*>(hmm + 2);
-    CK(cudaMemcpyAsync(hmm, static_cast<double*>(ctx->dscratch) + 1024, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hund, scratch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hund, sx.und, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    int rc = PCCM_OK;
-    if (*hund == 0u) {
-        *ok = true;
-        *min_out = hmm[0];
-        *max_out = hmm[1];
-        if (per_point && mem_kind == PCCM_HOST) rc = copy_out(ctx, per_point, d_pp, (size_t)c->n * sizeof(double), PCCM_HOST);
+    uint32_t nmm = P.c.nblk;
+    if (*hund > 0u) {
+        const int rc = ensure_pencil(ctx, c);
+        if (rc) return rc;
+        VxSelfFarParams F{};
+        F.s = P;
+        F.grid = c->grid; F.recs = static_cast<const uint4*>(c->recs); F.row_start = c->row_start;
+        F.minmax_extra = sx.mm + 2 * (size_t)P.c.nblk;
+        StageTimer t(ctx, &ctx->tm.knn_ms, 1);
+        vx_selffar_kernel<<<far_blocks, 128, 0, ctx->stream>>>(F);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        nmm += far_blocks;
     }
-    if (per_point && mem_kind == PCCM_HOST) dfree(ctx, d_pp);
-    dfree(ctx, scratch); dfree(ctx, vself); dfree(ctx, mm);
+    minmax_finalize_kernel<<<1, 256, 0, ctx->stream>>>(sx.mm, nmm, static_cast<double*>(ctx->dscratch) + 1024);
+    ctx->tm.total_launches++;
+    if (per_point) {
+        vx_selfout_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, ctx->stream>>>(P);
+        ctx->tm.total_launches++;
+    }
+    CK(cudaGetLastError());
+    double* hmm = static_cast<double*>(ctx->pinned) + 1024;
+    CK(cudaMemcpyAsync(hmm, static_cast<double*>(ctx->dscratch) + 1024, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = PCCM_OK;
+    if (per_point && mem_kind == PCCM_HOST) rc = copy_out(ctx, per_point, sx.d_pp, (size_t)c->n * sizeof(double), PCCM_HOST);
+    CK(cudaStreamSynchronize(ctx->stream));
+    *min_out = hmm[0];
+    *max_out = hmm[1];
     return rc;
 }
 
@@ -1747,12 +1919,11 @@ extern "C" int pccm_self_nn_minmax(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, 
     if (c->index_kind < 0) return fail(ctx, PCCM_ERR_STATE, "cloud is not indexed");
     if (begin < 0 || end < begin || end > c->n) return fail(ctx, PCCM_ERR_INVALID, "bad range [%lld, %lld)", (long long)begin, (long long)end);
     if (end == begin) { *min_out = INFINITY; *max_out = -INFINITY; return PCCM_OK; }
+    { const int rcs = vox_settle(ctx, c); if (rcs) return rcs; }
     if (ctx->use_vox && c->vox && c->n >= 2 && (!per_point || (begin == 0 && end == c->n))) {
-        // brick index: the pair search's row scans with the voxel's own bit cleared; no pencil index needed
-        bool ok = false;
-        const int rcv = vox_self_nn(ctx, c, begin, end, min_out, max_out, per_point, mem_kind, &ok);
-        if (rcv) return rcv;
-        if (ok) return PCCM_OK;      // else: some point is isolated by more than 8 voxels -> pencil path below
+        // brick index: the pair search's neighbourhood bits with the voxel's own bit cleared; isolated voxels are
+        // finished with the pencil search inside (the pencil index is only built when there are any)
+        return vox_self_nn(ctx, c, begin, end, min_out, max_out, per_point, mem_kind);
     }
     int rc = check_range(ctx, c, begin, end);
     if (rc) return rc;

@@ -43,22 +43,35 @@ struct StatsPartial {
     uint32_t not_int, not_f32, not_finite, rgb_not_u8;
 };
 
-// K0: bounding box + classification of coordinates (and colours) in one pass.
+// The same statistics as ONE record in device memory, for the kernels that plan the brick index without the
+// host (pccm_vox_kernels.cuh): integer bounding box (the minimum as 0x7fffffff - min so that a zeroed record is the
+// neutral element of atomicMax for every field) and the classification flags.
+struct DevStats {
+    uint32_t nmn[3], mx[3];
+    uint32_t flags, pad;
+};
+constexpr uint32_t kDevNotInt = 1u, kDevNotF32 = 2u, kDevNonFinite = 4u;
+
+// K0: bounding box + classification of coordinates (and colours) in one pass; integer-valued coordinates are
+// also written as 8-byte {x | y << 16, z} records -- the form every later pass of the brick index reads.
 __global__ void __launch_bounds__(kStatsThreads)
 stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
-             const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out) {
+             const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out, uint2* packed, DevStats* dev) {
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     uint32_t not_int = 0, not_f32 = 0, not_fin = 0, rgb_bad = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v3[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             double v = load_coord(xyz, dtype, stride, i, a);
+            v3[a] = v;
             if (!isfinite(v)) not_fin = 1;
             mn[a] = fmin(mn[a], v);
             mx[a] = fmax(mx[a], v);
             if (!(v >= 0.0 && v <= 32767.0 && v == floor(v))) not_int = 1;
             if ((double)(float)v != v) not_f32 = 1;
         }
+        if (packed) packed[i] = make_uint2(((uint32_t)(int)v3[0] & 0xffffu) | ((uint32_t)(int)v3[1] << 16), (uint32_t)(int)v3[2]);
         if (rgb != nullptr && rgb_dtype == PCCM_F64) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -95,6 +108,16 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
         }
         p.not_int = s_flags[0]; p.not_f32 = s_flags[1]; p.not_finite = s_flags[2]; p.rgb_not_u8 = s_flags[3];
         out[blockIdx.x] = p;
+        if (dev) {
+            if (!p.not_int) {
+                for (int a = 0; a < 3; ++a) {
+                    atomicMax(&dev->nmn[a], 0x7fffffffu - (uint32_t)(int)p.mn[a]);
+                    atomicMax(&dev->mx[a], (uint32_t)(int)p.mx[a]);
+                }
+            }
+            const uint32_t f = (p.not_int ? kDevNotInt : 0u) | (p.not_f32 ? kDevNotF32 : 0u) | (p.not_finite ? kDevNonFinite : 0u);
+            if (f) atomicOr(&dev->flags, f);
+        }
     }
 }
 

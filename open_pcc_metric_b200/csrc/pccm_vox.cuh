@@ -11,24 +11,24 @@
 //   dirbits / dirpre : bitmap over the brick grid of the cloud's bounding box + exclusive
 //                      popcount prefix  ->  slot of an occupied brick (slots follow (z, y, x))
 //   masks[slot][64]  : the occupancy words
-//   pre[slot][64]    : number of occupied voxels of the brick before row r
-//   base[slot]       : rank of the brick's first voxel; rank = base + pre + popc(bits below)
-//   recs[rank]       : {x | y << 16, z, rgb, idx} of the voxel's point with the SMALLEST original
-//                      index (only that one can win under the tie rule; atomicMin on the 64-bit
-//                      {idx, rgb} half of the record)
+//   rowbase[slot][64]: rank of the first voxel of row r of the brick (already global: brick base +
+//                      rows before r); rank = rowbase + popc(bits below).  The entry of the brick
+//                      past the last one holds the number of distinct voxels.
+//   vxyz[rank]       : {x | y << 16, z} of the voxel
+//   vkey[rank]       : {rgb, idx} of the voxel's point with the SMALLEST original index (only that
+//                      one can win under the tie rule; one 64-bit atomicMin per point)
 //   prank[i]         : rank of the voxel of input point i.  As queries the points of a voxel
 //                      share ONE search (one lane per voxel); the per-point epilogue runs in the
 //                      original order of the input and fetches its voxel's answer through prank.
 // Two clouds of a pair share the arrays (cloud 1's slots, ranks and points continue cloud 0's).
 //
-// Search.  The nearest occupied voxel of a row to the query's x is two bit scans (CLZ on the
-// bits at or below x, CLZ of the bit-reversed bits above): dx, hence dx^2 + dy^2 + dz^2 for the
-// whole row, with no point ever loaded.  The 3 x 3 (then 5 x 5) rows around the query decide
-// every query whose answer is closer than 2 (3) voxels -- exactly, because anything outside the
-// scanned rows / the +-16 window in x is at least that far.  Only the voxels that TIE at the
-// minimal distance are then looked up (rank -> record) to apply the smallest-index rule.
-// Queries that stay undecided go to vx_search_general (brick rings, up to a ring limit) and, beyond
-// that (clouds far apart, isolated outliers), to the pencil search of pccm_core.cuh.
+// Search.  A query's candidates closer than 2 voxels are the 27 bits of the 3 x 3 x 3 voxels around
+// it: three bits of each of nine occupancy rows.  Those 27 bits, sorted by the four distance levels
+// (0, 1, 2, 3), are the answer AND the list of voxels that tie at the minimum; only those are looked
+// up (rank -> vkey) to apply the smallest-index rule.  Queries with an empty 27-neighbourhood
+// (1-2 % on codec-like content) repeat the game on the 5 x 5 x 5 voxels (exact below distance 3),
+// then on whole bricks (vx_search_general: brick rings, up to a ring limit) and, beyond that (clouds
+// far apart, isolated outliers), go to the pencil search of pccm_core.cuh.
 #pragma once
 #include "pccm_core.cuh"
 
@@ -57,17 +57,6 @@ PCCM_HD int vx_clz(uint32_t v) {
     return v ? __builtin_clz(v) : 32;
 #endif
 }
-PCCM_HD uint32_t vx_brev(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return __brev(v);
-#else
-    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
-    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
-    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
-    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
-    return (v >> 16) | (v << 16);
-#endif
-}
 PCCM_HD int vx_popc(uint32_t v) {
 #if defined(__CUDA_ARCH__)
     return __popc(v);
@@ -82,12 +71,11 @@ PCCM_HD int vx_ffs(uint32_t v) {   // 1-based position of the lowest set bit, 0 
     return v ? __builtin_ctz(v) + 1 : 0;
 #endif
 }
-PCCM_HD uint32_t vx_fshr(uint32_t lo, uint32_t hi, int s) {   // low word of (hi:lo) >> (s & 31)
+PCCM_HD uint32_t vx_fshr(uint32_t lo, uint32_t hi, int s) {   // low word of (hi:lo) >> s, 0 <= s <= 32
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, (uint32_t)s);
+    return __funnelshift_rc(lo, hi, (uint32_t)s);
 #else
-    s &= 31;
-    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+    return s == 0 ? lo : (s >= 32 ? hi : (lo >> s) | (hi << (32 - s)));
 #endif
 }
 PCCM_HD uint32_t vx_atomic_or(uint32_t* p, uint32_t v) {
@@ -95,13 +83,6 @@ PCCM_HD uint32_t vx_atomic_or(uint32_t* p, uint32_t v) {
     return atomicOr(p, v);
 #else
     const uint32_t o = *p; *p = o | v; return o;
-#endif
-}
-PCCM_HD uint32_t vx_atomic_add(uint32_t* p, uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return atomicAdd(p, v);
-#else
-    const uint32_t o = *p; *p = o + v; return o;
 #endif
 }
 PCCM_HD unsigned long long vx_atomic_min64(unsigned long long* p, unsigned long long v) {
@@ -114,13 +95,6 @@ PCCM_HD unsigned long long vx_atomic_min64(unsigned long long* p, unsigned long 
 PCCM_HD uint32_t vx_ld32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
-#else
-    return *p;
-#endif
-}
-PCCM_HD uint32_t vx_ld16(const uint16_t* p) {
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)__ldg(p);
 #else
     return *p;
 #endif
@@ -155,10 +129,10 @@ struct VoxView {
     VoxDims g;
     const uint32_t* dirbits;
     const uint32_t* dirpre;
-    const uint32_t* masks;
-    const uint16_t* pre;
-    const uint32_t* base;            // [nblk_total + 1]
-    const uint4* recs;               // [n_total]
+    const uint32_t* masks;           // [nblk_total + 1][64]
+    const uint32_t* rowbase;         // [nblk_total + 1][64]
+    const uint2* vxyz;               // [n_total]
+    const uint2* vkey;               // [n_total]
     const uint32_t* prank;           // [n] this cloud's points, original order -> rank of their voxel
     uint32_t slot0, nblk;            // this cloud's bricks are slots [slot0, slot0 + nblk)
     uint32_t n;                      // points of this cloud
@@ -178,11 +152,13 @@ PCCM_HD uint32_t vx_rank(const VoxView& G, uint32_t slot, int r, int xbit) {
     VX_CHECK(slot < G.nblk_total && (unsigned)r < (unsigned)kVxRows && (unsigned)xbit < 32u);
     const uint32_t m = vx_ld32(G.masks + (size_t)slot * kVxRows + r);
     VX_CHECK((m >> xbit) & 1u);                       // the voxel we rank must be occupied
-    return vx_ld32(G.base + slot) + vx_ld16(G.pre + (size_t)slot * kVxRows + r) + (uint32_t)vx_popc(m & ((1u << xbit) - 1u));
+    return vx_ld32(G.rowbase + (size_t)slot * kVxRows + r) + (uint32_t)vx_popc(m & ((1u << xbit) - 1u));
 }
+// voxels of brick `slot` are the ranks [vx_brick_begin(slot), vx_brick_begin(slot + 1))
+PCCM_HD uint32_t vx_brick_begin(const VoxView& G, uint32_t slot) { return vx_ld32(G.rowbase + (size_t)slot * kVxRows); }
 // positions of the cloud's records in the joint array
-PCCM_HD uint32_t vx_ranked_begin(const VoxView& G) { return vx_ld32(G.base + G.slot0); }
-PCCM_HD uint32_t vx_ndistinct(const VoxView& G) { return vx_ld32(G.base + G.slot0 + G.nblk) - vx_ld32(G.base + G.slot0); }
+PCCM_HD uint32_t vx_ranked_begin(const VoxView& G) { return vx_brick_begin(G, G.slot0); }
+PCCM_HD uint32_t vx_ndistinct(const VoxView& G) { return vx_brick_begin(G, G.slot0 + G.nblk) - vx_brick_begin(G, G.slot0); }
 
 // ---- build, per point (the kernels call these once per input point, pass after pass) --------
 PCCM_HD void vx_mark_point(uint32_t* dirbits, uint32_t key) {
@@ -198,25 +174,29 @@ PCCM_HD void vx_fill_point(uint32_t* masks, uint32_t slot, int x, int y, int z) 
     const uint32_t bit = 1u << (x & 31);
     if (!(*w & bit)) vx_atomic_or(w, bit);
 }
-// pass 3 (after the brick prefixes): rank of the point's voxel; voxel coordinates into the record;
-// the smallest original index (with its colour) wins the record's {rgb, idx} half.  Records must
-// be pre-filled with 0xFF.
-PCCM_HD uint32_t vx_place_point(const uint32_t* masks, const uint16_t* pre, const uint32_t* base, uint4* recs,
+// pass 3 (after the row bases): rank of the point's voxel; voxel coordinates into vxyz; the smallest
+// original index (with its colour) wins vkey.  vkey must be pre-filled with 0xFF.
+PCCM_HD uint32_t vx_place_point(const uint32_t* masks, const uint32_t* rowbase, uint2* vxyz, uint2* vkey,
                                 uint32_t slot, int x, int y, int z, uint32_t rgb, uint32_t idx) {
     const int r = vx_row(y, z);
     const uint32_t m = masks[(size_t)slot * kVxRows + r];
-    const uint32_t rank = base[slot] + pre[(size_t)slot * kVxRows + r] + (uint32_t)vx_popc(m & ((1u << (x & 31)) - 1u));
+    const uint32_t rank = rowbase[(size_t)slot * kVxRows + r] + (uint32_t)vx_popc(m & ((1u << (x & 31)) - 1u));
     VX_CHECK((m >> (x & 31)) & 1u);
-    recs[rank].x = (uint32_t)x | ((uint32_t)y << 16);      // every point of the voxel writes the same two words
-    recs[rank].y = (uint32_t)z;
-    vx_atomic_min64(reinterpret_cast<unsigned long long*>(&recs[rank].z), ((unsigned long long)idx << 32) | rgb);
+    uint2 c;
+    c.x = (uint32_t)x | ((uint32_t)y << 16);             // every point of the voxel writes the same two words
+    c.y = (uint32_t)z;
+    vxyz[rank] = c;
+    vx_atomic_min64(reinterpret_cast<unsigned long long*>(vkey + rank), ((unsigned long long)idx << 32) | rgb);
     return rank;
 }
 
-// ---- staged search (rows within 2 of the query, x within 16) ---------------------------------
+// ---- staged search (rows within 2 of the query, x within 2) ----------------------------------
 // Region around query brick (bx, by, bz): rows y in [8 by - 2, 8 by + 10), z likewise; row i =
-// rz * 12 + ry holds the 64 bits x in [32 bx - 16, 32 bx + 48) as {lo, hi}.
-PCCM_HD uint2 vx_stage_row(const VoxView& S, const int* sslot, int i) {
+// rz * 12 + ry holds the 64 bits x in [32 bx - 2, 32 bx + 62) as {lo, hi}: bit (lx + 2 + dx) of the
+// pair is voxel x + dx for a query at x = 32 bx + lx.  rb[i] is the rank of the first voxel of the
+// row's centre word (the brick column the query brick is in): a candidate inside that column is
+// ranked from shared memory alone.
+PCCM_HD uint2 vx_stage_row(const VoxView& S, const int* sslot, int i, uint32_t& rb) {
     const int ry = i % kVxRegY, rz = i / kVxRegY;
     const int ny_i = ry < 2 ? 0 : (ry < 10 ? 1 : 2), nz_i = rz < 2 ? 0 : (rz < 10 ? 1 : 2);
     const int r_in = (((rz + 6) & 7) << 3) | ((ry + 6) & 7);
@@ -224,80 +204,135 @@ PCCM_HD uint2 vx_stage_row(const VoxView& S, const int* sslot, int i) {
     const uint32_t l = s3[0] >= 0 ? vx_ld32(S.masks + (size_t)s3[0] * kVxRows + r_in) : 0u;
     const uint32_t c = s3[1] >= 0 ? vx_ld32(S.masks + (size_t)s3[1] * kVxRows + r_in) : 0u;
     const uint32_t r = s3[2] >= 0 ? vx_ld32(S.masks + (size_t)s3[2] * kVxRows + r_in) : 0u;
+    rb = s3[1] >= 0 ? vx_ld32(S.rowbase + (size_t)s3[1] * kVxRows + r_in) : 0u;
     uint2 w;
-    w.x = (l >> 16) | (c << 16);
-    w.y = (c >> 16) | (r << 16);
+    w.x = (l >> 30) | (c << 2);
+    w.y = (c >> 30) | (r << 2);
     return w;
 }
+PCCM_HD uint32_t vx_centre_word(const uint2 w) { return (w.x >> 2) | (w.y << 30); }
 
-// distance from the query's x to the nearest occupied voxel of a row, below-or-at (dd: 0..16,
-// 17 = none in the window) and at-or-above (du: 0..15, 32 = none).  lx = x & 31.
-PCCM_HD void vx_row_dists(const uint2 w, int lx, int& dd, int& du) {
-    const uint32_t v = vx_fshr(w.x, w.y, lx);            // bit 16 = the query's own x
-    dd = vx_clz(v & 0x1FFFFu) - 15;
-    du = vx_clz(vx_brev(v >> 16));
+// bits x-2 .. x+2 of window row (ly + dy, lz + dz) as bits 0 .. 4
+PCCM_HD uint32_t vx_row5(const uint2* win, int lx, int ly, int lz, int dy, int dz) {
+    const uint2 w = win[(lz + dz) * kVxRegY + (ly + dy)];
+    return vx_fshr(w.x, w.y, lx) & 31u;
 }
 
-#define VX_ROW(DY, DZ)                                                                      \
-    {                                                                                       \
-        int dd, du;                                                                         \
-        vx_row_dists(win[(lz + (DZ)) * kVxRegY + (ly + (DY))], lx, dd, du);                 \
-        const int dx = dd < du ? dd : du;                                                   \
-        const uint32_t d2 = (uint32_t)(dx * dx + ((DY) * (DY) + (DZ) * (DZ)));               \
-        if (d2 < bd2) { bd2 = d2; rows = 0u; }                                              \
-        if (d2 == bd2) rows |= 1u << (((DZ) + 2) * 5 + (DY) + 2);                           \
+// The 27 voxels around the query: bit 9 (dz + 1) + 3 (dy + 1) + (dx + 1).
+PCCM_HD uint32_t vx_nb27(const uint2* win, int lx, int ly, int lz) {
+    uint32_t nb = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 9; ++j) {
+        const uint2 w = win[(lz + j / 3 - 1) * kVxRegY + (ly + j % 3 - 1)];
+        nb |= (vx_fshr(w.x, w.y, lx + 1) & 7u) << (3 * j);
     }
-
-// the 3 x 3 rows: decides every query with best d2 < 4.  ly, lz in [2, 10): row of the query in the region.
-PCCM_HD void vx_rows_inner(const uint2* win, int lx, int ly, int lz, uint32_t& bd2, uint32_t& rows) {
-    VX_ROW(0, 0)
-    VX_ROW(-1, 0) VX_ROW(1, 0) VX_ROW(0, -1) VX_ROW(0, 1)
-    VX_ROW(-1, -1) VX_ROW(1, -1) VX_ROW(-1, 1) VX_ROW(1, 1)
+    return nb;
 }
-// the eight rows around the query's own row (self nearest neighbour: the own row is handled apart)
-PCCM_HD void vx_rows_ring1(const uint2* win, int lx, int ly, int lz, uint32_t& bd2, uint32_t& rows) {
-    VX_ROW(-1, 0) VX_ROW(1, 0) VX_ROW(0, -1) VX_ROW(0, 1)
-    VX_ROW(-1, -1) VX_ROW(1, -1) VX_ROW(-1, 1) VX_ROW(1, 1)
+// distance levels of those 27 bits
+constexpr uint32_t kVxL0 = 1u << 13;                                                        // the query's own voxel
+constexpr uint32_t kVxL1 = (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22);
+constexpr uint32_t kVxL3 = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 18) | (1u << 20) | (1u << 24) | (1u << 26);
+constexpr uint32_t kVxL2 = 0x07FFFFFFu & ~(kVxL0 | kVxL1 | kVxL3);
+// the voxels at the minimal distance (0 when the neighbourhood is empty) and that squared distance
+PCCM_HD uint32_t vx_level27(uint32_t nb, uint32_t& d2) {
+    if (nb & kVxL0) { d2 = 0; return nb & kVxL0; }
+    if (nb & kVxL1) { d2 = 1; return nb & kVxL1; }
+    if (nb & kVxL2) { d2 = 2; return nb & kVxL2; }
+    d2 = 3;
+    return nb & kVxL3;
 }
-// the 16 rows of the 5 x 5 border: with them, every query with best d2 < 9.
-PCCM_HD void vx_rows_outer(const uint2* win, int lx, int ly, int lz, uint32_t& bd2, uint32_t& rows) {
-    VX_ROW(-2, 0) VX_ROW(2, 0) VX_ROW(0, -2) VX_ROW(0, 2)
-    VX_ROW(-2, -1) VX_ROW(2, -1) VX_ROW(-2, 1) VX_ROW(2, 1) VX_ROW(-1, -2) VX_ROW(1, -2) VX_ROW(-1, 2) VX_ROW(1, 2)
-    VX_ROW(-2, -2) VX_ROW(2, -2) VX_ROW(-2, 2) VX_ROW(2, 2)
-}
-#undef VX_ROW
 
 struct VxPick {           // the chosen neighbour
-    uint32_t idx, rgb, rank;
+    uint32_t idx, rgb;
     int ex, ey, ez;       // query - neighbour
 };
 
-PCCM_HD void vx_cand(const VoxView& S, const int* sslot, int bx, int by, int bz, int cx, int cy, int cz,
-                     int qx, int qy, int qz, VxPick& pk) {
-    const int nb = ((cz >> 3) - bz + 1) * 9 + ((cy >> 3) - by + 1) * 3 + ((cx >> 5) - bx + 1);
-    VX_CHECK((unsigned)nb < 27u && sslot[nb] >= 0);
-    const uint32_t rank = vx_rank(S, (uint32_t)sslot[nb], vx_row(cy, cz), cx & 31);
+// one candidate voxel (cx, cy, cz) = query + (dx, dy, dz), |d*| <= 2: its {rgb, idx}; smallest idx wins
+PCCM_HD void vx_cand(const VoxView& S, const int* sslot, const uint2* win, const uint32_t* rb,
+                     int lx, int ly, int lz, int dx, int dy, int dz, VxPick& pk) {
+    const int wi = (lz + dz) * kVxRegY + (ly + dy);
+    const int cxl = lx + dx;                                  // x of the candidate relative to the query's brick column
+    uint32_t rank;
+    if ((unsigned)cxl < 32u) {                                // inside the centre column: ranked from the staged words
+        const uint32_t c = vx_centre_word(win[wi]);
+        VX_CHECK((c >> cxl) & 1u);
+        rank = rb[wi] + (uint32_t)vx_popc(c & ((1u << cxl) - 1u));
+    } else {                                                  // left / right brick column (x of the brick 0, 1 or 30, 31)
+        const int ry = ly + dy, rz = lz + dz;
+        const int ny_i = ry < 2 ? 0 : (ry < 10 ? 1 : 2), nz_i = rz < 2 ? 0 : (rz < 10 ? 1 : 2);
+        const int nb = nz_i * 9 + ny_i * 3 + (cxl < 0 ? 0 : 2);
+        VX_CHECK(sslot[nb] >= 0);
+        rank = vx_rank(S, (uint32_t)sslot[nb], (((rz + 6) & 7) << 3) | ((ry + 6) & 7), cxl & 31);
+    }
     VX_CHECK(rank < S.n_total);
-    const uint2 a = vx_ld64(reinterpret_cast<const uint2*>(S.recs + rank) + 1);   // {rgb, idx}
-    if (a.y < pk.idx) { pk.idx = a.y; pk.rgb = a.x; pk.rank = rank; pk.ex = qx - cx; pk.ey = qy - cy; pk.ez = qz - cz; }
+    const uint2 a = vx_ld64(S.vkey + rank);                   // {rgb, idx}
+    if (a.y < pk.idx) { pk.idx = a.y; pk.rgb = a.x; pk.ex = -dx; pk.ey = -dy; pk.ez = -dz; }
 }
 
-// among the voxels that tie at the minimal distance (rows = the rows that reach it), the one whose
-// point has the smallest original index
-PCCM_HD void vx_pick(const VoxView& S, const int* sslot, const uint2* win, int bx, int by, int bz,
-                     int qx, int qy, int qz, uint32_t rows, VxPick& pk) {
-    const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
-    pk.idx = kVxNone;
-    while (rows) {
-        const int b = vx_ffs(rows) - 1;
-        rows &= rows - 1u;
-        const int jz = b / 5, dz = jz - 2, dy = b - jz * 5 - 2;
-        int dd, du;
-        vx_row_dists(win[(lz + dz) * kVxRegY + (ly + dy)], lx, dd, du);
-        const int dx = dd < du ? dd : du;
-        if (dd == dx) vx_cand(S, sslot, bx, by, bz, qx - dx, qy + dy, qz + dz, qx, qy, qz, pk);
-        if (du == dx && dx != 0) vx_cand(S, sslot, bx, by, bz, qx + dx, qy + dy, qz + dz, qx, qy, qz, pk);
+// among the voxels of a 27-bit candidate set the one whose point has the smallest original index
+PCCM_HD void vx_pick27(const VoxView& S, const int* sslot, const uint2* win, const uint32_t* rb,
+                       int lx, int ly, int lz, uint32_t cand, VxPick& pk) {
+    pk.idx = kVxNone; pk.rgb = 0; pk.ex = pk.ey = pk.ez = 0;
+    while (cand) {
+        const int b = vx_ffs(cand) - 1;
+        cand &= cand - 1u;
+        const int j = b / 3, dx = b - 3 * j - 1, dz = j / 3 - 1, dy = j - 3 * (dz + 1) - 1;
+        vx_cand(S, sslot, win, rb, lx, ly, lz, dx, dy, dz, pk);
     }
+}
+
+// The 5 x 5 x 5 voxels around a query whose 27-neighbourhood is empty: minimal squared distance (exact
+// when < 9: anything outside is 3+ voxels away in one axis) and the winner among the ties.
+// Returns kVxNone when those 125 voxels are empty too.
+PCCM_HD uint32_t vx_search125(const VoxView& S, const int* sslot, const uint2* win, const uint32_t* rb,
+                              int lx, int ly, int lz, VxPick& pk) {
+    uint32_t best = kVxNone;
+    for (int j = 0; j < 25; ++j) {
+        const int dy = j % 5 - 2, dz = j / 5 - 2;
+        const uint32_t v = vx_row5(win, lx, ly, lz, dy, dz);
+        if (!v) continue;
+        const uint32_t dx2 = (v & 4u) ? 0u : ((v & 10u) ? 1u : 4u);
+        const uint32_t d2 = dx2 + (uint32_t)(dy * dy + dz * dz);
+        best = d2 < best ? d2 : best;
+    }
+    pk.idx = kVxNone; pk.rgb = 0; pk.ex = pk.ey = pk.ez = 0;
+    if (best >= 9u) return best;
+    for (int j = 0; j < 25; ++j) {
+        const int dy = j % 5 - 2, dz = j / 5 - 2;
+        const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
+        if (byz > best) continue;
+        const uint32_t dx2 = best - byz;                      // 0, 1 or 4 when this row can tie
+        if (dx2 != 0u && dx2 != 1u && dx2 != 4u) continue;
+        const int dx = dx2 == 4u ? 2 : (int)dx2;
+        const uint32_t v = vx_row5(win, lx, ly, lz, dy, dz);
+        if ((v >> (2 - dx)) & 1u) vx_cand(S, sslot, win, rb, lx, ly, lz, -dx, dy, dz, pk);
+        if (dx && ((v >> (2 + dx)) & 1u)) vx_cand(S, sslot, win, rb, lx, ly, lz, dx, dy, dz, pk);
+    }
+    return best;
+}
+
+// ---- boundary distances (nearest OTHER voxel of the same cloud) on the staged rows --------------
+// minimal squared distance over the 26 / 124 voxels around the query (own voxel excluded); kVxNone when empty
+PCCM_HD uint32_t vx_self27(uint32_t nb) {
+    if (nb & kVxL1) return 1u;
+    if (nb & kVxL2) return 2u;
+    if (nb & kVxL3) return 3u;
+    return kVxNone;
+}
+PCCM_HD uint32_t vx_self125(const uint2* win, int lx, int ly, int lz) {
+    uint32_t best = kVxNone;
+    for (int j = 0; j < 25; ++j) {
+        const int dy = j % 5 - 2, dz = j / 5 - 2;
+        uint32_t v = vx_row5(win, lx, ly, lz, dy, dz);
+        if (dy == 0 && dz == 0) v &= ~4u;
+        if (!v) continue;
+        const uint32_t dx2 = (v & 4u) ? 0u : ((v & 10u) ? 1u : 4u);
+        const uint32_t d2 = dx2 + (uint32_t)(dy * dy + dz * dz);
+        best = d2 < best ? d2 : best;
+    }
+    return best;
 }
 
 // ---- general search: brick rings, any distance (exact) --------------------------------------
@@ -311,7 +346,7 @@ struct VxHit {
 PCCM_HD void vx_offer(const VoxView& S, uint32_t slot, int r, uint32_t d2, int cx, int cy, int cz, VxHit& h) {
     if (d2 > h.d2) return;
     const uint32_t rank = vx_rank(S, slot, r, cx & 31);
-    const uint2 a = vx_ld64(reinterpret_cast<const uint2*>(S.recs + rank) + 1);
+    const uint2 a = vx_ld64(S.vkey + rank);
     if (d2 < h.d2 || a.y < h.idx) { h.d2 = d2; h.idx = a.y; h.rgb = a.x; h.rank = rank; h.cx = cx; h.cy = cy; h.cz = cz; }
 }
 

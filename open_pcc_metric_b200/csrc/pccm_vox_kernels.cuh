@@ -1,10 +1,26 @@
-// pccm_vox_kernels.cuh -- sm_100a kernels of the occupancy-brick path for voxelised pairs:
-//   index build   vx_mark / vx_dircount / vx_fill / vx_brickpre / vx_place (+ the scans of pccm_kernels.cuh)
-//   query stage   vx_search_kernel   one warp per query brick, one lane per VOXEL, search rows staged in shared
-//                                    memory, tie look-ups, whole-brick scan for the rare undecided voxel
-//                 vx_general_kernel  what is still undecided: one warp per voxel over 125 bricks
-//                 vx_far_kernel      beyond 16 voxels: the pencil search (second round)
-//                 vx_epilogue_kernel one lane per query POINT in input order: D1 / D2 / colour + reduction records
+// pccm_vox_kernels.cuh -- sm_100a kernels of the occupancy-brick path for voxelised pairs.
+//
+// The whole pair evaluation is enqueued WITHOUT a host synchronisation: nothing the host would have to
+// wait for (bounding boxes, number of occupied bricks, number of distinct voxels) is a kernel argument or
+// an allocation size -- the kernels read those from a VoxPlan record in device memory that earlier kernels
+// of the same stream wrote, arrays are sized by capacities, and a status word tells the host at the one
+// synchronisation at the end (the result read-back) whether a capacity or an assumption (integer
+// coordinates, 8-bit colours) did not hold; only then is anything repeated.
+//
+//   index build   stats_kernel (pccm_kernels.cuh: bounding box + classification + 8-byte packed coordinates)
+//                 vx_mark_kernel      directory bit per occupied brick
+//                 vx_dirsum_kernel    popcount sums per directory chunk
+//                 vx_dirscan_kernel   directory prefix -> brick slots; writes the VoxPlan; zeroes the occupancy words
+//                 vx_fill_kernel      occupancy bit per point
+//                 vx_bricksum_kernel  voxels per chunk of bricks
+//                 vx_rowbase_kernel   rank of the first voxel of every brick row
+//                 vx_place_kernel     rank of every point; voxel coordinates and smallest index per voxel
+//   query stage   vx_search_kernel    one warp per query brick, one lane per VOXEL: 27-bit neighbourhood from the
+//                                     staged rows, tie look-ups, 125-bit neighbourhood and whole-brick scans for the
+//                                     few voxels whose neighbourhood is empty
+//                 vx_general_kernel   what is still undecided: one warp per voxel over 125 bricks
+//                 vx_far_kernel       beyond 16 voxels: the pencil search (second round)
+//                 vx_epilogue_kernel  one lane per query POINT in input order: D1 / D2 / colour + reduction records
 //   boundary      vx_dupflag / vx_selfnn / vx_selfout: distance to the nearest OTHER point of the same cloud
 // Per-point / per-query logic shared with the CPU stepping harness: pccm_vox.cuh.
 #pragma once
@@ -14,182 +30,414 @@
 namespace pccm {
 
 // ------------------------------------------------------------------------------------
-// build
+// plan
 // ------------------------------------------------------------------------------------
-struct VoxCloudBuild {
-    const void* xyz;
-    const void* rgb;
-    int64_t stride, rgb_stride;
-    int32_t dtype, rgb_dtype, rgb_in_rec;
-    uint32_t n;
-    VoxDims g;
-    uint32_t dir_off;          // word offset of this cloud's directory in the joint dirbits / dirpre
-};
-struct VoxBuild {
-    VoxCloudBuild c[2];
-    int32_t nclouds;
-    uint32_t n_total, ndirw_total, nblk_total;
-    uint32_t* dirbits;         // [ndirw_total]
-    uint32_t* dirpre;          // [ndirw_total + 1]
-    uint32_t* masks;           // [nblk_total][64]
-    uint16_t* pre;             // [nblk_total][64]
-    uint32_t* base;            // [nblk_total + 1]
-    uint4* recs;               // [n_total] 0xFF-filled
-    uint32_t* prank;           // [n_total] rank of the voxel of input point i (cloud 1's points follow cloud 0's)
-    uint2* packed;             // [n_total] scratch: {x | y << 16, z} of input point i (written by the fill pass)
-    uint32_t* pslot;           // [n_total] scratch: brick slot of input point i
+constexpr uint32_t kVxStNotInt = 1u;          // a coordinate is not an integer in [0, 32767]
+constexpr uint32_t kVxStDirOverflow = 2u;     // the brick grids of the bounding boxes exceed the directory capacity
+constexpr uint32_t kVxStBrickOverflow = 4u;   // more occupied bricks than the mask arrays hold
+constexpr uint32_t kVxStRgbNotU8 = 8u;        // a float colour is not k / 255 (the 8-bit colour arrays are invalid)
+
+constexpr int kVxDirChunk = 2048;             // directory words per scan block
+constexpr int kVxBrickChunk = 256;            // bricks per row-base chunk
+constexpr int kVxMaxBrickChunks = 1 << 16;
+
+struct VoxPlan {
+    VoxView view[2];
+    uint32_t status;
+    uint32_t nvox_total;                      // distinct voxels of both clouds
+    uint32_t ndirw[2], dir_off[2], ndirw_total;
+    uint32_t cap_dirw, cap_blk;
+    int32_t mn[2][3], mx[2][3];               // integer bounding boxes
 };
 
-__device__ __forceinline__ void vx_point(const VoxBuild& B, uint32_t i, int& c, uint32_t& li, int& x, int& y, int& z) {
-    c = (B.nclouds > 1 && i >= B.c[0].n) ? 1 : 0;
-    li = i - (c ? B.c[0].n : 0u);
-    const VoxCloudBuild& C = B.c[c];
-    x = (int)load_coord(C.xyz, C.dtype, C.stride, li, 0);
-    y = (int)load_coord(C.xyz, C.dtype, C.stride, li, 1);
-    z = (int)load_coord(C.xyz, C.dtype, C.stride, li, 2);
+struct VoxBuildArgs {                         // everything the host knows when it enqueues the build
+    const DevStats* stats[2];
+    const uint2* packed[2];                   // {x | y << 16, z} of every input point (stats_kernel)
+    const void* rgb[2];                       // colours for the voxel records: packed uchar4 arrays (or null)
+    uint32_t n[2];
+    uint32_t cap_dirw, cap_blk;
+    uint32_t* dirbits;                        // [cap_dirw] zeroed
+    uint32_t* dirpre;                         // [cap_dirw + 1]
+    uint32_t* dirsums;                        // [cap_dirw / kVxDirChunk + 1]
+    uint32_t* masks;                          // [cap_blk][64]
+    uint32_t* rowbase;                        // [cap_blk][64]
+    uint32_t* bricksums;                      // [cap_blk / kVxBrickChunk + 1]
+    uint2* vxyz;                              // [n_total]
+    uint2* vkey;                              // [n_total] 0xFF-filled
+    uint32_t* prank;                          // [n_total]
+    uint32_t* pslot;                          // [n_total] scratch: brick slot of input point i
+    VoxPlan* plan;
+};
+
+// Brick grids of the two clouds from the device-side statistics.  Cloud 1's directory starts at a chunk
+// boundary, so the number of bricks of cloud 0 is a sum of whole chunk sums.  Returns the status bits.
+__device__ __forceinline__ uint32_t vx_plan_dims(const VoxBuildArgs& A, VoxDims g[2], uint32_t ndirw[2], uint32_t dir_off[2],
+                                                 int32_t mn[2][3], int32_t mx[2][3]) {
+    uint32_t status = 0;
+    unsigned long long words = 0;
+    for (int c = 0; c < 2; ++c) {
+        const DevStats s = *A.stats[c];
+        if (s.flags & (kDevNotInt | kDevNonFinite)) status |= kVxStNotInt;
+        for (int a = 0; a < 3; ++a) { mn[c][a] = (int32_t)(0x7fffffffu - s.nmn[a]); mx[c][a] = (int32_t)s.mx[a]; }
+        if (status) { ndirw[c] = 0; dir_off[c] = 0; g[c] = VoxDims{0, 0, 0, 1, 1, 1}; continue; }
+        g[c].obx = mn[c][0] >> 5; g[c].oby = mn[c][1] >> 3; g[c].obz = mn[c][2] >> 3;
+        g[c].nbx = (mx[c][0] >> 5) - g[c].obx + 1;
+        g[c].nby = (mx[c][1] >> 3) - g[c].oby + 1;
+        g[c].nbz = (mx[c][2] >> 3) - g[c].obz + 1;
+        const unsigned long long bits = (unsigned long long)g[c].nbx * (unsigned long long)g[c].nby * (unsigned long long)g[c].nbz;
+        const unsigned long long w = (bits + 31ull) / 32ull;
+        dir_off[c] = (uint32_t)words;
+        ndirw[c] = (uint32_t)(w > 0xffffffffull ? 0xffffffffull : w);
+        words += w;
+        if (c == 0) words = (words + kVxDirChunk - 1) / kVxDirChunk * kVxDirChunk;
+        if (words > (unsigned long long)A.cap_dirw) status |= kVxStDirOverflow;
+    }
+    return status;
 }
 
-// The per-point passes are chains of dependent loads (coordinates -> directory -> masks -> atomic):
+struct VoxDimsSmem {
+    VoxDims g[2];
+    uint32_t ndirw[2], dir_off[2];
+    int32_t mn[2][3], mx[2][3];
+    uint32_t status;
+};
+__device__ __forceinline__ void vx_block_dims(const VoxBuildArgs& A, VoxDimsSmem& S) {
+    if (threadIdx.x == 0) S.status = vx_plan_dims(A, S.g, S.ndirw, S.dir_off, S.mn, S.mx);
+    __syncthreads();
+}
+
+// The per-point passes are chains of dependent accesses (coordinates -> directory -> masks -> atomic):
 // every thread carries kVxIlp points, stage by stage, so that their loads are in flight together.
 constexpr int kVxIlp = 2;
-__device__ __forceinline__ uint32_t vx_ilp_index(const VoxBuild& B, int k) {     // point k of this thread (>= n_total: none)
-    const uint32_t per = (B.n_total + kVxIlp - 1) / kVxIlp;
+__device__ __forceinline__ uint32_t vx_ilp_index(uint32_t n_total, int k) {     // point k of this thread (>= n_total: none)
+    const uint32_t per = (n_total + kVxIlp - 1) / kVxIlp;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     return t < per ? t + (uint32_t)k * per : 0xFFFFFFFFu;
 }
+__device__ __forceinline__ uint2 vx_point(const VoxBuildArgs& A, uint32_t i, int& c, uint32_t& li) {
+    c = i >= A.n[0] ? 1 : 0;
+    li = i - (c ? A.n[0] : 0u);
+    return __ldg(A.packed[c] + li);
+}
+#define VX_UNPACK(p, x, y, z) const int x = (int)((p).x & 0xffffu), y = (int)((p).x >> 16), z = (int)(p).y
 
-__global__ void vx_mark_kernel(const __grid_constant__ VoxBuild B) {
-    int c[kVxIlp], x[kVxIlp], y[kVxIlp], z[kVxIlp];
+__global__ void __launch_bounds__(256) vx_mark_kernel(const __grid_constant__ VoxBuildArgs A) {
+    __shared__ VoxDimsSmem S;
+    vx_block_dims(A, S);
+    if (S.status) return;
+    const uint32_t n_total = A.n[0] + A.n[1];
+    uint2 p[kVxIlp];
+    int c[kVxIlp];
     bool on[kVxIlp];
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k) {
-        const uint32_t i = vx_ilp_index(B, k);
-        on[k] = i < B.n_total;
+        const uint32_t i = vx_ilp_index(n_total, k);
+        on[k] = i < n_total;
         uint32_t li;
-        if (on[k]) vx_point(B, i, c[k], li, x[k], y[k], z[k]);
+        if (on[k]) p[k] = vx_point(A, i, c[k], li);
     }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
-        if (on[k]) vx_mark_point(B.dirbits + B.c[c[k]].dir_off, vx_key(B.c[c[k]].g, x[k], y[k], z[k]));
+        if (on[k]) {
+            VX_UNPACK(p[k], x, y, z);
+            vx_mark_point(A.dirbits + S.dir_off[c[k]], vx_key(S.g[c[k]], x, y, z));
+        }
 }
 
-__global__ void vx_dircount_kernel(const uint32_t* __restrict__ dirbits, uint32_t nw, uint32_t* __restrict__ dirpre) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= nw) dirpre[i] = i < nw ? (uint32_t)__popc(dirbits[i]) : 0u;
+template <int THREADS>
+__device__ __forceinline__ uint32_t vx_block_sum_u32(uint32_t v, uint32_t* sm) {   // result in every thread
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) r += sm[w];
+    return r;
 }
 
-__global__ void vx_fill_kernel(const __grid_constant__ VoxBuild B) {
-    int c[kVxIlp], x[kVxIlp], y[kVxIlp], z[kVxIlp];
+// popcount sum of every chunk of kVxDirChunk directory words
+__global__ void __launch_bounds__(256) vx_dirsum_kernel(const __grid_constant__ VoxBuildArgs A) {
+    __shared__ VoxDimsSmem S;
+    __shared__ uint32_t sm[8];
+    vx_block_dims(A, S);
+    if (S.status) return;
+    const uint32_t nw = S.dir_off[1] + S.ndirw[1];
+    const uint32_t w0 = blockIdx.x * kVxDirChunk;
+    if (w0 >= nw) return;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < kVxDirChunk / 256; ++k) {
+        const uint32_t w = w0 + k * 256 + threadIdx.x;
+        if (w < nw) acc += (uint32_t)__popc(A.dirbits[w]);
+    }
+    acc = vx_block_sum_u32<256>(acc, sm);
+    if (threadIdx.x == 0) A.dirsums[blockIdx.x] = acc;
+}
+
+// exclusive popcount prefix of the directory (dirpre), the VoxPlan, and the zeroing of the occupancy words of
+// the bricks that exist (+ the empty one past the last)
+__global__ void __launch_bounds__(256) vx_dirscan_kernel(const __grid_constant__ VoxBuildArgs A) {
+    __shared__ VoxDimsSmem S;
+    __shared__ uint32_t sm[8];
+    __shared__ uint32_t s_warp[8];
+    vx_block_dims(A, S);
+    const uint32_t nw = S.status ? 0u : S.dir_off[1] + S.ndirw[1];
+    const uint32_t nchunks = (nw + kVxDirChunk - 1) / kVxDirChunk;
+    const uint32_t split = S.status ? 0u : S.dir_off[1] / kVxDirChunk;     // chunks of cloud 0
+    uint32_t before = 0, total = 0, first = 0;
+    for (uint32_t j = threadIdx.x; j < nchunks; j += 256) {
+        const uint32_t v = A.dirsums[j];
+        total += v;
+        if (j < blockIdx.x) before += v;
+        if (j < split) first += v;
+    }
+    before = vx_block_sum_u32<256>(before, sm);
+    total = vx_block_sum_u32<256>(total, sm);
+    first = vx_block_sum_u32<256>(first, sm);
+    uint32_t status = S.status;
+    if (!status && (unsigned long long)total + 1ull > (unsigned long long)A.cap_blk) status |= kVxStBrickOverflow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        VoxPlan P;
+        for (int c = 0; c < 2; ++c) {
+            VoxView& V = P.view[c];
+            V.g = S.g[c];
+            V.dirbits = A.dirbits + S.dir_off[c];
+            V.dirpre = A.dirpre + S.dir_off[c];
+            V.masks = A.masks; V.rowbase = A.rowbase; V.vxyz = A.vxyz; V.vkey = A.vkey;
+            V.prank = A.prank + (c ? A.n[0] : 0u);
+            V.slot0 = c ? first : 0u;
+            V.nblk = c ? total - first : first;
+            V.n = A.n[c];
+            V.nblk_total = total;
+            V.n_total = A.n[0] + A.n[1];
+            P.ndirw[c] = S.ndirw[c]; P.dir_off[c] = S.dir_off[c];
+            for (int a = 0; a < 3; ++a) { P.mn[c][a] = S.mn[c][a]; P.mx[c][a] = S.mx[c][a]; }
+        }
+        P.status = status;
+        P.nvox_total = 0;
+        P.ndirw_total = nw;
+        P.cap_dirw = A.cap_dirw; P.cap_blk = A.cap_blk;
+        *A.plan = P;
+    }
+    if (status) return;
+    // dirpre of this block's chunk: thread t owns 8 consecutive words
+    const uint32_t w0 = blockIdx.x * kVxDirChunk + threadIdx.x * 8;
+    uint32_t cnt[8], mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        cnt[k] = (w0 + k < nw) ? (uint32_t)__popc(A.dirbits[w0 + k]) : 0u;
+        mine += cnt[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t run = before + incl - mine;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (w0 + k <= nw) A.dirpre[w0 + k] = run;            // (entry nw = the number of bricks)
+        run += cnt[k];
+    }
+    // occupancy words of bricks [0, total]: zero (the brick past the last one stays empty)
+    const size_t n4 = ((size_t)total + 1) * kVxRows / 4;
+    uint4* m4 = reinterpret_cast<uint4*>(A.masks);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ VoxBuildArgs A) {
+    const VoxPlan* __restrict__ P = A.plan;
+    if (P->status) return;
+    const uint32_t n_total = A.n[0] + A.n[1];
+    uint2 p[kVxIlp];
+    int c[kVxIlp];
     uint32_t idx[kVxIlp], slot[kVxIlp];
     bool on[kVxIlp];
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k) {
-        idx[k] = vx_ilp_index(B, k);
-        on[k] = idx[k] < B.n_total;
+        idx[k] = vx_ilp_index(n_total, k);
+        on[k] = idx[k] < n_total;
         uint32_t li;
-        if (on[k]) vx_point(B, idx[k], c[k], li, x[k], y[k], z[k]);
+        if (on[k]) p[k] = vx_point(A, idx[k], c[k], li);
     }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
         if (on[k]) {
-            const uint32_t off = B.c[c[k]].dir_off;
-            slot[k] = vx_slot_of_key(B.dirbits + off, B.dirpre + off, vx_key(B.c[c[k]].g, x[k], y[k], z[k]));
+            VX_UNPACK(p[k], x, y, z);
+            const VoxView& V = P->view[c[k]];
+            slot[k] = vx_slot_of_key(V.dirbits, V.dirpre, vx_key(V.g, x, y, z));
         }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
         if (on[k]) {
-            vx_fill_point(B.masks, slot[k], x[k], y[k], z[k]);
-            B.packed[idx[k]] = make_uint2((uint32_t)x[k] | ((uint32_t)y[k] << 16), (uint32_t)z[k]);   // later passes need not parse the input again
-            B.pslot[idx[k]] = slot[k];
+            VX_UNPACK(p[k], x, y, z);
+            VX_CHECK(slot[k] < P->view[0].nblk_total);
+            vx_fill_point(A.masks, slot[k], x, y, z);
+            A.pslot[idx[k]] = slot[k];
         }
 }
 
-// one warp per brick: exclusive prefix of the row popcounts, brick total -> base[slot] (scanned next)
-__global__ void __launch_bounds__(256) vx_brickpre_kernel(const __grid_constant__ VoxBuild B) {
-    __shared__ uint32_t s_tot[8];
-    const uint32_t slot = (blockIdx.x * 256u + threadIdx.x) >> 5;
+// voxels per chunk of kVxBrickChunk bricks (the brick past the last one counts as an empty brick)
+__global__ void __launch_bounds__(256) vx_bricksum_kernel(const __grid_constant__ VoxBuildArgs A) {
+    __shared__ uint32_t sm[8];
+    const VoxPlan* __restrict__ P = A.plan;
+    if (P->status) return;
+    const uint32_t nb = P->view[0].nblk_total + 1;
+    const uint32_t nchunks = (nb + kVxBrickChunk - 1) / kVxBrickChunk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = 0;
-    if (slot < B.nblk_total) {
-        const uint32_t* m = B.masks + (size_t)slot * kVxRows;
-        const uint32_t c0 = (uint32_t)__popc(m[2 * lane]), c1 = (uint32_t)__popc(m[2 * lane + 1]);
-        incl = c0 + c1;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        uint32_t acc = 0;
+        const uint32_t s0 = ch * kVxBrickChunk + warp * 32;
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t s = s0 + j;
+            if (s >= nb) break;
+            const uint2 m = __ldg(reinterpret_cast<const uint2*>(A.masks + (size_t)s * kVxRows) + lane);
+            acc += (uint32_t)(__popc(m.x) + __popc(m.y));
+        }
+        acc = vx_block_sum_u32<256>(acc, sm);
+        if (threadIdx.x == 0) A.bricksums[ch] = acc;
+    }
+}
+
+// rank of the first voxel of every row of every brick.  Block b owns a contiguous run of chunks: one strided
+// sum of the chunk sums before its run, then chunk after chunk with a running offset.
+__global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__ VoxBuildArgs A) {
+    __shared__ uint32_t sm[8];
+    __shared__ uint32_t s_wtot[8];
+    VoxPlan* P = A.plan;
+    if (P->status) return;
+    const uint32_t nb = P->view[0].nblk_total + 1;
+    const uint32_t nchunks = (nb + kVxBrickChunk - 1) / kVxBrickChunk;
+    const uint32_t c0 = (uint32_t)((unsigned long long)nchunks * blockIdx.x / gridDim.x);
+    const uint32_t c1 = (uint32_t)((unsigned long long)nchunks * (blockIdx.x + 1) / gridDim.x);
+    if (c0 >= c1) return;
+    uint32_t off = 0;
+    for (uint32_t j = threadIdx.x; j < c0; j += 256) off += A.bricksums[j];
+    off = vx_block_sum_u32<256>(off, sm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t ch = c0; ch < c1; ++ch) {
+        const uint32_t s0 = ch * kVxBrickChunk + warp * 32;
+        // phase A: total of each of this warp's 32 bricks (lane j keeps brick j's)
+        uint32_t tot = 0;
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t s = s0 + j;
+            uint32_t v = 0;
+            if (s < nb) {
+                const uint2 m = __ldg(reinterpret_cast<const uint2*>(A.masks + (size_t)s * kVxRows) + lane);
+                v = (uint32_t)(__popc(m.x) + __popc(m.y));
+            }
+            v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == j) tot = v;
+        }
+        uint32_t incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        const uint32_t ex = incl - c0 - c1;
-        B.pre[(size_t)slot * kVxRows + 2 * lane] = (uint16_t)ex;
-        B.pre[(size_t)slot * kVxRows + 2 * lane + 1] = (uint16_t)(ex + c0);
+        __syncthreads();                                     // (s_wtot of the previous chunk has been read)
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = off;
+        for (int w = 0; w < warp; ++w) wbase += s_wtot[w];
+        uint32_t chunk_total = 0;
+        for (int w = 0; w < 8; ++w) chunk_total += s_wtot[w];
+        const uint32_t brick_excl = wbase + incl - tot;      // lane j: base of brick j
+        // phase B: row bases
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t s = s0 + j;
+            if (s >= nb) break;
+            const uint2 m = __ldg(reinterpret_cast<const uint2*>(A.masks + (size_t)s * kVxRows) + lane);
+            const uint32_t a = (uint32_t)__popc(m.x), b = (uint32_t)__popc(m.y);
+            uint32_t in2 = a + b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, in2, o);
+                if (lane >= o) in2 += t;
+            }
+            const uint32_t base = __shfl_sync(0xffffffffu, brick_excl, j) + in2 - a - b;
+            reinterpret_cast<uint2*>(A.rowbase + (size_t)s * kVxRows)[lane] = make_uint2(base, base + a);
+        }
+        off += chunk_total;
     }
-    if (lane == 31) s_tot[warp] = incl;
-    __syncthreads();
-    // the block's eight brick totals leave as one full 32-byte sector (the entry past the last brick is zero)
-    if (threadIdx.x < 8) {
-        const uint32_t sl = blockIdx.x * 8u + threadIdx.x;
-        if (sl <= B.nblk_total) B.base[sl] = s_tot[threadIdx.x];
-    }
+    if (c1 == nchunks && threadIdx.x == 0) P->nvox_total = off;
 }
 
-__device__ __forceinline__ uint32_t vx_point_rgb(const VoxCloudBuild& C, uint32_t li) {
-    if (!C.rgb_in_rec) return 0u;   // colours that have already arrived ride in the record of the voxel's representative
-    if (C.rgb_dtype == PCCM_U8) {
-        const uint8_t* p = static_cast<const uint8_t*>(C.rgb) + (int64_t)li * C.rgb_stride;
-        return p[0] | (p[1] << 8) | (p[2] << 16);
-    }
-    return (uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 0) * 255.0) |
-           ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 1) * 255.0) << 8) |
-           ((uint32_t)rint(load_coord(C.rgb, PCCM_F64, C.rgb_stride, li, 2) * 255.0) << 16);
-}
-
-__global__ void vx_place_kernel(const __grid_constant__ VoxBuild B) {
+__global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ VoxBuildArgs A) {
+    const VoxPlan* __restrict__ P = A.plan;
+    if (P->status) return;
+    const uint32_t n_total = A.n[0] + A.n[1];
     uint32_t idx[kVxIlp], li[kVxIlp], slot[kVxIlp], rgba[kVxIlp];
-    uint2 pk[kVxIlp];
+    uint2 p[kVxIlp];
     bool on[kVxIlp];
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k) {
-        idx[k] = vx_ilp_index(B, k);
-        on[k] = idx[k] < B.n_total;
+        idx[k] = vx_ilp_index(n_total, k);
+        on[k] = idx[k] < n_total;
         if (on[k]) {
-            const int c = (B.nclouds > 1 && idx[k] >= B.c[0].n) ? 1 : 0;
-            li[k] = idx[k] - (c ? B.c[0].n : 0u);
-            pk[k] = B.packed[idx[k]];
-            slot[k] = B.pslot[idx[k]];
-            rgba[k] = vx_point_rgb(B.c[c], li[k]);
+            int c;
+            p[k] = vx_point(A, idx[k], c, li[k]);
+            slot[k] = A.pslot[idx[k]];
+            rgba[k] = A.rgb[c] ? (__ldg(static_cast<const uint32_t*>(A.rgb[c]) + li[k]) & 0xffffffu) : 0u;   // colours that have already arrived ride in vkey
         }
     }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
         if (on[k]) {
-            VX_CHECK(slot[k] < B.nblk_total);
-            const uint32_t rank = vx_place_point(B.masks, B.pre, B.base, B.recs, slot[k], (int)(pk[k].x & 0xffffu), (int)(pk[k].x >> 16), (int)pk[k].y, rgba[k], li[k]);
-            VX_CHECK(rank < B.n_total && rank >= B.base[slot[k]] && rank < B.base[slot[k] + 1]);
-            B.prank[idx[k]] = rank;
+            VX_UNPACK(p[k], x, y, z);
+            VX_CHECK(slot[k] < P->view[0].nblk_total);
+            const uint32_t rank = vx_place_point(A.masks, A.rowbase, A.vxyz, A.vkey, slot[k], x, y, z, rgba[k], li[k]);
+            VX_CHECK(rank < n_total);
+            A.prank[idx[k]] = rank;
         }
+}
+
+// float64 colours -> uchar4, checking on the way that every channel is k / 255 (else the plan's status says so and
+// the caller repeats the evaluation with float64 colour arrays)
+__global__ void pack_rgb_u8_check_kernel(const void* rgb, int64_t stride, int64_t n, uchar4* out, uint32_t* status) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool bad = false;
+    uint32_t v[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double c = load_coord(rgb, PCCM_F64, stride, i, a);
+        const double k = rint(c * 255.0);
+        if (!(k >= 0.0 && k <= 255.0 && k / 255.0 == c)) bad = true;
+        v[a] = (uint32_t)(k >= 0.0 && k <= 255.0 ? k : 0.0);
+    }
+    out[i] = make_uchar4((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2], 0);
+    if (bad) atomicOr(status, kVxStRgbNotU8);
 }
 
 // ------------------------------------------------------------------------------------
 // query
 // ------------------------------------------------------------------------------------
 struct VxDir {
-    VoxView q, s;
+    int32_t qc, sc;            // which view of the plan is the query / the search cloud
+    uint32_t nq;               // points of the query cloud
+    const uint32_t* qprank;    // [nq]
     CloudView qa, sa;          // attribute views (colours, normals) of the query / search cloud
     uint32_t flags;
     int32_t* idx_out;          // original query order, or null
     double* d2_out;
     uint32_t* todo;            // ranked positions of the voxels the staged search left undecided
-    uint32_t* todo_count;
     uint32_t* far;             // ... and of those the brick rings left undecided (pencil search)
-    uint32_t* far_count;
     RowGrid sgrid;             // pencil index of the search cloud (vx_far_kernel only)
     const uint4* srecs;
     const uint32_t* srow_start;
     uint32_t rec_off;          // first reduction record of this direction
-    uint32_t ntiles;           // ceil(q.n / kVxEpiTile): reduction records of one vx_epilogue_kernel pass
+    uint32_t ntiles;           // ceil(nq / kVxEpiTile): reduction records of one vx_epilogue_kernel pass
 };
 
 struct VxParams {
+    const VoxPlan* plan;
     VxDir dir[2];
     int32_t ndirs;
     int32_t normals_mode;
@@ -200,6 +448,7 @@ struct VxParams {
     uint4* vres;               // [n_total] by ranked position: {d2, packed (query - neighbour), neighbour idx, neighbour rgb};
                                // d2 == kVxNone while the voxel is undecided.  Pencil-round answers set the top bit of
                                // the neighbour idx and put the neighbour's position in the pencil records into .y
+    uint32_t* counters;        // [0..1] undecided per direction, [2..3] far per direction, [4] brick ticket of the search kernel
     int32_t pass;              // vx_epilogue_kernel: 0 = brick answers, 1 = pencil-round answers only
 };
 constexpr uint32_t kVxFarBit = 0x80000000u;
@@ -331,12 +580,12 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
             const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
             if (byz + (uint32_t)(dlo * dlo) == best) {
                 const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p - dlo) & 31);
-                const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(S.recs + rank) + 3);
+                const uint32_t i = __ldg(&S.vkey[rank].y);
                 if (i < bidx) { bidx = i; brank = rank; }
             }
             if (byz + (uint32_t)(dhi * dhi) == best) {
                 const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p + dhi) & 31);
-                const uint32_t i = __ldg(reinterpret_cast<const uint32_t*>(S.recs + rank) + 3);
+                const uint32_t i = __ldg(&S.vkey[rank].y);
                 if (i < bidx) { bidx = i; brank = rank; }
             }
         }
@@ -347,112 +596,193 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
     return best;
 }
 
-// SEARCH.  One warp = one brick of the query cloud.  The warp stages the search cloud's occupancy
-// rows around the brick (12 x 12 rows x 64 bits, 1.1 KB) in its private slice of shared memory,
-// then takes the brick's voxels 32 at a time, one lane per voxel: bit scans over the 3 x 3 (5 x 5)
-// rows, rank look-ups only for the voxels that tie at the minimum.  Integer work only; the answer of
-// every voxel goes to vres[] (16 bytes), undecided voxels to the todo list.
+// rank of candidate bit b of a 27-neighbourhood (see vx_cand)
+__device__ __forceinline__ uint32_t vx_cand_rank27(const VoxView& S, const int* sslot, const uint2* win, const uint32_t* rb,
+                                                   int lx, int ly, int lz, int b) {
+    const int j = b / 3, dx = b - 3 * j - 1, dz = j / 3 - 1, dy = j - 3 * (dz + 1) - 1;
+    const int wi = (lz + dz) * kVxRegY + (ly + dy);
+    const int cxl = lx + dx;
+    if ((unsigned)cxl < 32u) {
+        const uint32_t c = vx_centre_word(win[wi]);
+        return rb[wi] + (uint32_t)__popc(c & ((1u << cxl) - 1u));
+    }
+    const int ry = ly + dy, rz = lz + dz;
+    const int ny_i = ry < 2 ? 0 : (ry < 10 ? 1 : 2), nz_i = rz < 2 ? 0 : (rz < 10 ? 1 : 2);
+    return vx_rank(S, (uint32_t)sslot[nz_i * 9 + ny_i * 3 + (cxl < 0 ? 0 : 2)], (((rz + 6) & 7) << 3) | ((ry + 6) & 7), cxl & 31);
+}
+__device__ __forceinline__ uint32_t vx_pack_e27(int b) {     // packed (query - neighbour) of candidate bit b
+    const int j = b / 3, dx = b - 3 * j - 1, dz = j / 3 - 1, dy = j - 3 * (dz + 1) - 1;
+    return vx_pack_e(-dx, -dy, -dz);
+}
+
+// SEARCH.  One warp = one brick of the query cloud at a time (bricks are handed out by a ticket counter).  The warp
+// stages the search cloud's occupancy rows around the brick (12 x 12 rows x 64 bits) and the rank bases of the
+// centre column in its private slice of shared memory, then takes the brick's voxels 32 at a time, one lane per
+// voxel: 27-bit neighbourhood, distance level, and -- only when the evaluation needs the neighbour itself -- the
+// look-up of the voxels that tie at the minimum, two at a time.  The few voxels with an empty neighbourhood are
+// collected per brick and finished together: 125-bit neighbourhood, then whole-brick scans of the 27 bricks.
+// Integer work only; the answer of every voxel goes to vres[] (16 bytes), undecided voxels to the todo list.
 #ifndef PCCM_VX_THREADS
 #define PCCM_VX_THREADS 128
 #endif
 constexpr int kVxThreads = PCCM_VX_THREADS;
 constexpr int kVxWarps = kVxThreads / 32;
+constexpr int kVxPend = 64;
 
 #ifndef PCCM_VX_MINBLOCKS
-#define PCCM_VX_MINBLOCKS 10      // <= 48 registers: the rare whole-brick scan may spill, the staged search must not lose occupancy
+#define PCCM_VX_MINBLOCKS 10
 #endif
+
+struct VxWarpSmem {
+    uint2 win[kVxRegRows];
+    uint32_t rb[kVxRegRows];
+    int sslot[28];
+    int occ_slot[28];
+    int occ_id[28];
+    uint16_t pend[kVxPend];
+};
+
+// the voxels of a brick that the 27-neighbourhood left open (lane l takes pend[l]): 125-neighbourhood, whole-brick
+// scans, todo list
+__device__ __forceinline__ void vx_finish_pending(const VxParams& P, int d, const VoxView& Q, const VoxView& S,
+                                                  VxWarpSmem& W, uint32_t b0, int count, bool any_brick, int nocc) {
+    const VxDir& D = P.dir[d];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool active = lane < count;
+    const uint32_t t = b0 + (active ? (uint32_t)W.pend[lane] : 0u);
+    const uint2 qr = __ldg(Q.vxyz + t);
+    const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+    uint4 r = make_uint4(kVxNone, 0u, 0u, 0u);
+    bool done = false;
+    if (active && any_brick) {
+        VxPick pk;
+        const uint32_t bd2 = vx_search125(S, W.sslot, W.win, W.rb, qx & 31, (qy & 7) + 2, (qz & 7) + 2, pk);
+        if (bd2 < 9u) { r = make_uint4(bd2, vx_pack_e(pk.ex, pk.ey, pk.ez), pk.idx, pk.rgb); done = true; }
+    }
+    unsigned pend = any_brick ? __ballot_sync(full, active && !done) : 0u;
+    while (pend) {                 // nearest point 3+ voxels away: the whole warp scans the 27 neighbour bricks for one voxel
+        const int src = __ffs((int)pend) - 1;
+        pend &= pend - 1u;
+        const int sx = __shfl_sync(full, qx, src), sy = __shfl_sync(full, qy, src), sz = __shfl_sync(full, qz, src);
+        uint32_t nrank = kVxNone;
+        const uint32_t nd2 = vx_warp_bricks<3>(S, W.occ_slot, W.occ_id, nocc, sx, sy, sz, 81u, nrank);
+        if (nd2 < 81u && lane == src) {          // anything outside the 27 bricks is at least 9 voxels away
+            const uint2 nc = __ldg(S.vxyz + nrank), nk = __ldg(S.vkey + nrank);
+            r = make_uint4(nd2, vx_pack_e(qx - (int)(nc.x & 0xffffu), qy - (int)(nc.x >> 16), qz - (int)nc.y), nk.y, nk.x);
+            done = true;
+        }
+    }
+    if (active) P.vres[t] = r;
+    const unsigned und = __ballot_sync(full, active && !done);
+    if (und) {
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(P.counters + d, (uint32_t)__popc(und));
+        pos = __shfl_sync(full, pos, 0);
+        VX_CHECK(pos + (uint32_t)__popc(und) <= D.nq);
+        if (active && !done) D.todo[pos + __popc(und & ((1u << lane) - 1u))] = t;
+    }
+}
+
 __global__ void __launch_bounds__(kVxThreads, PCCM_VX_MINBLOCKS)
 vx_search_kernel(const __grid_constant__ VxParams P) {
-    __shared__ uint2 s_win[kVxWarps][kVxRegRows];
-    __shared__ int s_slot[kVxWarps][28];
-    __shared__ int s_occ[kVxWarps][2][28];
+    __shared__ VxWarpSmem s_w[kVxWarps];
     const unsigned full = 0xffffffffu;
+    const VoxPlan* __restrict__ plan = P.plan;
+    if (plan->status) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t gw = blockIdx.x * kVxWarps + warp;
-    const int d = (P.ndirs > 1 && gw >= P.dir[0].q.nblk) ? 1 : 0;
-    const VxDir& D = P.dir[d];
-    const uint32_t lb = gw - (d ? P.dir[0].q.nblk : 0u);
-    if (lb >= D.q.nblk) return;
-    const uint32_t slot = D.q.slot0 + lb;
-    const uint4* __restrict__ qrecs = D.q.recs;
-    const uint32_t b0 = __ldg(D.q.base + slot), b1 = __ldg(D.q.base + slot + 1);
-    uint32_t t_lo, t_hi;
-    vx_slice(P, D.q, t_lo, t_hi);
-    const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
-    if (t0 >= t1) return;
-    uint2* win = s_win[warp];
-    int* sslot = s_slot[warp];
-    int* occ_slot = s_occ[warp][0];
-    int* occ_id = s_occ[warp][1];
-    const uint2 first = __ldg(reinterpret_cast<const uint2*>(qrecs + b0));
-    const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
-    int myslot = -1;
-    if (lane < 27) {
-        myslot = vx_slot(D.s, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
-        sslot[lane] = myslot;
-    }
-    const unsigned occ = __ballot_sync(full, myslot >= 0);
-    const bool any_brick = occ != 0u;
-    const int nocc = __popc(occ);
-    if (myslot >= 0) {                       // compacted list of the occupied neighbour bricks (undecided voxels scan them whole)
-        const int k = __popc(occ & ((1u << lane) - 1u));
-        occ_slot[k] = myslot;
-        occ_id[k] = lane;
-    }
-    __syncwarp();
-    if (any_brick) {
-        for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(D.s, sslot, i);
+    VxWarpSmem& W = s_w[warp];
+    const uint32_t nblk_d0 = plan->view[P.dir[0].qc].nblk;
+    const uint32_t nwork = nblk_d0 + (P.ndirs > 1 ? plan->view[P.dir[1].qc].nblk : 0u);
+    for (;;) {
+        uint32_t gw = 0;
+        if (lane == 0) gw = atomicAdd(P.counters + 4, 1u);
+        gw = __shfl_sync(full, gw, 0);
+        if (gw >= nwork) break;
+        const int d = gw >= nblk_d0 ? 1 : 0;
+        const VxDir& D = P.dir[d];
+        const VoxView& Q = plan->view[D.qc];
+        const VoxView& S = plan->view[D.sc];
+        const uint32_t slot = Q.slot0 + (gw - (d ? nblk_d0 : 0u));
+        const uint32_t b0 = vx_brick_begin(Q, slot), b1 = vx_brick_begin(Q, slot + 1);
+        uint32_t t_lo, t_hi;
+        vx_slice(P, Q, t_lo, t_hi);
+        const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
+        if (t0 >= t1) continue;
+        const bool need_idx = D.idx_out != nullptr || (D.flags & PCCM_EVAL_COLOR) ||
+                              ((D.flags & PCCM_EVAL_D2) && P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR);
+        const bool need_e = (D.flags & PCCM_EVAL_D2) != 0;
+        const uint2* __restrict__ qxyz = Q.vxyz;
+        const uint2 first = __ldg(qxyz + b0);
+        const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+        __syncwarp();                                        // (the previous brick's window is no longer read)
+        int myslot = -1;
+        if (lane < 27) {
+            myslot = vx_slot(S, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
+            W.sslot[lane] = myslot;
+        }
+        const unsigned occ = __ballot_sync(full, myslot >= 0);
+        const bool any_brick = occ != 0u;
+        const int nocc = __popc(occ);
+        if (myslot >= 0) {                       // compacted list of the occupied neighbour bricks (whole-brick scans)
+            const int k = __popc(occ & ((1u << lane) - 1u));
+            W.occ_slot[k] = myslot;
+            W.occ_id[k] = lane;
+        }
         __syncwarp();
-    }
-    for (uint32_t tb = t0; tb < t1; tb += 32) {
-        const uint32_t t = tb + lane;
-        const bool active = t < t1;
-        const uint2 qr = __ldg(reinterpret_cast<const uint2*>(qrecs + (active ? t : t0)));
-        const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
-        uint32_t bd2 = kVxNone, rows = 0;
-        bool done = false;
         if (any_brick) {
-            const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
-            vx_rows_inner(win, lx, ly, lz, bd2, rows);
-            done = bd2 < 4u;
-            if (__any_sync(full, active && !done)) {
-                vx_rows_outer(win, lx, ly, lz, bd2, rows);
-                done = bd2 < 9u;
+            for (int i = lane; i < kVxRegRows; i += 32) {
+                uint32_t rb;
+                W.win[i] = vx_stage_row(S, W.sslot, i, rb);
+                W.rb[i] = rb;
+            }
+            __syncwarp();
+        }
+        int npend = 0;
+        for (uint32_t tb = t0; tb < t1; tb += 32) {
+            const uint32_t t = tb + lane;
+            const bool active = t < t1;
+            const uint2 qr = __ldg(qxyz + (active ? t : t0));
+            const int lx = (int)(qr.x & 31u), ly = (int)((qr.x >> 16) & 7u) + 2, lz = (int)(qr.y & 7u) + 2;
+            uint32_t bd2 = 0, cand = 0;
+            if (any_brick) cand = vx_level27(vx_nb27(W.win, lx, ly, lz), bd2);
+            const bool done = active && cand != 0u;
+            if (done) {
+                uint32_t bidx = kVxNone, brgb = 0u;
+                int bb = __ffs((int)cand) - 1;
+                if (need_idx || (need_e && (cand & (cand - 1u)))) {
+                    // the voxels that tie at the minimum, two look-ups in flight per trip
+                    uint32_t c2 = cand;
+                    do {
+                        const int b_a = __ffs((int)c2) - 1;
+                        c2 &= c2 - 1u;
+                        const int b_b = c2 ? __ffs((int)c2) - 1 : b_a;
+                        c2 &= c2 - 1u;
+                        const uint32_t r_a = vx_cand_rank27(S, W.sslot, W.win, W.rb, lx, ly, lz, b_a);
+                        const uint32_t r_b = vx_cand_rank27(S, W.sslot, W.win, W.rb, lx, ly, lz, b_b);
+                        VX_CHECK(r_a < S.n_total && r_b < S.n_total);
+                        const uint2 k_a = __ldg(S.vkey + r_a), k_b = __ldg(S.vkey + r_b);
+                        if (k_a.y < bidx) { bidx = k_a.y; brgb = k_a.x; bb = b_a; }
+                        if (k_b.y < bidx) { bidx = k_b.y; brgb = k_b.x; bb = b_b; }
+                    } while (c2);
+                }
+                P.vres[t] = make_uint4(bd2, vx_pack_e27(bb), bidx == kVxNone ? 0u : bidx, brgb);   // (no look-up: the index is not used)
+            }
+            const unsigned und = __ballot_sync(full, active && !done);
+            if (und) {
+                if (active && !done) W.pend[npend + __popc(und & ((1u << lane) - 1u))] = (uint16_t)(t - b0);
+                npend += __popc(und);
+                __syncwarp();
+                if (npend >= 32) {
+                    vx_finish_pending(P, d, Q, S, W, b0, 32, any_brick, nocc);
+                    __syncwarp();
+                    if (lane < npend - 32) W.pend[lane] = W.pend[32 + lane];
+                    npend -= 32;
+                    __syncwarp();
+                }
             }
         }
-        uint4 r = make_uint4(kVxNone, 0u, 0u, 0u);
-        if (active && done) {
-            VxPick pk;
-            vx_pick(D.s, sslot, win, bx, by, bz, qx, qy, qz, rows, pk);
-            r = make_uint4(bd2, vx_pack_e(pk.ex, pk.ey, pk.ez), pk.idx, pk.rgb);
-        }
-        // voxels the 5 x 5 rows left undecided (nearest point 3+ voxels away; rare): the whole warp scans the
-        // 27 neighbour bricks for one voxel at a time -- anything outside them is at least 9 voxels away
-#ifndef PCCM_VX_INKERNEL
-#define PCCM_VX_INKERNEL 1
-#endif
-        unsigned pend = (PCCM_VX_INKERNEL && any_brick) ? __ballot_sync(full, active && !done) : 0u;
-        while (pend) {
-            const int src = __ffs((int)pend) - 1;
-            pend &= pend - 1u;
-            const int sx = __shfl_sync(full, qx, src), sy = __shfl_sync(full, qy, src), sz = __shfl_sync(full, qz, src);
-            uint32_t nrank = kVxNone;
-            const uint32_t nd2 = vx_warp_bricks<3>(D.s, occ_slot, occ_id, nocc, sx, sy, sz, 81u, nrank);
-            if (nd2 < 81u && lane == src) {
-                const uint4 nr = __ldg(D.s.recs + nrank);
-                r = make_uint4(nd2, vx_pack_e(qx - (int)(nr.x & 0xffffu), qy - (int)(nr.x >> 16), qz - (int)nr.y), nr.w, nr.z);
-                done = true;
-            }
-        }
-        if (active) P.vres[t] = r;
-        const unsigned und = __ballot_sync(full, active && !done);
-        if (und) {
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(D.todo_count, (uint32_t)__popc(und));
-            pos = __shfl_sync(full, pos, 0);
-            VX_CHECK(pos + (uint32_t)__popc(und) <= D.q.n);
-            if (active && !done) D.todo[pos + __popc(und & ((1u << lane) - 1u))] = t;
-        }
+        if (npend) vx_finish_pending(P, d, Q, S, W, b0, npend, any_brick, nocc);
     }
 }
 
@@ -471,6 +801,8 @@ constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
 __global__ void __launch_bounds__(kVxEpiThreads)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     __shared__ double s_lut[256];
+    const VoxPlan* __restrict__ plan = P.plan;
+    if (plan->status) return;
     const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
     const VxDir& D = P.dir[d];
     const uint32_t tile = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
@@ -478,16 +810,15 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     __syncthreads();
     CloudView qa = D.qa, sa = D.sa;
     qa.lut255 = s_lut; sa.lut255 = s_lut;
-    uint32_t t_lo, t_hi;
-    vx_slice(P, D.q, t_lo, t_hi);
+    uint32_t t_lo = 0u, t_hi = kVxNone;                   // (kVxNone itself marks "no voxel")
+    if (P.world > 1) vx_slice(P, plan->view[D.qc], t_lo, t_hi);
     const uint32_t i0 = tile * kVxEpiTile + threadIdx.x;
     uint32_t rk[kVxEpiPer];
     uint4 v[kVxEpiPer];
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
         const uint32_t i = i0 + j * kVxEpiThreads;
-        rk[j] = i < D.q.n ? __ldg(D.q.prank + i) : kVxNone;
-        VX_CHECK(i >= D.q.n || rk[j] < D.q.n_total);
+        rk[j] = i < D.nq ? __ldg(D.qprank + i) : kVxNone;
     }
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j)
@@ -505,12 +836,11 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
         if (!far) {
             ex = (int)(v[j].y & 0xffu) - 128; ey = (int)((v[j].y >> 8) & 0xffu) - 128; ez = (int)((v[j].y >> 16) & 0xffu) - 128;
         } else {                                  // pencil-round answer: any distance, coordinates from the records
-            const uint2 qv = __ldg(reinterpret_cast<const uint2*>(D.q.recs + rk[j]));
+            const uint2 qv = __ldg(plan->view[D.qc].vxyz + rk[j]);
             const uint4 nr = __ldg(D.srecs + v[j].y);               // {xy, z, idx, rgb}
             ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
             nrgb = nr.w;
         }
-        VX_CHECK((v[j].z & ~kVxFarBit) < D.s.n);
         vx_epilogue(P, D, qa, sa, i, 0u, v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc);
     }
     BlockPartial r;
@@ -537,16 +867,20 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
     __shared__ int s_slot[4][128];
     __shared__ int s_occ[4][128];
     const unsigned full = 0xffffffffu;
+    const VoxPlan* __restrict__ plan = P.plan;
+    if (plan->status) return;
     const int lane = threadIdx.x & 31;
     int* bslot = s_slot[threadIdx.x >> 5];
     int* bocc = s_occ[threadIdx.x >> 5];
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int d = 0; d < P.ndirs; ++d) {
         const VxDir& D = P.dir[d];
-        const uint32_t ntodo = *D.todo_count;
+        const VoxView& Q = plan->view[D.qc];
+        const VoxView& S = plan->view[D.sc];
+        const uint32_t ntodo = P.counters[d];
         for (uint32_t w = gwarp; w < ntodo; w += nwarps) {
             const uint32_t t = D.todo[w];
-            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(D.q.recs + t));
+            const uint2 qr = __ldg(Q.vxyz + t);
             const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
             const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
             __syncwarp();
@@ -554,7 +888,7 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
             int nocc = 0;
             for (int b0 = 0; b0 < 125; b0 += 32) {
                 const int b = b0 + lane;
-                const int slot = b < 125 ? vx_slot(D.s, qbx + b % 5 - 2, qby + (b / 5) % 5 - 2, qbz + b / 25 - 2) : -1;
+                const int slot = b < 125 ? vx_slot(S, qbx + b % 5 - 2, qby + (b / 5) % 5 - 2, qbz + b / 25 - 2) : -1;
                 const unsigned has = __ballot_sync(full, slot >= 0);
                 if (slot >= 0) {
                     const int k = nocc + __popc(has & ((1u << lane) - 1u));
@@ -565,14 +899,14 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
             }
             __syncwarp();
             uint32_t brank = kVxNone;
-            const uint32_t best = vx_warp_bricks<5>(D.s, bslot, bocc, nocc, qx, qy, qz, 289u, brank);
+            const uint32_t best = vx_warp_bricks<5>(S, bslot, bocc, nocc, qx, qy, qz, 289u, brank);
             if (best >= 289u) {               // nothing certified within two brick rings
-                if (lane == 0) D.far[atomicAdd(D.far_count, 1u)] = t;
+                if (lane == 0) D.far[atomicAdd(P.counters + 2 + d, 1u)] = t;
                 continue;
             }
             if (lane == 0) {
-                const uint4 nr = __ldg(D.s.recs + brank);
-                P.vres[t] = make_uint4(best, vx_pack_e(qx - (int)(nr.x & 0xffffu), qy - (int)(nr.x >> 16), qz - (int)nr.y), nr.w, nr.z);
+                const uint2 nc = __ldg(S.vxyz + brank), nk = __ldg(S.vkey + brank);
+                P.vres[t] = make_uint4(best, vx_pack_e(qx - (int)(nc.x & 0xffffu), qy - (int)(nc.x >> 16), qz - (int)nc.y), nk.y, nk.x);
             }
         }
     }
@@ -582,13 +916,15 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
 // clouds, isolated outliers): exact pencil search, which skips empty space by its row table.
 __global__ void __launch_bounds__(128)
 vx_far_kernel(const __grid_constant__ VxParams P) {
+    const VoxPlan* __restrict__ plan = P.plan;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (int d = 0; d < P.ndirs; ++d) {
         const VxDir& D = P.dir[d];
-        const uint32_t nfar = *D.far_count;
+        const uint2* __restrict__ qxyz = plan->view[D.qc].vxyz;
+        const uint32_t nfar = P.counters[2 + d];
         for (uint32_t w = gtid; w < nfar; w += stride) {
             const uint32_t t = D.far[w];
-            const uint4 qr = __ldg(D.q.recs + t);
+            const uint2 qr = __ldg(qxyz + t);
             KInt::Q q;
             q.x = (int)(qr.x & 0xffffu); q.y = (int)(qr.x >> 16); q.z = (int)qr.y;
             Best1<KInt> best;
@@ -601,7 +937,7 @@ vx_far_kernel(const __grid_constant__ VxParams P) {
 
 // ------------------------------------------------------------------------------------
 // distance of every point to its nearest OTHER point (compute_nearest_neighbor_distance,
-// cloud_pair.py:108-109) on the brick index: the same row scans with the voxel's own bit cleared;
+// cloud_pair.py:108-109) on the brick index: the 26 / 124 voxels around the voxel on the staged rows;
 // a voxel that holds more than one point answers 0
 // ------------------------------------------------------------------------------------
 struct VxSelfParams {
@@ -611,7 +947,7 @@ struct VxSelfParams {
     uint32_t* dupbits;         // [n_total / 32 + 1] by rank: voxel holds more than one point
     uint32_t* vself;           // [n_total] by rank: squared distance to the nearest other point (kVxNone: not decided here)
     double* minmax;            // per brick {min, max} of the distances (sqrt)
-    uint32_t* undecided;       // voxels farther than 8 voxels from every other one (caller falls back to the pencil path)
+    uint32_t* undecided;       // [0] count, [1..] ranks of the voxels farther than 8 voxels from every other one
     double* per_point;         // optional, original order
 };
 
@@ -619,20 +955,19 @@ __global__ void vx_dupflag_kernel(const __grid_constant__ VxSelfParams P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t rank = __ldg(P.c.prank + i);
-    if (__ldg(reinterpret_cast<const uint32_t*>(P.c.recs + rank) + 3) != i) atomicOr(P.dupbits + (rank >> 5), 1u << (rank & 31u));
+    if (__ldg(&P.c.vkey[rank].y) != i) atomicOr(P.dupbits + (rank >> 5), 1u << (rank & 31u));
 }
 
 __global__ void __launch_bounds__(kVxThreads)
 vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
-    __shared__ uint2 s_win[kVxWarps][kVxRegRows];
-    __shared__ int s_slot[kVxWarps][28];
-    __shared__ int s_occ[kVxWarps][2][28];
+    __shared__ VxWarpSmem s_w[kVxWarps];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    VxWarpSmem& W = s_w[warp];
     const uint32_t lb = blockIdx.x * kVxWarps + warp;
     if (lb >= P.c.nblk) return;
     const uint32_t slot = P.c.slot0 + lb;
-    const uint32_t b0 = __ldg(P.c.base + slot), b1 = __ldg(P.c.base + slot + 1);
+    const uint32_t b0 = vx_brick_begin(P.c, slot), b1 = vx_brick_begin(P.c, slot + 1);
     const uint32_t r0 = vx_ranked_begin(P.c), nd = vx_ndistinct(P.c);
     const uint32_t t_lo = r0 + (uint32_t)((unsigned long long)nd * P.begin / (P.n ? P.n : 1u));
     const uint32_t t_hi = r0 + (uint32_t)((unsigned long long)nd * P.end / (P.n ? P.n : 1u));
@@ -640,60 +975,45 @@ vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
     uint32_t mn = kVxNone, mx = 0u;
     bool any = false;
     if (t0 < t1) {
-        uint2* win = s_win[warp];
-        int* sslot = s_slot[warp];
-        int* occ_slot = s_occ[warp][0];
-        int* occ_id = s_occ[warp][1];
-        const uint2 first = __ldg(reinterpret_cast<const uint2*>(P.c.recs + b0));
+        const uint2 first = __ldg(P.c.vxyz + b0);
         const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
         int myslot = -1;
         if (lane < 27) {
             myslot = vx_slot(P.c, bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1);
-            sslot[lane] = myslot;
+            W.sslot[lane] = myslot;
         }
         const unsigned occ = __ballot_sync(full, myslot >= 0);
         const int nocc = __popc(occ);
         if (myslot >= 0) {
             const int k = __popc(occ & ((1u << lane) - 1u));
-            occ_slot[k] = myslot;
-            occ_id[k] = lane;
+            W.occ_slot[k] = myslot;
+            W.occ_id[k] = lane;
         }
         __syncwarp();
-        for (int i = lane; i < kVxRegRows; i += 32) win[i] = vx_stage_row(P.c, sslot, i);
+        for (int i = lane; i < kVxRegRows; i += 32) {
+            uint32_t rb;
+            W.win[i] = vx_stage_row(P.c, W.sslot, i, rb);
+        }
         __syncwarp();
         for (uint32_t tb = t0; tb < t1; tb += 32) {
             const uint32_t t = tb + lane;
             const bool active = t < t1;
-            const uint2 qr = __ldg(reinterpret_cast<const uint2*>(P.c.recs + (active ? t : t0)));
+            const uint2 qr = __ldg(P.c.vxyz + (active ? t : t0));
             const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
             const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
-            // the voxel's own bit sits at bit 16 + lx of its row window: clear it in a private copy of that row
             const bool dup = active && ((__ldg(P.dupbits + (t >> 5)) >> (t & 31u)) & 1u);
-            uint32_t bd2 = kVxNone, rows = 0;
-            {
-                uint2 own = win[lz * kVxRegY + ly];
-                const int bit = 16 + lx;
-                if (bit < 32) own.x &= ~(1u << bit); else own.y &= ~(1u << (bit - 32));
-                int dd, du;
-                vx_row_dists(own, lx, dd, du);
-                const int dx = dd < du ? dd : du;
-                bd2 = (uint32_t)(dx * dx);
+            uint32_t bd2 = vx_self27(vx_nb27(W.win, lx, ly, lz));
+            if (__any_sync(full, active && !dup && bd2 == kVxNone)) {
+                if (bd2 == kVxNone) bd2 = vx_self125(W.win, lx, ly, lz);
             }
-            uint32_t nb = kVxNone, nrows = 0;
-            vx_rows_ring1(win, lx, ly, lz, nb, nrows);
-            bd2 = nb < bd2 ? nb : bd2;
-            bool done = bd2 < 4u;
-            if (__any_sync(full, active && !done && !dup)) {
-                vx_rows_outer(win, lx, ly, lz, bd2, rows);
-                done = bd2 < 9u;
-            }
+            bool done = bd2 < 9u;
             unsigned pend = __ballot_sync(full, active && !done && !dup);
             while (pend) {
                 const int src = __ffs((int)pend) - 1;
                 pend &= pend - 1u;
                 const int sx = __shfl_sync(full, qx, src), sy = __shfl_sync(full, qy, src), sz = __shfl_sync(full, qz, src);
                 uint32_t dummy = kVxNone;
-                const uint32_t nd2 = vx_warp_bricks<3, true>(P.c, occ_slot, occ_id, nocc, sx, sy, sz, 81u, dummy);
+                const uint32_t nd2 = vx_warp_bricks<3, true>(P.c, W.occ_slot, W.occ_id, nocc, sx, sy, sz, 81u, dummy);
                 if (nd2 < 81u && lane == src) { bd2 = nd2; done = true; }
             }
             if (active) {
@@ -702,7 +1022,12 @@ vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
                 if (v != kVxNone) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; any = true; }
             }
             const unsigned und = __ballot_sync(full, active && !dup && !done);
-            if (und && lane == 0) atomicAdd(P.undecided, (uint32_t)__popc(und));
+            if (und) {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(P.undecided, (uint32_t)__popc(und));
+                pos = __shfl_sync(full, pos, 0);
+                if (active && !dup && !done) P.undecided[1 + pos + __popc(und & ((1u << lane) - 1u))] = t;
+            }
         }
     }
     mn = __reduce_min_sync(full, mn);
@@ -712,6 +1037,37 @@ vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
         P.minmax[2 * lb] = wany ? sqrt((double)mn) : INFINITY;
         P.minmax[2 * lb + 1] = wany ? sqrt((double)mx) : -INFINITY;
     }
+}
+
+// The voxels vx_selfnn_kernel could not decide (no other voxel within 8): exact pencil search for the nearest
+// OTHER point (2-NN: the voxel's own point is the first hit); their min / max go to extra slots of the min / max array.
+struct VxSelfFarParams {
+    VxSelfParams s;
+    RowGrid grid;
+    const uint4* recs;
+    const uint32_t* row_start;
+    double* minmax_extra;      // [2 * nblocks]
+};
+__global__ void __launch_bounds__(128)
+vx_selffar_kernel(const __grid_constant__ VxSelfFarParams P) {
+    const uint32_t n = P.s.undecided[0];
+    double mn = INFINITY, mx = -INFINITY;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+        const uint32_t t = P.s.undecided[1 + w];
+        const uint2 qr = __ldg(P.s.c.vxyz + t);
+        KInt::Q q;
+        q.x = (int)(qr.x & 0xffffu); q.y = (int)(qr.x >> 16); q.z = (int)qr.y;
+        Best2Val<KInt> best;                 // the voxel holds exactly one point (itself, distance 0): the second one is the answer
+        best.init();
+        search<KInt>(P.grid, P.row_start, P.recs, q, best);
+        P.s.vself[t] = best.m2;
+        const double dd = sqrt((double)best.m2);
+        mn = fmin(mn, dd); mx = fmax(mx, dd);
+    }
+    __shared__ double sm[4];
+    const double bmn = block_min<128>(mn, sm);
+    const double bmx = block_max<128>(mx, sm);
+    if (threadIdx.x == 0) { P.minmax_extra[2 * blockIdx.x] = bmn; P.minmax_extra[2 * blockIdx.x + 1] = bmx; }
 }
 
 __global__ void vx_selfout_kernel(const __grid_constant__ VxSelfParams P) {

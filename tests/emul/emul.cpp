@@ -157,9 +157,8 @@ extern "C" int emul_knn_self(int kind, const double* pts, int64_t n, int k, doub
 #include "../../open_pcc_metric_b200/csrc/pccm_vox.cuh"
 
 struct VoxPair {
-    std::vector<uint32_t> dirbits, dirpre, masks, base, prank;
-    std::vector<uint16_t> pre;
-    std::vector<uint4> recs;
+    std::vector<uint32_t> dirbits, dirpre, masks, rowbase, prank;
+    std::vector<uint2> vxyz, vkey;
     VoxView view[2];
 };
 
@@ -182,26 +181,22 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
     auto coords = [&](int c, int64_t i, int& x, int& y, int& z) { x = (int)pts[c][3 * i]; y = (int)pts[c][3 * i + 1]; z = (int)pts[c][3 * i + 2]; };
     for (int c = 0; c < 2; ++c)                                   // vx_mark_kernel
         for (int64_t i = 0; i < n[c]; ++i) { int x, y, z; coords(c, i, x, y, z); vx_mark_point(V.dirbits.data() + dir_off[c], vx_key(g[c], x, y, z)); }
-    uint32_t run = 0;                                             // vx_dircount_kernel + exclusive scan
+    uint32_t run = 0;                                             // vx_dirsum_kernel + vx_dirscan_kernel
     for (uint32_t w = 0; w < nw; ++w) { V.dirpre[w] = run; run += (uint32_t)vx_popc(V.dirbits[w]); }
     V.dirpre[nw] = run;
     const uint32_t nblk0 = V.dirpre[ndirw[0]], nblk = run;
-    V.masks.assign((size_t)nblk * kVxRows, 0); V.pre.assign((size_t)nblk * kVxRows, 0); V.base.assign(nblk + 1, 0);
-    V.recs.resize(n_total);
-    memset(V.recs.data(), 0xff, (size_t)n_total * sizeof(uint4));
+    V.masks.assign((size_t)(nblk + 1) * kVxRows, 0); V.rowbase.assign((size_t)(nblk + 1) * kVxRows, 0);
+    V.vxyz.resize(n_total); V.vkey.resize(n_total);
+    memset(V.vkey.data(), 0xff, (size_t)n_total * sizeof(uint2));
     V.prank.assign(n_total, kVxNone);
     for (int c = 0; c < 2; ++c)                                   // vx_fill_kernel
         for (int64_t i = 0; i < n[c]; ++i) {
             int x, y, z; coords(c, i, x, y, z);
             vx_fill_point(V.masks.data(), vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z)), x, y, z);
         }
-    run = 0;                                                      // vx_brickpre_kernel + exclusive scan
-    for (uint32_t s = 0; s < nblk; ++s) {
-        uint32_t in = 0;
-        for (int r = 0; r < kVxRows; ++r) { V.pre[(size_t)s * kVxRows + r] = (uint16_t)in; in += (uint32_t)vx_popc(V.masks[(size_t)s * kVxRows + r]); }
-        V.base[s] = run; run += in;
-    }
-    V.base[nblk] = run;
+    run = 0;                                                      // vx_bricksum_kernel + vx_rowbase_kernel (the brick past the last one is empty)
+    for (uint32_t s = 0; s <= nblk; ++s)
+        for (int r = 0; r < kVxRows; ++r) { V.rowbase[(size_t)s * kVxRows + r] = run; run += (uint32_t)vx_popc(V.masks[(size_t)s * kVxRows + r]); }
     for (int c = 0; c < 2; ++c) {                                  // vx_place_kernel; arrival order of the atomics: odd indices
         std::vector<int64_t> order;                                 // downwards, then even ones upwards
         for (int64_t i = n[c]; i-- > 0;) if (i & 1) order.push_back(i);
@@ -209,13 +204,13 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
         for (int64_t i : order) {
             int x, y, z; coords(c, i, x, y, z);
             const uint32_t slot = vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z));
-            V.prank[(c ? n[0] : 0) + i] = vx_place_point(V.masks.data(), V.pre.data(), V.base.data(), V.recs.data(), slot, x, y, z, 0u, (uint32_t)i);
+            V.prank[(c ? n[0] : 0) + i] = vx_place_point(V.masks.data(), V.rowbase.data(), V.vxyz.data(), V.vkey.data(), slot, x, y, z, 0u, (uint32_t)i);
         }
     }
     for (int c = 0; c < 2; ++c) {
         VoxView& W = V.view[c];
         W.g = g[c]; W.dirbits = V.dirbits.data() + dir_off[c]; W.dirpre = V.dirpre.data() + dir_off[c];
-        W.masks = V.masks.data(); W.pre = V.pre.data(); W.base = V.base.data(); W.recs = V.recs.data();
+        W.masks = V.masks.data(); W.rowbase = V.rowbase.data(); W.vxyz = V.vxyz.data(); W.vkey = V.vkey.data();
         W.prank = V.prank.data() + (c ? n[0] : 0);
         W.slot0 = c ? nblk0 : 0; W.nblk = c ? nblk - nblk0 : nblk0; W.n = (uint32_t)n[c];
         W.nblk_total = nblk; W.n_total = n_total;
@@ -223,7 +218,20 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
     return true;
 }
 
-// stats: [0] staged-decided (inner rows only), [1] staged-decided (with outer rows), [2] undecided, [3] tail,
+// the staged window of one query brick: occupancy rows + rank bases of the centre column
+struct VoxWindow {
+    int sslot[27];
+    bool any_brick;
+    uint2 win[kVxRegRows];
+    uint32_t rb[kVxRegRows];
+};
+static void vox_stage(const VoxView& S, int bx, int by, int bz, VoxWindow& W) {
+    W.any_brick = false;
+    for (int l = 0; l < 27; ++l) { W.sslot[l] = vx_slot(S, bx + l % 3 - 1, by + (l / 3) % 3 - 1, bz + l / 9 - 1); W.any_brick |= W.sslot[l] >= 0; }
+    for (int r = 0; r < kVxRegRows; ++r) W.win[r] = vx_stage_row(S, W.sslot, r, W.rb[r]);
+}
+
+// stats: [0] decided by the 27-neighbourhood, [1] by the 125-neighbourhood, [2] undecided, [3] tail,
 // [4] left to the pencil search.  Returns 1 when the brick grid exceeds the directory budget.
 extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t ns, int max_ring, int32_t* idx, double* d2, int64_t* stats) {
     const double* pts[2] = {q, s};
@@ -238,64 +246,52 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
     for (int64_t i = 0; i < nq; ++i) { idx[i] = -2; d2[i] = -1; }
     std::vector<uint32_t> todo;
     // answer of the voxel at ranked position t (vres[]); every point of the voxel reads it through prank (epilogue)
-    std::vector<int64_t> res_idx(V.recs.size(), -2), res_d2(V.recs.size(), -1);
+    std::vector<int64_t> res_idx(V.vxyz.size(), -2), res_d2(V.vxyz.size(), -1);
     auto assign = [&](uint32_t t, uint32_t nidx, uint32_t nd2) { res_idx[t] = nidx; res_d2[t] = nd2; };
-    // vx_query_kernel: one "warp" per query brick
+    // vx_search_kernel: one "warp" per query brick
     for (uint32_t lb = 0; lb < Q.nblk; ++lb) {
-        const uint32_t slot = Q.slot0 + lb, t0 = Q.base[slot], t1 = Q.base[slot + 1];
-        const uint4 first = Q.recs[t0];
+        const uint32_t slot = Q.slot0 + lb, t0 = vx_brick_begin(Q, slot), t1 = vx_brick_begin(Q, slot + 1);
+        if (t0 >= t1) return -18;                        // every brick of the directory holds a voxel
+        const uint2 first = Q.vxyz[t0];
         const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
-        int sslot[27];
-        bool any_brick = false;
-        for (int l = 0; l < 27; ++l) { sslot[l] = vx_slot(S, bx + l % 3 - 1, by + (l / 3) % 3 - 1, bz + l / 9 - 1); any_brick |= sslot[l] >= 0; }
-        uint2 win[kVxRegRows];
-        if (any_brick) for (int r = 0; r < kVxRegRows; ++r) win[r] = vx_stage_row(S, sslot, r);
-        for (uint32_t tb = t0; tb < t1; tb += 32) {
-            uint32_t bd2[32], rows[32];
-            bool done[32], need_outer = false;
-            const uint32_t cnt = std::min<uint32_t>(32, t1 - tb);
-            for (uint32_t l = 0; l < cnt; ++l) {
-                const uint4 qr = Q.recs[tb + l];
-                bd2[l] = kVxNone; rows[l] = 0; done[l] = false;
-                if (any_brick) {
-                    vx_rows_inner(win, (int)(qr.x & 0xffffu) & 31, (int)((qr.x >> 16) & 7) + 2, (int)(qr.y & 7) + 2, bd2[l], rows[l]);
-                    done[l] = bd2[l] < 4u;
-                    if (!done[l]) need_outer = true;
+        VoxWindow W;
+        vox_stage(S, bx, by, bz, W);
+        for (uint32_t t = t0; t < t1; ++t) {
+            const uint2 qr = Q.vxyz[t];
+            const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
+            const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
+            if ((qx >> 5) != bx || (qy >> 3) != by || (qz >> 3) != bz) return -19;
+            VxPick pk;
+            uint32_t bd2 = kVxNone;
+            int stage = -1;
+            if (W.any_brick) {
+                const uint32_t cand = vx_level27(vx_nb27(W.win, lx, ly, lz), bd2);
+                if (cand) { vx_pick27(S, W.sslot, W.win, W.rb, lx, ly, lz, cand, pk); stage = 0; }
+                else {
+                    bd2 = vx_search125(S, W.sslot, W.win, W.rb, lx, ly, lz, pk);
+                    if (bd2 < 9u) stage = 1;
                 }
             }
-            for (uint32_t l = 0; l < cnt; ++l) {
-                const uint4 qr = Q.recs[tb + l];
-                const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
-                const bool inner = done[l];
-                if (any_brick && need_outer) {       // the whole warp runs the outer rows
-                    vx_rows_outer(win, qx & 31, (qy & 7) + 2, (qz & 7) + 2, bd2[l], rows[l]);
-                    done[l] = bd2[l] < 9u;
-                    if (inner && !done[l]) return -10;   // outer rows must never worsen a decided query
-                }
-                if (done[l]) {
-                    VxPick pk;
-                    vx_pick(S, sslot, win, bx, by, bz, qx, qy, qz, rows[l], pk);
-                    assign(tb + l, pk.idx, bd2[l]);
-                    if ((uint32_t)(pk.ex * pk.ex + pk.ey * pk.ey + pk.ez * pk.ez) != bd2[l]) return -11;
-                    const uint4 nr = S.recs[pk.rank];
-                    if (nr.w != pk.idx || qx - (int)(nr.x & 0xffffu) != pk.ex || qy - (int)(nr.x >> 16) != pk.ey || qz - (int)nr.y != pk.ez) return -12;
-                    stats[inner ? 0 : 1]++;
-                } else {
-                    todo.push_back(tb + l);
-                }
+            if (stage >= 0) {
+                assign(t, pk.idx, bd2);
+                if ((uint32_t)(pk.ex * pk.ex + pk.ey * pk.ey + pk.ez * pk.ez) != bd2) return -11;
+                if (pk.idx >= (uint32_t)ns) return -12;
+                if ((int)s[3 * pk.idx] != qx - pk.ex || (int)s[3 * pk.idx + 1] != qy - pk.ey || (int)s[3 * pk.idx + 2] != qz - pk.ez) return -12;
+                stats[stage]++;
+            } else {
+                todo.push_back(t);
             }
         }
     }
     // vx_general_kernel: undecided voxels
     stats[2] = (int64_t)todo.size();
     for (uint32_t t : todo) {
-        const uint4 qr = Q.recs[t];
+        const uint2 qr = Q.vxyz[t];
         VxHit h;
         // the search kernel first scans the 27 neighbour bricks (ring 1), vx_general_kernel rings 0..2
         if (vx_search_general(S, (int)(qr.x & 0xffffu), (int)(qr.x >> 16), (int)qr.y, h, max_ring < 1 ? max_ring : 1) ||
             vx_search_general(S, (int)(qr.x & 0xffffu), (int)(qr.x >> 16), (int)qr.y, h, max_ring)) {
-            const uint4 nr = S.recs[h.rank];
-            if (nr.w != h.idx) return -13;
+            if (S.vkey[h.rank].y != h.idx) return -13;
             assign(t, h.idx, h.d2);
         } else {                                    // vx_far_kernel
             KInt::Q qq; qq.x = (int)(qr.x & 0xffffu); qq.y = (int)(qr.x >> 16); qq.z = (int)qr.y;
@@ -309,10 +305,10 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
     // vx_epilogue_kernel: original order
     for (int64_t i = 0; i < nq; ++i) {
         const uint32_t t = Q.prank[i];
-        const uint4 qr = Q.recs[t];
+        const uint2 qr = Q.vxyz[t];
         if ((int)(qr.x & 0xffffu) != (int)q[3 * i] || (int)(qr.x >> 16) != (int)q[3 * i + 1] || (int)qr.y != (int)q[3 * i + 2]) return -15;
-        if (qr.w > (uint32_t)i) return -16;               // the record holds the smallest index of its voxel
-        if (qr.w != (uint32_t)i) stats[3]++;
+        if (Q.vkey[t].y > (uint32_t)i) return -16;               // the record holds the smallest index of its voxel
+        if (Q.vkey[t].y != (uint32_t)i) stats[3]++;
         idx[i] = (int32_t)res_idx[t]; d2[i] = (double)res_d2[t];
     }
     if ((uint32_t)stats[3] != Q.n - vx_ndistinct(Q)) return -17;
@@ -321,7 +317,7 @@ extern "C" int emul_vox_nn(const double* q, int64_t nq, const double* s, int64_t
 }
 
 // Boundary distances on the brick index (vx_selfnn_kernel): distance of every point to its nearest OTHER
-// point by the staged row scans with the voxel's own bit cleared; voxels that hold several points answer 0.
+// point from the 26 / 124 voxels around it on the staged rows; voxels that hold several points answer 0.
 // out[i] = squared distance, -1 where the staged rows cannot decide (the kernel scans whole bricks there,
 // the library falls back to the pencil k-NN beyond 8 voxels).  Returns the number of undecided points.
 extern "C" int64_t emul_vox_self(const double* pts_in, int64_t n_in, double* out) {
@@ -333,33 +329,22 @@ extern "C" int64_t emul_vox_self(const double* pts_in, int64_t n_in, double* out
     const uint32_t nd = vx_ndistinct(Q);
     std::vector<uint8_t> dup(nd, 0);
     for (int64_t i = 0; i < n_in; ++i)       // vx_dupflag_kernel
-        if (Q.recs[Q.prank[i]].w != (uint32_t)i) dup[Q.prank[i]] = 1;
+        if (Q.vkey[Q.prank[i]].y != (uint32_t)i) dup[Q.prank[i]] = 1;
     std::vector<int64_t> vself(nd, -1);
     for (uint32_t lb = 0; lb < Q.nblk; ++lb) {
-        const uint32_t slot = Q.slot0 + lb, t0 = Q.base[slot], t1 = Q.base[slot + 1];
-        const uint4 first = Q.recs[t0];
+        const uint32_t slot = Q.slot0 + lb, t0 = vx_brick_begin(Q, slot), t1 = vx_brick_begin(Q, slot + 1);
+        const uint2 first = Q.vxyz[t0];
         const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
-        int sslot[27];
-        for (int l = 0; l < 27; ++l) sslot[l] = vx_slot(Q, bx + l % 3 - 1, by + (l / 3) % 3 - 1, bz + l / 9 - 1);
-        uint2 win[kVxRegRows];
-        for (int r = 0; r < kVxRegRows; ++r) win[r] = vx_stage_row(Q, sslot, r);
+        VoxWindow W;
+        vox_stage(Q, bx, by, bz, W);
         for (uint32_t t = t0; t < t1; ++t) {
             if (dup[t]) { vself[t] = 0; continue; }
-            const uint4 qr = Q.recs[t];
+            const uint2 qr = Q.vxyz[t];
             const int qx = (int)(qr.x & 0xffffu), qy = (int)(qr.x >> 16), qz = (int)qr.y;
             const int lx = qx & 31, ly = (qy & 7) + 2, lz = (qz & 7) + 2;
-            uint2 own = win[lz * kVxRegY + ly];
-            const int bit = 16 + lx;
-            if (bit < 32) own.x &= ~(1u << bit); else own.y &= ~(1u << (bit - 32));
-            int dd, du;
-            vx_row_dists(own, lx, dd, du);
-            const int dx = dd < du ? dd : du;
-            uint32_t bd2 = (uint32_t)(dx * dx), nb = kVxNone, rows = 0;
-            vx_rows_ring1(win, lx, ly, lz, nb, rows);
-            bd2 = nb < bd2 ? nb : bd2;
-            bool done = bd2 < 4u;
-            if (!done) { vx_rows_outer(win, lx, ly, lz, bd2, rows); done = bd2 < 9u; }
-            if (done) vself[t] = bd2;
+            uint32_t bd2 = vx_self27(vx_nb27(W.win, lx, ly, lz));
+            if (bd2 == kVxNone) bd2 = vx_self125(W.win, lx, ly, lz);
+            if (bd2 < 9u) vself[t] = bd2;
         }
     }
     int64_t undecided = 0;
