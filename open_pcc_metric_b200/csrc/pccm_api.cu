@@ -33,11 +33,10 @@ struct pccm_ctx {
     cudaStream_t copy_stream = nullptr;   // host->device copies of attributes that are only needed by the query epilogue
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_sync = nullptr;         // host waits that must not cover work enqueued after them
-    // per-cloud pinned statistics buffers and events are recycled: cudaMallocHost / cudaFreeHost are
-    // synchronous OS-level calls (tens of microseconds) and a cloud lives for one evaluation
-    std::vector<void*> stats_pool;
+    // per-cloud events and pinned colour-flag words are recycled: creating them costs tens of microseconds
+    // and a cloud lives for one evaluation
     std::vector<cudaEvent_t> cloud_events;
-    size_t stats_pool_bytes = 0;
+    std::vector<int> flag_slots;          // free 4-byte words of ctx->pinned (kFlagPinnedOffset)
     std::string err;
     int profiling = 0;
     pccm_timings tm{};
@@ -52,6 +51,7 @@ struct pccm_ctx {
     void* pinned = nullptr;
     void* dscratch = nullptr;
     static constexpr size_t kScratch = 1 << 16;
+    static constexpr size_t kPinned = 3 << 16;      // results, flags, plan read-back + two statistics slots
     int sm_count = 148;
     int cell_override_shift = -1;   // debugging: PCCM_CELL_SHIFT
     double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
@@ -61,6 +61,7 @@ struct pccm_ctx {
     bool use_vox = true;            // KInt pairs: occupancy-brick index + bit-scan query (PCCM_VOX=0: pencil path only)
     bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
     int vx_search_blocks = 10;      // resident blocks per SM of the persistent brick search kernel (PCCM_VX_BLOCKS)
+    int mark_sample = 32;           // the brick directory is marked by 1 / mark_sample of the points first (PCCM_MARK_SAMPLE, 0 = one pass)
 };
 
 static thread_local std::string g_err;
@@ -148,12 +149,13 @@ struct pccm_cloud {
     int raw_rgb_dtype = PCCM_F64;
     int64_t raw_rgb_stride = 0;
     // statistics
-    StatsPartial* d_stats = nullptr;
-    StatsPartial* h_stats = nullptr;  // pinned
-    DevStats* d_dev = nullptr;        // behind d_stats: the same statistics as one device record (brick-index planning)
+    StatsPartial* d_stats = nullptr;  // one device block: [stats_blocks] partials, [1] their fold (what the host reads, on demand),
+                                      // the colour flag, the DevStats record and the packed coordinates
+    DevStats* d_dev = nullptr;        // the same statistics as one integer record (brick-index planning on the device)
     uint2* packed = nullptr;          // {x | y << 16, z} per point, written by the statistics pass (integer-valued clouds)
+    bool stats_fetched = false;       // the folded record is (being) copied to the pinned slot stats_slot
+    int stats_slot = 0;
     int stats_blocks = 0;
-    cudaEvent_t stats_done = nullptr;
     bool stats_ready = false;
     double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
     int data_kind = PCCM_KIND_F64;
@@ -162,7 +164,9 @@ struct pccm_cloud {
     cudaEvent_t rgb_ready = nullptr;
     bool rgb_pending = false;
     uint32_t* d_rgbflag = nullptr;   // behind d_stats
-    uint32_t* h_rgbflag = nullptr;   // behind h_stats (pinned)
+    uint32_t* h_rgbflag = nullptr;   // pinned word (ctx->flag_slots)
+    int flag_slot = -1;
+    bool rgb_unclassified = false;   // float64 colours on the device that nobody has classified yet (done on first need)
     bool vox_rgb_done = false;       // brick index: colours packed into their original-order array
     bool rgb_spec = false;           // rgb_u8 was packed before the k/255 classification was known (d_rgbflag is read at the next settle point)
     bool vox_rgb_in_recs = false;    // brick index: the voxel records carry the representative's colour
@@ -195,9 +199,9 @@ struct SharedIndex {
 };
 
 struct SharedVox {
-    uint32_t *dirbits = nullptr, *dirpre = nullptr, *dirsums = nullptr, *masks = nullptr, *rowbase = nullptr, *bricksums = nullptr,
-             *prank = nullptr;
-    uint2 *vxyz = nullptr, *vkey = nullptr;
+    uint32_t *dirbits = nullptr, *dirpre = nullptr, *dirsums = nullptr, *bricksums = nullptr, *prank = nullptr;
+    uint2 *rows = nullptr, *vxyz = nullptr, *vkey = nullptr;
+    unsigned char* arena = nullptr;  // ONE device allocation for all of the above (+ the plan)
     VoxPlan* dplan = nullptr;        // device: written by the build kernels, read by every brick kernel
     VoxPlan hplan{};                 // host copy, valid once the build has been settled
     bool pending = false;            // the build is enqueued but the host has not looked at its outcome yet
@@ -211,8 +215,7 @@ struct SharedVox {
 };
 
 static void free_vox(pccm_ctx* ctx, SharedVox* v) {
-    dfree(ctx, v->dirbits); dfree(ctx, v->dirpre); dfree(ctx, v->dirsums); dfree(ctx, v->masks); dfree(ctx, v->rowbase);
-    dfree(ctx, v->bricksums); dfree(ctx, v->prank); dfree(ctx, v->vxyz); dfree(ctx, v->vkey); dfree(ctx, v->dplan);
+    dfree(ctx, v->arena);          // every array of the index is a slice of this one block
     delete v;
 }
 static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
@@ -238,26 +241,42 @@ static size_t dtype_size(int dt) {
     return 0;
 }
 
-static int ensure_stats(pccm_ctx* ctx, pccm_cloud* c) {
+static constexpr size_t kStatsPinnedOffset = 65536;   // bytes into ctx->pinned: two slots for the per-block statistics partials of a cloud
+static constexpr size_t kStatsSlotBytes = 65536;
+static constexpr size_t kFlagPinnedOffset = 20480;    // ... : 1024 colour-flag words
+
+// the statistics partials of a cloud travel to the host only when host code needs them
+static int stats_fetch(pccm_ctx* ctx, pccm_cloud* c, int slot) {
+    if (c->stats_ready || c->n == 0) return PCCM_OK;
+    char* h = static_cast<char*>(ctx->pinned) + kStatsPinnedOffset + (size_t)slot * kStatsSlotBytes;
+    CK(cudaMemcpyAsync(h, c->d_stats, sizeof(StatsPartial) * (size_t)c->stats_blocks, cudaMemcpyDeviceToHost, ctx->stream));
+    c->stats_fetched = true;
+    c->stats_slot = slot;
+    return PCCM_OK;
+}
+static int stats_adopt(pccm_ctx* ctx, pccm_cloud* c) {      // after the stream has been synchronised behind stats_fetch
     if (c->stats_ready) return PCCM_OK;
-    if (c->n == 0) {
-        c->data_kind = PCCM_KIND_INT;
-        c->stats_ready = true;
-        return PCCM_OK;
-    }
-    CK(cudaEventSynchronize(c->stats_done));
-    bool not_int = false, not_f32 = false, not_fin = false, rgb_bad = false;
+    if (c->n == 0) { c->data_kind = PCCM_KIND_INT; c->stats_ready = true; return PCCM_OK; }
+    const StatsPartial* h = reinterpret_cast<const StatsPartial*>(static_cast<const char*>(ctx->pinned) + kStatsPinnedOffset + (size_t)c->stats_slot * kStatsSlotBytes);
+    c->stats_fetched = false;
+    bool not_int = false, not_f32 = false, not_fin = false;
     for (int a = 0; a < 3; ++a) { c->mn[a] = INFINITY; c->mx[a] = -INFINITY; }
     for (int b = 0; b < c->stats_blocks; ++b) {
-        const StatsPartial& p = c->h_stats[b];
+        const StatsPartial& p = h[b];
         for (int a = 0; a < 3; ++a) { c->mn[a] = std::min(c->mn[a], p.mn[a]); c->mx[a] = std::max(c->mx[a], p.mx[a]); }
-        not_int |= p.not_int != 0; not_f32 |= p.not_f32 != 0; not_fin |= p.not_finite != 0; rgb_bad |= p.rgb_not_u8 != 0;
+        not_int |= p.not_int != 0; not_f32 |= p.not_f32 != 0; not_fin |= p.not_finite != 0;
     }
     if (not_fin) return fail(ctx, PCCM_ERR_NONFINITE, "cloud has NaN or Inf coordinates");
     c->data_kind = !not_int ? PCCM_KIND_INT : (!not_f32 ? PCCM_KIND_F32 : PCCM_KIND_F64);
-    c->rgb_u8_ok = !rgb_bad;
     c->stats_ready = true;
     return PCCM_OK;
+}
+static int ensure_stats(pccm_ctx* ctx, pccm_cloud* c) {
+    if (c->stats_ready) return PCCM_OK;
+    const int rc = stats_fetch(ctx, c, 0);
+    if (rc) return rc;
+    if (c->n) CK(cudaStreamSynchronize(ctx->stream));
+    return stats_adopt(ctx, c);
 }
 
 // order the context stream after an in-flight normal upload (no-op when there is none)
@@ -275,7 +294,20 @@ static void wait_normals(pccm_ctx* ctx, pccm_cloud* c) {
 // colours in flight on the copy stream: wait (host: the classification decides the device format;
 // context stream: later kernels read the uploaded rows)
 static int ensure_colors(pccm_ctx* ctx, pccm_cloud* c) {
-    if (!c->has_colors || !c->rgb_pending) return PCCM_OK;
+    if (!c->has_colors) return PCCM_OK;
+    if (c->rgb_unclassified) {       // float64 colours handed over on the device: classify now
+            uint32_t* h = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kFlagPinnedOffset + 4096);
+        CK(cudaMemsetAsync(c->d_rgbflag, 0, sizeof(uint32_t), ctx->stream));
+        rgb_classify_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_stride, c->n, c->d_rgbflag);
+        ctx->tm.total_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h, c->d_rgbflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        c->rgb_u8_ok = *h == 0u;
+        c->rgb_unclassified = false;
+        return PCCM_OK;
+    }
+    if (!c->rgb_pending) return PCCM_OK;
     CK(cudaEventSynchronize(c->rgb_ready));
     CK(cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0));
     c->rgb_u8_ok = c->raw_rgb_dtype == PCCM_U8 || c->n == 0 || (c->h_rgbflag && *c->h_rgbflag == 0u);
@@ -283,8 +315,9 @@ static int ensure_colors(pccm_ctx* ctx, pccm_cloud* c) {
     return PCCM_OK;
 }
 
-// Colours of a cloud: upload (HOST) and classify (every channel == k / 255 ?) on the copy stream,
-// so that the statistics pass, the index build and the search never wait for them.
+// Colours of a cloud: HOST arrays are uploaded and classified (every channel == k / 255 ?) on the copy stream,
+// so that the statistics pass, the index build and the search never wait for them; DEVICE arrays are used where
+// they are (8-bit ones need nothing at all, float64 ones are classified when somebody needs to know).
 static int attach_colors(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, int dtype, int64_t stride, int mem_kind) {
     if (dtype != PCCM_F64 && dtype != PCCM_U8) return fail(ctx, PCCM_ERR_INVALID, "rgb must be F64 or U8");
     if (c->has_colors) return fail(ctx, PCCM_ERR_STATE, "cloud already has colours");
@@ -297,25 +330,33 @@ static int attach_colors(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, int dtyp
     c->raw_rgb_stride = stride;
     c->has_colors = true;
     if (c->n == 0) { c->rgb_u8_ok = true; return PCCM_OK; }
+    if (mem_kind == PCCM_DEVICE) {
+        c->raw_rgb = rgb;
+        c->rgb_u8_ok = dtype == PCCM_U8;
+        c->rgb_unclassified = dtype == PCCM_F64;
+        return PCCM_OK;
+    }
     cudaStream_t s = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
     if (!c->rgb_ready) {
         if (!ctx->cloud_events.empty()) { c->rgb_ready = ctx->cloud_events.back(); ctx->cloud_events.pop_back(); }
         else CK(cudaEventCreateWithFlags(&c->rgb_ready, cudaEventDisableTiming));
     }
+    if (dtype == PCCM_F64 && c->flag_slot < 0) {
+        if (ctx->flag_slots.empty()) return fail(ctx, PCCM_ERR_STATE, "too many live clouds with colours in flight");
+        c->flag_slot = ctx->flag_slots.back();
+        ctx->flag_slots.pop_back();
+        c->h_rgbflag = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kFlagPinnedOffset) + c->flag_slot;
+    }
     unsigned char* d = nullptr;
     const size_t bytes = (size_t)c->n * (size_t)stride;
-    if (mem_kind == PCCM_HOST) CK(dalloc(ctx, &d, bytes));
-    if (s != ctx->stream) {      // after the allocation above / after the caller's device data
+    CK(dalloc(ctx, &d, bytes));
+    if (s != ctx->stream) {      // after the allocation above
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CK(cudaStreamWaitEvent(s, ctx->ev_fork, 0));
     }
-    if (mem_kind == PCCM_HOST) {
-        CK(cudaMemcpyAsync(d, rgb, bytes, cudaMemcpyHostToDevice, s));
-        c->raw_rgb = d;
-        c->raw_rgb_owned = d;
-    } else {
-        c->raw_rgb = rgb;
-    }
+    CK(cudaMemcpyAsync(d, rgb, bytes, cudaMemcpyHostToDevice, s));
+    c->raw_rgb = d;
+    c->raw_rgb_owned = d;
     if (dtype == PCCM_F64) {
         CK(cudaMemsetAsync(c->d_rgbflag, 0, sizeof(uint32_t), s));
         rgb_classify_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(c->raw_rgb, stride, c->n, c->d_rgbflag);
@@ -328,6 +369,16 @@ static int attach_colors(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, int dtyp
     return PCCM_OK;
 }
 
+static void launch_pack_u8(pccm_ctx* ctx, const pccm_cloud* c, uchar4* out) {
+    const int threads = 256;
+    if (c->raw_rgb_dtype == PCCM_U8 && c->raw_rgb_stride == 3 && (reinterpret_cast<uintptr_t>(c->raw_rgb) & 3u) == 0) {
+        const int64_t groups = (c->n + 3) / 4;
+        pack_rgb_u8x4_kernel<<<(int)((groups + threads - 1) / threads), threads, 0, ctx->stream>>>(static_cast<const uint32_t*>(c->raw_rgb), c->n, out);
+    } else {
+        pack_rgb_u8_kernel<<<(int)((c->n + threads - 1) / threads), threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->n, out);
+    }
+}
+
 // colours: uchar4 when every channel is k/255, else packed float64
 static int finish_colors(pccm_ctx* ctx, pccm_cloud* c) {
     { const int rc0 = ensure_colors(ctx, c); if (rc0) return rc0; }
@@ -335,8 +386,8 @@ static int finish_colors(pccm_ctx* ctx, pccm_cloud* c) {
     const int threads = 256;
     const int blocks = (int)((c->n + threads - 1) / threads);
     if (c->raw_rgb_dtype == PCCM_U8 || c->rgb_u8_ok) {
-        CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n));
-        pack_rgb_u8_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->n, c->rgb_u8);
+        CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n + 4));
+        launch_pack_u8(ctx, c, c->rgb_u8);
     } else {
         CK(dalloc(ctx, &c->rgb_f64, (size_t)c->n * 3));
         pack_f64x3_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, PCCM_F64, c->raw_rgb_stride, c->n, c->rgb_f64);
@@ -408,8 +459,8 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-    ctx->stats_pool_bytes = sizeof(StatsPartial) * (size_t)ctx->sm_count * 4;
-    if (cudaMallocHost(&ctx->pinned, pccm_ctx::kScratch) != cudaSuccess || cudaMalloc(&ctx->dscratch, pccm_ctx::kScratch) != cudaSuccess) {
+    for (int k = 1023; k >= 0; --k) ctx->flag_slots.push_back(k);
+    if (cudaMallocHost(&ctx->pinned, pccm_ctx::kPinned) != cudaSuccess || cudaMalloc(&ctx->dscratch, pccm_ctx::kScratch) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, PCCM_ERR_CUDA, "scratch allocation failed");
     }
@@ -425,6 +476,7 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_VOX")) ctx->use_vox = atoi(s) != 0;
     if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
+    if (const char* s = getenv("PCCM_MARK_SAMPLE")) ctx->mark_sample = std::max(0, atoi(s));
     if (const char* s = getenv("PCCM_NORMALS_COUNTING")) ctx->normals_counting = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
@@ -438,7 +490,6 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     resolve_timers(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     for (auto e : ctx->cloud_events) cudaEventDestroy(e);
-    for (auto p : ctx->stats_pool) cudaFreeHost(p);
     for (int d = 0; d < 2; ++d) { dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]); }
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->pinned);
@@ -487,13 +538,13 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
     if (c->nrm_ready) cudaEventDestroy(c->nrm_ready);
     if (c->rgb_pending) {
         cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0);   // the frees below are ordered on the context stream
-        cudaEventSynchronize(c->rgb_ready);                  // ... and the pinned flag behind h_stats goes back to the pool
+        cudaEventSynchronize(c->rgb_ready);                  // ... and the pinned flag word goes back to the pool
     }
     if (c->rgb_ready) ctx->cloud_events.push_back(c->rgb_ready);
+    if (c->flag_slot >= 0) ctx->flag_slots.push_back(c->flag_slot);
     dfree(ctx, c->raw_owned);
     dfree(ctx, c->raw_rgb_owned);
-    dfree(ctx, c->d_stats);
-    dfree(ctx, c->packed);
+    dfree(ctx, c->d_stats);              // (the packed coordinates live in the same block)
     dfree(ctx, c->rgb_u8);
     dfree(ctx, c->rgb_f64);
     if (!c->normals_borrowed) dfree(ctx, c->normals);
@@ -508,11 +559,7 @@ extern "C" int pccm_cloud_destroy(pccm_ctx* ctx, pccm_cloud* c) {
         dfree(ctx, c->recs);
         dfree(ctx, c->row_start);
     }
-    if (c->h_stats) {
-        if (c->stats_done) cudaEventSynchronize(c->stats_done);   // the copy into the buffer has landed
-        ctx->stats_pool.push_back(c->h_stats);
-    }
-    if (c->stats_done) ctx->cloud_events.push_back(c->stats_done);
+    if (c->stats_fetched) cudaStreamSynchronize(ctx->stream);   // (a copy into the pinned slot is in flight: rare)
     delete c;
     return PCCM_OK;
 }
@@ -610,35 +657,24 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
     if (n) {
         StageTimer t(ctx, &ctx->tm.stats_ms);
         c->stats_blocks = (int)std::min<int64_t>((n + kStatsThreads - 1) / kStatsThreads, (int64_t)ctx->sm_count * 4);
-        cudaError_t e = dalloc(ctx, &c->d_stats, (size_t)c->stats_blocks + 2);
-        // integer-capable inputs also get their packed 8-byte coordinates (what the brick index is built from)
-        const bool want_packed = ctx->use_vox && xyz_dtype != PCCM_F32 && n <= 0x7fffffffLL;
-        if (e == cudaSuccess && want_packed) e = dalloc(ctx, &c->packed, (size_t)n);
+        // ONE device block per cloud: partials, their fold, the colour flag, the DevStats record and -- for integer-capable
+        // inputs -- the packed 8-byte coordinates the brick index is built from
+        const bool want_packed = ctx->use_vox && xyz_dtype != PCCM_F32;
+        const size_t head = ((size_t)c->stats_blocks + 2) * sizeof(StatsPartial);
+        unsigned char* blockp = nullptr;
+        cudaError_t e = dalloc(ctx, &blockp, head + (want_packed ? (size_t)n * sizeof(uint2) : 0));
         if (e == cudaSuccess) {
-            if (!ctx->stats_pool.empty()) {
-                c->h_stats = static_cast<StatsPartial*>(ctx->stats_pool.back());
-                ctx->stats_pool.pop_back();
-            } else {
-                e = cudaMallocHost(reinterpret_cast<void**>(&c->h_stats), ctx->stats_pool_bytes + sizeof(StatsPartial));
-            }
-        }
-        if (e == cudaSuccess) {
+            c->d_stats = reinterpret_cast<StatsPartial*>(blockp);
             c->d_rgbflag = reinterpret_cast<uint32_t*>(c->d_stats + c->stats_blocks);
             c->d_dev = reinterpret_cast<DevStats*>(c->d_stats + c->stats_blocks + 1);
-            c->h_rgbflag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_stats) + ctx->stats_pool_bytes);
+            if (want_packed) c->packed = reinterpret_cast<uint2*>(blockp + head);
             e = cudaMemsetAsync(c->d_stats + c->stats_blocks, 0, 2 * sizeof(StatsPartial), ctx->stream);
-        }
-        if (e == cudaSuccess) {
-            if (!ctx->cloud_events.empty()) { c->stats_done = ctx->cloud_events.back(); ctx->cloud_events.pop_back(); }
-            else e = cudaEventCreateWithFlags(&c->stats_done, cudaEventDisableTiming);
         }
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
         stats_kernel<<<c->stats_blocks, kStatsThreads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
-                                                                         nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev);   // colours are classified on the copy stream
+                                                                         nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev);   // colours are classified apart
         ctx->tm.total_launches++;
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsPartial) * c->stats_blocks, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(c->stats_done, ctx->stream);
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats launch: %s", cudaGetErrorString(e)); }
     }
     {   // attributes: needed by the epilogue only -> copy stream, behind the coordinates
@@ -935,7 +971,6 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
     dfree(ctx, c->raw_owned);
     c->raw_owned = nullptr;
     c->raw_xyz = nullptr;
-    dfree(ctx, c->packed);
     c->packed = nullptr;
     c->grid = g;
     c->index_kind = kind;
@@ -1104,15 +1139,16 @@ static int finish_colors(pccm_ctx* ctx, pccm_cloud* c);
 static int colors_u8_async(pccm_ctx* ctx, pccm_cloud* c) {
     if (!c->has_colors || c->rgb_u8 || c->rgb_f64 || c->n == 0) return PCCM_OK;
     if (c->rgb_pending && cudaEventQuery(c->rgb_ready) == cudaSuccess) { const int rc = ensure_colors(ctx, c); if (rc) return rc; }
-    if (!c->rgb_pending) return finish_colors(ctx, c);        // classification known: the ordinary path
-    CK(cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0));    // device-side wait for the upload + classification
-    CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n));
+    if (!c->rgb_pending && !c->rgb_unclassified) return finish_colors(ctx, c);        // classification known: the ordinary path
+    if (c->rgb_pending) CK(cudaStreamWaitEvent(ctx->stream, c->rgb_ready, 0));        // device-side wait for the upload + classification
+    CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n + 4));
     const int threads = 256, blocks = (int)((c->n + threads - 1) / threads);
-    if (c->raw_rgb_dtype == PCCM_U8) pack_rgb_u8_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, PCCM_U8, c->raw_rgb_stride, c->n, c->rgb_u8);
+    if (c->raw_rgb_dtype == PCCM_U8) launch_pack_u8(ctx, c, c->rgb_u8);
     else pack_rgb_u8_check_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_stride, c->n, c->rgb_u8, c->d_rgbflag);
     ctx->tm.total_launches++;
     CK(cudaGetLastError());
     c->rgb_spec = true;                                        // the raw colours stay until the flag has been read
+    c->rgb_unclassified = false;
     return PCCM_OK;
 }
 
@@ -1131,20 +1167,34 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     } while (0)
     const uint32_t ndirblocks = cap_dirw / kVxDirChunk + 1;
     const uint32_t nbrickchunks = cap_blk / kVxBrickChunk + 2;
-    uint32_t* pslot = nullptr;
-    CKV(dalloc(ctx, &v->dirbits, (size_t)cap_dirw));
-    CKV(dalloc(ctx, &v->dirpre, (size_t)cap_dirw + 1));
-    CKV(dalloc(ctx, &v->dirsums, (size_t)ndirblocks));
-    CKV(dalloc(ctx, &v->masks, (size_t)cap_blk * kVxRows));
-    CKV(dalloc(ctx, &v->rowbase, (size_t)cap_blk * kVxRows));
-    CKV(dalloc(ctx, &v->bricksums, (size_t)nbrickchunks));
-    CKV(dalloc(ctx, &v->vxyz, (size_t)n_total));
-    CKV(dalloc(ctx, &v->vkey, (size_t)n_total));
-    CKV(dalloc(ctx, &v->prank, (size_t)n_total));
-    CKV(dalloc(ctx, &v->dplan, 1));
-    CKV(dalloc(ctx, &pslot, (size_t)n_total));
+    // one allocation, sliced (a stream-ordered allocation costs a microsecond or two of host time, and the host is what
+    // feeds the GPU here); the scratch slot list lives at the end and is simply never read again
+    size_t off = 0;
+    auto slice = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_plan = slice(sizeof(VoxPlan));
+    const size_t o_dirbits = slice((size_t)cap_dirw * 4), o_dirpre = slice(((size_t)cap_dirw + 1) * 4), o_dirsums = slice((size_t)ndirblocks * 4);
+    const size_t o_dirbytes = slice(PCCM_DIR_BYTES ? (size_t)cap_dirw * 32 : 0);
+    const size_t o_rows = slice((size_t)cap_blk * kVxRows * 8);
+    const size_t o_bricksums = slice((size_t)nbrickchunks * 4);
+    const size_t o_vxyz = slice((size_t)n_total * 8), o_vkey = slice((size_t)n_total * 8), o_prank = slice((size_t)n_total * 4);
+    const size_t o_pslot = slice((size_t)n_total * 4);
+    CKV(dalloc(ctx, &v->arena, off));
+    v->dplan = reinterpret_cast<VoxPlan*>(v->arena + o_plan);
+    v->dirbits = reinterpret_cast<uint32_t*>(v->arena + o_dirbits);
+    v->dirpre = reinterpret_cast<uint32_t*>(v->arena + o_dirpre);
+    v->dirsums = reinterpret_cast<uint32_t*>(v->arena + o_dirsums);
+    v->rows = reinterpret_cast<uint2*>(v->arena + o_rows);
+    v->bricksums = reinterpret_cast<uint32_t*>(v->arena + o_bricksums);
+    v->vxyz = reinterpret_cast<uint2*>(v->arena + o_vxyz);
+    v->vkey = reinterpret_cast<uint2*>(v->arena + o_vkey);
+    v->prank = reinterpret_cast<uint32_t*>(v->arena + o_prank);
+    uint32_t* pslot = reinterpret_cast<uint32_t*>(v->arena + o_pslot);
+#if PCCM_DIR_BYTES
+    CKV(cudaMemsetAsync(v->arena + o_dirbytes, 0, (size_t)cap_dirw * 32, ctx->stream));
+#else
+    (void)o_dirbytes;
     CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
-    CKV(cudaMemsetAsync(v->vkey, 0xff, (size_t)n_total * sizeof(uint2), ctx->stream));
+#endif
     VoxBuildArgs A{};
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
@@ -1155,19 +1205,30 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
         // from the colour arrays by the epilogue -- the build never waits for them
         A.rgb[c] = nullptr;
         p->vox_rgb_in_recs = false;
-        if (p->has_colors && !p->rgb_f64 && (!p->rgb_pending || cudaEventQuery(p->rgb_ready) == cudaSuccess || p->raw_rgb_owned == nullptr)) {
+        if (p->has_colors && !p->rgb_f64 && (!p->rgb_pending || cudaEventQuery(p->rgb_ready) == cudaSuccess)) {
             const int rcc = colors_u8_async(ctx, p);
-            if (rcc) { dfree(ctx, pslot); return bail(rcc); }
+            if (rcc) return bail(rcc);
             if (p->rgb_u8) { A.rgb[c] = p->rgb_u8; p->vox_rgb_in_recs = true; }
         }
     }
     A.cap_dirw = cap_dirw; A.cap_blk = cap_blk;
-    A.dirbits = v->dirbits; A.dirpre = v->dirpre; A.dirsums = v->dirsums; A.masks = v->masks; A.rowbase = v->rowbase;
+    A.dirbytes = v->arena + o_dirbytes;
+    A.dirbits = v->dirbits; A.dirpre = v->dirpre; A.dirsums = v->dirsums; A.rows = v->rows;
     A.bricksums = v->bricksums; A.vxyz = v->vxyz; A.vkey = v->vkey; A.prank = v->prank; A.pslot = pslot; A.plan = v->dplan;
     const int threads = 256;
     const int blocks_ilp = (int)(((n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
-    const int brick_grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count * 4u, nbrickchunks);
-    vx_mark_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    const int brick_grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count * 8u, nbrickchunks);
+    {
+        const uint32_t per = (n_total + kVxIlp - 1) / kVxIlp;
+        const uint32_t sample = ctx->mark_sample > 0 && per > 65536u ? per / (uint32_t)ctx->mark_sample : 0u;
+        if (sample) {
+            A.mark_lo = 0; A.mark_hi = sample;
+            vx_mark_kernel<<<(sample + threads - 1) / threads, threads, 0, ctx->stream>>>(A);
+            ctx->tm.total_launches++;
+        }
+        A.mark_lo = sample; A.mark_hi = per;
+        vx_mark_kernel<<<(per - sample + threads - 1) / threads, threads, 0, ctx->stream>>>(A);
+    }
     vx_dirsum_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
     vx_dirscan_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
     vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
@@ -1176,7 +1237,6 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
     ctx->tm.total_launches += 7;
     CKV(cudaGetLastError());
-    dfree(ctx, pslot);
 #undef CKV
     v->pending = true;
     v->refs = 2;
@@ -1199,6 +1259,7 @@ static int vox_fetch(pccm_ctx* ctx, SharedVox* v) {
     CK(cudaMemcpyAsync(pin, v->dplan, sizeof(VoxPlan), cudaMemcpyDeviceToHost, ctx->stream));
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = v->owner[c];
+        if (p && v->pending) { const int rc = stats_fetch(ctx, p, c); if (rc) return rc; }
         uint32_t* flag = reinterpret_cast<uint32_t*>(pin + sizeof(VoxPlan)) + c;
         *flag = 0;
         if (p && p->rgb_spec) CK(cudaMemcpyAsync(flag, p->d_rgbflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1240,14 +1301,18 @@ static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo) {
         }
     }
     if (rc || !was_pending) return rc;
-    for (int c = 0; c < 2 && !rc; ++c) if (cl[c]) rc = ensure_stats(ctx, cl[c]);
-    if (rc) return rc;
+    for (int c = 0; c < 2 && !rc; ++c) if (cl[c]) rc = cl[c]->stats_fetched ? stats_adopt(ctx, cl[c]) : ensure_stats(ctx, cl[c]);
+    if (rc) {                                    // (NaN / Inf coordinates): no index
+        for (int c = 0; c < 2; ++c)
+            if (cl[c]) { release_vox(ctx, cl[c]); cl[c]->index_kind = -1; }
+        return rc;
+    }
     const uint32_t st = v->hplan.status;
     if (st == 0) {
         for (int c = 0; c < 2; ++c) {
             pccm_cloud* p = cl[c];
             if (!p) continue;
-            dfree(ctx, p->packed); p->packed = nullptr;
+            p->packed = nullptr;
             dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // vxyz holds every voxel, prank every point
         }
         return PCCM_OK;
@@ -1364,16 +1429,13 @@ extern "C" int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b
                 n_pair <= 0x7fffffffull && (force_kind == PCCM_KIND_AUTO || force_kind == PCCM_KIND_INT);
     if (spec && a->stats_ready && b->stats_ready && std::max(a->data_kind, b->data_kind) != PCCM_KIND_INT) spec = false;
     if (spec) {
-        // statistics that have already landed decide at once (no wait); otherwise the build is enqueued on the
-        // assumption that both clouds are voxelised -- the stream's statistics kernels say so on the device
-        for (pccm_cloud* c : {a, b})
-            if (!c->stats_ready && cudaEventQuery(c->stats_done) == cudaSuccess) { const int rc = ensure_stats(ctx, c); if (rc) return rc; }
-        if (a->stats_ready && b->stats_ready && std::max(a->data_kind, b->data_kind) != PCCM_KIND_INT) spec = false;
+        // (statistics the host already knows decide at once; otherwise the build is enqueued on the assumption that
+        // both clouds are voxelised -- the statistics kernels of the stream say so on the device)
     }
     if (spec) {
         pccm_cloud* cl[2] = {a, b};
         const uint32_t n_total = (uint32_t)n_pair;
-        const uint32_t cap_dirw = std::min(kVoxDefaultDirWords, std::max(1u << 12, pow2_ceil(n_total / 2)));
+        const uint32_t cap_dirw = std::min(kVoxDefaultDirWords, std::max(1u << 12, pow2_ceil(n_total / (PCCM_DIR_BYTES ? 8 : 2))));
         const uint32_t cap_blk = n_total <= (1u << 16) ? n_total + 2 : std::max(1u << 16, n_total / 8) + 2;
         return vox_enqueue(ctx, cl, cell_size, force_kind, cap_dirw, cap_blk);
     }
@@ -1427,7 +1489,7 @@ static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, doubl
         R.rgb[c] = p->raw_rgb; R.rgb_dtype[c] = p->raw_rgb_dtype; R.rgb_stride[c] = p->raw_rgb_stride;
         if (!R.rgb_in_rec[c]) { rc = finish_colors(ctx, p); if (rc) return rc; }
     }
-    for (int c = 0; c < 2; ++c) { dfree(ctx, cl[c]->packed); cl[c]->packed = nullptr; }
+    for (int c = 0; c < 2; ++c) cl[c]->packed = nullptr;
     if (kind == PCCM_KIND_INT) {
         if (ctx->use_rowsort) return build_pair_rowsort(ctx, cl, R);
         if (rowbits + xbits + 1 <= 32) return build_pair_impl<uint32_t, KIND_INT>(ctx, cl, R, xbits, rowbits);
@@ -1503,10 +1565,8 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
 // pencil search in a second round.  Results land where launch_query puts them.
 struct VoxScratch {           // freed on every exit path
     pccm_ctx* ctx;
-    uint32_t* todo = nullptr;
-    uint4* vres = nullptr;
-    BlockPartial* partials = nullptr;
-    ~VoxScratch() { dfree(ctx, todo); dfree(ctx, vres); dfree(ctx, partials); }
+    unsigned char* block = nullptr;
+    ~VoxScratch() { dfree(ctx, block); }
 };
 
 static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cloud* sc[2], QueryParams& Q, int rank, int world, bool* redo) {
@@ -1521,10 +1581,19 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     P.color_scale = Q.color_scale;
     const double* lut = reinterpret_cast<const double*>(static_cast<char*>(ctx->dscratch) + kLutOffset);
     const uint32_t n_total = v->n[0] + v->n[1];
-    VoxScratch sx{ctx};             // todo: [0..7] counters (undecided, far per direction, brick ticket), then the four lists
-    CK(dalloc(ctx, &sx.todo, 2 * (size_t)n_total + 8));
-    CK(dalloc(ctx, &sx.vres, (size_t)n_total));
-    CK(cudaMemsetAsync(sx.todo, 0, 8 * sizeof(uint32_t), ctx->stream));
+    // one scratch block: [0..7] counters (undecided, far per direction, brick ticket), the four voxel lists, the voxel
+    // answers, the reduction records
+    uint32_t max_tiles = 0;
+    for (int d = 0; d < ndirs; ++d) max_tiles = std::max(max_tiles, (v->n[qc[d]->vox_id] + kVxEpiTile - 1) / kVxEpiTile);
+    const size_t todo_bytes = ((2 * (size_t)n_total + 8) * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t vres_bytes = ((size_t)n_total * sizeof(uint4) + 255) & ~(size_t)255;
+    const size_t part_bytes = ((size_t)max_tiles * 4 + 1) * sizeof(BlockPartial);
+    VoxScratch sx{ctx};
+    CK(dalloc(ctx, &sx.block, todo_bytes + vres_bytes + part_bytes));
+    uint32_t* todo = reinterpret_cast<uint32_t*>(sx.block);
+    uint4* vres = reinterpret_cast<uint4*>(sx.block + todo_bytes);
+    BlockPartial* partials = reinterpret_cast<BlockPartial*>(sx.block + todo_bytes + vres_bytes);
+    CK(cudaMemsetAsync(todo, 0, 8 * sizeof(uint32_t), ctx->stream));
     uint32_t rec_stride = 0, ntiles = 0;
     for (int d = 0; d < ndirs; ++d) {
         VxDir& D = P.dir[d];
@@ -1540,15 +1609,14 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         D.qa.lut255 = D.sa.lut255 = lut;
         D.flags = Q.dir[d].flags;
         D.idx_out = Q.dir[d].idx_out; D.d2_out = Q.dir[d].d2_out;
-        D.todo = sx.todo + 8 + (d ? (size_t)v->n[P.dir[0].qc] : 0);
-        D.far = sx.todo + 8 + n_total + (d ? (size_t)v->n[P.dir[0].qc] : 0);
+        D.todo = todo + 8 + (d ? (size_t)v->n[P.dir[0].qc] : 0);
+        D.far = todo + 8 + n_total + (d ? (size_t)v->n[P.dir[0].qc] : 0);
         D.ntiles = (D.nq + kVxEpiTile - 1) / kVxEpiTile;
         rec_stride = std::max(rec_stride, 2u * D.ntiles);
         ntiles += D.ntiles;
     }
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
-    CK(dalloc(ctx, &sx.partials, (size_t)rec_stride * 2 + 1));
-    P.partials = sx.partials; P.vres = sx.vres; P.counters = sx.todo;
+    P.partials = partials; P.vres = vres; P.counters = todo;
     {
         StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage
         {
@@ -1569,7 +1637,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     CK(cudaGetLastError());
     // common fold: same record layout as the pencil path
     Q.rec_stride = rec_stride;
-    Q.partials = sx.partials;
+    Q.partials = partials;
     Q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->dscratch) + kTicketOffset);
     Q.out = static_cast<BlockPartial*>(ctx->dscratch);
     Q.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);
@@ -1585,7 +1653,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     };
     int rc = fold(1);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(hcnt, sx.todo, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hcnt, todo, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     rc = vox_fetch(ctx, v);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));          // the one host wait of build + evaluation

@@ -65,11 +65,14 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
         for (int a = 0; a < 3; ++a) {
             double v = load_coord(xyz, dtype, stride, i, a);
             v3[a] = v;
-            if (!isfinite(v)) not_fin = 1;
             mn[a] = fmin(mn[a], v);
             mx[a] = fmax(mx[a], v);
-            if (!(v >= 0.0 && v <= 32767.0 && v == floor(v))) not_int = 1;
-            if ((double)(float)v != v) not_f32 = 1;
+            const int iv = __double2int_rz(v);
+            if (!((double)iv == v && (unsigned)iv <= 32767u)) {      // the common case (voxelised content) costs one round trip through int
+                not_int = 1;
+                if (!isfinite(v)) not_fin = 1;
+                if ((double)(float)v != v) not_f32 = 1;
+            }
         }
         if (packed) packed[i] = make_uint2(((uint32_t)(int)v3[0] & 0xffffu) | ((uint32_t)(int)v3[1] << 16), (uint32_t)(int)v3[2]);
         if (rgb != nullptr && rgb_dtype == PCCM_F64) {
@@ -108,16 +111,14 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
         }
         p.not_int = s_flags[0]; p.not_f32 = s_flags[1]; p.not_finite = s_flags[2]; p.rgb_not_u8 = s_flags[3];
         out[blockIdx.x] = p;
-        if (dev) {
-            if (!p.not_int) {
-                for (int a = 0; a < 3; ++a) {
-                    atomicMax(&dev->nmn[a], 0x7fffffffu - (uint32_t)(int)p.mn[a]);
-                    atomicMax(&dev->mx[a], (uint32_t)(int)p.mx[a]);
-                }
+        if (!p.not_int) {
+            for (int a = 0; a < 3; ++a) {
+                atomicMax(&dev->nmn[a], 0x7fffffffu - (uint32_t)(int)p.mn[a]);
+                atomicMax(&dev->mx[a], (uint32_t)(int)p.mx[a]);
             }
-            const uint32_t f = (p.not_int ? kDevNotInt : 0u) | (p.not_f32 ? kDevNotF32 : 0u) | (p.not_finite ? kDevNonFinite : 0u);
-            if (f) atomicOr(&dev->flags, f);
         }
+        const uint32_t f = (p.not_int ? kDevNotInt : 0u) | (p.not_f32 ? kDevNotF32 : 0u) | (p.not_finite ? kDevNonFinite : 0u);
+        if (f) atomicOr(&dev->flags, f);
     }
 }
 
@@ -150,6 +151,25 @@ __global__ void pack_rgb_u8_kernel(const void* rgb, int rgb_dtype, int64_t strid
         c.w = 0;
     }
     out[i] = c;
+}
+
+// packed 3-byte colours -> uchar4, four points per thread (three aligned 32-bit loads, one 16-byte store)
+__global__ void pack_rgb_u8x4_kernel(const uint32_t* __restrict__ rgb, int64_t n, uchar4* __restrict__ out) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // group of four points
+    const int64_t i = 4 * q;
+    if (i >= n) return;
+    if (i + 4 <= n) {
+        const uint32_t a = __ldg(rgb + 3 * q), b = __ldg(rgb + 3 * q + 1), c = __ldg(rgb + 3 * q + 2);
+        uint4 o;
+        o.x = a & 0xffffffu;
+        o.y = (a >> 24) | ((b & 0xffffu) << 8);
+        o.z = (b >> 16) | ((c & 0xffu) << 16);
+        o.w = c >> 8;
+        reinterpret_cast<uint4*>(out)[q] = o;
+    } else {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(rgb);
+        for (int64_t k = i; k < n; ++k) out[k] = make_uchar4(p[3 * k], p[3 * k + 1], p[3 * k + 2], 0);
+    }
 }
 
 // strided rows of 3 (F64 / F32) -> packed double[n][3]

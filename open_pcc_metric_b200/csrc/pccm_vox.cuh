@@ -10,10 +10,10 @@
 // (one per (y, z)) of one 32-bit word: bit b of row r says voxel (32 bx + b, y, z) is occupied.
 //   dirbits / dirpre : bitmap over the brick grid of the cloud's bounding box + exclusive
 //                      popcount prefix  ->  slot of an occupied brick (slots follow (z, y, x))
-//   masks[slot][64]  : the occupancy words
-//   rowbase[slot][64]: rank of the first voxel of row r of the brick (already global: brick base +
-//                      rows before r); rank = rowbase + popc(bits below).  The entry of the brick
-//                      past the last one holds the number of distinct voxels.
+//   rows[slot][64]   : {occupancy word, rank of the first voxel of the row} (the rank is already global:
+//                      brick base + rows before r); rank of a voxel = row rank + popc(bits below) -- ONE
+//                      8-byte load.  The entry of the brick past the last one holds the number of
+//                      distinct voxels.
 //   vxyz[rank]       : {x | y << 16, z} of the voxel
 //   vkey[rank]       : {rgb, idx} of the voxel's point with the SMALLEST original index (only that
 //                      one can win under the tie rule; one 64-bit atomicMin per point)
@@ -78,11 +78,11 @@ PCCM_HD uint32_t vx_fshr(uint32_t lo, uint32_t hi, int s) {   // low word of (hi
     return s == 0 ? lo : (s >= 32 ? hi : (lo >> s) | (hi << (32 - s)));
 #endif
 }
-PCCM_HD uint32_t vx_atomic_or(uint32_t* p, uint32_t v) {
+PCCM_HD void vx_atomic_or(uint32_t* p, uint32_t v) {     // (no result: a reduction, not a round trip)
 #if defined(__CUDA_ARCH__)
-    return atomicOr(p, v);
+    atomicOr(p, v);
 #else
-    const uint32_t o = *p; *p = o | v; return o;
+    *p |= v;
 #endif
 }
 PCCM_HD unsigned long long vx_atomic_min64(unsigned long long* p, unsigned long long v) {
@@ -95,6 +95,15 @@ PCCM_HD unsigned long long vx_atomic_min64(unsigned long long* p, unsigned long 
 PCCM_HD uint32_t vx_ld32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// L2-fresh load for check-before-atomic patterns: an L1 hit could show a word as it was when the SM first read it,
+// and every thread of that SM would then repeat an atomic that has long been done
+PCCM_HD uint32_t vx_ld32_fresh(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
 #else
     return *p;
 #endif
@@ -129,8 +138,7 @@ struct VoxView {
     VoxDims g;
     const uint32_t* dirbits;
     const uint32_t* dirpre;
-    const uint32_t* masks;           // [nblk_total + 1][64]
-    const uint32_t* rowbase;         // [nblk_total + 1][64]
+    const uint2* rows;               // [nblk_total + 1][64] {occupancy word, rank of the row's first voxel}
     const uint2* vxyz;               // [n_total]
     const uint2* vkey;               // [n_total]
     const uint32_t* prank;           // [n] this cloud's points, original order -> rank of their voxel
@@ -150,12 +158,12 @@ PCCM_HD int vx_slot(const VoxView& G, int bx, int by, int bz) {
 }
 PCCM_HD uint32_t vx_rank(const VoxView& G, uint32_t slot, int r, int xbit) {
     VX_CHECK(slot < G.nblk_total && (unsigned)r < (unsigned)kVxRows && (unsigned)xbit < 32u);
-    const uint32_t m = vx_ld32(G.masks + (size_t)slot * kVxRows + r);
-    VX_CHECK((m >> xbit) & 1u);                       // the voxel we rank must be occupied
-    return vx_ld32(G.rowbase + (size_t)slot * kVxRows + r) + (uint32_t)vx_popc(m & ((1u << xbit) - 1u));
+    const uint2 m = vx_ld64(G.rows + (size_t)slot * kVxRows + r);
+    VX_CHECK((m.x >> xbit) & 1u);                     // the voxel we rank must be occupied
+    return m.y + (uint32_t)vx_popc(m.x & ((1u << xbit) - 1u));
 }
 // voxels of brick `slot` are the ranks [vx_brick_begin(slot), vx_brick_begin(slot + 1))
-PCCM_HD uint32_t vx_brick_begin(const VoxView& G, uint32_t slot) { return vx_ld32(G.rowbase + (size_t)slot * kVxRows); }
+PCCM_HD uint32_t vx_brick_begin(const VoxView& G, uint32_t slot) { return vx_ld32(&G.rows[(size_t)slot * kVxRows].y); }
 // positions of the cloud's records in the joint array
 PCCM_HD uint32_t vx_ranked_begin(const VoxView& G) { return vx_brick_begin(G, G.slot0); }
 PCCM_HD uint32_t vx_ndistinct(const VoxView& G) { return vx_brick_begin(G, G.slot0 + G.nblk) - vx_brick_begin(G, G.slot0); }
@@ -163,30 +171,39 @@ PCCM_HD uint32_t vx_ndistinct(const VoxView& G) { return vx_brick_begin(G, G.slo
 // ---- build, per point (the kernels call these once per input point, pass after pass) --------
 PCCM_HD void vx_mark_point(uint32_t* dirbits, uint32_t key) {
     const uint32_t bit = 1u << (key & 31u);
+#ifndef PCCM_MARK_MODE
+#define PCCM_MARK_MODE 0
+#endif
+#if PCCM_MARK_MODE == 0
     if (!(dirbits[key >> 5] & bit)) vx_atomic_or(dirbits + (key >> 5), bit);   // a stale read only costs a redundant atomic
+#elif PCCM_MARK_MODE == 1
+    if (!(vx_ld32_fresh(dirbits + (key >> 5)) & bit)) vx_atomic_or(dirbits + (key >> 5), bit);
+#else
+    vx_atomic_or(dirbits + (key >> 5), bit);
+#endif
 }
 PCCM_HD uint32_t vx_slot_of_key(const uint32_t* dirbits, const uint32_t* dirpre, uint32_t key) {
     const uint32_t w = dirbits[key >> 5];
     return dirpre[key >> 5] + (uint32_t)vx_popc(w & ((1u << (key & 31u)) - 1u));
 }
-PCCM_HD void vx_fill_point(uint32_t* masks, uint32_t slot, int x, int y, int z) {
-    uint32_t* w = masks + (size_t)slot * kVxRows + vx_row(y, z);
-    const uint32_t bit = 1u << (x & 31);
-    if (!(*w & bit)) vx_atomic_or(w, bit);
+PCCM_HD void vx_fill_point(uint2* rows, uint32_t slot, int x, int y, int z) {
+    // unconditional: one reduction at the L2 per point costs no more than the load that could avoid it
+    vx_atomic_or(&rows[(size_t)slot * kVxRows + vx_row(y, z)].x, 1u << (x & 31));
 }
 // pass 3 (after the row bases): rank of the point's voxel; voxel coordinates into vxyz; the smallest
 // original index (with its colour) wins vkey.  vkey must be pre-filled with 0xFF.
-PCCM_HD uint32_t vx_place_point(const uint32_t* masks, const uint32_t* rowbase, uint2* vxyz, uint2* vkey,
+PCCM_HD uint32_t vx_place_point(const uint2* rows, uint2* vxyz, uint2* vkey,
                                 uint32_t slot, int x, int y, int z, uint32_t rgb, uint32_t idx) {
-    const int r = vx_row(y, z);
-    const uint32_t m = masks[(size_t)slot * kVxRows + r];
-    const uint32_t rank = rowbase[(size_t)slot * kVxRows + r] + (uint32_t)vx_popc(m & ((1u << (x & 31)) - 1u));
-    VX_CHECK((m >> (x & 31)) & 1u);
-    uint2 c;
-    c.x = (uint32_t)x | ((uint32_t)y << 16);             // every point of the voxel writes the same two words
-    c.y = (uint32_t)z;
-    vxyz[rank] = c;
-    vx_atomic_min64(reinterpret_cast<unsigned long long*>(vkey + rank), ((unsigned long long)idx << 32) | rgb);
+    const uint2 m = vx_ld64(rows + (size_t)slot * kVxRows + vx_row(y, z));
+    const uint32_t rank = m.y + (uint32_t)vx_popc(m.x & ((1u << (x & 31)) - 1u));
+    VX_CHECK((m.x >> (x & 31)) & 1u);
+    const unsigned long long old = vx_atomic_min64(reinterpret_cast<unsigned long long*>(vkey + rank), ((unsigned long long)idx << 32) | rgb);
+    if (old == ~0ull) {                                  // the first point to arrive at the voxel writes its coordinates
+        uint2 c;
+        c.x = (uint32_t)x | ((uint32_t)y << 16);
+        c.y = (uint32_t)z;
+        vxyz[rank] = c;
+    }
     return rank;
 }
 
@@ -201,10 +218,13 @@ PCCM_HD uint2 vx_stage_row(const VoxView& S, const int* sslot, int i, uint32_t& 
     const int ny_i = ry < 2 ? 0 : (ry < 10 ? 1 : 2), nz_i = rz < 2 ? 0 : (rz < 10 ? 1 : 2);
     const int r_in = (((rz + 6) & 7) << 3) | ((ry + 6) & 7);
     const int* s3 = sslot + nz_i * 9 + ny_i * 3;
-    const uint32_t l = s3[0] >= 0 ? vx_ld32(S.masks + (size_t)s3[0] * kVxRows + r_in) : 0u;
-    const uint32_t c = s3[1] >= 0 ? vx_ld32(S.masks + (size_t)s3[1] * kVxRows + r_in) : 0u;
-    const uint32_t r = s3[2] >= 0 ? vx_ld32(S.masks + (size_t)s3[2] * kVxRows + r_in) : 0u;
-    rb = s3[1] >= 0 ? vx_ld32(S.rowbase + (size_t)s3[1] * kVxRows + r_in) : 0u;
+    const uint32_t l = s3[0] >= 0 ? vx_ld32(&S.rows[(size_t)s3[0] * kVxRows + r_in].x) : 0u;
+    uint2 cw;
+    cw.x = 0u; cw.y = 0u;
+    if (s3[1] >= 0) cw = vx_ld64(S.rows + (size_t)s3[1] * kVxRows + r_in);
+    const uint32_t r = s3[2] >= 0 ? vx_ld32(&S.rows[(size_t)s3[2] * kVxRows + r_in].x) : 0u;
+    const uint32_t c = cw.x;
+    rb = cw.y;
     uint2 w;
     w.x = (l >> 30) | (c << 2);
     w.y = (c >> 30) | (r << 2);
@@ -283,32 +303,64 @@ PCCM_HD void vx_pick27(const VoxView& S, const int* sslot, const uint2* win, con
     }
 }
 
-// The 5 x 5 x 5 voxels around a query whose 27-neighbourhood is empty: minimal squared distance (exact
-// when < 9: anything outside is 3+ voxels away in one axis) and the winner among the ties.
-// Returns kVxNone when those 125 voxels are empty too.
+// The 5 x 5 x 5 voxels around a query as 125 bits in four words: row j = 5 (dz + 2) + (dy + 2) sits in word j / 6
+// at bit 5 (j % 6), its five bits are dx = -2 .. 2.  The voxels at squared distance L are a compile-time mask.
+#if defined(__CUDACC__)
+#define PCCM_HDC __host__ __device__ constexpr
+#else
+#define PCCM_HDC constexpr
+#endif
+PCCM_HDC uint32_t vx_mask125(int L, int word) {
+    uint32_t m = 0;
+    for (int j = 0; j < 25; ++j) {
+        if (j / 6 != word) continue;
+        const int dy = j % 5 - 2, dz = j / 5 - 2;
+        for (int dx = -2; dx <= 2; ++dx)
+            if (dx * dx + dy * dy + dz * dz == L) m |= 1u << (5 * (j % 6) + dx + 2);
+    }
+    return m;
+}
+struct VxNb125 { uint32_t w[5]; };
+
+PCCM_HD void vx_nb125(const uint2* win, int lx, int ly, int lz, VxNb125& nb) {
+    nb.w[0] = nb.w[1] = nb.w[2] = nb.w[3] = nb.w[4] = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 25; ++j) nb.w[j / 6] |= vx_row5(win, lx, ly, lz, j % 5 - 2, j / 5 - 2) << (5 * (j % 6));
+}
+template <int L>
+PCCM_HD bool vx_level125(const VxNb125& nb, VxNb125& cand) {
+    constexpr uint32_t m0 = vx_mask125(L, 0), m1 = vx_mask125(L, 1), m2 = vx_mask125(L, 2), m3 = vx_mask125(L, 3), m4 = vx_mask125(L, 4);
+    cand.w[0] = nb.w[0] & m0; cand.w[1] = nb.w[1] & m1; cand.w[2] = nb.w[2] & m2; cand.w[3] = nb.w[3] & m3; cand.w[4] = nb.w[4] & m4;
+    return (cand.w[0] | cand.w[1] | cand.w[2] | cand.w[3] | cand.w[4]) != 0u;
+}
+
+// Minimal squared distance within those 125 voxels (exact when < 9: anything outside is 3+ voxels away in one
+// axis) and the winner among the voxels that tie at it.  Returns kVxNone when nothing closer than 3 is there.
 PCCM_HD uint32_t vx_search125(const VoxView& S, const int* sslot, const uint2* win, const uint32_t* rb,
                               int lx, int ly, int lz, VxPick& pk) {
-    uint32_t best = kVxNone;
-    for (int j = 0; j < 25; ++j) {
-        const int dy = j % 5 - 2, dz = j / 5 - 2;
-        const uint32_t v = vx_row5(win, lx, ly, lz, dy, dz);
-        if (!v) continue;
-        const uint32_t dx2 = (v & 4u) ? 0u : ((v & 10u) ? 1u : 4u);
-        const uint32_t d2 = dx2 + (uint32_t)(dy * dy + dz * dz);
-        best = d2 < best ? d2 : best;
-    }
+    VxNb125 nb, cand;
+    vx_nb125(win, lx, ly, lz, nb);
     pk.idx = kVxNone; pk.rgb = 0; pk.ex = pk.ey = pk.ez = 0;
-    if (best >= 9u) return best;
-    for (int j = 0; j < 25; ++j) {
-        const int dy = j % 5 - 2, dz = j / 5 - 2;
-        const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
-        if (byz > best) continue;
-        const uint32_t dx2 = best - byz;                      // 0, 1 or 4 when this row can tie
-        if (dx2 != 0u && dx2 != 1u && dx2 != 4u) continue;
-        const int dx = dx2 == 4u ? 2 : (int)dx2;
-        const uint32_t v = vx_row5(win, lx, ly, lz, dy, dz);
-        if ((v >> (2 - dx)) & 1u) vx_cand(S, sslot, win, rb, lx, ly, lz, -dx, dy, dz, pk);
-        if (dx && ((v >> (2 + dx)) & 1u)) vx_cand(S, sslot, win, rb, lx, ly, lz, dx, dy, dz, pk);
+    uint32_t best;
+    if (vx_level125<0>(nb, cand)) best = 0;
+    else if (vx_level125<1>(nb, cand)) best = 1;
+    else if (vx_level125<2>(nb, cand)) best = 2;
+    else if (vx_level125<3>(nb, cand)) best = 3;
+    else if (vx_level125<4>(nb, cand)) best = 4;
+    else if (vx_level125<5>(nb, cand)) best = 5;
+    else if (vx_level125<6>(nb, cand)) best = 6;
+    else if (vx_level125<8>(nb, cand)) best = 8;
+    else return kVxNone;
+    for (int k = 0; k < 5; ++k) {
+        uint32_t c = cand.w[k];
+        while (c) {
+            const int b = vx_ffs(c) - 1;
+            c &= c - 1u;
+            const int j = 6 * k + b / 5, dx = b % 5 - 2;
+            vx_cand(S, sslot, win, rb, lx, ly, lz, dx, j % 5 - 2, j / 5 - 2, pk);
+        }
     }
     return best;
 }
@@ -373,7 +425,7 @@ PCCM_HD void vx_scan_brick(const VoxView& S, uint32_t slot, int bx, int by, int 
             const uint32_t byz = dz2 + (uint32_t)(dy * dy);
             if (byz > h.d2) continue;
             const int r = (zi << 3) | yi;
-            const uint32_t m = vx_ld32(S.masks + (size_t)slot * kVxRows + r);
+            const uint32_t m = vx_ld32(&S.rows[(size_t)slot * kVxRows + r].x);
             if (!m) continue;
             int dlo, dhi;
             vx_row_nearest(m, p, dlo, dhi);

@@ -38,7 +38,7 @@ constexpr uint32_t kVxStBrickOverflow = 4u;   // more occupied bricks than the m
 constexpr uint32_t kVxStRgbNotU8 = 8u;        // a float colour is not k / 255 (the 8-bit colour arrays are invalid)
 
 constexpr int kVxDirChunk = 2048;             // directory words per scan block
-constexpr int kVxBrickChunk = 256;            // bricks per row-base chunk
+constexpr int kVxBrickChunk = 64;             // bricks per row-base chunk (8 warps x 8 bricks)
 constexpr int kVxMaxBrickChunks = 1 << 16;
 
 struct VoxPlan {
@@ -51,19 +51,20 @@ struct VoxPlan {
 };
 
 struct VoxBuildArgs {                         // everything the host knows when it enqueues the build
+    uint32_t mark_lo, mark_hi;                // vx_mark_kernel: this launch handles the thread slots [mark_lo, mark_hi) of the point passes
     const DevStats* stats[2];
     const uint2* packed[2];                   // {x | y << 16, z} of every input point (stats_kernel)
     const void* rgb[2];                       // colours for the voxel records: packed uchar4 arrays (or null)
     uint32_t n[2];
     uint32_t cap_dirw, cap_blk;
-    uint32_t* dirbits;                        // [cap_dirw] zeroed
+    uint32_t* dirbits;                        // [cap_dirw] zeroed (PCCM_DIR_BYTES: written by vx_dirsum_kernel)
+    uint8_t* dirbytes;                        // PCCM_DIR_BYTES: [cap_dirw * 32] zeroed -- one byte per brick of the grids, set by plain stores
     uint32_t* dirpre;                         // [cap_dirw + 1]
     uint32_t* dirsums;                        // [cap_dirw / kVxDirChunk + 1]
-    uint32_t* masks;                          // [cap_blk][64]
-    uint32_t* rowbase;                        // [cap_blk][64]
+    uint2* rows;                              // [cap_blk][64] {occupancy word, rank of the row's first voxel}
     uint32_t* bricksums;                      // [cap_blk / kVxBrickChunk + 1]
     uint2* vxyz;                              // [n_total]
-    uint2* vkey;                              // [n_total] 0xFF-filled
+    uint2* vkey;                              // [n_total] (0xFF-filled by vx_mark_kernel)
     uint32_t* prank;                          // [n_total]
     uint32_t* pslot;                          // [n_total] scratch: brick slot of input point i
     VoxPlan* plan;
@@ -108,7 +109,13 @@ __device__ __forceinline__ void vx_block_dims(const VoxBuildArgs& A, VoxDimsSmem
 
 // The per-point passes are chains of dependent accesses (coordinates -> directory -> masks -> atomic):
 // every thread carries kVxIlp points, stage by stage, so that their loads are in flight together.
-constexpr int kVxIlp = 2;
+#ifndef PCCM_VX_ILP
+#define PCCM_VX_ILP 2
+#endif
+#ifndef PCCM_DIR_BYTES
+#define PCCM_DIR_BYTES 0
+#endif
+constexpr int kVxIlp = PCCM_VX_ILP;
 __device__ __forceinline__ uint32_t vx_ilp_index(uint32_t n_total, int k) {     // point k of this thread (>= n_total: none)
     const uint32_t per = (n_total + kVxIlp - 1) / kVxIlp;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,26 +128,38 @@ __device__ __forceinline__ uint2 vx_point(const VoxBuildArgs& A, uint32_t i, int
 }
 #define VX_UNPACK(p, x, y, z) const int x = (int)((p).x & 0xffffu), y = (int)((p).x >> 16), z = (int)(p).y
 
+// Two launches: a small sample of the points first (its atomics meet little contention: thousands of points name the
+// same brick, and read-modify-writes of one directory word queue up at the L2), then everybody else -- who now finds
+// nearly every bit set on the first look (a cached look is enough: bits are only ever set).
 __global__ void __launch_bounds__(256) vx_mark_kernel(const __grid_constant__ VoxBuildArgs A) {
     __shared__ VoxDimsSmem S;
-    vx_block_dims(A, S);
-    if (S.status) return;
     const uint32_t n_total = A.n[0] + A.n[1];
+    const uint32_t per = (n_total + kVxIlp - 1) / kVxIlp;
+    const uint32_t t = A.mark_lo + blockIdx.x * blockDim.x + threadIdx.x;
     uint2 p[kVxIlp];
     int c[kVxIlp];
     bool on[kVxIlp];
 #pragma unroll
-    for (int k = 0; k < kVxIlp; ++k) {
-        const uint32_t i = vx_ilp_index(n_total, k);
+    for (int k = 0; k < kVxIlp; ++k) {                        // (the coordinates are on their way while thread 0 plans the grids)
+        const uint32_t i = t < A.mark_hi && t < per ? t + (uint32_t)k * per : 0xFFFFFFFFu;
         on[k] = i < n_total;
         uint32_t li;
-        if (on[k]) p[k] = vx_point(A, i, c[k], li);
+        if (on[k]) {
+            p[k] = vx_point(A, i, c[k], li);
+            A.vkey[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); // neutral element of the place pass's atomicMin
+        }
     }
+    vx_block_dims(A, S);
+    if (S.status) return;
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
         if (on[k]) {
             VX_UNPACK(p[k], x, y, z);
+#if PCCM_DIR_BYTES
+            A.dirbytes[(size_t)S.dir_off[c[k]] * 32 + vx_key(S.g[c[k]], x, y, z)] = 1;
+#else
             vx_mark_point(A.dirbits + S.dir_off[c[k]], vx_key(S.g[c[k]], x, y, z));
+#endif
         }
 }
 
@@ -169,7 +188,19 @@ __global__ void __launch_bounds__(256) vx_dirsum_kernel(const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < kVxDirChunk / 256; ++k) {
         const uint32_t w = w0 + k * 256 + threadIdx.x;
-        if (w < nw) acc += (uint32_t)__popc(A.dirbits[w]);
+        if (w < nw) {
+#if PCCM_DIR_BYTES
+            const uint4* b = reinterpret_cast<const uint4*>(A.dirbytes + (size_t)w * 32);
+            const uint4 lo = __ldg(b), hi = __ldg(b + 1);
+            auto bits4 = [](uint32_t v) { return ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)); };   // bytes are 0 or 1
+            const uint32_t m = bits4(lo.x) | (bits4(lo.y) << 4) | (bits4(lo.z) << 8) | (bits4(lo.w) << 12) |
+                               (bits4(hi.x) << 16) | (bits4(hi.y) << 20) | (bits4(hi.z) << 24) | (bits4(hi.w) << 28);
+            A.dirbits[w] = m;
+            acc += (uint32_t)__popc(m);
+#else
+            acc += (uint32_t)__popc(A.dirbits[w]);
+#endif
+        }
     }
     acc = vx_block_sum_u32<256>(acc, sm);
     if (threadIdx.x == 0) A.dirsums[blockIdx.x] = acc;
@@ -204,7 +235,7 @@ __global__ void __launch_bounds__(256) vx_dirscan_kernel(const __grid_constant__
             V.g = S.g[c];
             V.dirbits = A.dirbits + S.dir_off[c];
             V.dirpre = A.dirpre + S.dir_off[c];
-            V.masks = A.masks; V.rowbase = A.rowbase; V.vxyz = A.vxyz; V.vkey = A.vkey;
+            V.rows = A.rows; V.vxyz = A.vxyz; V.vkey = A.vkey;
             V.prank = A.prank + (c ? A.n[0] : 0u);
             V.slot0 = c ? first : 0u;
             V.nblk = c ? total - first : first;
@@ -246,8 +277,8 @@ __global__ void __launch_bounds__(256) vx_dirscan_kernel(const __grid_constant__
         run += cnt[k];
     }
     // occupancy words of bricks [0, total]: zero (the brick past the last one stays empty)
-    const size_t n4 = ((size_t)total + 1) * kVxRows / 4;
-    uint4* m4 = reinterpret_cast<uint4*>(A.masks);
+    const size_t n4 = ((size_t)total + 1) * kVxRows / 2;
+    uint4* m4 = reinterpret_cast<uint4*>(A.rows);
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) m4[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -278,12 +309,22 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
         if (on[k]) {
             VX_UNPACK(p[k], x, y, z);
             VX_CHECK(slot[k] < P->view[0].nblk_total);
-            vx_fill_point(A.masks, slot[k], x, y, z);
+            vx_fill_point(A.rows, slot[k], x, y, z);
             A.pslot[idx[k]] = slot[k];
         }
 }
 
-// voxels per chunk of kVxBrickChunk bricks (the brick past the last one counts as an empty brick)
+// voxels per chunk of kVxBrickChunk bricks (the brick past the last one counts as an empty brick).  A warp owns 8
+// bricks of the chunk: one coalesced 256-byte load each, all eight in flight together.
+__device__ __forceinline__ void vx_load_bricks8(const uint2* rows, uint32_t s0, uint32_t nb, int lane, uint2 m[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {              // lane l: rows 2l and 2l + 1 (one 16-byte load), occupancy words only
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (s0 + j < nb) q = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)(s0 + j) * kVxRows) + lane);
+        m[j] = make_uint2(q.x, q.z);
+    }
+}
+
 __global__ void __launch_bounds__(256) vx_bricksum_kernel(const __grid_constant__ VoxBuildArgs A) {
     __shared__ uint32_t sm[8];
     const VoxPlan* __restrict__ P = A.plan;
@@ -292,14 +333,11 @@ __global__ void __launch_bounds__(256) vx_bricksum_kernel(const __grid_constant_
     const uint32_t nchunks = (nb + kVxBrickChunk - 1) / kVxBrickChunk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        uint2 m[8];
+        vx_load_bricks8(A.rows, ch * kVxBrickChunk + warp * 8, nb, lane, m);
         uint32_t acc = 0;
-        const uint32_t s0 = ch * kVxBrickChunk + warp * 32;
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t s = s0 + j;
-            if (s >= nb) break;
-            const uint2 m = __ldg(reinterpret_cast<const uint2*>(A.masks + (size_t)s * kVxRows) + lane);
-            acc += (uint32_t)(__popc(m.x) + __popc(m.y));
-        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += (uint32_t)(__popc(m[j].x) + __popc(m[j].y));
         acc = vx_block_sum_u32<256>(acc, sm);
         if (threadIdx.x == 0) A.bricksums[ch] = acc;
     }
@@ -322,47 +360,41 @@ __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__
     off = vx_block_sum_u32<256>(off, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t ch = c0; ch < c1; ++ch) {
-        const uint32_t s0 = ch * kVxBrickChunk + warp * 32;
-        // phase A: total of each of this warp's 32 bricks (lane j keeps brick j's)
-        uint32_t tot = 0;
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t s = s0 + j;
-            uint32_t v = 0;
-            if (s < nb) {
-                const uint2 m = __ldg(reinterpret_cast<const uint2*>(A.masks + (size_t)s * kVxRows) + lane);
-                v = (uint32_t)(__popc(m.x) + __popc(m.y));
-            }
-            v = __reduce_add_sync(0xffffffffu, v);
-            if (lane == j) tot = v;
-        }
-        uint32_t incl = tot;
+        const uint32_t s0 = ch * kVxBrickChunk + warp * 8;
+        uint2 m[8];
+        vx_load_bricks8(A.rows, s0, nb, lane, m);
+        // inclusive prefix over the rows of each brick (lane l owns rows 2l, 2l+1); brick totals in lane 31
+        uint32_t in2[8], wtot = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        __syncthreads();                                     // (s_wtot of the previous chunk has been read)
-        if (lane == 31) s_wtot[warp] = incl;
-        __syncthreads();
-        uint32_t wbase = off;
-        for (int w = 0; w < warp; ++w) wbase += s_wtot[w];
-        uint32_t chunk_total = 0;
-        for (int w = 0; w < 8; ++w) chunk_total += s_wtot[w];
-        const uint32_t brick_excl = wbase + incl - tot;      // lane j: base of brick j
-        // phase B: row bases
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t s = s0 + j;
-            if (s >= nb) break;
-            const uint2 m = __ldg(reinterpret_cast<const uint2*>(A.masks + (size_t)s * kVxRows) + lane);
-            const uint32_t a = (uint32_t)__popc(m.x), b = (uint32_t)__popc(m.y);
-            uint32_t in2 = a + b;
+        for (int j = 0; j < 8; ++j) {
+            uint32_t v = (uint32_t)(__popc(m[j].x) + __popc(m[j].y));
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, in2, o);
-                if (lane >= o) in2 += t;
+                const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
             }
-            const uint32_t base = __shfl_sync(0xffffffffu, brick_excl, j) + in2 - a - b;
-            reinterpret_cast<uint2*>(A.rowbase + (size_t)s * kVxRows)[lane] = make_uint2(base, base + a);
+            in2[j] = v;
+        }
+        uint32_t bbase[8];                                   // base of brick j inside this warp's run
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bbase[j] = wtot;
+            wtot += __shfl_sync(0xffffffffu, in2[j], 31);
+        }
+        __syncthreads();                                     // (s_wtot of the previous chunk has been read)
+        if (lane == 0) s_wtot[warp] = wtot;
+        __syncthreads();
+        uint32_t wbase = off, chunk_total = 0;
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) wbase += s_wtot[w];
+            chunk_total += s_wtot[w];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (s0 + j >= nb) break;
+            const uint32_t a = (uint32_t)__popc(m[j].x), b = (uint32_t)__popc(m[j].y);
+            const uint32_t base = wbase + bbase[j] + in2[j] - a - b;
+            reinterpret_cast<uint4*>(A.rows + (size_t)(s0 + j) * kVxRows)[lane] = make_uint4(m[j].x, base, m[j].y, base + a);
         }
         off += chunk_total;
     }
@@ -392,7 +424,7 @@ __global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ V
         if (on[k]) {
             VX_UNPACK(p[k], x, y, z);
             VX_CHECK(slot[k] < P->view[0].nblk_total);
-            const uint32_t rank = vx_place_point(A.masks, A.rowbase, A.vxyz, A.vkey, slot[k], x, y, z, rgba[k], li[k]);
+            const uint32_t rank = vx_place_point(A.rows, A.vxyz, A.vkey, slot[k], x, y, z, rgba[k], li[k]);
             VX_CHECK(rank < n_total);
             A.prank[idx[k]] = rank;
         }
@@ -467,10 +499,13 @@ struct VxAcc {
     }
 };
 
-// epilogue of ONE query point: D1 (+ per-point outputs), D2 with the other cloud's normals, colour
+// epilogue of ONE query point: D1 (+ per-point outputs), D2 with the other cloud's normals, colour.
+// pre_n / pre_rgb: the normal at the query index and the query's own packed colour when the caller has already
+// loaded them (they depend on the point index only, so they can travel together with the rank look-up).
 __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, const CloudView& qa, const CloudView& sa,
                                             uint32_t qidx, uint32_t qrgb, uint32_t d2,
-                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a) {
+                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a,
+                                            const double* pre_n = nullptr, bool pre_rgb = false) {
     a.s1 += d2;
     a.m1 = d2 > a.m1 ? d2 : a.m1;
     a.cnt++;
@@ -478,16 +513,21 @@ __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, c
     if (D.d2_out) D.d2_out[qidx] = (double)d2;
     if (D.flags & PCCM_EVAL_D2) {
         const double e[3] = {(double)ex, (double)ey, (double)ez};
-        const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
-        double nv[3] = {__ldg(sa.normals + 3 * (size_t)ni), __ldg(sa.normals + 3 * (size_t)ni + 1),
-                        __ldg(sa.normals + 3 * (size_t)ni + 2)};
+        double nv[3];
+        if (pre_n) {
+            nv[0] = pre_n[0]; nv[1] = pre_n[1]; nv[2] = pre_n[2];
+        } else {
+            const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
+            nv[0] = __ldg(sa.normals + 3 * (size_t)ni); nv[1] = __ldg(sa.normals + 3 * (size_t)ni + 1); nv[2] = __ldg(sa.normals + 3 * (size_t)ni + 2);
+        }
         const double pe = plane_err2(e, nv);
         a.s2 = dadd(a.s2, pe);
         a.m2 = fmax(a.m2, pe);
     }
     if (D.flags & PCCM_EVAL_COLOR) {
         double cq[3], cn[3], c2[3], c2s[3];
-        load_color(qa, qidx, qrgb, cq);
+        if (pre_rgb) { cq[0] = qa.lut255[qrgb & 0xffu]; cq[1] = qa.lut255[(qrgb >> 8) & 0xffu]; cq[2] = qa.lut255[(qrgb >> 16) & 0xffu]; }
+        else load_color(qa, qidx, qrgb, cq);
         load_color(sa, nidx, nrgb, cn);
         color_diff2(P.T, cq, cn, P.color_scale, c2, c2s);
         for (int k = 0; k < 3; ++k) { a.cs[k] = dadd(a.cs[k], c2[k]); a.cm[k] = fmax(a.cm[k], c2s[k]); }
@@ -541,7 +581,11 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
         uint2 mb[kBatch];
 #pragma unroll
         for (int j = 0; j < kBatch; ++j)
-            mb[j] = k0 + j < n ? __ldg(reinterpret_cast<const uint2*>(S.masks + (size_t)slots[k0 + j] * kVxRows) + lane) : make_uint2(0u, 0u);
+        {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (k0 + j < n) q = __ldg(reinterpret_cast<const uint4*>(S.rows + (size_t)slots[k0 + j] * kVxRows) + lane);
+            mb[j] = make_uint2(q.x, q.z);
+        }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
             if (k0 + j >= n) break;
@@ -568,7 +612,8 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
     for (int k0 = 0; k0 < n; ++k0) {
         const int slot = slots[k0], b = ids[k0];
         const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
-        const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(S.masks + (size_t)slot * kVxRows) + lane);
+        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(S.rows + (size_t)slot * kVxRows) + lane);
+        const uint2 m2 = make_uint2(q2.x, q2.z);
         const int p = qx - (bx << 5);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -627,12 +672,12 @@ __device__ __forceinline__ uint32_t vx_pack_e27(int b) {     // packed (query - 
 #endif
 constexpr int kVxThreads = PCCM_VX_THREADS;
 constexpr int kVxWarps = kVxThreads / 32;
-constexpr int kVxPend = 64;
 
 #ifndef PCCM_VX_MINBLOCKS
 #define PCCM_VX_MINBLOCKS 10
 #endif
 
+constexpr int kVxPend = 64;
 struct VxWarpSmem {
     uint2 win[kVxRegRows];
     uint32_t rb[kVxRegRows];
@@ -643,11 +688,11 @@ struct VxWarpSmem {
 };
 
 // the voxels of a brick that the 27-neighbourhood left open (lane l takes pend[l]): 125-neighbourhood, whole-brick
-// scans, todo list
+// scans of the 27 neighbour bricks, todo list
 __device__ __forceinline__ void vx_finish_pending(const VxParams& P, int d, const VoxView& Q, const VoxView& S,
                                                   VxWarpSmem& W, uint32_t b0, int count, bool any_brick, int nocc) {
-    const VxDir& D = P.dir[d];
     const unsigned full = 0xffffffffu;
+    const VxDir& D = P.dir[d];
     const int lane = threadIdx.x & 31;
     const bool active = lane < count;
     const uint32_t t = b0 + (active ? (uint32_t)W.pend[lane] : 0u);
@@ -694,11 +739,18 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
     VxWarpSmem& W = s_w[warp];
     const uint32_t nblk_d0 = plan->view[P.dir[0].qc].nblk;
     const uint32_t nwork = nblk_d0 + (P.ndirs > 1 ? plan->view[P.dir[1].qc].nblk : 0u);
-    for (;;) {
-        uint32_t gw = 0;
-        if (lane == 0) gw = atomicAdd(P.counters + 4, 1u);
-        gw = __shfl_sync(full, gw, 0);
-        if (gw >= nwork) break;
+#ifndef PCCM_VX_TICKET
+#define PCCM_VX_TICKET 1          // bricks per ticket (measured: 4 per ticket costs 45 % -- the tail of the kernel is one ticket long)
+#endif
+    uint32_t ticket = 0, gw = 0, gw_end = 0;
+    if (lane == 0) ticket = atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);
+    for (;; ++gw) {
+        if (gw == gw_end) {
+            gw = __shfl_sync(full, ticket, 0);
+            if (gw >= nwork) break;
+            gw_end = min(gw + (uint32_t)PCCM_VX_TICKET, nwork);
+            if (lane == 0) ticket = atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);   // the next ticket travels while these bricks are searched
+        }
         const int d = gw >= nblk_d0 ? 1 : 0;
         const VxDir& D = P.dir[d];
         const VoxView& Q = plan->view[D.qc];
@@ -750,7 +802,15 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
             if (done) {
                 uint32_t bidx = kVxNone, brgb = 0u;
                 int bb = __ffs((int)cand) - 1;
-                if (need_idx || (need_e && (cand & (cand - 1u)))) {
+#ifndef PCCM_VX_SINGLE
+#define PCCM_VX_SINGLE 0          // (measured: a separate one-candidate path costs 5 % -- two code paths diverge more than one loop)
+#endif
+                if (PCCM_VX_SINGLE && !(cand & (cand - 1u))) {
+                    if (need_idx) {                          // one voxel at the minimum: its record, no tie to break
+                        const uint2 k_a = __ldg(S.vkey + vx_cand_rank27(S, W.sslot, W.win, W.rb, lx, ly, lz, bb));
+                        bidx = k_a.y; brgb = k_a.x;
+                    }
+                } else if (need_idx || need_e) {
                     // the voxels that tie at the minimum, two look-ups in flight per trip
                     uint32_t c2 = cand;
                     do {
@@ -769,7 +829,7 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
                 P.vres[t] = make_uint4(bd2, vx_pack_e27(bb), bidx == kVxNone ? 0u : bidx, brgb);   // (no look-up: the index is not used)
             }
             const unsigned und = __ballot_sync(full, active && !done);
-            if (und) {
+            if (und) {                                   // empty 27-neighbourhood (1-2 % of the voxels): collected per brick
                 if (active && !done) W.pend[npend + __popc(und & ((1u << lane) - 1u))] = (uint16_t)(t - b0);
                 npend += __popc(und);
                 __syncwarp();
@@ -794,11 +854,14 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
 // by voxel: a rank skips the points of voxels it did not search.
 constexpr int kVxEpiThreads = 256;
 #ifndef PCCM_VX_EPIPER
-#define PCCM_VX_EPIPER 4
+#define PCCM_VX_EPIPER 2
 #endif
 constexpr int kVxEpiPer = PCCM_VX_EPIPER;
 constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
-__global__ void __launch_bounds__(kVxEpiThreads)
+#ifndef PCCM_EPI_MINBLOCKS
+#define PCCM_EPI_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(kVxEpiThreads, PCCM_EPI_MINBLOCKS)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     __shared__ double s_lut[256];
     const VoxPlan* __restrict__ plan = P.plan;
@@ -815,10 +878,27 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     const uint32_t i0 = tile * kVxEpiTile + threadIdx.x;
     uint32_t rk[kVxEpiPer];
     uint4 v[kVxEpiPer];
+#ifndef PCCM_EPI_PRELOAD
+#define PCCM_EPI_PRELOAD 0          // (measured: requesting normals and colours before the gather costs registers and buys nothing)
+#endif
+    // everything that depends on the point index only is requested first: rank, own colour, and -- reference mode --
+    // the other cloud's normal at the QUERY index (quirk Q1 makes it a stream); the one gather (the voxel's answer)
+    // follows, and the arithmetic waits for nothing else
+    const bool pre_n = PCCM_EPI_PRELOAD && (D.flags & PCCM_EVAL_D2) && P.normals_mode != PCCM_NORMALS_BY_NEIGHBOUR;
+    const bool pre_c = PCCM_EPI_PRELOAD && (D.flags & PCCM_EVAL_COLOR) && qa.rgb_mode == 2;
+    double nrm[kVxEpiPer][3];
+    uint32_t qrgb[kVxEpiPer];
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
         const uint32_t i = i0 + j * kVxEpiThreads;
-        rk[j] = i < D.nq ? __ldg(D.qprank + i) : kVxNone;
+        const bool in = i < D.nq;
+        rk[j] = in ? __ldg(D.qprank + i) : kVxNone;
+        qrgb[j] = (pre_c && in) ? __ldg(reinterpret_cast<const uint32_t*>(qa.rgb_u8) + i) : 0u;
+        if (pre_n && in) {
+            nrm[j][0] = __ldg(sa.normals + 3 * (size_t)i); nrm[j][1] = __ldg(sa.normals + 3 * (size_t)i + 1); nrm[j][2] = __ldg(sa.normals + 3 * (size_t)i + 2);
+        } else {
+            nrm[j][0] = nrm[j][1] = nrm[j][2] = 0.0;
+        }
     }
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j)
@@ -841,7 +921,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
             ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
             nrgb = nr.w;
         }
-        vx_epilogue(P, D, qa, sa, i, 0u, v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc);
+        vx_epilogue(P, D, qa, sa, i, qrgb[j], v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc, pre_n ? nrm[j] : nullptr, pre_c);
     }
     BlockPartial r;
     vx_warp_record(acc, D.flags, r);
@@ -958,12 +1038,18 @@ __global__ void vx_dupflag_kernel(const __grid_constant__ VxSelfParams P) {
     if (__ldg(&P.c.vkey[rank].y) != i) atomicOr(P.dupbits + (rank >> 5), 1u << (rank & 31u));
 }
 
+struct VxSelfSmem {
+    uint2 win[kVxRegRows];
+    int sslot[28];
+    int occ_slot[28];
+    int occ_id[28];
+};
 __global__ void __launch_bounds__(kVxThreads)
 vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
-    __shared__ VxWarpSmem s_w[kVxWarps];
+    __shared__ VxSelfSmem s_w[kVxWarps];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    VxWarpSmem& W = s_w[warp];
+    VxSelfSmem& W = s_w[warp];
     const uint32_t lb = blockIdx.x * kVxWarps + warp;
     if (lb >= P.c.nblk) return;
     const uint32_t slot = P.c.slot0 + lb;

@@ -157,8 +157,8 @@ extern "C" int emul_knn_self(int kind, const double* pts, int64_t n, int k, doub
 #include "../../open_pcc_metric_b200/csrc/pccm_vox.cuh"
 
 struct VoxPair {
-    std::vector<uint32_t> dirbits, dirpre, masks, rowbase, prank;
-    std::vector<uint2> vxyz, vkey;
+    std::vector<uint32_t> dirbits, dirpre, prank;
+    std::vector<uint2> rows, vxyz, vkey;
     VoxView view[2];
 };
 
@@ -185,18 +185,18 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
     for (uint32_t w = 0; w < nw; ++w) { V.dirpre[w] = run; run += (uint32_t)vx_popc(V.dirbits[w]); }
     V.dirpre[nw] = run;
     const uint32_t nblk0 = V.dirpre[ndirw[0]], nblk = run;
-    V.masks.assign((size_t)(nblk + 1) * kVxRows, 0); V.rowbase.assign((size_t)(nblk + 1) * kVxRows, 0);
+    V.rows.assign((size_t)(nblk + 1) * kVxRows, uint2{0u, 0u});
     V.vxyz.resize(n_total); V.vkey.resize(n_total);
     memset(V.vkey.data(), 0xff, (size_t)n_total * sizeof(uint2));
     V.prank.assign(n_total, kVxNone);
     for (int c = 0; c < 2; ++c)                                   // vx_fill_kernel
         for (int64_t i = 0; i < n[c]; ++i) {
             int x, y, z; coords(c, i, x, y, z);
-            vx_fill_point(V.masks.data(), vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z)), x, y, z);
+            vx_fill_point(V.rows.data(), vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z)), x, y, z);
         }
     run = 0;                                                      // vx_bricksum_kernel + vx_rowbase_kernel (the brick past the last one is empty)
     for (uint32_t s = 0; s <= nblk; ++s)
-        for (int r = 0; r < kVxRows; ++r) { V.rowbase[(size_t)s * kVxRows + r] = run; run += (uint32_t)vx_popc(V.masks[(size_t)s * kVxRows + r]); }
+        for (int r = 0; r < kVxRows; ++r) { V.rows[(size_t)s * kVxRows + r].y = run; run += (uint32_t)vx_popc(V.rows[(size_t)s * kVxRows + r].x); }
     for (int c = 0; c < 2; ++c) {                                  // vx_place_kernel; arrival order of the atomics: odd indices
         std::vector<int64_t> order;                                 // downwards, then even ones upwards
         for (int64_t i = n[c]; i-- > 0;) if (i & 1) order.push_back(i);
@@ -204,13 +204,13 @@ static bool vox_build(const double* pts[2], const int64_t n[2], VoxPair& V) {
         for (int64_t i : order) {
             int x, y, z; coords(c, i, x, y, z);
             const uint32_t slot = vx_slot_of_key(V.dirbits.data() + dir_off[c], V.dirpre.data() + dir_off[c], vx_key(g[c], x, y, z));
-            V.prank[(c ? n[0] : 0) + i] = vx_place_point(V.masks.data(), V.rowbase.data(), V.vxyz.data(), V.vkey.data(), slot, x, y, z, 0u, (uint32_t)i);
+            V.prank[(c ? n[0] : 0) + i] = vx_place_point(V.rows.data(), V.vxyz.data(), V.vkey.data(), slot, x, y, z, 0u, (uint32_t)i);
         }
     }
     for (int c = 0; c < 2; ++c) {
         VoxView& W = V.view[c];
         W.g = g[c]; W.dirbits = V.dirbits.data() + dir_off[c]; W.dirpre = V.dirpre.data() + dir_off[c];
-        W.masks = V.masks.data(); W.rowbase = V.rowbase.data(); W.vxyz = V.vxyz.data(); W.vkey = V.vkey.data();
+        W.rows = V.rows.data(); W.vxyz = V.vxyz.data(); W.vkey = V.vkey.data();
         W.prank = V.prank.data() + (c ? n[0] : 0);
         W.slot0 = c ? nblk0 : 0; W.nblk = c ? nblk - nblk0 : nblk0; W.n = (uint32_t)n[c];
         W.nblk_total = nblk; W.n_total = n_total;

@@ -51,3 +51,16 @@ for it in range(50):
     ctx.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV); a.close(); b.close()
 ctx.synchronize()
 print(f"back to back: {(time.perf_counter() - t0) / 50 * 1e6:.1f} us per evaluation")
+# host time of each call when nothing but pair_eval waits for the GPU (the enqueue cost the GPU has to be fed with)
+acc.clear()
+for it in range(60):
+    if it == 10:
+        acc.clear()
+    a = t("cloud A", lambda: ctx.cloud(*dA), sync=False)
+    b = t("cloud B", lambda: ctx.cloud(*dB), sync=False)
+    t("build_pair", lambda: ctx.build_pair(a, b), sync=False)
+    t("pair_eval", lambda: ctx.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, YUV), sync=False)
+    t("close", lambda: (a.close(), b.close()), sync=False)
+print("enqueue only (pair_eval includes its one wait):")
+for k, (h, g) in acc.items():
+    print(f"{k:12s} {h / n * 1e6:15.1f}")
