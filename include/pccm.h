@@ -71,6 +71,8 @@ typedef struct pccm_cloud_info {
     int32_t index_kind;   /* pccm_kind of the built index, -1 if none */
     int32_t has_colors, colors_u8, has_normals, indexed;
     int32_t ny, nz;       /* pencil table dimensions */
+    int32_t sharded;      /* 0, or the number of ranks the pair this cloud was indexed with is split over (pccm_ctx_set_shard) */
+    int32_t reserved;
     double cell_size;
     double aabb_min[3], aabb_max[3];
 } pccm_cloud_info;
@@ -123,6 +125,14 @@ int pccm_ctx_synchronize(pccm_ctx* ctx);
 /* level 0 = off, 1 = time the query / k-NN kernels only, 2 = time every stage */
 int pccm_ctx_set_profiling(pccm_ctx* ctx, int level);
 int pccm_ctx_reset_timings(pccm_ctx* ctx);
+/* One pair over several GPUs (one context per GPU, the same calls on every rank, both clouds given to every rank):
+ * integer pairs built from now on are split by slabs of z that hold equal numbers of points -- this rank indexes its
+ * slab (+ a halo of two bricks) and evaluates the queries of its slab only; pccm_pair_eval / pccm_self_nn_minmax then
+ * return this rank's partial sums (pccm_dir_result.n counts its points) whatever rank / range they are called with,
+ * and the caller adds the ranks up (sums) / takes the extremes (max, min).  The cuts are computed on the device from a
+ * histogram the statistics pass takes along; nothing is exchanged inside the library.  Other pairs (float kinds) keep
+ * the rank / world arguments of pccm_pair_eval.  Set before the clouds are created; (0, 1) switches it off. */
+int pccm_ctx_set_shard(pccm_ctx* ctx, int rank, int world);
 int pccm_ctx_get_timings(pccm_ctx* ctx, pccm_timings* out);
 
 /* Replaces building an o3d.geometry.PointCloud + KDTreeFlann input (cloud_pair.py:59,65).

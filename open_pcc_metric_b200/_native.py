@@ -25,7 +25,7 @@ ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_NONFINITE, ERR_UNSUPPORTED = -1
 
 EXPORTS = [
     "pccm_version", "pccm_last_error", "pccm_ctx_create", "pccm_ctx_destroy", "pccm_ctx_synchronize",
-    "pccm_ctx_set_profiling", "pccm_ctx_reset_timings", "pccm_ctx_get_timings",
+    "pccm_ctx_set_profiling", "pccm_ctx_reset_timings", "pccm_ctx_get_timings", "pccm_ctx_set_shard",
     "pccm_cloud_create", "pccm_cloud_attach", "pccm_cloud_destroy", "pccm_cloud_info_get", "pccm_cloud_build_index", "pccm_pair_build_index",
     "pccm_cloud_set_normals", "pccm_cloud_get_normals", "pccm_estimate_normals", "pccm_knn_self",
     "pccm_self_nn_minmax", "pccm_nn", "pccm_pair_eval", "pccm_pair_get", "pccm_obb_sweep", "pccm_cloud_extremes", "pccm_cloud_outside_hull",
@@ -35,7 +35,8 @@ EXPORTS = [
 class CloudInfo(C.Structure):
     _fields_ = [("n", C.c_int64), ("data_kind", C.c_int32), ("index_kind", C.c_int32),
                 ("has_colors", C.c_int32), ("colors_u8", C.c_int32), ("has_normals", C.c_int32),
-                ("indexed", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("cell_size", C.c_double),
+                ("indexed", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("sharded", C.c_int32), ("reserved", C.c_int32),
+                ("cell_size", C.c_double),
                 ("aabb_min", C.c_double * 3), ("aabb_max", C.c_double * 3)]
 
 
@@ -91,6 +92,7 @@ def lib():
         "pccm_ctx_synchronize": [vp],
         "pccm_ctx_set_profiling": [vp, i32],
         "pccm_ctx_reset_timings": [vp],
+        "pccm_ctx_set_shard": [vp, i32, i32],
         "pccm_ctx_get_timings": [vp, C.POINTER(Timings)],
         "pccm_cloud_create": [vp, vp, i32, i64, i64, vp, i32, i64, vp, i32, i64, i32, C.POINTER(vp)],
         "pccm_cloud_attach": [vp, vp, vp, i32, i64, vp, i32, i64, i32],
@@ -213,6 +215,10 @@ class Context:
     def set_profiling(self, level: int):
         """0 = off, 1 = query / k-NN kernels only, 2 = every stage."""
         self.check(self.L.pccm_ctx_set_profiling(self.h, int(level)))
+
+    def set_shard(self, rank: int = 0, world: int = 1):
+        """Integer pairs built from now on are split over ``world`` ranks by slabs of z (see pccm_ctx_set_shard)."""
+        self.check(self.L.pccm_ctx_set_shard(self.h, int(rank), int(world)))
 
     def reset_timings(self):
         self.check(self.L.pccm_ctx_reset_timings(self.h))

@@ -82,12 +82,24 @@ class CloudPair:
         # coordinates of BOTH clouds first: statistics and the index build need nothing else, colours and
         # normals follow on the copy stream while the index is built (they are first read by the epilogue)
         self._dev = []
-        for c in self.clouds:
-            self._dev.append(self._ctx.cloud(_attr(c, "points") if _attr(c, "points") is not None else np.zeros((0, 3))))
-        for c, d in zip(self.clouds, self._dev):
-            d.attach(_attr(c, "colors"), _attr(c, "normals"))
-        self._ctx.build_pair(self._dev[0], self._dev[1], cell_size)
+        if world > 1:
+            # one pair over several GPUs: integer pairs are split by slabs of z inside the library (this rank indexes and
+            # queries its slab only); the partial sums are exchanged below with torch.distributed
+            self._ctx.set_shard(rank, world)
+        try:
+            for c in self.clouds:
+                self._dev.append(self._ctx.cloud(_attr(c, "points") if _attr(c, "points") is not None else np.zeros((0, 3))))
+            for c, d in zip(self.clouds, self._dev):
+                d.attach(_attr(c, "colors"), _attr(c, "normals"))
+            self._ctx.build_pair(self._dev[0], self._dev[1], cell_size)
+        except Exception:
+            self.close()
+            raise
+        finally:
+            if world > 1:
+                self._ctx.set_shard(0, 1)
         infos = [d.info() for d in self._dev]
+        self._sharded = bool(infos[0].sharded)
         kind = infos[0].index_kind
         self._n = tuple(int(i.n) for i in infos)
         self._aabb = tuple((np.array(i.aabb_min), np.array(i.aabb_max)) for i in infos)
@@ -100,6 +112,7 @@ class CloudPair:
         # the reference runs both NN passes in its constructor (cloud_pair.py:67-78) and
         # fails there on an empty search cloud; keep that behaviour
         if min(self._n) == 0:
+            self.close()
             raise IndexError("list index out of range")
 
     # ---- reference surface ---------------------------------------------------------
@@ -178,7 +191,10 @@ class CloudPair:
                 self._boundary = (np.float64(0.0), np.float64(0.0))
             else:
                 n0 = self._n[0]
-                b, e = n0 * self._rank // self._world, n0 * (self._rank + 1) // self._world
+                if self._sharded:      # split pair: the library reduces this rank's slab whatever range it is given
+                    b, e = 0, n0
+                else:
+                    b, e = n0 * self._rank // self._world, n0 * (self._rank + 1) // self._world
                 mn, mx, _ = self._dev[0].self_nn_minmax(b, e)
                 if self._world > 1:
                     mn, mx = self._exchange_minmax(mn, mx)

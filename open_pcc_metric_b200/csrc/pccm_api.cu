@@ -61,6 +61,7 @@ struct pccm_ctx {
     bool use_vox = true;            // KInt pairs: occupancy-brick index + bit-scan query (PCCM_VOX=0: pencil path only)
     bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
     int vx_search_blocks = 10;      // resident blocks per SM of the persistent brick search kernel (PCCM_VX_BLOCKS)
+    int shard_rank = 0, shard_world = 1;   // pccm_ctx_set_shard: pairs built from now on are split by z slabs over `world` ranks
     int mark_sample = 32;           // the brick directory is marked by 1 / mark_sample of the points first (PCCM_MARK_SAMPLE, 0 = one pass)
 };
 
@@ -153,7 +154,8 @@ struct pccm_cloud {
                                       // the colour flag, the DevStats record and the packed coordinates
     DevStats* d_dev = nullptr;        // the same statistics as one integer record (brick-index planning on the device)
     uint2* packed = nullptr;          // {x | y << 16, z} per point, written by the statistics pass (integer-valued clouds)
-    bool stats_fetched = false;       // the folded record is (being) copied to the pinned slot stats_slot
+    uint32_t* d_zhist = nullptr;      // sharded contexts: points per 8-voxel z layer (kZHistBins), in the same block
+    bool stats_fetched = false;       // the statistics partials are (being) copied to the pinned slot stats_slot
     int stats_slot = 0;
     int stats_blocks = 0;
     bool stats_ready = false;
@@ -205,6 +207,10 @@ struct SharedVox {
     VoxPlan* dplan = nullptr;        // device: written by the build kernels, read by every brick kernel
     VoxPlan hplan{};                 // host copy, valid once the build has been settled
     bool pending = false;            // the build is enqueued but the host has not looked at its outcome yet
+    bool sharded = false;            // built on a sharded context: only this rank's slab (+ halo) is indexed, only its layers are queried
+    bool full_need = false;          // ... but the whole pair is indexed (fallback: some query had to look beyond the halo)
+    int shard_rank = 0, shard_world = 1;
+    ShardPlan* dshard = nullptr;     // device: the cuts (in the arena)
     uint32_t cap_dirw = 0, cap_blk = 0;
     uint32_t n[2] = {0, 0};
     VoxView view[2];                 // = hplan.view
@@ -512,6 +518,13 @@ extern "C" int pccm_ctx_set_profiling(pccm_ctx* ctx, int level) {
     ctx->profiling = level;
     return PCCM_OK;
 }
+extern "C" int pccm_ctx_set_shard(pccm_ctx* ctx, int rank, int world) {
+    if (!ctx) return fail(nullptr, PCCM_ERR_INVALID, "ctx is NULL");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, PCCM_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+    ctx->shard_rank = rank;
+    ctx->shard_world = world;
+    return PCCM_OK;
+}
 extern "C" int pccm_ctx_reset_timings(pccm_ctx* ctx) {
     if (!ctx) return fail(nullptr, PCCM_ERR_INVALID, "ctx is NULL");
     CK(cudaStreamSynchronize(ctx->stream));
@@ -660,7 +673,9 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
         // ONE device block per cloud: partials, their fold, the colour flag, the DevStats record and -- for integer-capable
         // inputs -- the packed 8-byte coordinates the brick index is built from
         const bool want_packed = ctx->use_vox && xyz_dtype != PCCM_F32;
-        const size_t head = ((size_t)c->stats_blocks + 2) * sizeof(StatsPartial);
+        const bool want_hist = want_packed && ctx->shard_world > 1;
+        const size_t hist_bytes = want_hist ? (size_t)kZHistBins * sizeof(uint32_t) : 0;
+        const size_t head = ((size_t)c->stats_blocks + 2) * sizeof(StatsPartial) + hist_bytes;
         unsigned char* blockp = nullptr;
         cudaError_t e = dalloc(ctx, &blockp, head + (want_packed ? (size_t)n * sizeof(uint2) : 0));
         if (e == cudaSuccess) {
@@ -668,11 +683,12 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
             c->d_rgbflag = reinterpret_cast<uint32_t*>(c->d_stats + c->stats_blocks);
             c->d_dev = reinterpret_cast<DevStats*>(c->d_stats + c->stats_blocks + 1);
             if (want_packed) c->packed = reinterpret_cast<uint2*>(blockp + head);
-            e = cudaMemsetAsync(c->d_stats + c->stats_blocks, 0, 2 * sizeof(StatsPartial), ctx->stream);
+            if (want_hist) c->d_zhist = reinterpret_cast<uint32_t*>(c->d_stats + c->stats_blocks + 2);
+            e = cudaMemsetAsync(c->d_stats + c->stats_blocks, 0, 2 * sizeof(StatsPartial) + hist_bytes, ctx->stream);
         }
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
-        stats_kernel<<<c->stats_blocks, kStatsThreads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
-                                                                         nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev);   // colours are classified apart
+        stats_kernel<<<c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+                                                                                  nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);   // colours are classified apart
         ctx->tm.total_launches++;
         e = cudaGetLastError();
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats launch: %s", cudaGetErrorString(e)); }
@@ -720,6 +736,7 @@ extern "C" int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* c, pccm_cloud_info
     out->ny = c->grid.ny;
     out->nz = c->grid.nz;
     out->cell_size = c->cell_size;
+    out->sharded = c->vox && c->vox->sharded ? c->vox->shard_world : 0;
     for (int a = 0; a < 3; ++a) { out->aabb_min[a] = c->mn[a]; out->aabb_max[a] = c->mx[a]; }
     return PCCM_OK;
 }
@@ -1152,7 +1169,8 @@ static int colors_u8_async(pccm_ctx* ctx, pccm_cloud* c) {
     return PCCM_OK;
 }
 
-static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int force_kind, uint32_t cap_dirw, uint32_t cap_blk) {
+static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int force_kind, uint32_t cap_dirw, uint32_t cap_blk,
+                       bool full_need = false) {
     StageTimer t(ctx, &ctx->tm.vox_build_ms);
     const uint32_t n_total = (uint32_t)(cl[0]->n + cl[1]->n);
     SharedVox* v = new SharedVox();
@@ -1172,6 +1190,7 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     size_t off = 0;
     auto slice = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_plan = slice(sizeof(VoxPlan));
+    const size_t o_shard = slice(sizeof(ShardPlan));
     const size_t o_dirbits = slice((size_t)cap_dirw * 4), o_dirpre = slice(((size_t)cap_dirw + 1) * 4), o_dirsums = slice((size_t)ndirblocks * 4);
     const size_t o_dirbytes = slice(PCCM_DIR_BYTES ? (size_t)cap_dirw * 32 : 0);
     const size_t o_rows = slice((size_t)cap_blk * kVxRows * 8);
@@ -1189,6 +1208,14 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     v->vkey = reinterpret_cast<uint2*>(v->arena + o_vkey);
     v->prank = reinterpret_cast<uint32_t*>(v->arena + o_prank);
     uint32_t* pslot = reinterpret_cast<uint32_t*>(v->arena + o_pslot);
+    v->sharded = ctx->shard_world > 1 && cl[0]->d_zhist && cl[1]->d_zhist;
+    v->full_need = full_need;
+    v->shard_rank = ctx->shard_rank; v->shard_world = ctx->shard_world;
+    if (v->sharded) {
+        v->dshard = reinterpret_cast<ShardPlan*>(v->arena + o_shard);
+        vx_shardplan_kernel<<<1, 1024, 0, ctx->stream>>>(cl[0]->d_zhist, cl[1]->d_zhist, v->shard_rank, v->shard_world, v->dshard);
+        ctx->tm.total_launches++;
+    }
 #if PCCM_DIR_BYTES
     CKV(cudaMemsetAsync(v->arena + o_dirbytes, 0, (size_t)cap_dirw * 32, ctx->stream));
 #else
@@ -1196,6 +1223,8 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
 #endif
     VoxBuildArgs A{};
+    A.shard = v->dshard;
+    A.full_need = full_need ? 1 : 0;
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
         A.stats[c] = p->d_dev;
@@ -1312,6 +1341,7 @@ static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo) {
         for (int c = 0; c < 2; ++c) {
             pccm_cloud* p = cl[c];
             if (!p) continue;
+            if (v->sharded && !v->full_need) continue;      // (a query that has to look beyond the halo needs the whole pair again)
             p->packed = nullptr;
             dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;   // vxyz holds every voxel, prank every point
         }
@@ -1321,6 +1351,8 @@ static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo) {
     *redo = true;
     const double cell = v->cell_size;
     const int fk = v->force_kind;
+    const bool full_need = v->full_need;
+    const int shard_rank = v->shard_rank, shard_world = v->sharded ? v->shard_world : 1;
     uint32_t cap_dirw = v->cap_dirw, cap_blk = v->cap_blk;
     bool retry_vox = !(st & kVxStNotInt) && cl[0] && cl[1];
     if (retry_vox && (st & kVxStDirOverflow)) {
@@ -1341,7 +1373,10 @@ static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo) {
     for (int c = 0; c < 2; ++c)
         if (cl[c]) { release_vox(ctx, cl[c]); cl[c]->index_kind = -1; }
     if (retry_vox) {
-        rc = vox_enqueue(ctx, cl, cell, fk, cap_dirw, cap_blk);
+        const int sr = ctx->shard_rank, sw = ctx->shard_world;      // the rebuilt index is split the way the first one was
+        ctx->shard_rank = shard_rank; ctx->shard_world = shard_world;
+        rc = vox_enqueue(ctx, cl, cell, fk, cap_dirw, cap_blk, full_need);
+        ctx->shard_rank = sr; ctx->shard_world = sw;
         if (rc) return rc;
         SharedVox* nv = cl[0]->vox;
         rc = vox_fetch(ctx, nv);
@@ -1378,10 +1413,30 @@ static int vox_colors(pccm_ctx* ctx, pccm_cloud* c) {
     return PCCM_OK;
 }
 
+// A split pair whose queries (or a k-NN / hull call) have to look beyond the slab this rank indexed: index the whole
+// pair after all (this rank still queries its own layers only).  Needs both clouds alive (their coordinates were kept).
+static int vox_make_full(pccm_ctx* ctx, pccm_cloud* c) {
+    SharedVox* v = c->vox;
+    if (!v || !v->sharded || v->full_need) return PCCM_OK;
+    pccm_cloud* cl[2] = {v->owner[0], v->owner[1]};
+    if (!cl[0] || !cl[1]) return fail(ctx, PCCM_ERR_STATE, "a split pair needs both clouds alive to widen its index");
+    const double cell = v->cell_size;
+    const int fk = v->force_kind;
+    const uint32_t cap_dirw = kVoxDefaultDirWords;
+    const uint32_t cap_blk = std::max(1u << 16, (v->n[0] + v->n[1]) / 8) + 2;
+    const int sr = ctx->shard_rank, sw = ctx->shard_world;
+    ctx->shard_rank = v->shard_rank; ctx->shard_world = v->shard_world;
+    for (int k = 0; k < 2; ++k) { release_vox(ctx, cl[k]); cl[k]->index_kind = -1; }
+    int rc = vox_enqueue(ctx, cl, cell, fk, cap_dirw, cap_blk, true);
+    ctx->shard_rank = sr; ctx->shard_world = sw;
+    if (rc) return rc;
+    return vox_settle(ctx, c);
+}
+
 // Pencil index of a brick-indexed cloud, built on first use (self k-NN, normals, hull prefilter,
 // far queries) for both clouds of the pair from the brick records.
 static int ensure_pencil(pccm_ctx* ctx, pccm_cloud* c) {
-    { const int rc = vox_settle(ctx, c); if (rc) return rc; }
+    { int rc = vox_settle(ctx, c); if (!rc) rc = vox_make_full(ctx, c); if (rc) return rc; }
     if (c->recs || c->row_start || !c->vox) return PCCM_OK;
     SharedVox* v = c->vox;
     pccm_cloud* cl[2] = {v->owner[0], v->owner[1]};
@@ -1576,7 +1631,8 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     P.plan = v->dplan;
     P.ndirs = ndirs;
     P.normals_mode = Q.normals_mode;
-    P.rank = rank; P.world = world;
+    P.rank = v->sharded ? 0 : rank;           // (a split pair is cut by layers of z on the device, not by voxel ranks)
+    P.world = v->sharded ? 1 : world;
     memcpy(P.T, Q.T, sizeof P.T);
     P.color_scale = Q.color_scale;
     const double* lut = reinterpret_cast<const double*>(static_cast<char*>(ctx->dscratch) + kLutOffset);
@@ -1662,6 +1718,12 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     ctx->tm.vox_undecided = (int64_t)hcnt[0] + hcnt[1];
     ctx->tm.vox_far = (int64_t)hcnt[2] + hcnt[3];
     ctx->tm.vox_tail = (int64_t)n_total - (int64_t)v->hplan.nvox_total;
+    if (hcnt[2] + hcnt[3] > 0 && v->sharded && !v->full_need) {
+        // a query of this rank has to look beyond the halo: index the whole pair, evaluate again
+        rc = vox_make_full(ctx, qc[0]);
+        *redo = true;
+        return rc;
+    }
     if (hcnt[2] + hcnt[3] > 0) {
         // second round: pencil search for the far voxels, the epilogue of their points, fold again
         for (int d = 0; d < ndirs; ++d) {
@@ -1895,6 +1957,8 @@ static int vox_self_nn(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end,
     P.c = v->view[c->vox_id];
     P.n = (uint32_t)c->n;
     P.begin = (uint32_t)begin; P.end = (uint32_t)end;
+    P.own_zlo = v->hplan.shard.own_zlo; P.own_zhi = v->hplan.shard.own_zhi;
+    if (v->sharded) { P.begin = 0; P.end = P.n; }          // split pairs: this rank's layers instead of a slice of the points
     const uint32_t n_total = P.c.n_total, nwords = (n_total + 31u) / 32u;
     const uint32_t far_blocks = (uint32_t)ctx->sm_count * 2u;
     SelfScratch sx{ctx};
@@ -1921,6 +1985,11 @@ static int vox_self_nn(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end,
     CK(cudaMemcpyAsync(hund, sx.und, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     uint32_t nmm = P.c.nblk;
+    if (*hund > 0u && v->sharded && !v->full_need) {        // an isolated voxel: its nearest neighbour may lie outside the slab
+        const int rc = vox_make_full(ctx, c);
+        if (rc) return rc;
+        return vox_self_nn(ctx, c, begin, end, min_out, max_out, per_point, mem_kind);
+    }
     if (*hund > 0u) {
         const int rc = ensure_pencil(ctx, c);
         if (rc) return rc;

@@ -51,12 +51,20 @@ struct DevStats {
     uint32_t flags, pad;
 };
 constexpr uint32_t kDevNotInt = 1u, kDevNotF32 = 2u, kDevNonFinite = 4u;
+constexpr int kZHistBins = 4096;          // 8-voxel layers of a 15-bit coordinate range
 
 // K0: bounding box + classification of coordinates (and colours) in one pass; integer-valued coordinates are
 // also written as 8-byte {x | y << 16, z} records -- the form every later pass of the brick index reads.
 __global__ void __launch_bounds__(kStatsThreads)
 stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
-             const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out, uint2* packed, DevStats* dev) {
+             const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out, uint2* packed, DevStats* dev, uint32_t* zhist) {
+    // zhist (sharded builds: one pair split over several GPUs by slabs of z): points per 8-voxel layer, kZHistBins
+    // bins, accumulated per block in dynamic shared memory
+    extern __shared__ uint32_t s_hist[];
+    if (zhist) {
+        for (int b = threadIdx.x; b < kZHistBins; b += kStatsThreads) s_hist[b] = 0;
+        __syncthreads();
+    }
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     uint32_t not_int = 0, not_f32 = 0, not_fin = 0, rgb_bad = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -75,6 +83,7 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
             }
         }
         if (packed) packed[i] = make_uint2(((uint32_t)(int)v3[0] & 0xffffu) | ((uint32_t)(int)v3[1] << 16), (uint32_t)(int)v3[2]);
+        if (zhist) atomicAdd(&s_hist[min(max((int)v3[2], 0) >> 3, kZHistBins - 1)], 1u);
         if (rgb != nullptr && rgb_dtype == PCCM_F64) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -88,6 +97,9 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
     __shared__ uint32_t s_flags[4];
     if (threadIdx.x < 4) s_flags[threadIdx.x] = 0;
     __syncthreads();
+    if (zhist)
+        for (int b = threadIdx.x; b < kZHistBins; b += kStatsThreads)
+            if (s_hist[b]) atomicAdd(zhist + b, s_hist[b]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {

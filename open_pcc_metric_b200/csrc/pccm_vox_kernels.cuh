@@ -41,8 +41,19 @@ constexpr int kVxDirChunk = 2048;             // directory words per scan block
 constexpr int kVxBrickChunk = 64;             // bricks per row-base chunk (8 warps x 8 bricks)
 constexpr int kVxMaxBrickChunks = 1 << 16;
 
+// One pair split over the GPUs of a box: every rank holds both clouds, OWNS the queries of a slab of
+// 8-voxel z layers (cut so that the slabs hold equal numbers of points) and indexes only what those queries can see:
+// its slab plus a halo of kVxHaloBricks bricks.  The cuts come from the z histogram of the statistics pass, on the
+// device, identically on every rank -- nothing is exchanged until the partial sums at the very end.
+constexpr int kVxHaloBricks = 2;          // vx_general_kernel certifies answers closer than 17 voxels from bricks within +-2
+struct ShardPlan {
+    int32_t own_zlo, own_zhi;             // brick layers [own_zlo, own_zhi) whose voxels this rank queries
+    int32_t need_zlo, need_zhi;           // brick layers [need_zlo, need_zhi] that are indexed
+};
+
 struct VoxPlan {
     VoxView view[2];
+    ShardPlan shard;                          // (own = everything, need = everything when the pair is not split)
     uint32_t status;
     uint32_t nvox_total;                      // distinct voxels of both clouds
     uint32_t ndirw[2], dir_off[2], ndirw_total;
@@ -51,6 +62,8 @@ struct VoxPlan {
 };
 
 struct VoxBuildArgs {                         // everything the host knows when it enqueues the build
+    const ShardPlan* shard;                   // null: the whole pair is indexed and queried here
+    int32_t full_need;                        // sharded, but index everything (the fallback when a query has to look beyond its halo)
     uint32_t mark_lo, mark_hi;                // vx_mark_kernel: this launch handles the thread slots [mark_lo, mark_hi) of the point passes
     const DevStats* stats[2];
     const uint2* packed[2];                   // {x | y << 16, z} of every input point (stats_kernel)
@@ -70,21 +83,85 @@ struct VoxBuildArgs {                         // everything the host knows when 
     VoxPlan* plan;
 };
 
+// The cuts: layer z belongs to rank k when k / world of all points (both clouds) lie in the layers below it.
+__global__ void __launch_bounds__(1024) vx_shardplan_kernel(const uint32_t* __restrict__ zh0, const uint32_t* __restrict__ zh1,
+                                                            int rank, int world, ShardPlan* out) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_pre[kZHistBins];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int kPer = kZHistBins / 1024;
+    unsigned long long v[kPer], mine = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { v[k] = (unsigned long long)zh0[t * kPer + k] + zh1[t * kPer + k]; mine += v[k]; }
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long run = incl - mine;
+    for (int w = 0; w < warp; ++w) run += s_w[w];
+    unsigned long long total = 0;
+    for (int w = 0; w < 32; ++w) total += s_w[w];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { run += v[k]; s_pre[t * kPer + k] = run; }       // inclusive prefix per layer
+    __syncthreads();
+    // cut(k) = number of layers whose inclusive prefix is <= total * k / world
+    const unsigned long long lo_t = total * (unsigned long long)rank / (unsigned long long)world;
+    const unsigned long long hi_t = total * (unsigned long long)(rank + 1) / (unsigned long long)world;
+    int clo = 0, chi = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        clo += s_pre[t * kPer + k] <= lo_t ? 1 : 0;
+        chi += s_pre[t * kPer + k] <= hi_t ? 1 : 0;
+    }
+    clo = __reduce_add_sync(0xffffffffu, clo);
+    chi = __reduce_add_sync(0xffffffffu, chi);
+    __shared__ int s_c[2][32];
+    if (lane == 0) { s_c[0][warp] = clo; s_c[1][warp] = chi; }
+    __syncthreads();
+    if (t == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < 32; ++w) { a += s_c[0][w]; b += s_c[1][w]; }
+        ShardPlan sp;
+        sp.own_zlo = rank == 0 ? -(1 << 30) : a;
+        sp.own_zhi = rank == world - 1 ? (1 << 30) : b;
+        sp.need_zlo = rank == 0 ? -(1 << 30) : a - kVxHaloBricks;
+        sp.need_zhi = rank == world - 1 ? (1 << 30) : b - 1 + kVxHaloBricks;
+        *out = sp;
+    }
+}
+
 // Brick grids of the two clouds from the device-side statistics.  Cloud 1's directory starts at a chunk
 // boundary, so the number of bricks of cloud 0 is a sum of whole chunk sums.  Returns the status bits.
+__device__ __forceinline__ ShardPlan vx_shard_of(const VoxBuildArgs& A) {
+    ShardPlan sp;
+    sp.own_zlo = -(1 << 30); sp.own_zhi = 1 << 30; sp.need_zlo = -(1 << 30); sp.need_zhi = 1 << 30;
+    if (A.shard) {
+        sp = *A.shard;
+        if (A.full_need) { sp.need_zlo = -(1 << 30); sp.need_zhi = 1 << 30; }
+    }
+    return sp;
+}
 __device__ __forceinline__ uint32_t vx_plan_dims(const VoxBuildArgs& A, VoxDims g[2], uint32_t ndirw[2], uint32_t dir_off[2],
-                                                 int32_t mn[2][3], int32_t mx[2][3]) {
+                                                 int32_t mn[2][3], int32_t mx[2][3], ShardPlan& sp) {
     uint32_t status = 0;
     unsigned long long words = 0;
+    sp = vx_shard_of(A);
     for (int c = 0; c < 2; ++c) {
         const DevStats s = *A.stats[c];
         if (s.flags & (kDevNotInt | kDevNonFinite)) status |= kVxStNotInt;
         for (int a = 0; a < 3; ++a) { mn[c][a] = (int32_t)(0x7fffffffu - s.nmn[a]); mx[c][a] = (int32_t)s.mx[a]; }
         if (status) { ndirw[c] = 0; dir_off[c] = 0; g[c] = VoxDims{0, 0, 0, 1, 1, 1}; continue; }
-        g[c].obx = mn[c][0] >> 5; g[c].oby = mn[c][1] >> 3; g[c].obz = mn[c][2] >> 3;
+        g[c].obx = mn[c][0] >> 5; g[c].oby = mn[c][1] >> 3;
         g[c].nbx = (mx[c][0] >> 5) - g[c].obx + 1;
         g[c].nby = (mx[c][1] >> 3) - g[c].oby + 1;
-        g[c].nbz = (mx[c][2] >> 3) - g[c].obz + 1;
+        // layers of this cloud inside the slab that is indexed here (an empty intersection keeps one layer with no bit set)
+        const int zlo = max(mn[c][2] >> 3, sp.need_zlo), zhi = min(mx[c][2] >> 3, sp.need_zhi);
+        g[c].obz = zlo;
+        g[c].nbz = zhi >= zlo ? zhi - zlo + 1 : 1;
         const unsigned long long bits = (unsigned long long)g[c].nbx * (unsigned long long)g[c].nby * (unsigned long long)g[c].nbz;
         const unsigned long long w = (bits + 31ull) / 32ull;
         dir_off[c] = (uint32_t)words;
@@ -97,13 +174,14 @@ __device__ __forceinline__ uint32_t vx_plan_dims(const VoxBuildArgs& A, VoxDims 
 }
 
 struct VoxDimsSmem {
+    ShardPlan sp;
     VoxDims g[2];
     uint32_t ndirw[2], dir_off[2];
     int32_t mn[2][3], mx[2][3];
     uint32_t status;
 };
 __device__ __forceinline__ void vx_block_dims(const VoxBuildArgs& A, VoxDimsSmem& S) {
-    if (threadIdx.x == 0) S.status = vx_plan_dims(A, S.g, S.ndirw, S.dir_off, S.mn, S.mx);
+    if (threadIdx.x == 0) S.status = vx_plan_dims(A, S.g, S.ndirw, S.dir_off, S.mn, S.mx, S.sp);
     __syncthreads();
 }
 
@@ -127,6 +205,7 @@ __device__ __forceinline__ uint2 vx_point(const VoxBuildArgs& A, uint32_t i, int
     return __ldg(A.packed[c] + li);
 }
 #define VX_UNPACK(p, x, y, z) const int x = (int)((p).x & 0xffffu), y = (int)((p).x >> 16), z = (int)(p).y
+__device__ __forceinline__ bool vx_in_slab(const ShardPlan& sp, const uint2& p) { const int bz = (int)p.y >> 3; return bz >= sp.need_zlo && bz <= sp.need_zhi; }
 
 // Two launches: a small sample of the points first (its atomics meet little contention: thousands of points name the
 // same brick, and read-modify-writes of one directory word queue up at the L2), then everybody else -- who now finds
@@ -153,7 +232,7 @@ __global__ void __launch_bounds__(256) vx_mark_kernel(const __grid_constant__ Vo
     if (S.status) return;
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
-        if (on[k]) {
+        if (on[k] && vx_in_slab(S.sp, p[k])) {
             VX_UNPACK(p[k], x, y, z);
 #if PCCM_DIR_BYTES
             A.dirbytes[(size_t)S.dir_off[c[k]] * 32 + vx_key(S.g[c[k]], x, y, z)] = 1;
@@ -245,6 +324,7 @@ __global__ void __launch_bounds__(256) vx_dirscan_kernel(const __grid_constant__
             P.ndirw[c] = S.ndirw[c]; P.dir_off[c] = S.dir_off[c];
             for (int a = 0; a < 3; ++a) { P.mn[c][a] = S.mn[c][a]; P.mx[c][a] = S.mx[c][a]; }
         }
+        P.shard = S.sp;
         P.status = status;
         P.nvox_total = 0;
         P.ndirw_total = nw;
@@ -297,13 +377,16 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
         uint32_t li;
         if (on[k]) p[k] = vx_point(A, idx[k], c[k], li);
     }
+    const ShardPlan sp = P->shard;
 #pragma unroll
-    for (int k = 0; k < kVxIlp; ++k)
+    for (int k = 0; k < kVxIlp; ++k) {
+        on[k] = on[k] && vx_in_slab(sp, p[k]);
         if (on[k]) {
             VX_UNPACK(p[k], x, y, z);
             const VoxView& V = P->view[c[k]];
             slot[k] = vx_slot_of_key(V.dirbits, V.dirpre, vx_key(V.g, x, y, z));
         }
+    }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
         if (on[k]) {
@@ -405,6 +488,7 @@ __global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ V
     const VoxPlan* __restrict__ P = A.plan;
     if (P->status) return;
     const uint32_t n_total = A.n[0] + A.n[1];
+    const ShardPlan sp = P->shard;
     uint32_t idx[kVxIlp], li[kVxIlp], slot[kVxIlp], rgba[kVxIlp];
     uint2 p[kVxIlp];
     bool on[kVxIlp];
@@ -415,6 +499,11 @@ __global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ V
         if (on[k]) {
             int c;
             p[k] = vx_point(A, idx[k], c, li[k]);
+            if (!vx_in_slab(sp, p[k])) {                    // not indexed on this rank: no voxel, no query
+                A.prank[idx[k]] = kVxNone;
+                on[k] = false;
+                continue;
+            }
             slot[k] = A.pslot[idx[k]];
             rgba[k] = A.rgb[c] ? (__ldg(static_cast<const uint32_t*>(A.rgb[c]) + li[k]) & 0xffffffu) : 0u;   // colours that have already arrived ride in vkey
         }
@@ -767,6 +856,10 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
         const uint2* __restrict__ qxyz = Q.vxyz;
         const uint2 first = __ldg(qxyz + b0);
         const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
+        if (bz < plan->shard.own_zlo || bz >= plan->shard.own_zhi) {       // halo brick of a split pair: another rank's queries
+            for (uint32_t t = t0 + lane; t < t1; t += 32) P.vres[t] = make_uint4(kVxNone, 0u, 0u, 0u);
+            continue;
+        }
         __syncwarp();                                        // (the previous brick's window is no longer read)
         int myslot = -1;
         if (lane < 27) {
@@ -1024,6 +1117,7 @@ struct VxSelfParams {
     VoxView c;
     uint32_t n;                // points of the cloud
     uint32_t begin, end;       // slice of the cloud's points [begin, end) -> the same share of its voxels
+    int32_t own_zlo, own_zhi;  // split pairs: only the voxels of these brick layers (the slice is then everything)
     uint32_t* dupbits;         // [n_total / 32 + 1] by rank: voxel holds more than one point
     uint32_t* vself;           // [n_total] by rank: squared distance to the nearest other point (kVxNone: not decided here)
     double* minmax;            // per brick {min, max} of the distances (sqrt)
@@ -1035,6 +1129,7 @@ __global__ void vx_dupflag_kernel(const __grid_constant__ VxSelfParams P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t rank = __ldg(P.c.prank + i);
+    if (rank == kVxNone) return;                       // (split pair: the point is outside this rank's slab)
     if (__ldg(&P.c.vkey[rank].y) != i) atomicOr(P.dupbits + (rank >> 5), 1u << (rank & 31u));
 }
 
@@ -1060,7 +1155,12 @@ vx_selfnn_kernel(const __grid_constant__ VxSelfParams P) {
     const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
     uint32_t mn = kVxNone, mx = 0u;
     bool any = false;
-    if (t0 < t1) {
+    bool mine = t0 < t1;
+    if (mine) {
+        const int bz0 = (int)__ldg(&P.c.vxyz[b0].y) >> 3;
+        mine = bz0 >= P.own_zlo && bz0 < P.own_zhi;
+    }
+    if (mine) {
         const uint2 first = __ldg(P.c.vxyz + b0);
         const int bx = (int)(first.x & 0xffffu) >> 5, by = (int)(first.x >> 16) >> 3, bz = (int)first.y >> 3;
         int myslot = -1;
@@ -1159,8 +1259,8 @@ vx_selffar_kernel(const __grid_constant__ VxSelfFarParams P) {
 __global__ void vx_selfout_kernel(const __grid_constant__ VxSelfParams P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const uint32_t v = P.vself[__ldg(P.c.prank + i)];
-    P.per_point[i] = sqrt((double)v);
+    const uint32_t rank = __ldg(P.c.prank + i);
+    P.per_point[i] = rank == kVxNone ? NAN : sqrt((double)P.vself[rank]);
 }
 
 }  // namespace pccm

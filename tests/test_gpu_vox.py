@@ -234,3 +234,49 @@ def test_brick_indexed_cloud_outlives_its_partner_and_joins_other_pairs(ctxs):
     r = vox.pair_eval(b, c, 0)
     assert r.dir[0].n == len(B) and r.dir[1].n == len(C)
     b.close(); c.close()
+
+
+@pytest.mark.parametrize("name", ["surface", "dense_dups_outliers", "sparse", "far_apart", "one_point_each"])
+def test_split_pair_slabs_add_up_to_the_whole(ctxs, name):
+    """pccm_ctx_set_shard: every rank indexes and queries its slab of z only (halo of two bricks); the partial
+    results of the ranks add up to the single-GPU evaluation -- D1 sums / maxima / boundary distances bit for bit,
+    float sums to rounding; queries that must look beyond the halo make that rank index the whole pair."""
+    from open_pcc_metric_b200 import _native as N
+    vox, _ = ctxs
+    A, B = _case(name)
+    n = min(len(A), len(B))
+    A, B = A[:n], B[:n]
+    rng = np.random.default_rng(12)
+    ca, na = _attrs(rng, n)
+    cb, nb = _attrs(rng, n)
+    flags = N.EVAL_D2 | N.EVAL_COLOR
+    a, b = vox.cloud(A, ca, na), vox.cloud(B, cb, nb)
+    vox.build_pair(a, b)
+    full = vox.pair_eval(a, b, flags, YUV)
+    fmn, fmx, _ = (a.self_nn_minmax() if n >= 2 else (0.0, 0.0, None))
+    a.close(); b.close()
+    for world in (2, 5):
+        parts, mm = [], []
+        for r in range(world):
+            vox.set_shard(r, world)
+            try:
+                a, b = vox.cloud(A, ca, na), vox.cloud(B, cb, nb)
+                vox.build_pair(a, b)
+            finally:
+                vox.set_shard(0, 1)
+            assert a.info().sharded == world
+            parts.append(vox.pair_eval(a, b, flags, YUV, rank=r, world=world))
+            if n >= 2:
+                mm.append(a.self_nn_minmax()[:2])
+            a.close(); b.close()
+        for d in range(2):
+            assert sum(p.dir[d].n for p in parts) == full.dir[d].n == n, (name, world, d)
+            assert sum(p.dir[d].sum_d1_u64 for p in parts) == full.dir[d].sum_d1_u64
+            assert max(p.dir[d].max_d1 for p in parts) == full.dir[d].max_d1
+            assert max(p.dir[d].max_d2 for p in parts) == full.dir[d].max_d2
+            assert np.isclose(sum(p.dir[d].sum_d2 for p in parts), full.dir[d].sum_d2, rtol=1e-12)
+            for c in range(3):
+                assert np.isclose(sum(p.dir[d].color_sum[c] for p in parts), full.dir[d].color_sum[c], rtol=1e-12)
+                assert max(p.dir[d].color_max[c] for p in parts) == full.dir[d].color_max[c]
+        if n >= 2:
+            assert min(m[0] for m in mm) == fmn and max(m[1] for m in mm) == fmx, (name, world)

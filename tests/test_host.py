@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     import ctypes
     assert ctypes.sizeof(N.DirResult) == 8 * 3 + 4 * 2 + 8 * 4 + 8 * 6
     assert ctypes.sizeof(N.PairResult) == 2 * ctypes.sizeof(N.DirResult)
-    assert ctypes.sizeof(N.CloudInfo) == 8 + 4 * 8 + 8 + 8 * 6
+    assert ctypes.sizeof(N.CloudInfo) == 8 + 4 * 10 + 8 + 8 * 6
     assert ctypes.sizeof(N.Timings) == 13 * 8 + 7 * 8   # 13 stage timers, 7 counters (include/pccm.h)
 
 
