@@ -18,25 +18,28 @@ def slice_range(n: int, rank: int, world: int):
 
 
 def exchange_partials(vals, world: int, group=None, device="cpu"):
-    """vals: per direction dict(sum_u64, d2_valid, sum_d1, max_d1, sum_d2, max_d2, csum[3], cmax[3]).
-    All-gathers every rank's record and reduces on the host: integer sums exactly
-    (Python ints), float sums in fixed rank order (deterministic for a given world)."""
+    """vals: per direction dict(sum_u64, d2_valid, sum_d1, max_d1, sum_d2, max_d2, csum[3], cmax[3][, n]).
+    ONE all_gather of every rank's record (the 64-bit integer sum travels as two exact 32-bit halves) and a
+    reduction on the host: integer sums exactly (Python ints), float sums in fixed rank order (deterministic
+    for a given world)."""
     import torch
     import torch.distributed as dist
-    fl = torch.tensor([[v["sum_d1"], v["max_d1"], v["sum_d2"], v["max_d2"], *v["csum"], *v["cmax"]] for v in vals],
-                      dtype=torch.float64, device=device)
-    it = torch.tensor([[v["sum_u64"], int(v["d2_valid"])] for v in vals], dtype=torch.int64, device=device)
-    fl_all = [torch.empty_like(fl) for _ in range(world)]
-    it_all = [torch.empty_like(it) for _ in range(world)]
-    dist.all_gather(fl_all, fl, group=group)
-    dist.all_gather(it_all, it, group=group)
-    fl_all = torch.stack(fl_all).cpu().numpy()   # (world, ndir, 10)
-    it_all = torch.stack(it_all).cpu().numpy()
+    rows = []
+    for v in vals:
+        u = int(v["sum_u64"])
+        rows.append([v["sum_d1"], v["max_d1"], v["sum_d2"], v["max_d2"], *v["csum"], *v["cmax"],
+                     float(u >> 32), float(u & 0xffffffff), float(bool(v["d2_valid"])), float(v.get("n", 0))])
+    fl = torch.tensor(rows, dtype=torch.float64, device=device)
+    parts = [torch.empty_like(fl) for _ in range(world)]
+    dist.all_gather(parts, fl, group=group)
+    fl_all = torch.stack(parts).cpu().numpy()    # (world, ndir, 14)
     out = []
     for d, v in enumerate(vals):
         r = dict(v)
-        r["sum_u64"] = int(sum(int(x) for x in it_all[:, d, 0]))
-        r["d2_valid"] = bool(it_all[:, d, 1].min())
+        r["sum_u64"] = int(sum((int(x[10]) << 32) + int(x[11]) for x in fl_all[:, d]))
+        r["d2_valid"] = bool(fl_all[:, d, 12].min())
+        if "n" in v:
+            r["n"] = int(fl_all[:, d, 13].sum())
         acc = np.zeros(10)
         acc[list(MAX_SLOTS)] = -np.inf
         for w in range(world):

@@ -33,7 +33,7 @@ def reference_structure(A, B, color_scheme="yuv", point_to_plane=True, sample=50
     t0 = time.perf_counter()
     trees = tuple(cKDTree(c.points, leafsize=15) for c in clouds)      # cloud_pair.py:65
     build_s = time.perf_counter() - t0
-    T = COLOR_TRANSFORMS[color_scheme]
+    T = COLOR_TRANSFORMS[color_scheme] if color_scheme else None
     n_total = len(A) + len(B)
     work_s = 0.0
     n_sampled = 0
@@ -78,7 +78,7 @@ def cpu_best(A, B, color_scheme="yuv", point_to_plane=True, max_queries=None):
     clouds = (A, B)
     t0 = time.perf_counter()
     trees = tuple(cKDTree(c.points, leafsize=15) for c in clouds)
-    T = COLOR_TRANSFORMS[color_scheme]
+    T = COLOR_TRANSFORMS[color_scheme] if color_scheme else None
     n = 0
     for q, s in ((0, 1), (1, 0)):
         Q, S = clouds[q], clouds[s]
