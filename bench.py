@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="queries per direction timed through the reference's per-point loops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard-of", default=None, help="R,W: time what rank R of W would do on a split pair, on one GPU, without the exchange (tuning aid)")
     return ap.parse_args()
 
 
@@ -99,9 +100,9 @@ class Workload:
             self.gen = lambda rank: synth.synth_pair(self.bits, self.points, synth.BASE_SEED + 2 + 1000 * (rank if self.frames_mode else 0),
                                                      step=2, dedup=False, oversample=4)
         elif cfg == "split":
-            self.bits, self.points = 12, args.points or 10_000_000
-            self.name = "north_star: ONE synthetic vox12 ~10M-pt pair + RGB + given normals, D1+D2+YUV, z-slab split over the GPUs"
-            self.gen = lambda rank: self._vox12(synth, True)
+            self.bits, self.points = 12, args.points or 10_500_000
+            self.name = "north_star: ONE synthetic vox12 >=10M-pt pair + RGB + given normals, D1+D2+YUV, z-slab split over the GPUs"
+            self.gen = lambda rank: self._vox12(synth, True, oversample=2, tol=0.04)
         elif cfg == "3":
             self.bits, self.points = 12, args.points or 4_000_000
             self.name = "configs[2]: synthetic vox12 ~4M-pt pair without normals: kNN+PCA normals, D1/D2/Hausdorff"
@@ -116,8 +117,18 @@ class Workload:
             self.gen = lambda rank: self._lidar(synth)
         self.peak = float((1 << self.bits) - 1) if self.bits else None
 
-    def _vox12(self, synth, attrs):
-        A = synth.synth_vox(12, self.points, synth.BASE_SEED + 3, with_colors=attrs, with_normals=attrs, oversample=3)
+    def _vox12(self, synth, attrs, oversample=3, tol=0.02):
+        # (generating 10M voxelised surface points takes a minute of numpy: keep them for later runs on the same box)
+        cache = os.path.join("/tmp", f"pccm_bench_vox12_{self.points}_{int(attrs)}_{oversample}.npz")
+        if os.path.exists(cache):
+            z = np.load(cache)
+            A = synth.Cloud(z["p"], z["c"] if attrs else None, z["n"] if attrs else None)
+        else:
+            A = synth.synth_vox(12, self.points, synth.BASE_SEED + 3, with_colors=attrs, with_normals=attrs, oversample=oversample, tol=tol)
+            try:
+                np.savez(cache, p=A.points, c=A.colors if attrs else np.zeros(0), n=A.normals if attrs else np.zeros(0))
+            except OSError:
+                pass
         return A, synth.degrade(A, 2, synth.BASE_SEED + 3, 12, dedup=False)
 
     def _lidar(self, synth):
@@ -332,6 +343,7 @@ def main():
     nq = n_a + n_b
 
     flags = (N.EVAL_D2) | (N.EVAL_COLOR if W.color else 0)
+    emulate = tuple(int(x) for x in args.shard_of.split(",")) if args.shard_of else None
     devstr = f"cuda:{local_rank}"
 
     def fused_dict(res):
@@ -340,7 +352,7 @@ def main():
 
     # ---- the step: C ABI, device-resident raw arrays
     def step_device(shard=None):
-        sh = shard if shard is not None else ((rank, world) if W.split else (0, 1))
+        sh = shard if shard is not None else ((rank, world) if W.split else (emulate or (0, 1)))
         if sh[1] > 1:
             ctx.set_shard(*sh)
         try:
@@ -357,7 +369,7 @@ def main():
         out = fused_dict(res)
         if W.hausdorff:
             out[0]["self_nn"] = a.self_nn_minmax()[:2]
-        if sh[1] > 1 and shard is None:
+        if sh[1] > 1 and shard is None and world > 1:
             out = D.exchange_partials(out, world, None, devstr)      # NCCL all_gather of the partial records, inside the step
         a.close()
         b.close()

@@ -62,6 +62,7 @@ struct pccm_ctx {
     bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
     int vx_search_blocks = 10;      // resident blocks per SM of the persistent brick search kernel (PCCM_VX_BLOCKS)
     int shard_rank = 0, shard_world = 1;   // pccm_ctx_set_shard: pairs built from now on are split by z slabs over `world` ranks
+    bool shard_sel = true;          // split pairs: fill / place walk a compacted list of the slab's points (PCCM_SHARD_SEL=0: every point)
     int mark_sample = 32;           // the brick directory is marked by 1 / mark_sample of the points first (PCCM_MARK_SAMPLE, 0 = one pass)
 };
 
@@ -483,6 +484,7 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
     if (const char* s = getenv("PCCM_MARK_SAMPLE")) ctx->mark_sample = std::max(0, atoi(s));
+    if (const char* s = getenv("PCCM_SHARD_SEL")) ctx->shard_sel = atoi(s) != 0;
     if (const char* s = getenv("PCCM_NORMALS_COUNTING")) ctx->normals_counting = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
@@ -1191,12 +1193,16 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     auto slice = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_plan = slice(sizeof(VoxPlan));
     const size_t o_shard = slice(sizeof(ShardPlan));
+    const size_t o_selcnt = slice(4);               // (directly in front of the directory bits: one memset clears both)
     const size_t o_dirbits = slice((size_t)cap_dirw * 4), o_dirpre = slice(((size_t)cap_dirw + 1) * 4), o_dirsums = slice((size_t)ndirblocks * 4);
     const size_t o_dirbytes = slice(PCCM_DIR_BYTES ? (size_t)cap_dirw * 32 : 0);
     const size_t o_rows = slice((size_t)cap_blk * kVxRows * 8);
     const size_t o_bricksums = slice((size_t)nbrickchunks * 4);
     const size_t o_vxyz = slice((size_t)n_total * 8), o_vkey = slice((size_t)n_total * 8), o_prank = slice((size_t)n_total * 4);
     const size_t o_pslot = slice((size_t)n_total * 4);
+    const bool sharded = ctx->shard_world > 1 && cl[0]->d_zhist && cl[1]->d_zhist;
+    const bool use_sel = sharded && !full_need && ctx->shard_sel;
+    const size_t o_sel = slice(use_sel ? (size_t)n_total * 4 : 0);
     CKV(dalloc(ctx, &v->arena, off));
     v->dplan = reinterpret_cast<VoxPlan*>(v->arena + o_plan);
     v->dirbits = reinterpret_cast<uint32_t*>(v->arena + o_dirbits);
@@ -1208,7 +1214,7 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     v->vkey = reinterpret_cast<uint2*>(v->arena + o_vkey);
     v->prank = reinterpret_cast<uint32_t*>(v->arena + o_prank);
     uint32_t* pslot = reinterpret_cast<uint32_t*>(v->arena + o_pslot);
-    v->sharded = ctx->shard_world > 1 && cl[0]->d_zhist && cl[1]->d_zhist;
+    v->sharded = sharded;
     v->full_need = full_need;
     v->shard_rank = ctx->shard_rank; v->shard_world = ctx->shard_world;
     if (v->sharded) {
@@ -1220,11 +1226,13 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     CKV(cudaMemsetAsync(v->arena + o_dirbytes, 0, (size_t)cap_dirw * 32, ctx->stream));
 #else
     (void)o_dirbytes;
-    CKV(cudaMemsetAsync(v->dirbits, 0, (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
+    CKV(cudaMemsetAsync(v->arena + o_selcnt, 0, (o_dirbits - o_selcnt) + (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
 #endif
     VoxBuildArgs A{};
     A.shard = v->dshard;
     A.full_need = full_need ? 1 : 0;
+    A.sel = use_sel ? reinterpret_cast<uint32_t*>(v->arena + o_sel) : nullptr;
+    A.sel_count = use_sel ? reinterpret_cast<uint32_t*>(v->arena + o_selcnt) : nullptr;
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
         A.stats[c] = p->d_dev;
@@ -1260,10 +1268,13 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     }
     vx_dirsum_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
     vx_dirscan_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
-    vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    const int sel_grid = ctx->sm_count * 8;
+    if (use_sel) vx_fill_sel_kernel<<<sel_grid, threads, 0, ctx->stream>>>(A);
+    else vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
     vx_bricksum_kernel<<<brick_grid, threads, 0, ctx->stream>>>(A);
     vx_rowbase_kernel<<<brick_grid, threads, 0, ctx->stream>>>(A);
-    vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    if (use_sel) vx_place_sel_kernel<<<sel_grid, threads, 0, ctx->stream>>>(A);
+    else vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
     ctx->tm.total_launches += 7;
     CKV(cudaGetLastError());
 #undef CKV

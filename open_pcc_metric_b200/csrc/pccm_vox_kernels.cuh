@@ -62,6 +62,8 @@ struct VoxPlan {
 };
 
 struct VoxBuildArgs {                         // everything the host knows when it enqueues the build
+    uint32_t* sel;                            // split pairs: the input points inside this rank's slab, compacted by vx_mark_kernel
+    uint32_t* sel_count;                      //   (unordered; fill and place walk this list instead of every point); null otherwise
     const ShardPlan* shard;                   // null: the whole pair is indexed and queried here
     int32_t full_need;                        // sharded, but index everything (the fallback when a query has to look beyond its halo)
     uint32_t mark_lo, mark_hi;                // vx_mark_kernel: this launch handles the thread slots [mark_lo, mark_hi) of the point passes
@@ -212,6 +214,8 @@ __device__ __forceinline__ bool vx_in_slab(const ShardPlan& sp, const uint2& p) 
 // nearly every bit set on the first look (a cached look is enough: bits are only ever set).
 __global__ void __launch_bounds__(256) vx_mark_kernel(const __grid_constant__ VoxBuildArgs A) {
     __shared__ VoxDimsSmem S;
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_base;
     const uint32_t n_total = A.n[0] + A.n[1];
     const uint32_t per = (n_total + kVxIlp - 1) / kVxIlp;
     const uint32_t t = A.mark_lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,14 +229,45 @@ __global__ void __launch_bounds__(256) vx_mark_kernel(const __grid_constant__ Vo
         uint32_t li;
         if (on[k]) {
             p[k] = vx_point(A, i, c[k], li);
-            A.vkey[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); // neutral element of the place pass's atomicMin
+            if (!A.sel) A.vkey[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); // neutral element of the place pass's atomicMin
         }
     }
     vx_block_dims(A, S);
     if (S.status) return;
+    bool in[kVxIlp];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kVxIlp; ++k) {
+        in[k] = on[k] && vx_in_slab(S.sp, p[k]);
+        mine += in[k] ? 1u : 0u;
+    }
+    if (A.sel) {
+        // split pair: the points of this rank's slab go to a compacted list (block-wise: one atomic per block), the
+        // others get "no voxel" as their rank right here
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t off = incl - mine, total = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
+        if (threadIdx.x == 0) s_base = total ? atomicAdd(A.sel_count, total) : 0u;
+        __syncthreads();
+        off += s_base;
+#pragma unroll
+        for (int k = 0; k < kVxIlp; ++k) {
+            const uint32_t i = t + (uint32_t)k * per;
+            if (in[k]) A.sel[off++] = i;
+            else if (on[k]) A.prank[i] = kVxNone;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k)
-        if (on[k] && vx_in_slab(S.sp, p[k])) {
+        if (in[k]) {
             VX_UNPACK(p[k], x, y, z);
 #if PCCM_DIR_BYTES
             A.dirbytes[(size_t)S.dir_off[c[k]] * 32 + vx_key(S.g[c[k]], x, y, z)] = 1;
@@ -395,6 +430,41 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
             vx_fill_point(A.rows, slot[k], x, y, z);
             A.pslot[idx[k]] = slot[k];
         }
+}
+
+// split pairs: the same two passes over the compacted list of this rank's points (grid-stride: its length is only
+// known on the device)
+__global__ void __launch_bounds__(256) vx_fill_sel_kernel(const __grid_constant__ VoxBuildArgs A) {
+    const VoxPlan* __restrict__ P = A.plan;
+    if (P->status) return;
+    const uint32_t nsel = *A.sel_count, stride = gridDim.x * blockDim.x;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nsel; w += stride) {
+        const uint32_t i = A.sel[w];
+        int c;
+        uint32_t li;
+        const uint2 p = vx_point(A, i, c, li);
+        VX_UNPACK(p, x, y, z);
+        const VoxView& V = P->view[c];
+        const uint32_t slot = vx_slot_of_key(V.dirbits, V.dirpre, vx_key(V.g, x, y, z));
+        VX_CHECK(slot < V.nblk_total);
+        vx_fill_point(A.rows, slot, x, y, z);
+        A.pslot[w] = slot;
+        A.vkey[w] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);       // (there are at most nsel voxels)
+    }
+}
+__global__ void __launch_bounds__(256) vx_place_sel_kernel(const __grid_constant__ VoxBuildArgs A) {
+    const VoxPlan* __restrict__ P = A.plan;
+    if (P->status) return;
+    const uint32_t nsel = *A.sel_count, stride = gridDim.x * blockDim.x;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nsel; w += stride) {
+        const uint32_t i = A.sel[w];
+        int c;
+        uint32_t li;
+        const uint2 p = vx_point(A, i, c, li);
+        VX_UNPACK(p, x, y, z);
+        const uint32_t rgba = A.rgb[c] ? (__ldg(static_cast<const uint32_t*>(A.rgb[c]) + li) & 0xffffffu) : 0u;
+        A.prank[i] = vx_place_point(A.rows, A.vxyz, A.vkey, A.pslot[w], x, y, z, rgba, li);
+    }
 }
 
 // voxels per chunk of kVxBrickChunk bricks (the brick past the last one counts as an empty brick).  A warp owns 8
@@ -949,8 +1019,12 @@ constexpr int kVxEpiThreads = 256;
 #ifndef PCCM_VX_EPIPER
 #define PCCM_VX_EPIPER 2
 #endif
+#ifndef PCCM_VX_EPIITER
+#define PCCM_VX_EPIITER 1          // (measured: 4 trips per block cost 20 % at N = 1 -- fewer, longer blocks hide less latency)
+#endif
 constexpr int kVxEpiPer = PCCM_VX_EPIPER;
-constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
+constexpr int kVxEpiIter = PCCM_VX_EPIITER;      // trips per block: the k / 255 table and the record fold are paid once per kVxEpiTile points
+constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer * kVxEpiIter;
 #ifndef PCCM_EPI_MINBLOCKS
 #define PCCM_EPI_MINBLOCKS 6
 #endif
@@ -968,7 +1042,11 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     qa.lut255 = s_lut; sa.lut255 = s_lut;
     uint32_t t_lo = 0u, t_hi = kVxNone;                   // (kVxNone itself marks "no voxel")
     if (P.world > 1) vx_slice(P, plan->view[D.qc], t_lo, t_hi);
-    const uint32_t i0 = tile * kVxEpiTile + threadIdx.x;
+    VxAcc acc;
+    acc.init();
+    for (int it = 0; it < kVxEpiIter; ++it) {
+    const uint32_t i0 = tile * kVxEpiTile + it * (kVxEpiThreads * kVxEpiPer) + threadIdx.x;
+    if (i0 - threadIdx.x >= D.nq) break;
     uint32_t rk[kVxEpiPer];
     uint4 v[kVxEpiPer];
 #ifndef PCCM_EPI_PRELOAD
@@ -996,8 +1074,6 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j)
         v[j] = (rk[j] >= t_lo && rk[j] < t_hi) ? __ldg(P.vres + rk[j]) : make_uint4(kVxNone, 0u, 0u, 0u);
-    VxAcc acc;
-    acc.init();
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
         if (v[j].x == kVxNone) continue;
@@ -1015,6 +1091,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
             nrgb = nr.w;
         }
         vx_epilogue(P, D, qa, sa, i, qrgb[j], v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc, pre_n ? nrm[j] : nullptr, pre_c);
+    }
     }
     BlockPartial r;
     vx_warp_record(acc, D.flags, r);
