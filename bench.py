@@ -526,6 +526,41 @@ def main():
                                  "what": "same API, clouds held as uint16 / uchar / float32 (float32 normals change D2 only)",
                                  "d1_and_colour_identical_to_float64_inputs": bool(same)}
 
+    if not args.no_e2e and W.cfg == "4":
+        # configs[3]: the sequence API from pinned host float64 frames, pipelined (two contexts alternate: the uploads of
+        # frame t+1 run under the kernels of frame t) against one frame at a time.  Several contexts = several streams: timed
+        # with the wall clock between device-wide synchronisations.
+        from open_pcc_metric_b200.sequence import evaluate_sequence
+
+        def pinned(a):
+            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = a
+            return t.numpy()
+        A2, B2 = W.gen(rank + 500)
+        host = [(Cloud(pinned(A.points), pinned(A.colors), pinned(A.normals)), Cloud(pinned(B.points), pinned(B.colors), pinned(B.normals))),
+                (Cloud(pinned(A2.points), pinned(A2.colors), pinned(A2.normals)), Cloud(pinned(B2.points), pinned(B2.colors), pinned(B2.normals)))]
+        nframes = max(8, min(steps, 40))
+        seq = [host[t % 2] for t in range(nframes)]
+        qf = sum(len(a.points) + len(b.points) for a, b in seq)
+        res_seq = {}
+        for depth in (1, 2):
+            evaluate_sequence(seq[:4], opts, ctx=ctx, pipeline=depth, peak="resolution", resolution_bits=W.bits)       # warm-up
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            evaluate_sequence(seq, opts, ctx=ctx, pipeline=depth, peak="resolution", resolution_bits=W.bits)
+            torch.cuda.synchronize()
+            dt = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            res_seq[depth] = dt
+        h2d = sum(x.nbytes for a, b in seq for c in (a, b) for x in (c.points, c.colors, c.normals)) // nframes
+        e2e = {"value": qf * per_rank_jobs / (res_seq[2] * 1e-3), "unit": UNIT, "ms_per_step": res_seq[2] / nframes,
+               "frames_per_s": nframes * per_rank_jobs / (res_seq[2] * 1e-3), "frames": nframes * per_rank_jobs,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * 96 + 16),
+               "one_frame_at_a_time": {"ms_per_frame": res_seq[1] / nframes, "frames_per_s": nframes * per_rank_jobs / (res_seq[1] * 1e-3)},
+               "api": "evaluate_sequence(frames of host float64 clouds, color=yuv, point_to_plane, pipeline=2): per-frame CloudPair + MetricCalculator, "
+                      "frames round-robin over the ranks; wall clock between device-wide synchronisations"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not W.estimate_normals:
         from oracle import cpu_baseline as cb

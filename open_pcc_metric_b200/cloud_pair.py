@@ -98,14 +98,12 @@ class CloudPair:
         finally:
             if world > 1:
                 self._ctx.set_shard(0, 1)
-        infos = [d.info() for d in self._dev]
-        self._sharded = bool(infos[0].sharded)
-        kind = infos[0].index_kind
-        self._n = tuple(int(i.n) for i in infos)
-        self._aabb = tuple((np.array(i.aabb_min), np.array(i.aabb_max)) for i in infos)
-        self._has_normals = [bool(i.has_normals) for i in infos]
-        self._has_colors = tuple(bool(i.has_colors) for i in infos)
-        self.kind = kind
+        # everything above is only ENQUEUED (uploads, statistics, index build): what the host has to wait for -- coordinate
+        # kind, bounding boxes -- is fetched on first use, so that a caller can prepare the next pair in the meantime
+        self._infos = None
+        self._n = tuple(0 if _attr(c, "points") is None else len(c.points) for c in self.clouds)
+        self._has_normals = [_attr(c, "normals") is not None for c in self.clouds]
+        self._has_colors = tuple(_attr(c, "colors") is not None for c in self.clouds)
         if eager_normals:
             for k in range(2):
                 self._ensure_normals(k)
@@ -114,6 +112,23 @@ class CloudPair:
         if min(self._n) == 0:
             self.close()
             raise IndexError("list index out of range")
+
+    def _info(self):
+        if self._infos is None:
+            self._infos = [d.info() for d in self._dev]
+        return self._infos
+
+    @property
+    def kind(self):
+        return self._info()[0].index_kind
+
+    @property
+    def _sharded(self):
+        return bool(self._info()[0].sharded)
+
+    @property
+    def _aabb(self):
+        return tuple((np.array(i.aabb_min), np.array(i.aabb_max)) for i in self._info())
 
     # ---- reference surface ---------------------------------------------------------
     @property

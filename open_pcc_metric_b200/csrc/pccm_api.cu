@@ -5,7 +5,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +66,11 @@ struct pccm_ctx {
     bool use_vox = true;            // KInt pairs: occupancy-brick index + bit-scan query (PCCM_VOX=0: pencil path only)
     bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
     int vx_search_blocks = 10;      // resident blocks per SM of the persistent brick search kernel (PCCM_VX_BLOCKS)
+    struct HostNarrow* narrow = nullptr;   // host threads + pinned ring for narrowing float64 host arrays (created on first use)
+    bool host_narrow = false;              // PCCM_HOST_NARROW=1: narrow float64 host arrays on the way up.  Off by default: measured on
+                                           // the B200 boxes (PCIe 5 x16, 54 GB/s from pinned memory) eight host threads pack 24 MB
+                                           // in 0.5 ms -- the time the link needs for the unpacked array; it pays on slower links only
+    int host_threads = 0;                  // PCCM_HOST_THREADS (0 = min(hardware threads, 8))
     int shard_rank = 0, shard_world = 1;   // pccm_ctx_set_shard: pairs built from now on are split by z slabs over `world` ranks
     bool shard_sel = true;          // split pairs: fill / place walk a compacted list of the slab's points (PCCM_SHARD_SEL=0: every point)
     int mark_sample = 32;           // the brick directory is marked by 1 / mark_sample of the points first (PCCM_MARK_SAMPLE, 0 = one pass)
@@ -210,6 +220,11 @@ struct SharedVox {
     bool pending = false;            // the build is enqueued but the host has not looked at its outcome yet
     bool sharded = false;            // built on a sharded context: only this rank's slab (+ halo) is indexed, only its layers are queried
     bool full_need = false;          // ... but the whole pair is indexed (fallback: some query had to look beyond the halo)
+    struct HostNarrow* narrow = nullptr;   // host threads + pinned ring for narrowing float64 host arrays (created on first use)
+    bool host_narrow = false;              // PCCM_HOST_NARROW=1: narrow float64 host arrays on the way up.  Off by default: measured on
+                                           // the B200 boxes (PCIe 5 x16, 54 GB/s from pinned memory) eight host threads pack 24 MB
+                                           // in 0.5 ms -- the time the link needs for the unpacked array; it pays on slower links only
+    int host_threads = 0;                  // PCCM_HOST_THREADS (0 = min(hardware threads, 8))
     int shard_rank = 0, shard_world = 1;
     ShardPlan* dshard = nullptr;     // device: the cuts (in the arena)
     uint32_t cap_dirw = 0, cap_blk = 0;
@@ -233,6 +248,8 @@ static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
     if (--v->refs == 0) free_vox(ctx, v);
 }
 
+static constexpr int64_t kNarrowChunk = 1 << 17;       // host-side narrowing: rows per chunk
+static int upload_narrowed(pccm_ctx* ctx, const double* src, int64_t n, int es, cudaStream_t s, unsigned char* d, bool* ok);
 static int vox_settle(pccm_ctx* ctx, pccm_cloud* c);
 static int vox_fetch(pccm_ctx* ctx, SharedVox* v);
 static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo);
@@ -348,6 +365,28 @@ static int attach_colors(pccm_ctx* ctx, pccm_cloud* c, const void* rgb, int dtyp
         if (!ctx->cloud_events.empty()) { c->rgb_ready = ctx->cloud_events.back(); ctx->cloud_events.pop_back(); }
         else CK(cudaEventCreateWithFlags(&c->rgb_ready, cudaEventDisableTiming));
     }
+    if (dtype == PCCM_F64 && stride == 24 && c->n >= kNarrowChunk && ctx->host_narrow) {
+        // 8-bit colours stored as k / 255.0: packed to 3 bytes per row by the host threads (which is also their classification)
+        unsigned char* d8 = nullptr;
+        CK(dalloc(ctx, &d8, (size_t)c->n * 3 + 16));
+        if (s != ctx->stream) {
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+        }
+        bool narrowed = false;
+        const int rcn = upload_narrowed(ctx, static_cast<const double*>(rgb), c->n, 1, s, d8, &narrowed);
+        if (rcn) { dfree(ctx, d8); return rcn; }
+        if (narrowed) {
+            c->raw_rgb = d8; c->raw_rgb_owned = d8;
+            c->raw_rgb_dtype = PCCM_U8; c->raw_rgb_stride = 3;
+            CK(cudaEventRecord(c->rgb_ready, s));
+            c->rgb_pending = true;
+            return PCCM_OK;
+        }
+        CK(cudaEventRecord(ctx->ev_fork, s));                 // (the abandoned chunk copies still target d8: free it behind them)
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
+        dfree(ctx, d8);
+    }
     if (dtype == PCCM_F64 && c->flag_slot < 0) {
         if (ctx->flag_slots.empty()) return fail(ctx, PCCM_ERR_STATE, "too many live clouds with colours in flight");
         c->flag_slot = ctx->flag_slots.back();
@@ -404,6 +443,192 @@ static int finish_colors(pccm_ctx* ctx, pccm_cloud* c) {
     dfree(ctx, c->raw_rgb_owned);
     c->raw_rgb_owned = nullptr;
     c->raw_rgb = nullptr;
+    return PCCM_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// host-side narrowing of float64 HOST arrays (the form Open3D / numpy hand over)
+//
+// Voxelised coordinates are integers and 8-bit colours are k / 255: 24 bytes per row where 6 (uint16 x 3) or 3 (uchar x 3)
+// say the same.  The end-to-end path is bound by the host->device copy, so the rows are narrowed WHILE CHECKING that
+// nothing is lost -- by a few host threads, chunk by chunk, into a ring of pinned staging slots -- and every finished
+// chunk's copy is enqueued at once (it overlaps the packing of the next chunks).  A value that does not fit stops the
+// attempt and the array goes up unchanged.  Results are identical by construction: the device would have made the same
+// conversion (stats_kernel / the colour classification) after the copy.
+// --------------------------------------------------------------------------------------
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    std::function<void(int64_t)> job;
+    int64_t next = 0, count = 0, finished = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+    explicit HostPool(int nthreads) {
+        for (int t = 0; t < nthreads; ++t)
+            threads.emplace_back([this] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return stop || (epoch != seen && next < count); });
+                    if (stop) return;
+                    const uint64_t e = epoch;
+                    while (next < count && epoch == e) {
+                        const int64_t i = next++;
+                        lk.unlock();
+                        job(i);
+                        lk.lock();
+                        if (++finished == count) done_cv.notify_all();
+                    }
+                    seen = e;
+                }
+            });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    // run fn(0..n-1) on the pool; the caller may poll `ready` flags the job sets -- returns after all have finished
+    void start(int64_t n, std::function<void(int64_t)> fn) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(fn); next = 0; count = n; finished = 0; ++epoch;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        done_cv.wait(lk, [&] { return finished == count; });
+    }
+};
+
+static constexpr int kNarrowSlots = 16;                // pinned staging ring (6 bytes per row and slot at most)
+
+struct HostNarrow {
+    HostPool* pool = nullptr;
+    unsigned char* ring = nullptr;                     // pinned: kNarrowSlots x kNarrowChunk x 6 bytes
+    cudaEvent_t slot_free[kNarrowSlots] = {};
+    bool slot_used[kNarrowSlots] = {};
+};
+
+static bool narrow_chunk_u16_scalar(const double* src, int64_t n, uint16_t* dst) {
+    bool ok = true;
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = src[i];
+        const int iv = (int)v;
+        ok &= (double)iv == v && (unsigned)iv <= 32767u;
+        dst[i] = (uint16_t)iv;
+    }
+    return ok;
+}
+static bool narrow_chunk_u8_scalar(const double* src, int64_t n, uint8_t* dst) {
+    bool ok = true;
+    for (int64_t i = 0; i < n; ++i) {
+        const double c = src[i];
+        const double k = std::nearbyint(c * 255.0);
+        ok &= k >= 0.0 && k <= 255.0 && k / 255.0 == c;
+        dst[i] = (uint8_t)(k >= 0.0 && k <= 255.0 ? k : 0.0);
+    }
+    return ok;
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+// four values per step (AVX2): the packing must run several times faster than the PCIe link it feeds
+__attribute__((target("avx2"))) static bool narrow_chunk_u16_avx2(const double* src, int64_t n, uint16_t* dst) {
+    __m256d bad = _mm256_setzero_pd();
+    const __m256d lo = _mm256_set1_pd(0.0), hi = _mm256_set1_pd(32767.0);
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const __m256d v = _mm256_loadu_pd(src + i);
+        const __m128i iv = _mm256_cvttpd_epi32(v);
+        const __m256d back = _mm256_cvtepi32_pd(iv);
+        // not equal after the round trip (also NaN), below 0 or above 32767
+        bad = _mm256_or_pd(bad, _mm256_or_pd(_mm256_cmp_pd(back, v, _CMP_NEQ_UQ), _mm256_or_pd(_mm256_cmp_pd(v, lo, _CMP_LT_OQ), _mm256_cmp_pd(v, hi, _CMP_GT_OQ))));
+        const __m128i p16 = _mm_packus_epi32(iv, iv);
+        _mm_storel_epi64(reinterpret_cast<__m128i*>(dst + i), p16);
+    }
+    bool ok = _mm256_movemask_pd(bad) == 0;
+    if (i < n) ok &= narrow_chunk_u16_scalar(src + i, n - i, dst + i);
+    return ok;
+}
+__attribute__((target("avx2"))) static bool narrow_chunk_u8_avx2(const double* src, int64_t n, uint8_t* dst) {
+    __m256d bad = _mm256_setzero_pd();
+    const __m256d lo = _mm256_set1_pd(0.0), hi = _mm256_set1_pd(255.0), s255 = _mm256_set1_pd(255.0);
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const __m256d c = _mm256_loadu_pd(src + i);
+        const __m256d k = _mm256_round_pd(_mm256_mul_pd(c, s255), _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+        const __m256d q = _mm256_div_pd(k, s255);
+        bad = _mm256_or_pd(bad, _mm256_or_pd(_mm256_cmp_pd(q, c, _CMP_NEQ_UQ), _mm256_or_pd(_mm256_cmp_pd(k, lo, _CMP_LT_OQ), _mm256_cmp_pd(k, hi, _CMP_GT_OQ))));
+        const __m128i iv = _mm256_cvttpd_epi32(k);
+        const __m128i p16 = _mm_packus_epi32(iv, iv);
+        const __m128i p8 = _mm_packus_epi16(p16, p16);
+        const int w = _mm_cvtsi128_si32(p8);
+        memcpy(dst + i, &w, 4);
+    }
+    bool ok = _mm256_movemask_pd(bad) == 0;
+    if (i < n) ok &= narrow_chunk_u8_scalar(src + i, n - i, dst + i);
+    return ok;
+}
+static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+#else
+static const bool g_have_avx2 = false;
+static bool narrow_chunk_u16_avx2(const double* s, int64_t n, uint16_t* d) { return narrow_chunk_u16_scalar(s, n, d); }
+static bool narrow_chunk_u8_avx2(const double* s, int64_t n, uint8_t* d) { return narrow_chunk_u8_scalar(s, n, d); }
+#endif
+static bool narrow_chunk_u16(const double* src, int64_t rows, uint16_t* dst) {
+    return g_have_avx2 ? narrow_chunk_u16_avx2(src, 3 * rows, dst) : narrow_chunk_u16_scalar(src, 3 * rows, dst);
+}
+static bool narrow_chunk_u8(const double* src, int64_t rows, uint8_t* dst) {
+    return g_have_avx2 ? narrow_chunk_u8_avx2(src, 3 * rows, dst) : narrow_chunk_u8_scalar(src, 3 * rows, dst);
+}
+
+static HostNarrow* host_narrow_get(pccm_ctx* ctx);
+
+// rows of 3 float64 (packed) -> rows of 3 uint16 / uint8 on the device.  *ok = false: some value does not fit (nothing
+// usable was produced).  The copies run on `s`.
+static int upload_narrowed(pccm_ctx* ctx, const double* src, int64_t n, int es, cudaStream_t s, unsigned char* d, bool* ok) {
+    *ok = false;
+    HostNarrow* H = host_narrow_get(ctx);
+    if (!H) return PCCM_OK;
+    const int64_t nchunks = (n + kNarrowChunk - 1) / kNarrowChunk;
+    std::vector<std::atomic<int>> state((size_t)nchunks);       // 0 = not packed yet, 1 = packed, 2 = packed but a value did not fit
+    for (auto& f : state) f.store(0, std::memory_order_relaxed);
+    std::atomic<int64_t> released{std::min<int64_t>(nchunks, kNarrowSlots)};     // chunks whose slot may be written
+    std::atomic<bool> bad{false};
+    for (int k = 0; k < kNarrowSlots; ++k)
+        if (H->slot_used[k]) { cudaEventSynchronize(H->slot_free[k]); H->slot_used[k] = false; }
+    H->pool->start(nchunks, [&](int64_t i) {
+        while (i >= released.load(std::memory_order_acquire)) {
+            if (bad.load(std::memory_order_relaxed)) { state[(size_t)i].store(2, std::memory_order_release); return; }
+            std::this_thread::yield();
+        }
+        const int64_t r0 = i * kNarrowChunk, rows = std::min(kNarrowChunk, n - r0);
+        unsigned char* slot = H->ring + (size_t)(i % kNarrowSlots) * kNarrowChunk * 6;
+        const bool fits = bad.load(std::memory_order_relaxed) ? false
+                          : (es == 2 ? narrow_chunk_u16(src + 3 * r0, rows, reinterpret_cast<uint16_t*>(slot))
+                                     : narrow_chunk_u8(src + 3 * r0, rows, slot));
+        if (!fits) bad.store(true, std::memory_order_relaxed);
+        state[(size_t)i].store(fits ? 1 : 2, std::memory_order_release);
+    });
+    cudaError_t err = cudaSuccess;
+    for (int64_t i = 0; i < nchunks; ++i) {
+        int st;
+        while ((st = state[(size_t)i].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+        if (st == 2 || bad.load(std::memory_order_relaxed)) { bad.store(true); released.store(nchunks, std::memory_order_release); break; }
+        const int64_t r0 = i * kNarrowChunk, rows = std::min(kNarrowChunk, n - r0);
+        const int k = (int)(i % kNarrowSlots);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d + (size_t)r0 * 3 * es, H->ring + (size_t)k * kNarrowChunk * 6, (size_t)rows * 3 * es, cudaMemcpyHostToDevice, s);
+        if (err == cudaSuccess) err = cudaEventRecord(H->slot_free[k], s);
+        H->slot_used[k] = true;
+        if (i + kNarrowSlots < nchunks) {               // the chunk that will reuse this slot may go once this copy has landed
+            if (err == cudaSuccess) err = cudaEventSynchronize(H->slot_free[k]);
+            H->slot_used[k] = false;
+            released.store(i + kNarrowSlots + 1, std::memory_order_release);
+        }
+    }
+    H->pool->wait();
+    if (err != cudaSuccess) return fail(ctx, PCCM_ERR_CUDA, "narrowed upload: %s", cudaGetErrorString(err));
+    *ok = !bad.load();
     return PCCM_OK;
 }
 
@@ -485,6 +710,8 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
     if (const char* s = getenv("PCCM_MARK_SAMPLE")) ctx->mark_sample = std::max(0, atoi(s));
     if (const char* s = getenv("PCCM_SHARD_SEL")) ctx->shard_sel = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_HOST_NARROW")) ctx->host_narrow = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_HOST_THREADS")) ctx->host_threads = std::max(0, atoi(s));
     if (const char* s = getenv("PCCM_NORMALS_COUNTING")) ctx->normals_counting = atoi(s) != 0;
     if (const char* s = getenv("PCCM_CELL_SCALE")) ctx->cell_scale = atof(s);
     *out = ctx;
@@ -498,6 +725,12 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     resolve_timers(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     for (auto e : ctx->cloud_events) cudaEventDestroy(e);
+    if (ctx->narrow) {
+        delete ctx->narrow->pool;
+        for (auto e : ctx->narrow->slot_free) if (e) cudaEventDestroy(e);
+        if (ctx->narrow->ring) cudaFreeHost(ctx->narrow->ring);
+        delete ctx->narrow;
+    }
     for (int d = 0; d < 2; ++d) { dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]); }
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->pinned);
@@ -508,6 +741,18 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCCM_OK;
+}
+
+static HostNarrow* host_narrow_get(pccm_ctx* ctx) {
+    if (ctx->narrow) return ctx->narrow;
+    HostNarrow* H = new HostNarrow();
+    if (cudaMallocHost(reinterpret_cast<void**>(&H->ring), (size_t)kNarrowSlots * kNarrowChunk * 6) != cudaSuccess) { cudaGetLastError(); delete H; return nullptr; }
+    for (auto& e : H->slot_free)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    int nt = ctx->host_threads > 0 ? ctx->host_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    H->pool = new HostPool(nt);
+    ctx->narrow = H;
+    return H;
 }
 
 extern "C" int pccm_ctx_synchronize(pccm_ctx* ctx) {
@@ -666,7 +911,15 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
         StageTimer t(ctx, &ctx->tm.upload_ms);
         c->raw_dtype = xyz_dtype;
         c->raw_stride = xyz_stride;
-        if (n) rc = upload_rows(ctx, xyz, xyz_dtype, n, &c->raw_stride, mem_kind, &c->raw_xyz, &c->raw_owned);
+        bool narrowed = false;
+        if (n >= kNarrowChunk && mem_kind == PCCM_HOST && xyz_dtype == PCCM_F64 && (xyz_stride == 0 || xyz_stride == 24) && ctx->host_narrow) {
+            unsigned char* d = nullptr;
+            CK(dalloc(ctx, &d, (size_t)n * 6));
+            rc = upload_narrowed(ctx, static_cast<const double*>(xyz), n, 2, ctx->stream, d, &narrowed);
+            if (narrowed) { c->raw_xyz = d; c->raw_owned = d; c->raw_dtype = PCCM_U16; c->raw_stride = 6; }
+            else dfree(ctx, d);
+        }
+        if (n && !rc && !narrowed) rc = upload_rows(ctx, xyz, xyz_dtype, n, &c->raw_stride, mem_kind, &c->raw_xyz, &c->raw_owned);
     }
     if (rc) { pccm_cloud_destroy(ctx, c); return rc; }
     if (n) {

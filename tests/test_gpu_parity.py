@@ -371,7 +371,7 @@ def test_config2_full_size_properties(ctx):
     assert not z.any() and np.array_equal(i2, np.arange(len(A)))
 
 
-def test_sequence_evaluation_is_per_frame(ctx):
+def test_sequence_evaluation_is_per_frame(ctx, tmp_path):
     """Config-4 shape at test scale: every frame gets its own values (the reference's class-level
     memo, quirk Q2, would repeat frame 0), equal to evaluating each pair alone."""
     from open_pcc_metric_b200.calculator import MetricCalculator
@@ -389,6 +389,20 @@ def test_sequence_evaluation_is_per_frame(ctx):
         got = df[df["frame"] == t].drop(columns="frame").reset_index(drop=True)
         assert got.equals(alone)
     assert df[df["frame"] == 0]["value"].tolist() != df[df["frame"] == 1]["value"].tolist()
+    # pipelined (two contexts alternate, uploads of frame t+1 under the kernels of frame t), lazy frames, CSV stream:
+    # the same table, in frame order
+    import pandas as pd
+    lazy = [(lambda f=f: f) for f in frames + frames]
+    path = str(tmp_path / "seq.csv")
+    dfp = evaluate_sequence(lazy, opts, ctx=ctx, pipeline=2, csv_path=path, peak="resolution", resolution_bits=7)
+    assert dfp["frame"].tolist() == sorted(dfp["frame"].tolist()) and len(dfp) == 6 * 20
+    for t in range(6):
+        got = dfp[dfp["frame"] == t].drop(columns="frame").reset_index(drop=True)
+        assert got.equals(df[df["frame"] == t % 3].drop(columns="frame").reset_index(drop=True))
+    back = pd.read_csv(path)
+    assert len(back) == len(dfp) and back["frame"].tolist() == dfp["frame"].tolist() and back["label"].tolist() == dfp["label"].tolist()
+    single = evaluate_sequence(frames, opts, ctx=ctx, pipeline=1, peak="resolution", resolution_bits=7)
+    assert single.equals(df)
 
 
 def test_cli_end_to_end(ctx, tmp_path):

@@ -280,3 +280,42 @@ def test_split_pair_slabs_add_up_to_the_whole(ctxs, name):
                 assert max(p.dir[d].color_max[c] for p in parts) == full.dir[d].color_max[c]
         if n >= 2:
             assert min(m[0] for m in mm) == fmn and max(m[1] for m in mm) == fmx, (name, world)
+
+
+def test_host_narrowing_is_transparent(ctxs):
+    """float64 HOST coordinates / colours are narrowed to uint16 / uchar by host threads while being checked (AVX2 or
+    scalar); values that do not fit (a fraction, a colour that is not k / 255, NaN) make the array go up unchanged.
+    Either way the evaluation is bit-identical to the one without narrowing."""
+    from open_pcc_metric_b200 import _native as N
+    from open_pcc_metric_b200.synth import synth_pair
+    plain, _ = ctxs
+    os.environ["PCCM_HOST_NARROW"] = "1"           # (opt-in: it only pays on links slower than the packing threads)
+    try:
+        vox = N.Context(0)
+    finally:
+        del os.environ["PCCM_HOST_NARROW"]
+    A, B = synth_pair(10, 300_000, 5, dedup=False, oversample=4)
+    n = len(A)
+    assert n > 2 * (1 << 17)                       # several chunks, the last one partial
+    flags = N.EVAL_D2 | N.EVAL_COLOR
+    variants = {"clean": (A.points, A.colors)}
+    P2 = A.points.copy(); P2[n - 3, 1] += 0.5      # a fraction in the last chunk: the pair becomes a float pair
+    variants["fraction"] = (P2, A.colors)
+    C2 = A.colors.copy(); C2[n // 2, 2] = 0.3      # not k / 255: float64 colour arrays
+    variants["odd colour"] = (A.points, C2)
+    for name, (pts, col) in variants.items():
+        outs = []
+        for ctx in (vox, plain):
+            a, b = ctx.cloud(pts, col, A.normals), ctx.cloud(B.points, B.colors, B.normals)
+            ctx.build_pair(a, b)
+            assert bool(a.info().colors_u8) == (name != "odd colour")
+            assert a.info().index_kind == (1 if name == "fraction" else 0) or name == "fraction"
+            outs.append(bytes(ctx.pair_eval(a, b, flags, YUV)))
+            a.close(); b.close()
+        assert outs[0] == outs[1], name
+    bad = A.points.copy(); bad[7, 0] = np.nan
+    c = vox.cloud(bad)
+    with pytest.raises(N.PccmError, match="NaN"):
+        c.build_index()
+    c.close()
+    vox.close()
