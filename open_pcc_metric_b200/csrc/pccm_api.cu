@@ -1,7 +1,6 @@
 // pccm_api.cu -- host orchestration + C ABI (include/pccm.h) of libpccm.so.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared ...
 // There is no CPU path: every entry point needs a CUDA device.
-#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -62,7 +61,6 @@ struct pccm_ctx {
     double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
     uint32_t short_row = 0;         // rows up to this length skip the binary search (PCCM_SHORT_ROW; measured: never a win)
     bool normals_counting = true;   // KInt normals by counting selection (PCCM_NORMALS_COUNTING=0: list-based kernel only)
-    bool use_rowsort = true;        // KInt pair build: counting sort + per-row sort instead of CUB radix (PCCM_ROWSORT=0 disables)
     bool use_vox = true;            // KInt pairs: occupancy-brick index + bit-scan query (PCCM_VOX=0: pencil path only)
     bool eager_pencil = false;      // build the pencil index of brick-indexed pairs at once instead of on first use (PCCM_EAGER_PENCIL=1)
     int vx_search_blocks = 10;      // resident blocks per SM of the persistent brick search kernel (PCCM_VX_BLOCKS)
@@ -250,6 +248,7 @@ static void release_vox(pccm_ctx* ctx, pccm_cloud* c) {
 
 static constexpr int64_t kNarrowChunk = 1 << 17;       // host-side narrowing: rows per chunk
 static int upload_narrowed(pccm_ctx* ctx, const double* src, int64_t n, int es, cudaStream_t s, unsigned char* d, bool* ok);
+static int build_rowsort_kind(pccm_ctx* ctx, int kind, pccm_cloud* cl[2], const PairRaw& R);
 static int vox_settle(pccm_ctx* ctx, pccm_cloud* c);
 static int vox_fetch(pccm_ctx* ctx, SharedVox* v);
 static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo);
@@ -704,7 +703,6 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     }
     if (const char* s = getenv("PCCM_CELL_SHIFT")) ctx->cell_override_shift = atoi(s);
     if (const char* s = getenv("PCCM_SHORT_ROW")) ctx->short_row = (uint32_t)atoi(s);
-    if (const char* s = getenv("PCCM_ROWSORT")) ctx->use_rowsort = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VOX")) ctx->use_vox = atoi(s) != 0;
     if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
@@ -1029,18 +1027,6 @@ static int bits_for(uint64_t v) {
     return b;
 }
 
-template <class KeyT>
-static int sort_pairs(pccm_ctx* ctx, KeyT* keys_in, KeyT* keys_out, uint32_t* vals_in, uint32_t* vals_out, uint32_t n, int end_bit) {
-    size_t bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, ctx->stream));
-    unsigned char* tmp = nullptr;
-    CK(dalloc(ctx, &tmp, bytes));
-    CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, ctx->stream));
-    dfree(ctx, tmp);
-    ctx->tm.library_launches += 1 + (end_bit + 7) / 8;
-    return PCCM_OK;
-}
-
 static int exclusive_scan(pccm_ctx* ctx, uint32_t* data, size_t count) {
     if (count <= kScanSmallMax) {
         scan_small_kernel<false><<<1, kScanSmallThreads, 0, ctx->stream>>>(data, (uint32_t)count, nullptr);
@@ -1135,201 +1121,38 @@ extern "C" int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* c, double cell_
     int xbits = 0;
     choose_grid(ctx, c, kind, cell_size, g, xbits);
     c->cell_size = g.h;
-    const size_t nrows = (size_t)g.ny * g.nz;
-    const int rowbits = std::max(1, bits_for(nrows - 1));
-    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
-
-    CK(dalloc(ctx, &c->row_start, nrows + 1));
-    uint32_t *vals_a = nullptr, *vals_b = nullptr;
-    CK(dalloc(ctx, &vals_a, (size_t)n));
-    CK(dalloc(ctx, &vals_b, (size_t)n));
-    uint32_t* sorted_vals = vals_b;
-    {
-        StageTimer t(ctx, &ctx->tm.keys_ms);
-        CK(cudaMemsetAsync(c->row_start, 0, (nrows + 1) * sizeof(uint32_t), ctx->stream));
-    }
-    if (kind == PCCM_KIND_INT && rowbits + xbits <= 32) {
-        uint32_t *ka = nullptr, *kb = nullptr;
-        CK(dalloc(ctx, &ka, (size_t)n));
-        CK(dalloc(ctx, &kb, (size_t)n));
-        {
-            StageTimer t(ctx, &ctx->tm.keys_ms);
-            keys_int_kernel<uint32_t><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, xbits, ka, vals_a, c->row_start);
-            ctx->tm.total_launches++;
-        }
-        {
-            StageTimer t(ctx, &ctx->tm.sort_ms);
-            rc = sort_pairs<uint32_t>(ctx, ka, kb, vals_a, vals_b, n, rowbits + xbits);
-        }
-        dfree(ctx, ka); dfree(ctx, kb);
-        if (rc) return rc;
-    } else if (kind == PCCM_KIND_INT || kind == PCCM_KIND_F32) {
-        unsigned long long *ka = nullptr, *kb = nullptr;
-        CK(dalloc(ctx, &ka, (size_t)n));
-        CK(dalloc(ctx, &kb, (size_t)n));
-        int end_bit;
-        {
-            StageTimer t(ctx, &ctx->tm.keys_ms);
-            if (kind == PCCM_KIND_INT) {
-                keys_int_kernel<unsigned long long><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, xbits, ka, vals_a, c->row_start);
-                end_bit = rowbits + xbits;
-            } else {
-                keys_f32_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, ka, vals_a, c->row_start);
-                end_bit = 32 + rowbits;
-            }
-            ctx->tm.total_launches++;
-        }
-        {
-            StageTimer t(ctx, &ctx->tm.sort_ms);
-            rc = sort_pairs<unsigned long long>(ctx, ka, kb, vals_a, vals_b, n, end_bit);
-        }
-        dfree(ctx, ka); dfree(ctx, kb);
-        if (rc) return rc;
-    } else {  // F64: LSD in two stable sorts -- by full-precision x, then by row
-        unsigned long long *ka = nullptr, *kb = nullptr;
-        uint32_t *rowkeys = nullptr, *rk_a = nullptr, *rk_b = nullptr;
-        CK(dalloc(ctx, &ka, (size_t)n));
-        CK(dalloc(ctx, &kb, (size_t)n));
-        CK(dalloc(ctx, &rowkeys, (size_t)n));
-        CK(dalloc(ctx, &rk_a, (size_t)n));
-        CK(dalloc(ctx, &rk_b, (size_t)n));
-        {
-            StageTimer t(ctx, &ctx->tm.keys_ms);
-            keys_f64_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, g, ka, rowkeys, vals_a, c->row_start);
-            ctx->tm.total_launches++;
-        }
-        {
-            StageTimer t(ctx, &ctx->tm.sort_ms);
-            rc = sort_pairs<unsigned long long>(ctx, ka, kb, vals_a, vals_b, n, 64);
-            if (!rc) {
-                gather_u32_kernel<<<blocks, threads, 0, ctx->stream>>>(rowkeys, vals_b, n, rk_a);
-                ctx->tm.total_launches++;
-                rc = sort_pairs<uint32_t>(ctx, rk_a, rk_b, vals_b, vals_a, n, rowbits);
-            }
-        }
-        sorted_vals = vals_a;
-        dfree(ctx, ka); dfree(ctx, kb); dfree(ctx, rowkeys); dfree(ctx, rk_a); dfree(ctx, rk_b);
-        if (rc) return rc;
-    }
-    CK(cudaGetLastError());
-    {
-        StageTimer t(ctx, &ctx->tm.table_ms);
-        rc = exclusive_scan(ctx, c->row_start, nrows + 1);
-        if (rc) return rc;
-    }
-    {
-        StageTimer t(ctx, &ctx->tm.reorder_ms);
-        if (kind == PCCM_KIND_INT) {
-            uint4* r = nullptr;
-            CK(dalloc(ctx, &r, (size_t)n));
-            reorder_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, c->rgb_u8, r);
-            c->recs = r;
-            c->rgb_in_rec = c->rgb_u8 != nullptr;
-        } else if (kind == PCCM_KIND_F32) {
-            float4* r = nullptr;
-            CK(dalloc(ctx, &r, (size_t)n));
-            reorder_kernel<KF32><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, nullptr, r);
-            c->recs = r;
-        } else {
-            RecF64* r = nullptr;
-            CK(dalloc(ctx, &r, (size_t)n));
-            reorder_kernel<KF64><<<blocks, threads, 0, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n, sorted_vals, nullptr, r);
-            c->recs = r;
-        }
-        ctx->tm.total_launches++;
-        CK(cudaGetLastError());
-    }
-    dfree(ctx, vals_a); dfree(ctx, vals_b);
-    dfree(ctx, c->raw_owned);
-    c->raw_owned = nullptr;
-    c->raw_xyz = nullptr;
-    c->packed = nullptr;
-    c->grid = g;
-    c->index_kind = kind;
-    return PCCM_OK;
+    // the pair build with an empty partner: counting sort by row + per-row sort networks (no library sort)
+    PairRaw R{};
+    R.g[0] = g;
+    R.g[1].ny = R.g[1].nz = 0;
+    R.n[0] = n; R.n[1] = 0;
+    R.xyz[0] = c->raw_xyz; R.dtype[0] = c->raw_dtype; R.stride[0] = c->raw_stride;
+    R.table_off[0] = 0; R.table_off[1] = (uint32_t)((size_t)g.ny * g.nz);
+    R.rgb_in_rec[0] = kind == PCCM_KIND_INT && c->rgb_u8 != nullptr;
+    R.rgb[0] = c->rgb_u8; R.rgb_dtype[0] = PCCM_U8; R.rgb_stride[0] = sizeof(uchar4);
+    pccm_cloud* cl[2] = {c, nullptr};
+    return build_rowsort_kind(ctx, kind, cl, R);
 }
 
-// Joint build of the two clouds of a pair (same result as two pccm_cloud_build_index calls,
-// half the launches): one key pass, one radix sort with the cloud id as the top key bit, one
-// scan of the joint row histogram, one reorder.  Falls back to separate builds for the F64
-// kind (two-pass sort), empty clouds, or clouds that are already indexed.
-template <class KeyT, int KIND>
-static int build_pair_impl(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R, int xbits, int rowbits) {
-    const uint32_t n = R.n[0] + R.n[1];
-    const size_t nrows[2] = {(size_t)R.g[0].ny * R.g[0].nz, (size_t)R.g[1].ny * R.g[1].nz};
-    const size_t ntab = nrows[0] + nrows[1] + 1;
-    const int cbit = KIND == KIND_INT ? rowbits + xbits : 32 + rowbits;
-    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
-    SharedIndex* sh = new SharedIndex();
-    KeyT *ka = nullptr, *kb = nullptr;
-    uint32_t *va = nullptr, *vb = nullptr;
-    CK(dalloc(ctx, &sh->table, ntab));
-    CK(dalloc(ctx, &ka, (size_t)n));
-    CK(dalloc(ctx, &kb, (size_t)n));
-    CK(dalloc(ctx, &va, (size_t)n));
-    CK(dalloc(ctx, &vb, (size_t)n));
-    {
-        StageTimer t(ctx, &ctx->tm.keys_ms);
-        CK(cudaMemsetAsync(sh->table, 0, ntab * sizeof(uint32_t), ctx->stream));
-        keys_pair_kernel<KeyT, KIND><<<blocks, threads, 0, ctx->stream>>>(R, xbits, cbit, ka, va, sh->table);
-        ctx->tm.total_launches++;
-        CK(cudaGetLastError());
-    }
-    int rc;
-    {
-        StageTimer t(ctx, &ctx->tm.sort_ms);
-        rc = sort_pairs<KeyT>(ctx, ka, kb, va, vb, n, cbit + 1);
-    }
-    dfree(ctx, ka); dfree(ctx, kb);
-    if (!rc) {
-        StageTimer t(ctx, &ctx->tm.table_ms);
-        rc = exclusive_scan(ctx, sh->table, ntab);
-    }
-    if (!rc) {
-        StageTimer t(ctx, &ctx->tm.reorder_ms);
-        if (KIND == KIND_INT) {
-            uint4* r = nullptr;
-            CK(dalloc(ctx, &r, (size_t)n));
-            reorder_pair_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(R, vb, r);
-            sh->recs = r;
-        } else {
-            float4* r = nullptr;
-            CK(dalloc(ctx, &r, (size_t)n));
-            reorder_pair_kernel<KF32><<<blocks, threads, 0, ctx->stream>>>(R, vb, r);
-            sh->recs = r;
-        }
-        ctx->tm.total_launches++;
-        CK(cudaGetLastError());
-    }
-    dfree(ctx, va); dfree(ctx, vb);
-    if (rc) { dfree(ctx, sh->table); delete sh; return rc; }
-    sh->refs = 2;
-    for (int c = 0; c < 2; ++c) {
-        pccm_cloud* p = cl[c];
-        p->shared = sh;
-        p->recs = sh->recs;
-        p->row_start = sh->table + R.table_off[c];
-        p->base = c ? R.n[0] : 0u;
-        p->grid = R.g[c];
-        p->cell_size = R.g[c].h;
-        p->index_kind = KIND;
-        p->rgb_in_rec = R.rgb_in_rec[c] != 0;
-        dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;
-        if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
-    }
-    return PCCM_OK;
-}
+// Index build without a radix sort, for every coordinate kind and for one cloud or a pair: counting sort by row
+// (histogram ranks + scan) and a hand-written per-row sort by (x, index) -- 64-bit items for integer and float32
+// coordinates, 128-bit ones for float64.  cl[1] may be null (single cloud; R.n[1] == 0).
+template <class K> struct RecOf;
+template <> struct RecOf<KInt> { typedef uint4 T; };
+template <> struct RecOf<KF32> { typedef float4 T; };
+template <> struct RecOf<KF64> { typedef RecF64 T; };
 
-// KInt pair build without the radix sort: counting sort by row (histogram ranks + scan) and a
-// hand-written per-row sort by (x, index).  Same records / table as build_pair_impl.
-static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R) {
+template <class K>
+static int build_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R) {
+    constexpr int KIND = K::kind;
+    typedef typename RowItem<KIND>::T Item;
     const uint32_t n = R.n[0] + R.n[1];
-    const size_t nrows = (size_t)R.g[0].ny * R.g[0].nz + (size_t)R.g[1].ny * R.g[1].nz;
+    const size_t nrows = (size_t)R.g[0].ny * R.g[0].nz + (R.n[1] || cl[1] ? (size_t)R.g[1].ny * R.g[1].nz : 0);
     const size_t ntab = nrows + 1;
     const int threads = 256, blocks = (int)((n + threads - 1) / threads);
     SharedIndex* sh = new SharedIndex();
     uint32_t *rowof = nullptr, *rank = nullptr, *long_rows = nullptr;
-    unsigned long long* items = nullptr;
+    Item* items = nullptr;
     CK(dalloc(ctx, &sh->table, ntab));
     CK(dalloc(ctx, &rowof, (size_t)n));
     CK(dalloc(ctx, &rank, (size_t)n));
@@ -1339,7 +1162,7 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
         StageTimer t(ctx, &ctx->tm.keys_ms);
         CK(cudaMemsetAsync(sh->table, 0, ntab * sizeof(uint32_t), ctx->stream));
         CK(cudaMemsetAsync(long_rows, 0, sizeof(uint32_t), ctx->stream));
-        rowrank_pair_kernel<<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table);
+        if (n) rowrank_pair_kernel<KIND><<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
     }
@@ -1348,21 +1171,47 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
         StageTimer t(ctx, &ctx->tm.table_ms);
         rc = exclusive_scan(ctx, sh->table, ntab);
     }
-    if (!rc) {
+    if (!rc && n) {
         StageTimer t(ctx, &ctx->tm.sort_ms);
-        scatter_pair_kernel<<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table, items);
+        scatter_pair_kernel<KIND><<<blocks, threads, 0, ctx->stream>>>(R, rowof, rank, sh->table, items);
         const uint32_t wblocks = (uint32_t)((nrows * 32 + kRowSortThreads - 1) / kRowSortThreads);
-        rowsort_warp_kernel<<<wblocks, kRowSortThreads, 0, ctx->stream>>>(sh->table, (uint32_t)nrows, items, long_rows + 1, long_rows);
-        rowsort_medium_kernel<<<ctx->sm_count * 14, kRowSortThreads, 0, ctx->stream>>>(sh->table, items, long_rows + 1, long_rows);
-        rowsort_block_kernel<<<ctx->sm_count * 2, kRowSortThreads, 0, ctx->stream>>>(sh->table, items, long_rows + 1, long_rows);
+        const int medium_grid = ctx->sm_count * (KIND == KIND_F64 ? 7 : 14);
+        rowsort_warp_kernel<KIND><<<wblocks, kRowSortThreads, 0, ctx->stream>>>(sh->table, sh->table + 1, (uint32_t)nrows, nullptr, items, long_rows + 1, long_rows);
+        rowsort_medium_kernel<KIND><<<medium_grid, kRowSortThreads, 0, ctx->stream>>>(sh->table, sh->table + 1, items, long_rows + 1, long_rows);
+        rowsort_block_kernel<KIND><<<ctx->sm_count * 2, kRowSortThreads, 0, ctx->stream>>>(sh->table, sh->table + 1, items, long_rows + 1, long_rows, 0);
         ctx->tm.total_launches += 4;
+        // rows longer than a block sorts in shared memory: cut into x buckets (a second counting sort inside the row), then
+        // the same three kernels over the buckets.  Everything is sized by upper bounds; the counts stay on the device.
+        const uint32_t max_split = n / RowSortCap<KIND>::block + 1;
+        if (n > RowSortCap<KIND>::block) {
+            const uint32_t max_buckets = n / kSplitTarget + max_split + 1;
+            SplitRow* srows = nullptr;
+            uint32_t *bmeta = nullptr, *long2 = nullptr;        // bmeta: [0..1] counters, then bcount / bstart / bend
+            Item* items_alt = nullptr;
+            CK(dalloc(ctx, &srows, (size_t)max_split));
+            CK(dalloc(ctx, &bmeta, 2 + 3 * (size_t)max_buckets));
+            CK(dalloc(ctx, &long2, (size_t)max_buckets + 1));
+            CK(dalloc(ctx, &items_alt, (size_t)n));
+            CK(cudaMemsetAsync(bmeta, 0, (2 + (size_t)max_buckets) * sizeof(uint32_t), ctx->stream));
+            CK(cudaMemsetAsync(long2, 0, sizeof(uint32_t), ctx->stream));
+            uint32_t *bcount = bmeta + 2, *bstart = bcount + max_buckets, *bend = bstart + max_buckets;
+            rowsplit_find_kernel<KIND><<<(unsigned)((nrows + 255) / 256), 256, 0, ctx->stream>>>(sh->table, (uint32_t)nrows, srows, bmeta);
+            rowsplit_kernel<KIND><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(srows, bmeta, items, items_alt, rowof, rank, bcount, bstart, bend);
+            rowsplit_copyback_kernel<KIND><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(srows, bmeta, items, items_alt);
+            const uint32_t bblocks = (uint32_t)(((size_t)max_buckets * 32 + kRowSortThreads - 1) / kRowSortThreads);
+            rowsort_warp_kernel<KIND><<<bblocks, kRowSortThreads, 0, ctx->stream>>>(bstart, bend, max_buckets, bmeta + 1, items, long2 + 1, long2);
+            rowsort_medium_kernel<KIND><<<medium_grid, kRowSortThreads, 0, ctx->stream>>>(bstart, bend, items, long2 + 1, long2);
+            rowsort_block_kernel<KIND><<<ctx->sm_count * 2, kRowSortThreads, 0, ctx->stream>>>(bstart, bend, items, long2 + 1, long2, 1);
+            ctx->tm.total_launches += 6;
+            dfree(ctx, srows); dfree(ctx, bmeta); dfree(ctx, long2); dfree(ctx, items_alt);
+        }
         CK(cudaGetLastError());
     }
     if (!rc) {
         StageTimer t(ctx, &ctx->tm.reorder_ms);
-        uint4* r = nullptr;
+        typename RecOf<K>::T* r = nullptr;
         CK(dalloc(ctx, &r, (size_t)n));
-        reorder_items_pair_kernel<KInt><<<blocks, threads, 0, ctx->stream>>>(R, items, r);
+        if (n) reorder_items_pair_kernel<K><<<blocks, threads, 0, ctx->stream>>>(R, items, r);
         sh->recs = r;
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
@@ -1380,13 +1229,20 @@ static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R
         p->base = c ? R.n[0] : 0u;
         p->grid = R.g[c];
         p->cell_size = R.g[c].h;
-        p->index_kind = PCCM_KIND_INT;
+        p->index_kind = KIND;
         p->rgb_in_rec = R.rgb_in_rec[c] != 0;
+        p->packed = nullptr;
         dfree(ctx, p->raw_owned); p->raw_owned = nullptr; p->raw_xyz = nullptr;
         if (p->rgb_in_rec) { dfree(ctx, p->raw_rgb_owned); p->raw_rgb_owned = nullptr; p->raw_rgb = nullptr; }
     }
     return PCCM_OK;
 }
+static int build_rowsort_kind(pccm_ctx* ctx, int kind, pccm_cloud* cl[2], const PairRaw& R) {
+    if (kind == PCCM_KIND_INT) return build_rowsort<KInt>(ctx, cl, R);
+    if (kind == PCCM_KIND_F32) return build_rowsort<KF32>(ctx, cl, R);
+    return build_rowsort<KF64>(ctx, cl, R);
+}
+static int build_pair_rowsort(pccm_ctx* ctx, pccm_cloud* cl[2], const PairRaw& R) { return build_rowsort<KInt>(ctx, cl, R); }
 
 // Occupancy-brick index of a KInt pair (pccm_vox.cuh), enqueued WITHOUT waiting for anything: the bounding
 // boxes, the number of occupied bricks and the number of distinct voxels stay on the device (VoxPlan); arrays are
@@ -1773,7 +1629,7 @@ static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, doubl
         kind = force_kind;
     }
     pccm_cloud* cl[2] = {a, b};
-    const bool separate = kind == PCCM_KIND_F64 || a == b || a->n == 0 || b->n == 0 || a->index_kind >= 0 || b->index_kind >= 0 ||
+    const bool separate = a == b || a->n == 0 || b->n == 0 || a->index_kind >= 0 || b->index_kind >= 0 ||
                           (uint64_t)a->n + (uint64_t)b->n > 0x7fffffffull;
     if (separate) {
         rc = pccm_cloud_build_index(ctx, a, cell_size, kind);
@@ -1782,7 +1638,6 @@ static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, doubl
     }
     (void)allow_vox;
     PairRaw R{};
-    int xbits = 1, rowbits = 1;
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = cl[c];
         if (!p->raw_xyz) return fail(ctx, PCCM_ERR_STATE, "raw coordinates already released");
@@ -1794,8 +1649,6 @@ static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, doubl
         R.g[c] = g;
         R.n[c] = (uint32_t)p->n;
         R.xyz[c] = p->raw_xyz; R.dtype[c] = p->raw_dtype; R.stride[c] = p->raw_stride;
-        xbits = std::max(xbits, xb);
-        rowbits = std::max(rowbits, bits_for((uint64_t)g.ny * g.nz - 1));
     }
     R.table_off[0] = 0;
     R.table_off[1] = (uint32_t)((size_t)R.g[0].ny * R.g[0].nz);
@@ -1809,12 +1662,7 @@ static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, doubl
         if (!R.rgb_in_rec[c]) { rc = finish_colors(ctx, p); if (rc) return rc; }
     }
     for (int c = 0; c < 2; ++c) cl[c]->packed = nullptr;
-    if (kind == PCCM_KIND_INT) {
-        if (ctx->use_rowsort) return build_pair_rowsort(ctx, cl, R);
-        if (rowbits + xbits + 1 <= 32) return build_pair_impl<uint32_t, KIND_INT>(ctx, cl, R, xbits, rowbits);
-        return build_pair_impl<unsigned long long, KIND_INT>(ctx, cl, R, xbits, rowbits);
-    }
-    return build_pair_impl<unsigned long long, KIND_F32>(ctx, cl, R, xbits, rowbits);
+    return build_rowsort_kind(ctx, kind, cl, R);
 }
 
 // --------------------------------------------------------------------------------------

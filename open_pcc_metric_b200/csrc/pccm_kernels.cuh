@@ -205,59 +205,6 @@ __device__ __forceinline__ unsigned long long flip_f64(double d) {
     return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
 }
 
-template <class KeyT>
-__global__ void keys_int_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, RowGrid g, int xbits,
-                                KeyT* keys, uint32_t* vals, uint32_t* row_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int x = (int)load_coord(xyz, dtype, stride, i, 0);
-    int y = (int)load_coord(xyz, dtype, stride, i, 1);
-    int z = (int)load_coord(xyz, dtype, stride, i, 2);
-    uint32_t cy = (uint32_t)((y - g.iy0) >> g.shift), cz = (uint32_t)((z - g.iz0) >> g.shift);
-    uint32_t row = cz * (uint32_t)g.ny + cy;
-    keys[i] = ((KeyT)row << xbits) | (KeyT)x;
-    vals[i] = i;
-    atomicAdd(row_count + row, 1u);
-}
-
-__device__ __forceinline__ uint32_t float_row(const RowGrid& g, double y, double z) {
-    int cy = (int)floor((y - g.y0) * g.inv_h), cz = (int)floor((z - g.z0) * g.inv_h);
-    cy = cy < 0 ? 0 : (cy >= g.ny ? g.ny - 1 : cy);
-    cz = cz < 0 ? 0 : (cz >= g.nz ? g.nz - 1 : cz);
-    return (uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy;
-}
-
-__global__ void keys_f32_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, RowGrid g,
-                                unsigned long long* keys, uint32_t* vals, uint32_t* row_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double x = load_coord(xyz, dtype, stride, i, 0);
-    uint32_t row = float_row(g, load_coord(xyz, dtype, stride, i, 1), load_coord(xyz, dtype, stride, i, 2));
-    keys[i] = ((unsigned long long)row << 32) | flip_f32((float)x);
-    vals[i] = i;
-    atomicAdd(row_count + row, 1u);
-}
-
-__global__ void keys_f64_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, RowGrid g,
-                                unsigned long long* xkeys, uint32_t* rowkeys, uint32_t* vals, uint32_t* row_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double x = load_coord(xyz, dtype, stride, i, 0);
-    uint32_t row = float_row(g, load_coord(xyz, dtype, stride, i, 1), load_coord(xyz, dtype, stride, i, 2));
-    xkeys[i] = flip_f64(x);
-    rowkeys[i] = row;
-    vals[i] = i;
-    atomicAdd(row_count + row, 1u);
-}
-
-__global__ void gather_u32_kernel(const uint32_t* src, const uint32_t* idx, uint32_t n, uint32_t* out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = src[idx[i]];
-}
-
-// ------------------------------------------------------------------------------------
-// K3: gather raw points into sorted records
-// ------------------------------------------------------------------------------------
 template <class K> struct RecPack;
 template <> struct RecPack<KInt> {
     static __device__ __forceinline__ uint4 make(double x, double y, double z, uint32_t idx, uint32_t rgba) {
@@ -274,18 +221,6 @@ template <> struct RecPack<KF64> {
         RecF64 r; r.x = x; r.y = y; r.z = z; r.idx = idx; return r;
     }
 };
-
-template <class K>
-__global__ void reorder_kernel(const void* xyz, int dtype, int64_t stride, uint32_t n, const uint32_t* __restrict__ vals,
-                               const uchar4* __restrict__ rgb_u8, typename K::Rec* __restrict__ recs) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t src = vals[i];
-    uint32_t rgba = 0;
-    if (rgb_u8 != nullptr) { uchar4 c = rgb_u8[src]; rgba = c.x | (c.y << 8) | (c.z << 16); }
-    recs[i] = RecPack<K>::make(load_coord(xyz, dtype, stride, src, 0), load_coord(xyz, dtype, stride, src, 1),
-                               load_coord(xyz, dtype, stride, src, 2), src, rgba);
-}
 
 // ------------------------------------------------------------------------------------
 // exclusive prefix sum of the row histogram -> pencil table (hand-written, three launches:
@@ -429,56 +364,15 @@ __device__ __forceinline__ uint32_t pair_src(const PairRaw& R, int c, uint32_t l
     return __ldg(R.vprank + R.vprank_off[c] + li);
 }
 
+__device__ __forceinline__ uint32_t float_row(const RowGrid& g, double y, double z) {
+    int cy = (int)floor((y - g.y0) * g.inv_h), cz = (int)floor((z - g.z0) * g.inv_h);
+    cy = cy < 0 ? 0 : (cy >= g.ny ? g.ny - 1 : cy);
+    cz = cz < 0 ? 0 : (cz >= g.nz ? g.nz - 1 : cz);
+    return (uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy;
+}
 __device__ __forceinline__ uint32_t int_row(const RowGrid& g, int y, int z) {
     uint32_t cy = (uint32_t)((y - g.iy0) >> g.shift), cz = (uint32_t)((z - g.iz0) >> g.shift);
     return cz * (uint32_t)g.ny + cy;
-}
-
-template <class KeyT, int KIND>
-__global__ void keys_pair_kernel(const __grid_constant__ PairRaw R, int xbits, int cbit,
-                                 KeyT* keys, uint32_t* vals, uint32_t* table) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n[0] + R.n[1]) return;
-    const int c = i >= R.n[0];
-    const uint32_t li = i - (c ? R.n[0] : 0u);
-    const RowGrid& g = R.g[c];
-    uint32_t row;
-    KeyT key;
-    if constexpr (KIND == KIND_INT) {
-        const int x = (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 0);
-        row = int_row(g, (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1),
-                      (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
-        key = ((KeyT)row << xbits) | (KeyT)x;
-    } else {
-        const double x = load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 0);
-        row = float_row(g, load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1), load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
-        key = ((KeyT)row << 32) | (KeyT)flip_f32((float)x);
-    }
-    keys[i] = key | ((KeyT)c << cbit);
-    vals[i] = li;
-    atomicAdd(table + R.table_off[c] + row, 1u);
-}
-
-template <class K>
-__global__ void reorder_pair_kernel(const __grid_constant__ PairRaw R, const uint32_t* __restrict__ vals,
-                                    typename K::Rec* __restrict__ recs) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n[0] + R.n[1]) return;
-    const int c = i >= R.n[0];
-    const uint32_t src = vals[i];
-    uint32_t rgba = 0;
-    if (R.rgb_in_rec[c]) {
-        if (R.rgb_dtype[c] == PCCM_U8) {
-            const uint8_t* p = static_cast<const uint8_t*>(R.rgb[c]) + (int64_t)src * R.rgb_stride[c];
-            rgba = p[0] | (p[1] << 8) | (p[2] << 16);
-        } else {
-            rgba = (uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 0) * 255.0) |
-                   ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 1) * 255.0) << 8) |
-                   ((uint32_t)rint(load_coord(R.rgb[c], PCCM_F64, R.rgb_stride[c], src, 2) * 255.0) << 16);
-        }
-    }
-    recs[i] = RecPack<K>::make(load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 0), load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 1),
-                               load_coord(R.xyz[c], R.dtype[c], R.stride[c], src, 2), src, rgba);
 }
 
 // ------------------------------------------------------------------------------------
@@ -487,93 +381,128 @@ __global__ void reorder_pair_kernel(const __grid_constant__ PairRaw R, const uin
 // (x, original index).  Rows are short on voxelised clouds (a 2x2 tube crosses the surface a
 // few times), so most of them fit one warp: bitonic network over lanes with shuffles.
 // ------------------------------------------------------------------------------------
+// Sort items: (x key, point index), compared as one number.  Integer and float32 coordinates fit a 64-bit word
+// (32-bit order-preserving key | index); float64 x needs its 64 bits, so its items are a pair of words.
+struct Item128 {
+    unsigned long long k, i;
+};
+template <int KIND> struct RowItem {
+    typedef unsigned long long T;
+    static __device__ __forceinline__ T make(double x, uint32_t li) {
+        const uint32_t key = KIND == KIND_INT ? (uint32_t)(int)x : flip_f32((float)x);
+        return ((unsigned long long)key << 32) | li;
+    }
+    static __device__ __forceinline__ T inf() { return ~0ull; }
+    static __device__ __forceinline__ bool less(T a, T b) { return a < b; }
+    static __device__ __forceinline__ uint32_t index(T a) { return (uint32_t)a; }
+    static __device__ __forceinline__ T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+};
+template <> struct RowItem<KIND_F64> {
+    typedef Item128 T;
+    static __device__ __forceinline__ T make(double x, uint32_t li) { T t; t.k = flip_f64(x); t.i = li; return t; }
+    static __device__ __forceinline__ T inf() { T t; t.k = ~0ull; t.i = ~0ull; return t; }
+    static __device__ __forceinline__ bool less(const T& a, const T& b) { return a.k < b.k || (a.k == b.k && a.i < b.i); }
+    static __device__ __forceinline__ uint32_t index(const T& a) { return (uint32_t)a.i; }
+    static __device__ __forceinline__ T shfl_xor(const T& v, int m) {
+        T t; t.k = __shfl_xor_sync(0xffffffffu, v.k, m); t.i = __shfl_xor_sync(0xffffffffu, v.i, m); return t;
+    }
+};
+
 // pass 1: row of every point + its arrival rank inside the row (the histogram's atomicAdd)
+template <int KIND>
 __global__ void rowrank_pair_kernel(const __grid_constant__ PairRaw R, uint32_t* __restrict__ rowof,
                                     uint32_t* __restrict__ rank, uint32_t* table) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
     const uint32_t li = pair_src(R, c, i - (c ? R.n[0] : 0u));
-    const uint32_t row = R.table_off[c] + int_row(R.g[c], (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1),
-                                                  (int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2));
+    const double y = load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 1), z = load_coord(R.xyz[c], R.dtype[c], R.stride[c], li, 2);
+    const uint32_t row = R.table_off[c] + (KIND == KIND_INT ? int_row(R.g[c], (int)y, (int)z) : float_row(R.g[c], y, z));
     rowof[i] = row;
     rank[i] = atomicAdd(table + row, 1u);
 }
 
 // pass 2 (after the exclusive scan of the table): scatter (x, idx) items into their row segment
+template <int KIND>
 __global__ void scatter_pair_kernel(const __grid_constant__ PairRaw R, const uint32_t* __restrict__ rowof,
                                     const uint32_t* __restrict__ rank, const uint32_t* __restrict__ table,
-                                    unsigned long long* __restrict__ items) {
+                                    typename RowItem<KIND>::T* __restrict__ items) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
     const uint32_t li = i - (c ? R.n[0] : 0u);
-    const uint32_t x = (uint32_t)(int)load_coord(R.xyz[c], R.dtype[c], R.stride[c], pair_src(R, c, li), 0);
-    items[table[rowof[i]] + rank[i]] = ((unsigned long long)x << 32) | li;
-}
-
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
-    return __shfl_xor_sync(0xffffffffu, v, m);
+    items[table[rowof[i]] + rank[i]] = RowItem<KIND>::make(load_coord(R.xyz[c], R.dtype[c], R.stride[c], pair_src(R, c, li), 0), li);
 }
 
 // pass 3a: one warp per row, rows of <= 32 items: bitonic network over lanes (shuffles, registers
 // only, no shared memory -> full occupancy); longer rows are queued.
 constexpr int kRowSortThreads = 256;
-constexpr uint32_t kRowSortWarpSmem = 512;
+template <int KIND> struct RowSortCap {          // items a warp / a block sorts in shared memory
+    static constexpr uint32_t warp = KIND == KIND_F64 ? 256 : 512;
+    static constexpr uint32_t block = KIND == KIND_F64 ? 2048 : 4096;
+};
+// (segments: row r of the pencil table is [seg_lo[r], seg_hi[r]) with seg_lo = table, seg_hi = table + 1; the buckets
+// of split rows come with their own two arrays and a count that only the device knows)
+template <int KIND>
 __global__ void __launch_bounds__(kRowSortThreads)
-rowsort_warp_kernel(const uint32_t* __restrict__ table, uint32_t nrows, unsigned long long* __restrict__ items,
-                    uint32_t* __restrict__ long_rows, uint32_t* long_count) {
+rowsort_warp_kernel(const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, uint32_t nrows, const uint32_t* nrows_dev,
+                    typename RowItem<KIND>::T* __restrict__ items, uint32_t* __restrict__ long_rows, uint32_t* long_count) {
+    typedef RowItem<KIND> I;
     const uint32_t row = (blockIdx.x * kRowSortThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (row >= nrows) return;
-    const uint32_t lo = table[row], hi = table[row + 1];
+    if (row >= (nrows_dev ? min(nrows, *nrows_dev) : nrows)) return;
+    const uint32_t lo = seg_lo[row], hi = seg_hi[row];
     const uint32_t len = hi - lo;
     if (len < 2) return;
     if (len > 32) {
         if (lane == 0) long_rows[atomicAdd(long_count, 1u)] = row;
         return;
     }
-    unsigned long long v = lane < (int)len ? items[lo + lane] : ~0ull;
+    typename I::T v = lane < (int)len ? items[lo + lane] : I::inf();
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const unsigned long long o = shfl_xor_u64(v, j);
+            const typename I::T o = I::shfl_xor(v, j);
             const bool up = ((lane & k) == 0);            // ascending block
             const bool lower = ((lane & j) == 0);
             const bool take_min = (up == lower);
-            v = take_min ? (v < o ? v : o) : (v > o ? v : o);
+            const bool o_less = I::less(o, v);
+            v = (take_min == o_less) ? o : v;
         }
     }
     if (lane < (int)len) items[lo + lane] = v;
 }
 
-// pass 3b: queued rows of 33..kRowSortWarpSmem items: one warp each, network in the warp's
+// pass 3b: queued rows of 33..RowSortCap::warp items: one warp each, network in the warp's
 // private slice of shared memory (no block barrier); a fixed grid walks the queue.
+template <int KIND>
 __global__ void __launch_bounds__(kRowSortThreads)
-rowsort_medium_kernel(const uint32_t* __restrict__ table, unsigned long long* __restrict__ items,
+rowsort_medium_kernel(const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, typename RowItem<KIND>::T* __restrict__ items,
                       const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count) {
-    __shared__ unsigned long long smw[kRowSortThreads / 32][kRowSortWarpSmem];
+    typedef RowItem<KIND> I;
+    constexpr uint32_t kCap = RowSortCap<KIND>::warp;
+    __shared__ typename I::T smw[kRowSortThreads / 32][kCap];
     const int lane = threadIdx.x & 31;
-    unsigned long long* sm = smw[threadIdx.x >> 5];
+    typename I::T* sm = smw[threadIdx.x >> 5];
     const uint32_t count = *long_count;
     const uint32_t nwarps = gridDim.x * (kRowSortThreads / 32);
     for (uint32_t w = (blockIdx.x * kRowSortThreads + threadIdx.x) >> 5; w < count; w += nwarps) {
         const uint32_t row = long_rows[w];
-        const uint32_t lo = table[row], len = table[row + 1] - lo;
-        if (len > kRowSortWarpSmem) continue;              // block kernel
+        const uint32_t lo = seg_lo[row], len = seg_hi[row] - lo;
+        if (len > kCap) continue;                          // block kernel
         uint32_t p2 = 64;
         while (p2 < len) p2 <<= 1;
-        for (uint32_t i = lane; i < p2; i += 32) sm[i] = i < len ? items[lo + i] : ~0ull;
+        for (uint32_t i = lane; i < p2; i += 32) sm[i] = i < len ? items[lo + i] : I::inf();
         __syncwarp();
         for (uint32_t k = 2; k <= p2; k <<= 1)
             for (uint32_t j = k >> 1; j > 0; j >>= 1) {
                 for (uint32_t t = lane; t < (p2 >> 1); t += 32) {
                     const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
                     const uint32_t l = i | j;
-                    const unsigned long long a = sm[i], b = sm[l];
+                    const typename I::T a = sm[i], b = sm[l];
                     const bool up = (i & k) == 0;
-                    if ((a > b) == up) { sm[i] = b; sm[l] = a; }
+                    if (I::less(b, a) == up) { sm[i] = b; sm[l] = a; }
                 }
                 __syncwarp();
             }
@@ -582,31 +511,34 @@ rowsort_medium_kernel(const uint32_t* __restrict__ table, unsigned long long* __
     }
 }
 
-// pass 4: one block per long row: bitonic sort in shared memory (<= kRowSortSmem items) or,
+// pass 4: one block per long row: bitonic sort in shared memory (<= RowSortCap::block items) or,
 // for degenerate inputs (e.g. thousands of duplicates of one voxel column), in global memory
-constexpr uint32_t kRowSortSmem = 4096;
+template <int KIND>
 __global__ void __launch_bounds__(kRowSortThreads)
-rowsort_block_kernel(const uint32_t* __restrict__ table, unsigned long long* __restrict__ items,
-                     const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count) {
-    __shared__ unsigned long long sm[kRowSortSmem];
+rowsort_block_kernel(const uint32_t* __restrict__ seg_lo, const uint32_t* __restrict__ seg_hi, typename RowItem<KIND>::T* __restrict__ items,
+                     const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count, int allow_global) {
+    typedef RowItem<KIND> I;
+    constexpr uint32_t kCap = RowSortCap<KIND>::block;
+    __shared__ typename I::T sm[kCap];
     const uint32_t count = *long_count;
     for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
         const uint32_t row = long_rows[w];
-        const uint32_t lo = table[row], len = table[row + 1] - lo;
-        if (len <= kRowSortWarpSmem) continue;             // done by rowsort_medium_kernel
+        const uint32_t lo = seg_lo[row], len = seg_hi[row] - lo;
+        if (len <= RowSortCap<KIND>::warp) continue;       // done by rowsort_medium_kernel
+        if (len > kCap && !allow_global) continue;         // split into x buckets first (rowsplit_* kernels)
         uint32_t p2 = 64;
         while (p2 < len) p2 <<= 1;
-        if (p2 <= kRowSortSmem) {
-            for (uint32_t i = threadIdx.x; i < p2; i += kRowSortThreads) sm[i] = i < len ? items[lo + i] : ~0ull;
+        if (p2 <= kCap) {
+            for (uint32_t i = threadIdx.x; i < p2; i += kRowSortThreads) sm[i] = i < len ? items[lo + i] : I::inf();
             __syncthreads();
             for (uint32_t k = 2; k <= p2; k <<= 1)
                 for (uint32_t j = k >> 1; j > 0; j >>= 1) {
                     for (uint32_t i = threadIdx.x; i < p2; i += kRowSortThreads) {
                         const uint32_t l = i ^ j;
                         if (l > i) {
-                            const unsigned long long a = sm[i], b = sm[l];
+                            const typename I::T a = sm[i], b = sm[l];
                             const bool up = (i & k) == 0;
-                            if ((a > b) == up) { sm[i] = b; sm[l] = a; }
+                            if (I::less(b, a) == up) { sm[i] = b; sm[l] = a; }
                         }
                     }
                     __syncthreads();
@@ -617,17 +549,17 @@ rowsort_block_kernel(const uint32_t* __restrict__ table, unsigned long long* __r
             // global-memory network in the all-ascending form (first sub-stage of every merge
             // pairs i with i ^ (k - 1)): the minimum always goes to the lower index, so the
             // virtual +inf padding beyond len never has to move and is simply skipped
-            unsigned long long* a = items + lo;
+            typename I::T* a = items + lo;
             for (uint32_t k = 2; k <= p2; k <<= 1) {
                 for (uint32_t i = threadIdx.x; i < len; i += kRowSortThreads) {
                     const uint32_t l = i ^ (k - 1);
-                    if (l > i && l < len) { const unsigned long long x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+                    if (l > i && l < len) { const typename I::T x = a[i], y = a[l]; if (I::less(y, x)) { a[i] = y; a[l] = x; } }
                 }
                 __syncthreads();
                 for (uint32_t j = k >> 2; j > 0; j >>= 1) {
                     for (uint32_t i = threadIdx.x; i < len; i += kRowSortThreads) {
                         const uint32_t l = i ^ j;
-                        if (l > i && l < len) { const unsigned long long x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+                        if (l > i && l < len) { const typename I::T x = a[i], y = a[l]; if (I::less(y, x)) { a[i] = y; a[l] = x; } }
                     }
                     __syncthreads();
                 }
@@ -636,14 +568,118 @@ rowsort_block_kernel(const uint32_t* __restrict__ table, unsigned long long* __r
     }
 }
 
+// Rows longer than a block can sort in shared memory (a LiDAR ground plane puts tens of thousands of points into one
+// pencil) are first cut into BUCKETS of x -- a second counting sort inside the row: bucket = position of the x key in
+// the row's [min, max] key range, about kSplitTarget items each -- and the buckets are then sorted like rows.
+constexpr uint32_t kSplitTarget = 256;
+struct SplitRow {
+    uint32_t row, lo, len, nb, boff;
+    unsigned long long kmin, kmax;
+};
+template <int KIND> __device__ __forceinline__ unsigned long long item_key(const typename RowItem<KIND>::T& v);
+template <> __device__ __forceinline__ unsigned long long item_key<KIND_INT>(const unsigned long long& v) { return v >> 32; }
+template <> __device__ __forceinline__ unsigned long long item_key<KIND_F32>(const unsigned long long& v) { return v >> 32; }
+template <> __device__ __forceinline__ unsigned long long item_key<KIND_F64>(const Item128& v) { return v.k; }
+
+__device__ __forceinline__ uint32_t split_bucket(const SplitRow& S, unsigned long long key) {
+    const double span = (double)(S.kmax - S.kmin) + 1.0;
+    const uint32_t b = (uint32_t)((double)(key - S.kmin) / span * (double)S.nb);       // monotone in key
+    return b < S.nb ? b : S.nb - 1;
+}
+
+// which rows are split, and where their buckets live (counters[0] = split rows, counters[1] = buckets)
+template <int KIND>
+__global__ void rowsplit_find_kernel(const uint32_t* __restrict__ table, uint32_t nrows, SplitRow* __restrict__ rows, uint32_t* counters) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const uint32_t lo = table[r], len = table[r + 1] - lo;
+    if (len <= RowSortCap<KIND>::block) return;
+    SplitRow S;
+    S.row = r; S.lo = lo; S.len = len;
+    S.nb = (len + kSplitTarget - 1) / kSplitTarget;
+    S.boff = atomicAdd(counters + 1, S.nb);
+    S.kmin = 0; S.kmax = 0;
+    rows[atomicAdd(counters, 1u)] = S;
+}
+// per split row (one block each): key range; bucket of every item + its arrival rank; bucket boundaries; scatter
+template <int KIND>
+__global__ void __launch_bounds__(256)
+rowsplit_kernel(SplitRow* __restrict__ rows, const uint32_t* __restrict__ counters, const typename RowItem<KIND>::T* __restrict__ items,
+                typename RowItem<KIND>::T* __restrict__ items_alt, uint32_t* __restrict__ bucket_of, uint32_t* __restrict__ rank_of,
+                uint32_t* __restrict__ bcount, uint32_t* __restrict__ bstart, uint32_t* __restrict__ bend) {
+    __shared__ unsigned long long s_k[2][8];
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nsplit = counters[0];
+    for (uint32_t w = blockIdx.x; w < nsplit; w += gridDim.x) {
+        SplitRow S = rows[w];
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        for (uint32_t i = threadIdx.x; i < S.len; i += 256) {
+            const unsigned long long k = item_key<KIND>(items[S.lo + i]);
+            kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+            kmin = a < kmin ? a : kmin; kmax = b > kmax ? b : kmax;
+        }
+        __syncthreads();
+        if (lane == 0) { s_k[0][warp] = kmin; s_k[1][warp] = kmax; }
+        __syncthreads();
+        for (int q = 0; q < 8; ++q) { kmin = s_k[0][q] < kmin ? s_k[0][q] : kmin; kmax = s_k[1][q] > kmax ? s_k[1][q] : kmax; }
+        S.kmin = kmin; S.kmax = kmax;
+        // buckets + arrival ranks (bcount is zero on entry)
+        for (uint32_t i = threadIdx.x; i < S.len; i += 256) {
+            const uint32_t b = split_bucket(S, item_key<KIND>(items[S.lo + i]));
+            bucket_of[S.lo + i] = b;
+            rank_of[S.lo + i] = atomicAdd(bcount + S.boff + b, 1u);
+        }
+        __syncthreads();
+        // exclusive prefix of the bucket counts -> [bstart, bend) of every bucket, absolute positions
+        if (threadIdx.x == 0) s_run = S.lo;
+        __syncthreads();
+        for (uint32_t b0 = 0; b0 < S.nb; b0 += 256) {
+            const uint32_t b = b0 + threadIdx.x;
+            const uint32_t c = b < S.nb ? bcount[S.boff + b] : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_w[warp] = incl;
+            __syncthreads();
+            uint32_t base = s_run;
+            for (int q = 0; q < warp; ++q) base += s_w[q];
+            if (b < S.nb) { bstart[S.boff + b] = base + incl - c; bend[S.boff + b] = base + incl; }
+            __syncthreads();
+            if (threadIdx.x == 255) s_run = base + incl;
+            __syncthreads();
+        }
+        for (uint32_t i = threadIdx.x; i < S.len; i += 256)
+            items_alt[bstart[S.boff + bucket_of[S.lo + i]] + rank_of[S.lo + i]] = items[S.lo + i];
+        __syncthreads();
+    }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256)
+rowsplit_copyback_kernel(const SplitRow* __restrict__ rows, const uint32_t* __restrict__ counters, typename RowItem<KIND>::T* __restrict__ items,
+                         const typename RowItem<KIND>::T* __restrict__ items_alt) {
+    const uint32_t nsplit = counters[0];
+    for (uint32_t w = blockIdx.x; w < nsplit; w += gridDim.x) {
+        const uint32_t lo = rows[w].lo, len = rows[w].len;
+        for (uint32_t i = threadIdx.x; i < len; i += 256) items[lo + i] = items_alt[lo + i];
+    }
+}
+
 // records from sorted (x, idx) items
 template <class K>
-__global__ void reorder_items_pair_kernel(const __grid_constant__ PairRaw R, const unsigned long long* __restrict__ items,
+__global__ void reorder_items_pair_kernel(const __grid_constant__ PairRaw R, const typename RowItem<K::kind>::T* __restrict__ items,
                                           typename K::Rec* __restrict__ recs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n[0] + R.n[1]) return;
     const int c = i >= R.n[0];
-    const uint32_t src = (uint32_t)items[i];
+    const uint32_t src = RowItem<K::kind>::index(items[i]);
     uint32_t rgba = 0;
     if (R.rgb_in_rec[c]) {
         if (R.rgb_dtype[c] == PCCM_U8) {
