@@ -54,7 +54,12 @@ typedef enum pccm_kind { PCCM_KIND_AUTO = -1, PCCM_KIND_INT = 0, PCCM_KIND_F32 =
 enum {
     PCCM_EVAL_D2 = 1,        /* point-to-plane error (metric.py:124-179, point_to_plane=True) */
     PCCM_EVAL_COLOR = 2,     /* colour error on matched points (metric.py:302-333, 389-426) */
-    PCCM_EVAL_PERPOINT = 4   /* keep per-point idx / d2 for pccm_pair_get */
+    PCCM_EVAL_PERPOINT = 4,  /* keep per-point idx / d2 for pccm_pair_get */
+    PCCM_EVAL_TIE_AVERAGE = 8 /* opt-in, beyond the reference (which keeps whichever tied neighbour its KD-tree visited first,
+                                cloud_pair.py:22-23): plane error and colour of a query are AVERAGED over every point of the search
+                                cloud at the minimal distance (MPEG pc_error style) -- the plane error of each tied point with that
+                                point's own normal, the colour as the mean colour of the tied points.  D1, maxima of D1 and the
+                                per-point outputs are unaffected.  Runs on the pencil index. */
 };
 enum {
     PCCM_NORMALS_BY_QUERY_INDEX = 0, /* reference behaviour, metric.py:130 + :148-152 (quirk Q1) */

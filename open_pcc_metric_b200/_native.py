@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("PCCM_LIB", os.path.join(_HERE, "libpccm.so"))  # PCCM
 F64, F32, I32, U16, U8 = 0, 1, 2, 3, 4
 HOST, DEVICE = 0, 1
 KIND_AUTO, KIND_INT, KIND_F32, KIND_F64 = -1, 0, 1, 2
-EVAL_D2, EVAL_COLOR, EVAL_PERPOINT = 1, 2, 4
+EVAL_D2, EVAL_COLOR, EVAL_PERPOINT, EVAL_TIE_AVERAGE = 1, 2, 4, 8
 NORMALS_BY_QUERY_INDEX, NORMALS_BY_NEIGHBOUR = 0, 1
 GET_IDX, GET_D2 = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_NONFINITE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6

@@ -12,6 +12,10 @@ neighbour colours) are produced only when a getter asks for them.
 Extra keyword-only options (all default to the reference's behaviour):
   normals_mode  "reference" -> D2 uses the other cloud's normal at the QUERY index
                 (metric.py:130,148-152, quirk Q1); "neighbour" -> normal of the match.
+  ties          "first" (the reference keeps ONE nearest neighbour, cloud_pair.py:22-23; here: the one with the smallest
+                index) | "average" -> plane error and colour are averaged over every point at the minimal distance,
+                each tied point with its own normal (MPEG pc_error style).  Affects the fused D2 /
+                colour reductions only (GeoMSE / GeoPSNR point-to-plane, ColorMSE / ColorPSNR, their Hausdorff forms).
   peak          "obb" (reference, cloud_pair.py:111-112) | "aabb_diag" | "resolution"
   eager_normals estimate missing normals in the constructor like cloud_pair.py:61-64
                 (default: on first use; values are identical).
@@ -59,11 +63,14 @@ class CloudPair:
     def __init__(self, origin_cloud, reconst_cloud, *, ctx: N.Context | None = None,
                  normals_mode: str = "reference", peak: str = "obb", resolution_bits: int | None = None,
                  eager_normals: bool = False, knn: int = 30, cell_size: float = 0.0,
-                 rank: int = 0, world: int = 1, group=None):
+                 rank: int = 0, world: int = 1, group=None, ties: str = "first"):
         if normals_mode not in ("reference", "neighbour"):
             raise ValueError("normals_mode must be 'reference' or 'neighbour'")
         if peak not in ("obb", "aabb_diag", "resolution"):
             raise ValueError("peak must be 'obb', 'aabb_diag' or 'resolution'")
+        if ties not in ("first", "average"):
+            raise ValueError("ties must be 'first' or 'average'")
+        self._ties = ties
         self.clouds = (origin_cloud, reconst_cloud)
         self._ctx = ctx or default_context()
         self._normals_mode = normals_mode
@@ -239,6 +246,8 @@ class CloudPair:
             flags |= N.EVAL_COLOR
             T = np.array(_COLOR_TRANSFORMS[color_scheme], dtype=np.float64)
             scale = 255.0 if color_scheme == "rgb" else 1.0  # metric.py:421-424
+        if self._ties == "average" and flags:
+            flags |= N.EVAL_TIE_AVERAGE
         mode = N.NORMALS_BY_QUERY_INDEX if self._normals_mode == "reference" else N.NORMALS_BY_NEIGHBOUR
         raw = self._ctx.pair_eval(self._dev[0], self._dev[1], flags, T, scale, mode, self._rank, self._world)
         dirs = [raw.dir[0], raw.dir[1]]

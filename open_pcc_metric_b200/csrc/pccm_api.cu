@@ -1960,7 +1960,7 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
     bool vox = false;
     pccm_cloud* sc[2] = {b, a};
     for (int attempt = 0; attempt < 3; ++attempt) {
-        vox = ctx->use_vox && a->vox && a->vox == b->vox && a != b && a->index_kind == PCCM_KIND_INT;
+        vox = ctx->use_vox && a->vox && a->vox == b->vox && a != b && a->index_kind == PCCM_KIND_INT && !(flags & PCCM_EVAL_TIE_AVERAGE);
         if (vox && (flags & PCCM_EVAL_COLOR))
             for (int d = 0; d < 2; ++d) { rc = vox_colors(ctx, cl[d]); if (rc) return rc; }
         if (!vox) {

@@ -989,6 +989,36 @@ __device__ __forceinline__ void stage_window(const RowGrid& g, const uint32_t* _
     __syncthreads();
 }
 
+// PCCM_EVAL_TIE_AVERAGE: second walk of the search with the minimal distance known -- every point AT that distance
+// contributes its plane error (its own normal) and its colour.
+template <class K>
+struct TieSum {
+    typename K::D target;
+    const CloudView* s;
+    const typename K::Rec* srecs;
+    typename K::Q q;
+    uint32_t flags;
+    uint32_t cnt;
+    double pe_sum, c_sum[3];
+    __device__ __forceinline__ typename K::D worst() const { return target; }
+    __device__ __forceinline__ void offer(typename K::D d, uint32_t idx, uint32_t pos) {
+        if (d != target) return;
+        ++cnt;
+        const typename K::Rec nr = load_rec(srecs + pos);
+        if (flags & PCCM_EVAL_D2) {
+            const typename K::Q nq = K::rec_q(nr);
+            const double e[3] = {dsub((double)q.x, (double)nq.x), dsub((double)q.y, (double)nq.y), dsub((double)q.z, (double)nq.z)};
+            const double nv[3] = {__ldg(s->normals + 3 * (size_t)idx), __ldg(s->normals + 3 * (size_t)idx + 1), __ldg(s->normals + 3 * (size_t)idx + 2)};
+            pe_sum = dadd(pe_sum, plane_err2(e, nv));
+        }
+        if (flags & PCCM_EVAL_COLOR) {
+            double cn[3];
+            load_color(*s, idx, rec_rgba<K>(nr), cn);
+            for (int k = 0; k < 3; ++k) c_sum[k] = dadd(c_sum[k], cn[k]);
+        }
+    }
+};
+
 // One launch covers both directions: blocks [0, dir[0].ntiles) serve direction 0, the rest
 // direction 1; a block is one tile of kQueryThreads consecutive queries of the sorted order
 // (the hardware block scheduler balances the very uneven tile costs).  Each warp reduces its 32
@@ -1040,7 +1070,19 @@ pair_query_kernel(const __grid_constant__ QueryParams P) {
         acc.max_d1 = d1;
         if (D.idx_out) D.idx_out[qidx] = (int32_t)best.idx;
         if (D.d2_out) D.d2_out[qidx] = d1;
-        if (D.flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
+        if ((D.flags & PCCM_EVAL_TIE_AVERAGE) && (D.flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR))) {
+            TieSum<K> ts;
+            ts.target = best.d2; ts.s = &D.s; ts.srecs = srecs; ts.q = q; ts.flags = D.flags; ts.cnt = 0;
+            ts.pe_sum = 0; ts.c_sum[0] = ts.c_sum[1] = ts.c_sum[2] = 0;
+            search<K>(D.s.grid, D.s.row_start, srecs, q, ts);
+            const double inv = 1.0 / (double)ts.cnt;           // (cnt >= 1: the best point itself)
+            if (D.flags & PCCM_EVAL_D2) { acc.sum_d2 = dmul(ts.pe_sum, inv); acc.max_d2 = acc.sum_d2; }
+            if (D.flags & PCCM_EVAL_COLOR) {
+                double cq[3], cn[3] = {dmul(ts.c_sum[0], inv), dmul(ts.c_sum[1], inv), dmul(ts.c_sum[2], inv)};
+                load_color(D.q, qidx, rec_rgba<K>(qr), cq);
+                color_diff2(P.T, cq, cn, P.color_scale, acc.csum, acc.cmax);
+            }
+        } else if (D.flags & (PCCM_EVAL_D2 | PCCM_EVAL_COLOR)) {
             const Rec nr = load_rec(srecs + best.pos);
             if (D.flags & PCCM_EVAL_D2) {
                 const Q nq = K::rec_q(nr);

@@ -168,6 +168,37 @@ class PairOracle:
             return 10 * np.log10(COLOR_PEAK[scheme] ** 2 / self.color_hausdorff(is_left, scheme))
 
 
+def tie_average(oracle: "PairOracle", is_left, scheme=None):
+    """Beyond the reference (MPEG pc_error style): per query, EVERY point of the search cloud at the
+    minimal squared distance counts -- its plane error (q - p_t) . n_t with its own normal, squared, and its colour;
+    returns (mean over the tied points of the squared plane errors, squared difference between the transformed query
+    colour and the transformed MEAN colour of the tied points or None).  Brute force: small clouds only."""
+    qi, si = (0, 1) if is_left else (1, 0)
+    Q, S = oracle.pts[qi], oracle.pts[si]
+    nrm = oracle.nrm[si]
+    pe2 = np.empty(len(Q))
+    cd2 = None if scheme is None else np.empty((len(Q), 3))
+    for i in range(len(Q)):
+        d = Q[i] - S
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        tied = np.nonzero(d2 == d2.min())[0]
+        e = Q[i] - S[tied]
+        n = nrm[tied]
+        pe = (e[:, 0] * n[:, 0] + e[:, 1] * n[:, 1]) + e[:, 2] * n[:, 2]
+        acc = 0.0
+        for v in pe * pe:                     # (index order, one addition at a time: what the kernel's accumulator does)
+            acc += v
+        pe2[i] = acc * (1.0 / len(tied))
+        if scheme is not None:
+            csum = np.zeros(3)
+            for t in tied:
+                csum = csum + oracle.col[si][t]
+            cbar = csum * (1.0 / len(tied))
+            diff = transform_colors(oracle.col[qi][i:i + 1], scheme)[0] - transform_colors(cbar[None, :], scheme)[0]
+            cd2[i] = diff * diff
+    return pe2, cd2
+
+
 def symmetric(lvalue, rvalue, is_proportional):
     """metric.py:475-485."""
     values = [lvalue, rvalue]

@@ -590,3 +590,42 @@ def test_integration_md_stub_runs(ctx):
     assert np.array_equal(ir, oi[:, 0]) and np.array_equal(dr, od[:, 0])
     nrm = gpu.estimate_normals(ha, len(A))
     assert nrm.shape == (3000, 3) and np.allclose(np.linalg.norm(nrm, axis=1), 1.0)
+
+
+@pytest.mark.parametrize("name", ["ties", "vox_small", "float_small"])
+def test_tie_average_mode_matches_fixture_and_restatement(golden, ctx, name):
+    """PCCM_EVAL_TIE_AVERAGE (beyond the reference): plane error and colour averaged over every point at the
+    minimal distance; against tests/golden/tie_average.json and the live brute-force restatement (rtol 1e-6 as for D2 /
+    colour; D1 is unaffected and stays exact), through the C ABI and through CloudPair(ties="average")."""
+    import json
+    from conftest import GOLDEN
+    from open_pcc_metric_b200 import _native as N
+    from open_pcc_metric_b200.cloud_pair import CloudPair
+    from open_pcc_metric_b200.synth import Cloud
+    rec = json.load(open(os.path.join(GOLDEN, "tie_average.json")))[name]
+    i = golden(name).inputs()
+    n = rec["n"]
+    rng = np.random.default_rng(rec["seed"])
+    nrm = [rng.normal(0, 1, (n, 3)) for _ in range(2)]
+    nrm = [v / np.linalg.norm(v, axis=1, keepdims=True) for v in nrm]
+    col = [rng.integers(0, 256, (n, 3)).astype(np.float64) / 255.0 for _ in range(2)]
+    A, B = i["pts_a"][:n], i["pts_b"][:n]
+    T = np.array([[0.25, 0.5, 0.25], [1, 0, -1], [-0.5, 1, -0.5]])
+    a, b = ctx.cloud(A, col[0], nrm[0]), ctx.cloud(B, col[1], nrm[1])
+    ctx.build_pair(a, b)
+    plain = ctx.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR, T, 1.0, N.NORMALS_BY_NEIGHBOUR)
+    res = ctx.pair_eval(a, b, N.EVAL_D2 | N.EVAL_COLOR | N.EVAL_TIE_AVERAGE, T, 1.0, N.NORMALS_BY_NEIGHBOUR)
+    o = rp.PairOracle(A, B, col[0], col[1], nrm[0], nrm[1])
+    for d, key in ((0, "left"), (1, "right")):
+        x = res.dir[d]
+        assert x.sum_d1_u64 == plain.dir[d].sum_d1_u64 and x.max_d1 == plain.dir[d].max_d1 and x.sum_d1 == plain.dir[d].sum_d1
+        pe2, cd2 = rp.tie_average(o, d == 0, "yuv")
+        for want_sum, want_max, want_c in ((float.fromhex(rec[key]["sum_d2"]), float.fromhex(rec[key]["max_d2"]), [float.fromhex(v) for v in rec[key]["color_sum"]]),
+                                           (pe2.sum(), pe2.max(), cd2.sum(0))):
+            assert np.isclose(x.sum_d2, want_sum, rtol=1e-6) and np.isclose(x.max_d2, want_max, rtol=1e-6)
+            assert np.allclose(list(x.color_sum), want_c, rtol=1e-6)
+    a.close(); b.close()
+    pair = CloudPair(Cloud(A, col[0], nrm[0]), Cloud(B, col[1], nrm[1]), ctx=ctx, ties="average", normals_mode="neighbour")
+    f = pair.fused(True, True, "yuv")
+    assert np.isclose(f.sum_d2, float.fromhex(rec["left"]["sum_d2"]), rtol=1e-6)
+    pair.close()

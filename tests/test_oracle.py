@@ -162,3 +162,29 @@ def test_minimal_obb_known_box():
     pts = np.concatenate([box, corners]) @ R.T + 5.0
     ext = o3s.minimal_obb_extent(pts)
     assert np.allclose(sorted(ext), [1.0, 2.0, 4.0], atol=1e-9)
+
+
+def test_tie_average_fixture_matches_the_restatement(golden):
+    """tests/golden/tie_average.json (oracle/make_golden_ties.py): the brute-force restatement of the tie-averaged
+    mode reproduces its committed values bit for bit, and differs from the single-neighbour values exactly where ties exist."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from oracle import reference_port as rp
+    fx = json.load(open(os.path.join(GOLDEN, "tie_average.json")))
+    for name, rec in fx.items():
+        i = golden(name).inputs()
+        n = rec["n"]
+        rng = np.random.default_rng(rec["seed"])
+        nrm = [rng.normal(0, 1, (n, 3)) for _ in range(2)]
+        nrm = [v / np.linalg.norm(v, axis=1, keepdims=True) for v in nrm]
+        col = [rng.integers(0, 256, (n, 3)).astype(np.float64) / 255.0 for _ in range(2)]
+        o = rp.PairOracle(i["pts_a"][:n], i["pts_b"][:n], col[0], col[1], nrm[0], nrm[1])
+        for is_left, key in ((True, "left"), (False, "right")):
+            pe2, cd2 = rp.tie_average(o, is_left, "yuv")
+            assert float(pe2.sum()).hex() == rec[key]["sum_d2"] and float(pe2.max()).hex() == rec[key]["max_d2"]
+            assert [float(x).hex() for x in cd2.sum(0)] == rec[key]["color_sum"]
+        if name == "ties":       # the lattice fixture has ties: averaging must change the plane error
+            q, s = o.pts[0], o.pts[1]
+            single = (o.error_vector(True) * o.nrm[1][o.idx[0]]).sum(1) ** 2
+            assert not np.allclose(single.sum(), rp.tie_average(o, True)[0].sum())
