@@ -132,15 +132,15 @@ class Workload:
         return A, synth.degrade(A, 2, synth.BASE_SEED + 3, 12, dedup=False)
 
     def _lidar(self, synth):
-        A, B = synth.synth_lidar(self.points, synth.BASE_SEED + 5)
-        m = min(len(A), len(B))          # the reference's D2 needs |search| >= |query| in both directions (quirk Q1)
-        return synth.Cloud(A.points[:m]), synth.Cloud(B.points[:m])
+        # one point of B per point of A (the reference's D2 needs |search| >= |query| in both directions, quirk Q1):
+        # both clouds have the stated size
+        return synth.synth_lidar(self.points, synth.BASE_SEED + 5, dedup=False)
 
     def config(self, n_a, n_b, world, distinct_b=None):
         return {
             "workload": self.name, "n_a": int(n_a), "n_b": int(n_b), "queries_per_step": int(n_a + n_b),
             "degraded_cloud": "one point per input point (dedup=False: quirk Q1 -- the reference's D2 is only defined when the search "
-                              "cloud is at least as long as the query cloud)" if self.bits else "2 cm lattice + jitter, truncated to equal length",
+                              "cloud is at least as long as the query cloud)" if self.bits else "one point per input point: 2 cm lattice + N(0, 5 mm) jitter",
             "distinct_voxels_b": None if distinct_b is None else int(distinct_b),
             "coordinate_kind": ("int (vox%d)" % self.bits) if self.bits else "float32",
             "inputs": "float64 coordinates and normals, uchar colours (device arm); float64 everywhere (e2e arm)" if self.bits else "float32 coordinates",
@@ -409,7 +409,12 @@ def main():
             if world > 1:
                 dist.barrier()
             wall = time.perf_counter() - t0
-            ms = sum(a.elapsed_time(b) for a, b in evs)
+            per_step = [a.elapsed_time(b) for a, b in evs]
+            ms = sum(per_step)
+            if os.environ.get("PCCM_BENCH_VERBOSE"):
+                q = sorted(per_step)
+                print(f"[timed] {getattr(fn, '__name__', 'step')}: n={len(q)} min={q[0]:.3f} median={q[len(q) // 2]:.3f} max={q[-1]:.3f} ms; "
+                      f"slowest at steps {sorted(range(len(per_step)), key=lambda i: -per_step[i])[:5]}", file=sys.stderr, flush=True)
             tm = ctx.timings()
             ctx.set_profiling(0)
         return ms, wall, tm, last
@@ -430,6 +435,11 @@ def main():
     total_queries = nq * steps * per_rank_jobs
     value = total_queries / (ms_dev_max * 1e-3)
 
+    # per-stage device time (separate short loop with every stage and every kernel of the query stage bracketed by events;
+    # the event pairs keep those kernels from overlapping their launches, so the timed region above brackets the stage only)
+    _, _, tm2, _ = timed(step_device, 10, 1, 2)
+    stages = {k: round(v / 10, 5) for k, v in tm2.items() if k.endswith("_ms")}
+
     # ---- roofline of the dominant kernel(s), measured live with CUDA events inside the library
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -437,7 +447,7 @@ def main():
     else:
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     q_launches = max(1, tm["query_launches"])
-    brick = tm.get("vox_epilogue_ms", 0) > 0
+    brick = tm2.get("vox_epilogue_ms", 0) > 0
     if W.estimate_normals:
         # normal estimation dominates: k=30 self k-NN + PCA, 24 B / point (12 B read + 12 B normal written)
         k_ms = tm["knn_ms"] / steps
@@ -449,8 +459,9 @@ def main():
                 "note": "compute bound by design (counting selection / top-k lists), reported against the HBM roofline the task names"}
     else:
         q_ms_avg = tm["query_ms"] / q_launches
-        q_split = {"vx_search_kernel": tm["vox_search_ms"] / q_launches, "vx_general_kernel": tm.get("vox_tail_ms", 0) / q_launches,
-                   "vx_epilogue_kernel": tm.get("vox_epilogue_ms", 0) / q_launches} if brick else None
+        q2 = max(1, tm2["query_launches"])
+        q_split = {"vx_search_kernel": tm2["vox_search_ms"] / q2, "vx_general_kernel": tm2.get("vox_tail_ms", 0) / q2,
+                   "vx_epilogue_kernel": tm2.get("vox_epilogue_ms", 0) / q2} if brick else None
         own = sum(r["n"] for r in step_device(shard=(rank, world))) if W.split else nq     # queries this rank's launches reduce
         achieved = W.alg_bytes * own / (q_ms_avg * 1e-3) / 1e9
         traffic = None
@@ -459,7 +470,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "kernel": "query stage = vx_search_kernel + vx_general_kernel + vx_epilogue_kernel" if brick else "pair_query_kernel",
-                "launch_ms_by_kernel": q_split,
+                "launch_ms_by_kernel": q_split,          # (from the separate stage loop: events around every kernel)
                 # the two kernels of the stage against their own share of the algorithmic traffic (24 B/query
                 # for the search -- query + search coordinates; the rest for the epilogue -- normal + two colours)
                 "by_kernel": None if not brick else {
@@ -467,9 +478,6 @@ def main():
                     for k, ab in (("vx_search_kernel", 24), ("vx_epilogue_kernel", W.alg_bytes - 24)) if q_split[k] > 0},
                 "peak_source": peak_src, "alg_bytes_per_query": W.alg_bytes, "queries_per_launch": own, "avg_launch_ms": q_ms_avg}
 
-    # per-stage device time (separate short loop with every stage bracketed by events; informational)
-    _, _, tm2, _ = timed(step_device, 5, 1, 2)
-    stages = {k: round(v / 5, 5) for k, v in tm2.items() if k.endswith("_ms")}
 
     # strong scaling: the same pair, unsplit, on ONE GPU (rank 0, outside the timed region)
     strong_ref = None

@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pccm_kernels.cuh"
@@ -56,6 +58,11 @@ struct pccm_ctx {
     void* dscratch = nullptr;
     static constexpr size_t kScratch = 1 << 16;
     static constexpr size_t kPinned = 3 << 16;      // results, flags, plan read-back + two statistics slots
+    // device blocks of this context, recycled (see dalloc)
+    std::multimap<size_t, void*> dev_free;            // released blocks by (bucketed) size
+    std::unordered_map<void*, size_t> dev_live;       // blocks handed out -> their bucketed size
+    size_t dev_cached = 0, dev_cache_cap = 0;         // bytes in dev_free / the most it may hold
+    bool dev_cache = true;                            // PCCM_DEV_CACHE=0: every block straight from / to the driver's pool
     int sm_count = 148;
     int cell_override_shift = -1;   // debugging: PCCM_CELL_SHIFT
     double cell_scale = 1.0;        // debugging: PCCM_CELL_SCALE
@@ -71,6 +78,7 @@ struct pccm_ctx {
     int host_threads = 0;                  // PCCM_HOST_THREADS (0 = min(hardware threads, 8))
     int shard_rank = 0, shard_world = 1;   // pccm_ctx_set_shard: pairs built from now on are split by z slabs over `world` ranks
     bool shard_sel = true;          // split pairs: fill / place walk a compacted list of the slab's points (PCCM_SHARD_SEL=0: every point)
+    bool pdl = true;                // programmatic dependent launch along the kernel chains of an evaluation (PCCM_PDL=0: ordinary launches)
     int mark_sample = 32;           // the brick directory is marked by 1 / mark_sample of the points first (PCCM_MARK_SAMPLE, 0 = one pass)
 };
 
@@ -93,6 +101,29 @@ static int fail(pccm_ctx* ctx, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess)                                                                       \
             return fail(ctx, PCCM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
+
+// Launch of a kernel that begins with pdl_enter(): with the programmatic-serialisation attribute its blocks may become
+// resident while the previous kernel of the stream is still draining (pccm_kernels.cuh, pdl_enter).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(pccm_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ctx->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// zero `bytes` (a multiple of 4, 4-byte aligned) on `st` with a kernel of the chain (see zero_words_kernel)
+static inline cudaError_t dzero(pccm_ctx* ctx, void* p, size_t bytes, cudaStream_t st) {
+    const size_t nwords = (bytes + 3) / 4;
+    if (nwords == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((nwords + 1023) / 1024, (size_t)ctx->sm_count * 8);
+    ctx->tm.total_launches++;
+    return launch_chain(ctx, zero_words_kernel, blocks, 256, 0, st, static_cast<uint32_t*>(p), nwords);
+}
 
 struct StageTimer {
     pccm_ctx* ctx;
@@ -133,14 +164,62 @@ static void resolve_timers(pccm_ctx* ctx) {
     ctx->pending.clear();
 }
 
+// Device memory of a context is stream-ordered on ctx->stream (a block may be used by work enqueued after dalloc and must
+// not be used by work enqueued after dfree) and RECYCLED inside the context: released blocks wait in a size-bucketed
+// list and the next request of that bucket takes one -- a cloud pair allocates the same dozen sizes evaluation after
+// evaluation.  The driver's own pool (cudaMallocAsync / cudaFreeAsync) gives the same semantics, but measured end to
+// end it stalls the host for tens to hundreds of milliseconds now and then when an allocation meets frees of the
+// previous evaluation that are still in flight (tools/e2e_bisect.py: steady 3.1 ms per pair with a device
+// synchronisation between evaluations, p90 20 ms / max 490 ms without); it still backs the cache.
+static size_t dev_bucket(size_t bytes) {
+    if (bytes < 512) return 512;
+    size_t g = 512;                                   // granularity: 1/8 of the largest power of two below the size
+    while ((g << 4) <= bytes) g <<= 1;
+    return (bytes + g - 1) / g * g;
+}
+static void dev_cache_trim(pccm_ctx* ctx, size_t keep) {
+    while (ctx->dev_cached > keep && !ctx->dev_free.empty()) {
+        auto it = std::prev(ctx->dev_free.end());     // largest first
+        cudaFreeAsync(it->second, ctx->stream);
+        ctx->dev_cached -= it->first;
+        ctx->dev_free.erase(it);
+    }
+}
+static cudaError_t dalloc_bytes(pccm_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    if (!ctx->dev_cache) return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    const size_t b = dev_bucket(bytes);
+    auto it = ctx->dev_free.find(b);
+    if (it != ctx->dev_free.end()) {
+        *p = it->second;
+        ctx->dev_cached -= b;
+        ctx->dev_free.erase(it);
+    } else {
+        cudaError_t e = cudaMallocAsync(p, b, ctx->stream);
+        if (e != cudaSuccess) {                       // out of memory: give the cached blocks back and try once more
+            cudaGetLastError();
+            dev_cache_trim(ctx, 0);
+            cudaStreamSynchronize(ctx->stream);
+            e = cudaMallocAsync(p, b, ctx->stream);
+            if (e != cudaSuccess) { *p = nullptr; return e; }
+        }
+    }
+    ctx->dev_live[*p] = b;
+    return cudaSuccess;
+}
 template <class T>
 static cudaError_t dalloc(pccm_ctx* ctx, T** p, size_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    return cudaMallocAsync(reinterpret_cast<void**>(p), count * sizeof(T), ctx->stream);
+    return dalloc_bytes(ctx, reinterpret_cast<void**>(p), count * sizeof(T));
 }
 static void dfree(pccm_ctx* ctx, void* p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->dev_live.find(p);
+    if (it == ctx->dev_live.end()) { cudaFreeAsync(p, ctx->stream); return; }     // (not from the cache: PCCM_DEV_CACHE=0)
+    const size_t b = it->second;
+    ctx->dev_live.erase(it);
+    ctx->dev_free.emplace(b, p);
+    ctx->dev_cached += b;
+    if (ctx->dev_cached > ctx->dev_cache_cap) dev_cache_trim(ctx, ctx->dev_cache_cap / 2);
 }
 
 // --------------------------------------------------------------------------------------
@@ -309,7 +388,7 @@ static void wait_normals(pccm_ctx* ctx, pccm_cloud* c) {
         c->nrm_pending = false;
     }
     if (c->nrm_stage) {              // (after the wait: the free is ordered behind the conversion)
-        cudaFreeAsync(c->nrm_stage, ctx->stream);
+        dfree(ctx, c->nrm_stage);
         c->nrm_stage = nullptr;
     }
 }
@@ -418,9 +497,9 @@ static void launch_pack_u8(pccm_ctx* ctx, const pccm_cloud* c, uchar4* out) {
     const int threads = 256;
     if (c->raw_rgb_dtype == PCCM_U8 && c->raw_rgb_stride == 3 && (reinterpret_cast<uintptr_t>(c->raw_rgb) & 3u) == 0) {
         const int64_t groups = (c->n + 3) / 4;
-        pack_rgb_u8x4_kernel<<<(int)((groups + threads - 1) / threads), threads, 0, ctx->stream>>>(static_cast<const uint32_t*>(c->raw_rgb), c->n, out);
+        launch_chain(ctx, pack_rgb_u8x4_kernel, (int)((groups + threads - 1) / threads), threads, 0, ctx->stream, static_cast<const uint32_t*>(c->raw_rgb), c->n, out);
     } else {
-        pack_rgb_u8_kernel<<<(int)((c->n + threads - 1) / threads), threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->n, out);
+        launch_chain(ctx, pack_rgb_u8_kernel, (int)((c->n + threads - 1) / threads), threads, 0, ctx->stream, c->raw_rgb, c->raw_rgb_dtype, c->raw_rgb_stride, c->n, out);
     }
 }
 
@@ -689,6 +768,11 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = (size_t)16 << 30;
+        ctx->dev_cache_cap = total_b / 4;             // released blocks kept for reuse: at most a quarter of the device
+    }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (int k = 1023; k >= 0; --k) ctx->flag_slots.push_back(k);
     if (cudaMallocHost(&ctx->pinned, pccm_ctx::kPinned) != cudaSuccess || cudaMalloc(&ctx->dscratch, pccm_ctx::kScratch) != cudaSuccess) {
@@ -706,6 +790,8 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_VOX")) ctx->use_vox = atoi(s) != 0;
     if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
+    if (const char* s = getenv("PCCM_PDL")) ctx->pdl = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_DEV_CACHE")) ctx->dev_cache = atoi(s) != 0;
     if (const char* s = getenv("PCCM_MARK_SAMPLE")) ctx->mark_sample = std::max(0, atoi(s));
     if (const char* s = getenv("PCCM_SHARD_SEL")) ctx->shard_sel = atoi(s) != 0;
     if (const char* s = getenv("PCCM_HOST_NARROW")) ctx->host_narrow = atoi(s) != 0;
@@ -730,6 +816,7 @@ extern "C" int pccm_ctx_destroy(pccm_ctx* ctx) {
         delete ctx->narrow;
     }
     for (int d = 0; d < 2; ++d) { dfree(ctx, ctx->pp_idx[d]); dfree(ctx, ctx->pp_d2[d]); }
+    dev_cache_trim(ctx, 0);
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->pinned);
     cudaFree(ctx->dscratch);
@@ -937,10 +1024,10 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
             c->d_dev = reinterpret_cast<DevStats*>(c->d_stats + c->stats_blocks + 1);
             if (want_packed) c->packed = reinterpret_cast<uint2*>(blockp + head);
             if (want_hist) c->d_zhist = reinterpret_cast<uint32_t*>(c->d_stats + c->stats_blocks + 2);
-            e = cudaMemsetAsync(c->d_stats + c->stats_blocks, 0, 2 * sizeof(StatsPartial) + hist_bytes, ctx->stream);
+            e = dzero(ctx, c->d_stats + c->stats_blocks, 2 * sizeof(StatsPartial) + hist_bytes, ctx->stream);
         }
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
-        stats_kernel<<<c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream>>>(c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+        launch_chain(ctx, stats_kernel, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
                                                                                   nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);   // colours are classified apart
         ctx->tm.total_launches++;
         e = cudaGetLastError();
@@ -1272,7 +1359,7 @@ static int colors_u8_async(pccm_ctx* ctx, pccm_cloud* c) {
     CK(dalloc(ctx, &c->rgb_u8, (size_t)c->n + 4));
     const int threads = 256, blocks = (int)((c->n + threads - 1) / threads);
     if (c->raw_rgb_dtype == PCCM_U8) launch_pack_u8(ctx, c, c->rgb_u8);
-    else pack_rgb_u8_check_kernel<<<blocks, threads, 0, ctx->stream>>>(c->raw_rgb, c->raw_rgb_stride, c->n, c->rgb_u8, c->d_rgbflag);
+    else launch_chain(ctx, pack_rgb_u8_check_kernel, blocks, threads, 0, ctx->stream, c->raw_rgb, c->raw_rgb_stride, c->n, c->rgb_u8, c->d_rgbflag);
     ctx->tm.total_launches++;
     CK(cudaGetLastError());
     c->rgb_spec = true;                                        // the raw colours stay until the flag has been read
@@ -1328,14 +1415,14 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     v->shard_rank = ctx->shard_rank; v->shard_world = ctx->shard_world;
     if (v->sharded) {
         v->dshard = reinterpret_cast<ShardPlan*>(v->arena + o_shard);
-        vx_shardplan_kernel<<<1, 1024, 0, ctx->stream>>>(cl[0]->d_zhist, cl[1]->d_zhist, v->shard_rank, v->shard_world, v->dshard);
+        launch_chain(ctx, vx_shardplan_kernel, 1, 1024, 0, ctx->stream, cl[0]->d_zhist, cl[1]->d_zhist, v->shard_rank, v->shard_world, v->dshard);
         ctx->tm.total_launches++;
     }
 #if PCCM_DIR_BYTES
     CKV(cudaMemsetAsync(v->arena + o_dirbytes, 0, (size_t)cap_dirw * 32, ctx->stream));
 #else
     (void)o_dirbytes;
-    CKV(cudaMemsetAsync(v->arena + o_selcnt, 0, (o_dirbits - o_selcnt) + (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
+    CKV(dzero(ctx, v->arena + o_selcnt, (o_dirbits - o_selcnt) + (size_t)cap_dirw * sizeof(uint32_t), ctx->stream));
 #endif
     VoxBuildArgs A{};
     A.shard = v->dshard;
@@ -1369,21 +1456,21 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
         const uint32_t sample = ctx->mark_sample > 0 && per > 65536u ? per / (uint32_t)ctx->mark_sample : 0u;
         if (sample) {
             A.mark_lo = 0; A.mark_hi = sample;
-            vx_mark_kernel<<<(sample + threads - 1) / threads, threads, 0, ctx->stream>>>(A);
+            launch_chain(ctx, vx_mark_kernel, (sample + threads - 1) / threads, threads, 0, ctx->stream, A);
             ctx->tm.total_launches++;
         }
         A.mark_lo = sample; A.mark_hi = per;
-        vx_mark_kernel<<<(per - sample + threads - 1) / threads, threads, 0, ctx->stream>>>(A);
+        launch_chain(ctx, vx_mark_kernel, (per - sample + threads - 1) / threads, threads, 0, ctx->stream, A);
     }
-    vx_dirsum_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
-    vx_dirscan_kernel<<<ndirblocks, threads, 0, ctx->stream>>>(A);
+    launch_chain(ctx, vx_dirsum_kernel, ndirblocks, threads, 0, ctx->stream, A);
+    launch_chain(ctx, vx_dirscan_kernel, ndirblocks, threads, 0, ctx->stream, A);
     const int sel_grid = ctx->sm_count * 8;
-    if (use_sel) vx_fill_sel_kernel<<<sel_grid, threads, 0, ctx->stream>>>(A);
-    else vx_fill_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
-    vx_bricksum_kernel<<<brick_grid, threads, 0, ctx->stream>>>(A);
-    vx_rowbase_kernel<<<brick_grid, threads, 0, ctx->stream>>>(A);
-    if (use_sel) vx_place_sel_kernel<<<sel_grid, threads, 0, ctx->stream>>>(A);
-    else vx_place_kernel<<<blocks_ilp, threads, 0, ctx->stream>>>(A);
+    if (use_sel) launch_chain(ctx, vx_fill_sel_kernel, sel_grid, threads, 0, ctx->stream, A);
+    else launch_chain(ctx, vx_fill_kernel, blocks_ilp, threads, 0, ctx->stream, A);
+    launch_chain(ctx, vx_bricksum_kernel, brick_grid, threads, 0, ctx->stream, A);
+    launch_chain(ctx, vx_rowbase_kernel, brick_grid, threads, 0, ctx->stream, A);
+    if (use_sel) launch_chain(ctx, vx_place_sel_kernel, sel_grid, threads, 0, ctx->stream, A);
+    else launch_chain(ctx, vx_place_kernel, blocks_ilp, threads, 0, ctx->stream, A);
     ctx->tm.total_launches += 7;
     CKV(cudaGetLastError());
 #undef CKV
@@ -1714,7 +1801,7 @@ static int launch_query(pccm_ctx* ctx, int kind, QueryParams& P) {
     CK(cudaGetLastError());
     {
         StageTimer t(ctx, &ctx->tm.finalize_ms);
-        finalize_kernel<<<P.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream>>>(P);
+        launch_chain(ctx, finalize_kernel, P.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream, P);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1761,7 +1848,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     uint32_t* todo = reinterpret_cast<uint32_t*>(sx.block);
     uint4* vres = reinterpret_cast<uint4*>(sx.block + todo_bytes);
     BlockPartial* partials = reinterpret_cast<BlockPartial*>(sx.block + todo_bytes + vres_bytes);
-    CK(cudaMemsetAsync(todo, 0, 8 * sizeof(uint32_t), ctx->stream));
+    CK(dzero(ctx, todo, 8 * sizeof(uint32_t), ctx->stream));
     uint32_t rec_stride = 0, ntiles = 0;
     for (int d = 0; d < ndirs; ++d) {
         VxDir& D = P.dir[d];
@@ -1786,19 +1873,20 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
     P.partials = partials; P.vres = vres; P.counters = todo;
     {
-        StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage
+        StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage (level 1: ONE event pair, so that the three
+                                                         // kernels stay chained; the per-kernel split needs level 2)
         {
-            StageTimer t(ctx, &ctx->tm.vox_search_ms, 1);
-            vx_search_kernel<<<ctx->sm_count * ctx->vx_search_blocks, kVxThreads, 0, ctx->stream>>>(P);
+            StageTimer t(ctx, &ctx->tm.vox_search_ms, 2);
+            launch_chain(ctx, vx_search_kernel, ctx->sm_count * ctx->vx_search_blocks, kVxThreads, 0, ctx->stream, P);
             ctx->tm.query_launches++;
         }
         {
-            StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
-            vx_general_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(P);
+            StageTimer t(ctx, &ctx->tm.vox_tail_ms, 2);
+            launch_chain(ctx, vx_general_kernel, ctx->sm_count * 4, 128, 0, ctx->stream, P);
         }
         {
-            StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 1);
-            vx_epilogue_kernel<<<ntiles, kVxEpiThreads, 0, ctx->stream>>>(P);
+            StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 2);
+            launch_chain(ctx, vx_epilogue_kernel, ntiles, kVxEpiThreads, 0, ctx->stream, P);
         }
         ctx->tm.total_launches += 3;
     }
@@ -1813,7 +1901,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     auto fold = [&](uint32_t passes) -> int {
         StageTimer t(ctx, &ctx->tm.finalize_ms);
         for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = passes * P.dir[d].ntiles;
-        finalize_kernel<<<Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream>>>(Q);
+        launch_chain(ctx, finalize_kernel, Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream, Q);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1848,9 +1936,9 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         }
         P.pass = 1;
         {
-            StageTimer t(ctx, &ctx->tm.vox_tail_ms, 1);
-            vx_far_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(P);
-            vx_epilogue_kernel<<<ntiles, kVxEpiThreads, 0, ctx->stream>>>(P);
+            StageTimer t(ctx, &ctx->tm.vox_tail_ms, 2);
+            launch_chain(ctx, vx_far_kernel, ctx->sm_count * 8, 128, 0, ctx->stream, P);
+            launch_chain(ctx, vx_epilogue_kernel, ntiles, kVxEpiThreads, 0, ctx->stream, P);
             ctx->tm.total_launches += 2;
             CK(cudaGetLastError());
         }
@@ -2082,8 +2170,8 @@ static int vox_self_nn(pccm_ctx* ctx, pccm_cloud* c, int64_t begin, int64_t end,
         if (mem_kind == PCCM_DEVICE) sx.d_pp = per_point;
         else { CK(dalloc(ctx, &sx.d_pp, (size_t)c->n)); sx.own_pp = true; }
     }
-    CK(cudaMemsetAsync(sx.scratch, 0, ((size_t)nwords + 1) * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(sx.und, 0, sizeof(uint32_t), ctx->stream));
+    CK(dzero(ctx, sx.scratch, ((size_t)nwords + 1) * sizeof(uint32_t), ctx->stream));
+    CK(dzero(ctx, sx.und, sizeof(uint32_t), ctx->stream));
     P.undecided = sx.und; P.dupbits = sx.scratch; P.vself = sx.vself; P.minmax = sx.mm; P.per_point = sx.d_pp;
     uint32_t* hund = reinterpret_cast<uint32_t*>(static_cast<double*>(ctx->pinned) + 1024 + 2);
     {

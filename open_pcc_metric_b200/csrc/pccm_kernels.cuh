@@ -10,6 +10,26 @@
 
 namespace pccm {
 
+// Programmatic dependent launch (sm_90+ griddepcontrol): kernels of one evaluation are enqueued back to back on one
+// stream; launched with the programmatic-serialisation attribute (launch_chain in pccm_api.cu) a kernel's blocks become
+// resident while the previous kernel drains its last wave, and pdl_enter() -- the first statement of every such
+// kernel -- holds them until that kernel has completed and its writes are visible.  Every chained kernel waits
+// unconditionally, so completion stays transitive along the chain.  Both instructions are no-ops under an ordinary launch.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_launch();
+    pdl_wait();
+}
+
+// Zeroing as a KERNEL of the chain instead of cudaMemsetAsync: a memset may be handed to a copy engine, where it queues
+// behind the attribute uploads of the copy stream (measured end to end: the index build then waits ~2 ms for 96 MB
+// of colours and normals it does not need), and a memset node also cuts the programmatic-launch chain.
+__global__ void zero_words_kernel(uint32_t* __restrict__ p, size_t nwords) {
+    pdl_enter();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
 constexpr int kStatsThreads = 256;
 constexpr int kQueryThreads = 128;
 constexpr int kKnnThreads = 64;
@@ -58,6 +78,7 @@ constexpr int kZHistBins = 4096;          // 8-voxel layers of a 15-bit coordina
 __global__ void __launch_bounds__(kStatsThreads)
 stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
              const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out, uint2* packed, DevStats* dev, uint32_t* zhist) {
+    pdl_enter();
     // zhist (sharded builds: one pair split over several GPUs by slabs of z): points per 8-voxel layer, kZHistBins
     // bins, accumulated per block in dynamic shared memory
     extern __shared__ uint32_t s_hist[];
@@ -150,6 +171,7 @@ __global__ void rgb_classify_kernel(const void* rgb, int64_t stride, int64_t n, 
 
 // colours -> uchar4 (original order).  F64 input must have passed the k/255 test.
 __global__ void pack_rgb_u8_kernel(const void* rgb, int rgb_dtype, int64_t stride, int64_t n, uchar4* out) {
+    pdl_enter();
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uchar4 c;
@@ -167,6 +189,7 @@ __global__ void pack_rgb_u8_kernel(const void* rgb, int rgb_dtype, int64_t strid
 
 // packed 3-byte colours -> uchar4, four points per thread (three aligned 32-bit loads, one 16-byte store)
 __global__ void pack_rgb_u8x4_kernel(const uint32_t* __restrict__ rgb, int64_t n, uchar4* __restrict__ out) {
+    pdl_enter();
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // group of four points
     const int64_t i = 4 * q;
     if (i >= n) return;
@@ -1133,6 +1156,7 @@ __device__ __forceinline__ void block_fold(BlockPartial& a, BlockPartial* sm, Bl
 }
 
 __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_constant__ QueryParams P) {
+    pdl_enter();
     __shared__ BlockPartial sm[kFinalThreads / 32];
     __shared__ bool is_last;
     const int d = blockIdx.x / kFinalChunks, c = blockIdx.x % kFinalChunks;

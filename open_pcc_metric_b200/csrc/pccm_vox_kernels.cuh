@@ -88,6 +88,7 @@ struct VoxBuildArgs {                         // everything the host knows when 
 // The cuts: layer z belongs to rank k when k / world of all points (both clouds) lie in the layers below it.
 __global__ void __launch_bounds__(1024) vx_shardplan_kernel(const uint32_t* __restrict__ zh0, const uint32_t* __restrict__ zh1,
                                                             int rank, int world, ShardPlan* out) {
+    pdl_enter();
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_pre[kZHistBins];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -213,6 +214,7 @@ __device__ __forceinline__ bool vx_in_slab(const ShardPlan& sp, const uint2& p) 
 // same brick, and read-modify-writes of one directory word queue up at the L2), then everybody else -- who now finds
 // nearly every bit set on the first look (a cached look is enough: bits are only ever set).
 __global__ void __launch_bounds__(256) vx_mark_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     __shared__ VoxDimsSmem S;
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_base;
@@ -291,6 +293,7 @@ __device__ __forceinline__ uint32_t vx_block_sum_u32(uint32_t v, uint32_t* sm) {
 
 // popcount sum of every chunk of kVxDirChunk directory words
 __global__ void __launch_bounds__(256) vx_dirsum_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     __shared__ VoxDimsSmem S;
     __shared__ uint32_t sm[8];
     vx_block_dims(A, S);
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(256) vx_dirsum_kernel(const __grid_constant__ 
 // exclusive popcount prefix of the directory (dirpre), the VoxPlan, and the zeroing of the occupancy words of
 // the bricks that exist (+ the empty one past the last)
 __global__ void __launch_bounds__(256) vx_dirscan_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     __shared__ VoxDimsSmem S;
     __shared__ uint32_t sm[8];
     __shared__ uint32_t s_warp[8];
@@ -398,6 +402,7 @@ __global__ void __launch_bounds__(256) vx_dirscan_kernel(const __grid_constant__
 }
 
 __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     const VoxPlan* __restrict__ P = A.plan;
     if (P->status) return;
     const uint32_t n_total = A.n[0] + A.n[1];
@@ -435,6 +440,7 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
 // split pairs: the same two passes over the compacted list of this rank's points (grid-stride: its length is only
 // known on the device)
 __global__ void __launch_bounds__(256) vx_fill_sel_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     const VoxPlan* __restrict__ P = A.plan;
     if (P->status) return;
     const uint32_t nsel = *A.sel_count, stride = gridDim.x * blockDim.x;
@@ -453,6 +459,7 @@ __global__ void __launch_bounds__(256) vx_fill_sel_kernel(const __grid_constant_
     }
 }
 __global__ void __launch_bounds__(256) vx_place_sel_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     const VoxPlan* __restrict__ P = A.plan;
     if (P->status) return;
     const uint32_t nsel = *A.sel_count, stride = gridDim.x * blockDim.x;
@@ -479,6 +486,7 @@ __device__ __forceinline__ void vx_load_bricks8(const uint2* rows, uint32_t s0, 
 }
 
 __global__ void __launch_bounds__(256) vx_bricksum_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     __shared__ uint32_t sm[8];
     const VoxPlan* __restrict__ P = A.plan;
     if (P->status) return;
@@ -499,6 +507,7 @@ __global__ void __launch_bounds__(256) vx_bricksum_kernel(const __grid_constant_
 // rank of the first voxel of every row of every brick.  Block b owns a contiguous run of chunks: one strided
 // sum of the chunk sums before its run, then chunk after chunk with a running offset.
 __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     __shared__ uint32_t sm[8];
     __shared__ uint32_t s_wtot[8];
     VoxPlan* P = A.plan;
@@ -555,6 +564,7 @@ __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__
 }
 
 __global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ VoxBuildArgs A) {
+    pdl_enter();
     const VoxPlan* __restrict__ P = A.plan;
     if (P->status) return;
     const uint32_t n_total = A.n[0] + A.n[1];
@@ -592,6 +602,7 @@ __global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ V
 // float64 colours -> uchar4, checking on the way that every channel is k / 255 (else the plan's status says so and
 // the caller repeats the evaluation with float64 colour arrays)
 __global__ void pack_rgb_u8_check_kernel(const void* rgb, int64_t stride, int64_t n, uchar4* out, uint32_t* status) {
+    pdl_enter();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     bool bad = false;
@@ -890,6 +901,7 @@ __device__ __forceinline__ void vx_finish_pending(const VxParams& P, int d, cons
 
 __global__ void __launch_bounds__(kVxThreads, PCCM_VX_MINBLOCKS)
 vx_search_kernel(const __grid_constant__ VxParams P) {
+    pdl_enter();
     __shared__ VxWarpSmem s_w[kVxWarps];
     const unsigned full = 0xffffffffu;
     const VoxPlan* __restrict__ plan = P.plan;
@@ -1031,12 +1043,15 @@ constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer * kVxEpiIter;
 __global__ void __launch_bounds__(kVxEpiThreads, PCCM_EPI_MINBLOCKS)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     __shared__ double s_lut[256];
-    const VoxPlan* __restrict__ plan = P.plan;
-    if (plan->status) return;
+    pdl_launch();
     const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
     const VxDir& D = P.dir[d];
     const uint32_t tile = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
     s_lut[threadIdx.x] = D.qa.lut255[threadIdx.x];       // k / 255.0 table: shared memory instead of six global loads per point
+                                                         // (written when the context was created: read ahead of the wait)
+    pdl_wait();
+    const VoxPlan* __restrict__ plan = P.plan;
+    if (plan->status) return;
     __syncthreads();
     CloudView qa = D.qa, sa = D.sa;
     qa.lut255 = s_lut; sa.lut255 = s_lut;
@@ -1114,6 +1129,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
 // pencil search (second round).
 __global__ void __launch_bounds__(128)
 vx_general_kernel(const __grid_constant__ VxParams P) {
+    pdl_enter();
     __shared__ int s_slot[4][128];
     __shared__ int s_occ[4][128];
     const unsigned full = 0xffffffffu;
@@ -1166,6 +1182,7 @@ vx_general_kernel(const __grid_constant__ VxParams P) {
 // clouds, isolated outliers): exact pencil search, which skips empty space by its row table.
 __global__ void __launch_bounds__(128)
 vx_far_kernel(const __grid_constant__ VxParams P) {
+    pdl_enter();
     const VoxPlan* __restrict__ plan = P.plan;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (int d = 0; d < P.ndirs; ++d) {

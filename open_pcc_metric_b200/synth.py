@@ -147,11 +147,12 @@ def synth_pair(bits: int, target_n: int, seed: int, step: int = 2, with_colors=T
     return A, B
 
 
-def synth_lidar(target_n: int, seed: int):
+def synth_lidar(target_n: int, seed: int, dedup: bool = True):
     """LiDAR-style float32 scene (config 5): rolling ground plane + boxes + cylinders,
     density ~ 1/max(r,2)^2 from the origin.  Returns (A, B) float32-valued clouds
     (stored as float32 arrays) where B is A snapped to a 2 cm lattice, de-duplicated
-    and jittered by N(0, 5 mm)."""
+    and jittered by N(0, 5 mm).  dedup=False keeps one (separately jittered) point of B per
+    point of A, so that both clouds have target_n points."""
     rng = np.random.default_rng(np.random.PCG64(seed))
     n_ground = int(0.6 * target_n)
     n_obj = target_n - n_ground
@@ -182,8 +183,11 @@ def synth_lidar(target_n: int, seed: int):
     A = np.concatenate(parts).astype(np.float32)
     A = A[rng.permutation(len(A))]
     q = np.round(A.astype(np.float64) / 0.02)
-    key = ((q[:, 0] + 8192).astype(np.int64) << 42) | ((q[:, 1] + 8192).astype(np.int64) << 21) | (q[:, 2] + 8192).astype(np.int64)
-    _, first = np.unique(key, return_index=True)
-    first = first[rng.permutation(first.size)]
+    if dedup:
+        key = ((q[:, 0] + 8192).astype(np.int64) << 42) | ((q[:, 1] + 8192).astype(np.int64) << 21) | (q[:, 2] + 8192).astype(np.int64)
+        _, first = np.unique(key, return_index=True)
+        first = first[rng.permutation(first.size)]
+    else:
+        first = rng.permutation(len(A))
     B = (q[first] * 0.02 + rng.normal(0, 0.005, (first.size, 3))).astype(np.float32)
     return Cloud(np.ascontiguousarray(A)), Cloud(np.ascontiguousarray(B))
