@@ -1849,24 +1849,26 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     uint4* vres = reinterpret_cast<uint4*>(sx.block + todo_bytes);
     BlockPartial* partials = reinterpret_cast<BlockPartial*>(sx.block + todo_bytes + vres_bytes);
     CK(dzero(ctx, todo, 8 * sizeof(uint32_t), ctx->stream));
-    uint32_t rec_stride = 0, ntiles = 0;
+    uint32_t rec_stride = 0, ntiles = 0, all_tiles = 0;
     for (int d = 0; d < ndirs; ++d) {
         VxDir& D = P.dir[d];
         D.qc = qc[d]->vox_id; D.sc = sc[d]->vox_id;
         D.nq = v->n[D.qc];
         D.qprank = v->prank + (D.qc ? v->n[0] : 0u);
         D.qa = Q.dir[d].q; D.sa = Q.dir[d].s;
-        // own colour: streamed from the packed array; neighbour colour: in the voxel answer when the records carry it
-        D.qa.rgb_mode = !qc[d]->has_colors ? 0 : (qc[d]->rgb_u8 ? 2 : 3);
-        D.sa.rgb_mode = !sc[d]->has_colors ? 0 : (sc[d]->vox_rgb_in_recs ? 1 : (sc[d]->rgb_u8 ? 2 : 3));
-        D.qa.rgb_u8 = qc[d]->rgb_u8; D.qa.rgb_f64 = qc[d]->rgb_f64;
-        D.sa.rgb_u8 = sc[d]->rgb_u8; D.sa.rgb_f64 = sc[d]->rgb_f64;
-        D.qa.lut255 = D.sa.lut255 = lut;
         D.flags = Q.dir[d].flags;
         D.idx_out = Q.dir[d].idx_out; D.d2_out = Q.dir[d].d2_out;
         D.todo = todo + 8 + (d ? (size_t)v->n[P.dir[0].qc] : 0);
         D.far = todo + 8 + n_total + (d ? (size_t)v->n[P.dir[0].qc] : 0);
-        D.ntiles = (D.nq + kVxEpiTile - 1) / kVxEpiTile;
+        D.npt_tiles = (D.nq + kVxEpiTile - 1) / kVxEpiTile;
+        all_tiles += D.npt_tiles;
+    }
+    for (int d = 0; d < ndirs; ++d) {
+        // blocks of the epilogue: one resident wave, shared out by the directions' sizes (a function of the two point
+        // counts only -- float sums are reproducible on any GPU); small pairs keep one tile per block
+        VxDir& D = P.dir[d];
+        D.ntiles = all_tiles <= kVxEpiGrid ? D.npt_tiles
+                                           : std::max<uint32_t>(1u, (uint32_t)((uint64_t)kVxEpiGrid * D.npt_tiles / all_tiles));
         rec_stride = std::max(rec_stride, 2u * D.ntiles);
         ntiles += D.ntiles;
     }
@@ -1883,6 +1885,22 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         {
             StageTimer t(ctx, &ctx->tm.vox_tail_ms, 2);
             launch_chain(ctx, vx_general_kernel, ctx->sm_count * 4, 128, 0, ctx->stream, P);
+        }
+        // The search reads coordinates only.  Colours and normals that are still being uploaded on the copy stream are
+        // waited for HERE, so that the search runs underneath their copies and only the epilogue is left behind the last byte.
+        for (int d = 0; d < ndirs; ++d) {
+            if (P.dir[d].flags & PCCM_EVAL_COLOR) { const int rcc = vox_colors(ctx, qc[d]); if (rcc) return rcc; }
+            if (P.dir[d].flags & PCCM_EVAL_D2) { wait_normals(ctx, qc[d]); wait_normals(ctx, sc[d]); }
+        }
+        for (int d = 0; d < ndirs; ++d) {
+            VxDir& D = P.dir[d];
+            if (P.dir[d].flags & PCCM_EVAL_COLOR) { const int rcc = vox_colors(ctx, sc[d]); if (rcc) return rcc; }
+            // own colour: streamed from the packed array; neighbour colour: in the voxel answer when the records carry it
+            D.qa.rgb_mode = !qc[d]->has_colors ? 0 : (qc[d]->rgb_u8 ? 2 : 3);
+            D.sa.rgb_mode = !sc[d]->has_colors ? 0 : (sc[d]->vox_rgb_in_recs ? 1 : (sc[d]->rgb_u8 ? 2 : 3));
+            D.qa.rgb_u8 = qc[d]->rgb_u8; D.qa.rgb_f64 = qc[d]->rgb_f64;
+            D.sa.rgb_u8 = sc[d]->rgb_u8; D.sa.rgb_f64 = sc[d]->rgb_f64;
+            D.qa.lut255 = D.sa.lut255 = lut;
         }
         {
             StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 2);
@@ -2011,11 +2029,8 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
     int rc = check_pair(ctx, a, b);
     if (rc) return rc;
     if (a->n == 0 || b->n == 0) return fail(ctx, PCCM_ERR_INDEX, "empty cloud (reference: IndexError at cloud_pair.py:23)");
-    if (flags & PCCM_EVAL_D2) {
-        if (!a->has_normals || !b->has_normals) return fail(ctx, PCCM_ERR_STATE, "D2 needs normals on both clouds (set or estimate them)");
-        wait_normals(ctx, a);
-        wait_normals(ctx, b);
-    }
+    if ((flags & PCCM_EVAL_D2) && (!a->has_normals || !b->has_normals))
+        return fail(ctx, PCCM_ERR_STATE, "D2 needs normals on both clouds (set or estimate them)");
     if (flags & PCCM_EVAL_COLOR) {
         if (!a->has_colors || !b->has_colors) return fail(ctx, PCCM_ERR_STATE, "colour metrics need colours on both clouds");
         if (!color_matrix) return fail(ctx, PCCM_ERR_INVALID, "color_matrix is NULL");
@@ -2049,9 +2064,10 @@ extern "C" int pccm_pair_eval(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, uint3
     pccm_cloud* sc[2] = {b, a};
     for (int attempt = 0; attempt < 3; ++attempt) {
         vox = ctx->use_vox && a->vox && a->vox == b->vox && a != b && a->index_kind == PCCM_KIND_INT && !(flags & PCCM_EVAL_TIE_AVERAGE);
-        if (vox && (flags & PCCM_EVAL_COLOR))
-            for (int d = 0; d < 2; ++d) { rc = vox_colors(ctx, cl[d]); if (rc) return rc; }
+        // attributes still on their way up (copy stream) are waited for where they are first read: at once on the pencil
+        // path (one fused kernel), between the search and the epilogue on the brick path (launch_vox_query)
         if (!vox) {
+            if (flags & PCCM_EVAL_D2) { wait_normals(ctx, a); wait_normals(ctx, b); }
             rc = ensure_pencil(ctx, a);
             if (!rc) rc = ensure_pencil(ctx, b);
             if (!rc) rc = check_pair(ctx, a, b);

@@ -635,7 +635,8 @@ struct VxDir {
     const uint4* srecs;
     const uint32_t* srow_start;
     uint32_t rec_off;          // first reduction record of this direction
-    uint32_t ntiles;           // ceil(nq / kVxEpiTile): reduction records of one vx_epilogue_kernel pass
+    uint32_t ntiles;           // blocks (= reduction records) of this direction in one vx_epilogue_kernel pass
+    uint32_t npt_tiles;        // ceil(nq / kVxEpiTile): tiles of points, dealt round-robin to those blocks
 };
 
 struct VxParams {
@@ -670,12 +671,9 @@ struct VxAcc {
 };
 
 // epilogue of ONE query point: D1 (+ per-point outputs), D2 with the other cloud's normals, colour.
-// pre_n / pre_rgb: the normal at the query index and the query's own packed colour when the caller has already
-// loaded them (they depend on the point index only, so they can travel together with the rank look-up).
 __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, const CloudView& qa, const CloudView& sa,
                                             uint32_t qidx, uint32_t qrgb, uint32_t d2,
-                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a,
-                                            const double* pre_n = nullptr, bool pre_rgb = false) {
+                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a) {
     a.s1 += d2;
     a.m1 = d2 > a.m1 ? d2 : a.m1;
     a.cnt++;
@@ -684,20 +682,15 @@ __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, c
     if (D.flags & PCCM_EVAL_D2) {
         const double e[3] = {(double)ex, (double)ey, (double)ez};
         double nv[3];
-        if (pre_n) {
-            nv[0] = pre_n[0]; nv[1] = pre_n[1]; nv[2] = pre_n[2];
-        } else {
-            const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
-            nv[0] = __ldg(sa.normals + 3 * (size_t)ni); nv[1] = __ldg(sa.normals + 3 * (size_t)ni + 1); nv[2] = __ldg(sa.normals + 3 * (size_t)ni + 2);
-        }
+        const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
+        nv[0] = __ldg(sa.normals + 3 * (size_t)ni); nv[1] = __ldg(sa.normals + 3 * (size_t)ni + 1); nv[2] = __ldg(sa.normals + 3 * (size_t)ni + 2);
         const double pe = plane_err2(e, nv);
         a.s2 = dadd(a.s2, pe);
         a.m2 = fmax(a.m2, pe);
     }
     if (D.flags & PCCM_EVAL_COLOR) {
         double cq[3], cn[3], c2[3], c2s[3];
-        if (pre_rgb) { cq[0] = qa.lut255[qrgb & 0xffu]; cq[1] = qa.lut255[(qrgb >> 8) & 0xffu]; cq[2] = qa.lut255[(qrgb >> 16) & 0xffu]; }
-        else load_color(qa, qidx, qrgb, cq);
+        load_color(qa, qidx, qrgb, cq);
         load_color(sa, nidx, nrgb, cn);
         color_diff2(P.T, cq, cn, P.color_scale, c2, c2s);
         for (int k = 0; k < 3; ++k) { a.cs[k] = dadd(a.cs[k], c2[k]); a.cm[k] = fmax(a.cm[k], c2s[k]); }
@@ -1021,32 +1014,34 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
     }
 }
 
-// EPILOGUE.  Threads walk the query POINTS in the ORIGINAL order of the input (4 per thread, strided so
-// that every load is coalesced): own colour, the other cloud's normal at the query index (quirk Q1)
-// and the per-point outputs stream; only the voxel's 16-byte answer is a gather (through prank).
-// Points that share a voxel share its answer.  A block is a fixed tile of kVxEpiTile points and
-// writes one reduction record -> float sums do not depend on scheduling.  Multi-GPU slices are cut
-// by voxel: a rank skips the points of voxels it did not search.
+// EPILOGUE.  Threads walk the query POINTS in the ORIGINAL order of the input (coalesced): own colour, the other
+// cloud's normal at the query index (quirk Q1) and the per-point outputs stream; only the voxel's 16-byte answer is a
+// gather (through prank).  Points that share a voxel share its answer.  The grid is ONE resident wave of at most
+// kVxEpiGrid blocks (a constant, not the SM count: the float sums must not depend on the GPU); the tiles of
+// kVxEpiTile points of a direction are dealt round-robin to the direction's blocks, a thread keeps its sums in
+// registers across its tiles and the block writes ONE reduction record at the end -> the warp / block folds are paid
+// once per ~9 points of a thread instead of once per 2, and the sums depend on (n_a, n_b) only, not on scheduling.
+// Multi-GPU slices are cut by voxel: a rank skips the points of voxels it did not search.
 constexpr int kVxEpiThreads = 256;
 #ifndef PCCM_VX_EPIPER
 #define PCCM_VX_EPIPER 2
 #endif
-#ifndef PCCM_VX_EPIITER
-#define PCCM_VX_EPIITER 1          // (measured: 4 trips per block cost 20 % at N = 1 -- fewer, longer blocks hide less latency)
-#endif
 constexpr int kVxEpiPer = PCCM_VX_EPIPER;
-constexpr int kVxEpiIter = PCCM_VX_EPIITER;      // trips per block: the k / 255 table and the record fold are paid once per kVxEpiTile points
-constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer * kVxEpiIter;
+constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
 #ifndef PCCM_EPI_MINBLOCKS
-#define PCCM_EPI_MINBLOCKS 6
+#define PCCM_EPI_MINBLOCKS 5         // (51 registers: the sums of a thread stay in registers; 6 blocks = 42 registers spill them)
 #endif
+#ifndef PCCM_VX_EPIGRID
+#define PCCM_VX_EPIGRID 740            // 148 SMs x 5 resident blocks on a B200 (measured: 592 / 740 / 888 / 1480 / 1776 blocks within 1 us)
+#endif
+constexpr uint32_t kVxEpiGrid = PCCM_VX_EPIGRID;
 __global__ void __launch_bounds__(kVxEpiThreads, PCCM_EPI_MINBLOCKS)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     __shared__ double s_lut[256];
     pdl_launch();
     const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
     const VxDir& D = P.dir[d];
-    const uint32_t tile = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
+    const uint32_t blk = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
     s_lut[threadIdx.x] = D.qa.lut255[threadIdx.x];       // k / 255.0 table: shared memory instead of six global loads per point
                                                          // (written when the context was created: read ahead of the wait)
     pdl_wait();
@@ -1059,32 +1054,14 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     if (P.world > 1) vx_slice(P, plan->view[D.qc], t_lo, t_hi);
     VxAcc acc;
     acc.init();
-    for (int it = 0; it < kVxEpiIter; ++it) {
-    const uint32_t i0 = tile * kVxEpiTile + it * (kVxEpiThreads * kVxEpiPer) + threadIdx.x;
-    if (i0 - threadIdx.x >= D.nq) break;
+    for (uint32_t tile = blk; tile < D.npt_tiles; tile += D.ntiles) {
+    const uint32_t i0 = tile * kVxEpiTile + threadIdx.x;
     uint32_t rk[kVxEpiPer];
     uint4 v[kVxEpiPer];
-#ifndef PCCM_EPI_PRELOAD
-#define PCCM_EPI_PRELOAD 0          // (measured: requesting normals and colours before the gather costs registers and buys nothing)
-#endif
-    // everything that depends on the point index only is requested first: rank, own colour, and -- reference mode --
-    // the other cloud's normal at the QUERY index (quirk Q1 makes it a stream); the one gather (the voxel's answer)
-    // follows, and the arithmetic waits for nothing else
-    const bool pre_n = PCCM_EPI_PRELOAD && (D.flags & PCCM_EVAL_D2) && P.normals_mode != PCCM_NORMALS_BY_NEIGHBOUR;
-    const bool pre_c = PCCM_EPI_PRELOAD && (D.flags & PCCM_EVAL_COLOR) && qa.rgb_mode == 2;
-    double nrm[kVxEpiPer][3];
-    uint32_t qrgb[kVxEpiPer];
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
         const uint32_t i = i0 + j * kVxEpiThreads;
-        const bool in = i < D.nq;
-        rk[j] = in ? __ldg(D.qprank + i) : kVxNone;
-        qrgb[j] = (pre_c && in) ? __ldg(reinterpret_cast<const uint32_t*>(qa.rgb_u8) + i) : 0u;
-        if (pre_n && in) {
-            nrm[j][0] = __ldg(sa.normals + 3 * (size_t)i); nrm[j][1] = __ldg(sa.normals + 3 * (size_t)i + 1); nrm[j][2] = __ldg(sa.normals + 3 * (size_t)i + 2);
-        } else {
-            nrm[j][0] = nrm[j][1] = nrm[j][2] = 0.0;
-        }
+        rk[j] = i < D.nq ? __ldg(D.qprank + i) : kVxNone;
     }
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j)
@@ -1105,7 +1082,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
             ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
             nrgb = nr.w;
         }
-        vx_epilogue(P, D, qa, sa, i, qrgb[j], v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc, pre_n ? nrm[j] : nullptr, pre_c);
+        vx_epilogue(P, D, qa, sa, i, 0u, v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc);
     }
     }
     BlockPartial r;
@@ -1116,7 +1093,7 @@ vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     if (threadIdx.x == 0) {
         BlockPartial o = sm[0];
         for (int w = 1; w < kVxEpiThreads / 32; ++w) partial_merge(o, sm[w]);
-        P.partials[D.rec_off + (uint32_t)P.pass * D.ntiles + tile] = o;
+        P.partials[D.rec_off + (uint32_t)P.pass * D.ntiles + blk] = o;
     }
 }
 
