@@ -2460,6 +2460,19 @@ extern "C" int pccm_cloud_outside_hull(pccm_ctx* ctx, pccm_cloud* c, const doubl
     return PCCM_OK;
 }
 
+// trace builds (-DPCCM_VX_TRACE): per-warp {start ns, end ns, bricks, voxels} of the last search launch; returns the warps copied
+extern "C" int pccm_debug_trace(unsigned long long* out, int max_warps) {
+#if defined(PCCM_VX_TRACE)
+    cudaDeviceSynchronize();
+    const int n = std::min(max_warps, (int)pccm::kVxTraceWarps);
+    if (cudaMemcpyFromSymbol(out, pccm::g_vx_trace, (size_t)n * 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    return n;
+#else
+    (void)out; (void)max_warps;
+    return -1;
+#endif
+}
+
 // debug builds (-DPCCM_VX_DEBUG): number of range-check violations the brick kernels have counted so far
 extern "C" int pccm_debug_errors(void) {
 #if defined(PCCM_VX_DEBUG)

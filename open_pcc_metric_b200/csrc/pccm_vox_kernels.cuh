@@ -727,10 +727,13 @@ __device__ __forceinline__ void vx_slice(const VxParams& P, const VoxView& Q, ui
 
 // Warp-cooperative exact search of one query over a list of occupied bricks (slots[k], ids[k]; id
 // = position in a DIM^3 neighbourhood centred on the query's brick).  Lane l owns rows 2l and
-// 2l+1 of every brick (one coalesced load of the 64 occupancy words).  Pass 1: minimal squared
-// distance by bit scans only.  Pass 2 (when that distance is below `limit`, i.e. certified): the
-// smallest original index among the voxels at that distance.  Returns the distance; rank is valid
-// when it is below `limit`.
+// 2l+1 of every brick (one coalesced load of the 64 occupancy words).  The bricks are visited NEAREST
+// FIRST (by the distance from the query to the brick's box, four bricks in flight per step) and the
+// visit stops at the first brick whose box is farther than the best distance found: a voxel whose
+// neighbour is 3 .. 8 voxels away touches a handful of the 27 bricks, not all of them.  Pass 1:
+// minimal squared distance by bit scans only.  Pass 2 (when that distance is below `limit`, i.e.
+// certified): the smallest original index among the voxels at that distance, in the bricks whose box
+// is not farther than it.  Returns the distance; rank is valid when it is below `limit`.
 template <int DIM, bool SELF = false>
 __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* slots, const int* ids, int n,
                                                    int qx, int qy, int qz, uint32_t limit, uint32_t& rank_out) {
@@ -740,19 +743,55 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
     const int qbx = qx >> 5, qby = qy >> 3, qbz = qz >> 3;
     uint32_t best = kVxNone;
     constexpr int kBatch = 4;                      // bricks in flight per step (independent coalesced loads; 8 spills)
-    for (int k0 = 0; k0 < n; k0 += kBatch) {
+    constexpr int kOwn = (DIM * DIM * DIM + 31) / 32;      // list entries per lane: entry k belongs to lane k % 32
+    // squared distance from the query to the box of my entries (kVxNone: no entry)
+    uint32_t gap[kOwn];
+#pragma unroll
+    for (int o = 0; o < kOwn; ++o) {
+        const int k = o * 32 + lane;
+        gap[o] = kVxNone;
+        if (k < n) {
+            const int b = ids[k];
+            const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
+            const int gx = vx_gap(qx, bx << 5, (bx << 5) + 31), gy = vx_gap(qy, by << 3, (by << 3) + 7), gz = vx_gap(qz, bz << 3, (bz << 3) + 7);
+            gap[o] = (uint32_t)(gx * gx + gy * gy + gz * gz);
+        }
+    }
+    uint32_t left[kOwn];                           // my entries not visited yet
+#pragma unroll
+    for (int o = 0; o < kOwn; ++o) left[o] = gap[o];
+    for (;;) {
+        // the (up to) kBatch nearest unvisited entries: key = gap << 8 | entry
+        int sel[kBatch];
+        int nsel = 0;
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            uint32_t key = kVxNone;
+#pragma unroll
+            for (int o = 0; o < kOwn; ++o)
+                if (left[o] != kVxNone) { const uint32_t kk = (left[o] << 8) | (uint32_t)(o * 32 + lane); key = kk < key ? kk : key; }
+            key = __reduce_min_sync(full, key);
+            sel[j] = -1;
+            if (key != kVxNone && (key >> 8) <= best) {          // (a box farther than the best cannot hold anything nearer or tied)
+                sel[j] = (int)(key & 0xffu);
+                ++nsel;
+#pragma unroll
+                for (int o = 0; o < kOwn; ++o)
+                    if (o * 32 + lane == sel[j]) left[o] = kVxNone;
+            }
+        }
+        if (!nsel) break;
         uint2 mb[kBatch];
 #pragma unroll
-        for (int j = 0; j < kBatch; ++j)
-        {
+        for (int j = 0; j < kBatch; ++j) {
             uint4 q = make_uint4(0u, 0u, 0u, 0u);
-            if (k0 + j < n) q = __ldg(reinterpret_cast<const uint4*>(S.rows + (size_t)slots[k0 + j] * kVxRows) + lane);
+            if (sel[j] >= 0) q = __ldg(reinterpret_cast<const uint4*>(S.rows + (size_t)slots[sel[j]] * kVxRows) + lane);
             mb[j] = make_uint2(q.x, q.z);
         }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
-            if (k0 + j >= n) break;
-            const int b = ids[k0 + j];
+            if (sel[j] < 0) continue;
+            const int b = ids[sel[j]];
             const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
             const int p = qx - (bx << 5);
 #pragma unroll
@@ -768,33 +807,39 @@ __device__ __forceinline__ uint32_t vx_warp_bricks(const VoxView& S, const int* 
                 best = d2 < best ? d2 : best;
             }
         }
+        best = __reduce_min_sync(full, best);
     }
-    best = __reduce_min_sync(full, best);
     if (SELF || best >= limit) return best;
     uint32_t bidx = kVxNone, brank = kVxNone;
-    for (int k0 = 0; k0 < n; ++k0) {
-        const int slot = slots[k0], b = ids[k0];
-        const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
-        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(S.rows + (size_t)slot * kVxRows) + lane);
-        const uint2 m2 = make_uint2(q2.x, q2.z);
-        const int p = qx - (bx << 5);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t m = k ? m2.y : m2.x;
-            if (!m) continue;
-            const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
-            int dlo, dhi;
-            vx_row_nearest(m, p, dlo, dhi);
-            const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
-            if (byz + (uint32_t)(dlo * dlo) == best) {
-                const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p - dlo) & 31);
-                const uint32_t i = __ldg(&S.vkey[rank].y);
-                if (i < bidx) { bidx = i; brank = rank; }
-            }
-            if (byz + (uint32_t)(dhi * dhi) == best) {
-                const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p + dhi) & 31);
-                const uint32_t i = __ldg(&S.vkey[rank].y);
-                if (i < bidx) { bidx = i; brank = rank; }
+    for (int o = 0; o < kOwn; ++o) {
+        unsigned cand = __ballot_sync(full, gap[o] <= best);       // entries whose box can hold a voxel at the minimal distance
+        while (cand) {
+            const int k0 = o * 32 + __ffs((int)cand) - 1;
+            cand &= cand - 1u;
+            const int slot = slots[k0], b = ids[k0];
+            const int bx = qbx + b % DIM - DIM / 2, by = qby + (b / DIM) % DIM - DIM / 2, bz = qbz + b / (DIM * DIM) - DIM / 2;
+            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(S.rows + (size_t)slot * kVxRows) + lane);
+            const uint2 m2 = make_uint2(q2.x, q2.z);
+            const int p = qx - (bx << 5);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t m = k ? m2.y : m2.x;
+                if (!m) continue;
+                const int r = 2 * lane + k, dy = qy - ((by << 3) + (r & 7)), dz = qz - ((bz << 3) + (r >> 3));
+                int dlo, dhi;
+                vx_row_nearest(m, p, dlo, dhi);
+                const uint32_t byz = (uint32_t)(dy * dy + dz * dz);
+                if (byz + (uint32_t)(dlo * dlo) == best) {
+                    const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p - dlo) & 31);
+                    const uint32_t i = __ldg(&S.vkey[rank].y);
+                    if (i < bidx) { bidx = i; brank = rank; }
+                }
+                if (byz + (uint32_t)(dhi * dhi) == best) {
+                    const uint32_t rank = vx_rank(S, (uint32_t)slot, r, (p + dhi) & 31);
+                    const uint32_t i = __ldg(&S.vkey[rank].y);
+                    if (i < bidx) { bidx = i; brank = rank; }
+                }
             }
         }
     }
@@ -892,9 +937,27 @@ __device__ __forceinline__ void vx_finish_pending(const VxParams& P, int d, cons
     }
 }
 
+#if defined(PCCM_VX_TRACE)
+// trace builds (tools/search_trace.py): per warp of the last vx_search_kernel launch {start, end (globaltimer ns), bricks, voxels}
+constexpr int kVxTraceWarps = 16384;
+__device__ unsigned long long g_vx_trace[kVxTraceWarps][4];
+__device__ __forceinline__ unsigned long long vx_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 __global__ void __launch_bounds__(kVxThreads, PCCM_VX_MINBLOCKS)
 vx_search_kernel(const __grid_constant__ VxParams P) {
     pdl_enter();
+#if defined(PCCM_VX_TRACE)
+    const unsigned long long tr_t0 = vx_now();
+    unsigned long long tr_bricks = 0, tr_vox = 0;
+    struct TraceOut {
+        unsigned long long t0; unsigned long long* b; unsigned long long* v;
+        __device__ ~TraceOut() {
+            const uint32_t w = blockIdx.x * (uint32_t)kVxWarps + (threadIdx.x >> 5);
+            if ((threadIdx.x & 31) == 0 && w < (uint32_t)kVxTraceWarps) { g_vx_trace[w][0] = t0; g_vx_trace[w][1] = vx_now(); g_vx_trace[w][2] = *b; g_vx_trace[w][3] = *v; }
+        }
+    } tr_out{tr_t0, &tr_bricks, &tr_vox};
+#endif
     __shared__ VxWarpSmem s_w[kVxWarps];
     const unsigned full = 0xffffffffu;
     const VoxPlan* __restrict__ plan = P.plan;
@@ -906,14 +969,18 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
 #ifndef PCCM_VX_TICKET
 #define PCCM_VX_TICKET 1          // bricks per ticket (measured: 4 per ticket costs 45 % -- the tail of the kernel is one ticket long)
 #endif
-    uint32_t ticket = 0, gw = 0, gw_end = 0;
-    if (lane == 0) ticket = atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);
-    for (;; ++gw) {
+    // The first brick of a warp is its own number (no ticket: thousands of warps asking one counter at once would all
+    // stand in that queue before any of them starts); the others come from the ticket counter, which therefore counts
+    // from the number of warps.  The next ticket is requested before the current brick is searched.
+    const uint32_t nwarps = gridDim.x * (uint32_t)kVxWarps;
+    uint32_t ticket = 0, gw = blockIdx.x * (uint32_t)kVxWarps + (uint32_t)warp, gw_end = gw + 1u;
+    if (lane == 0) ticket = nwarps + atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);
+    for (; gw < nwork; ++gw) {
         if (gw == gw_end) {
             gw = __shfl_sync(full, ticket, 0);
             if (gw >= nwork) break;
             gw_end = min(gw + (uint32_t)PCCM_VX_TICKET, nwork);
-            if (lane == 0) ticket = atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);   // the next ticket travels while these bricks are searched
+            if (lane == 0) ticket = nwarps + atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);   // the next ticket travels while these bricks are searched
         }
         const int d = gw >= nblk_d0 ? 1 : 0;
         const VxDir& D = P.dir[d];
@@ -925,6 +992,9 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
         vx_slice(P, Q, t_lo, t_hi);
         const uint32_t t0 = max(b0, t_lo), t1 = min(b1, t_hi);
         if (t0 >= t1) continue;
+#if defined(PCCM_VX_TRACE)
+        tr_bricks++; tr_vox += t1 - t0;
+#endif
         const bool need_idx = D.idx_out != nullptr || (D.flags & PCCM_EVAL_COLOR) ||
                               ((D.flags & PCCM_EVAL_D2) && P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR);
         const bool need_e = (D.flags & PCCM_EVAL_D2) != 0;
