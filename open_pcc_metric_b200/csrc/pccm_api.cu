@@ -290,6 +290,7 @@ struct SharedIndex {
 
 struct SharedVox {
     uint32_t *dirbits = nullptr, *dirpre = nullptr, *dirsums = nullptr, *bricksums = nullptr, *prank = nullptr;
+    uint32_t *bcursor = nullptr, *border = nullptr;      // bricks by size class (vx_rowbase_kernel -> vx_search_kernel)
     uint2 *rows = nullptr, *vxyz = nullptr, *vkey = nullptr;
     unsigned char* arena = nullptr;  // ONE device allocation for all of the above (+ the plan)
     VoxPlan* dplan = nullptr;        // device: written by the build kernels, read by every brick kernel
@@ -1389,11 +1390,13 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     auto slice = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_plan = slice(sizeof(VoxPlan));
     const size_t o_shard = slice(sizeof(ShardPlan));
-    const size_t o_selcnt = slice(4);               // (directly in front of the directory bits: one memset clears both)
+    const size_t o_selcnt = slice(256);             // [0] selected points, [16 ..] bricks per size class (directly in front of
+                                                    // the directory bits: one zeroing pass clears all of it)
     const size_t o_dirbits = slice((size_t)cap_dirw * 4), o_dirpre = slice(((size_t)cap_dirw + 1) * 4), o_dirsums = slice((size_t)ndirblocks * 4);
     const size_t o_dirbytes = slice(PCCM_DIR_BYTES ? (size_t)cap_dirw * 32 : 0);
     const size_t o_rows = slice((size_t)cap_blk * kVxRows * 8);
     const size_t o_bricksums = slice((size_t)nbrickchunks * 4);
+    const size_t o_border = slice((size_t)kVxSizeClasses * cap_blk * 4);
     const size_t o_vxyz = slice((size_t)n_total * 8), o_vkey = slice((size_t)n_total * 8), o_prank = slice((size_t)n_total * 4);
     const size_t o_pslot = slice((size_t)n_total * 4);
     const bool sharded = ctx->shard_world > 1 && cl[0]->d_zhist && cl[1]->d_zhist;
@@ -1406,6 +1409,8 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     v->dirsums = reinterpret_cast<uint32_t*>(v->arena + o_dirsums);
     v->rows = reinterpret_cast<uint2*>(v->arena + o_rows);
     v->bricksums = reinterpret_cast<uint32_t*>(v->arena + o_bricksums);
+    v->bcursor = reinterpret_cast<uint32_t*>(v->arena + o_selcnt) + 16;
+    v->border = reinterpret_cast<uint32_t*>(v->arena + o_border);
     v->vxyz = reinterpret_cast<uint2*>(v->arena + o_vxyz);
     v->vkey = reinterpret_cast<uint2*>(v->arena + o_vkey);
     v->prank = reinterpret_cast<uint32_t*>(v->arena + o_prank);
@@ -1447,6 +1452,7 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     A.cap_dirw = cap_dirw; A.cap_blk = cap_blk;
     A.dirbytes = v->arena + o_dirbytes;
     A.dirbits = v->dirbits; A.dirpre = v->dirpre; A.dirsums = v->dirsums; A.rows = v->rows;
+    A.bcursor = v->bcursor; A.border = v->border;
     A.bricksums = v->bricksums; A.vxyz = v->vxyz; A.vkey = v->vkey; A.prank = v->prank; A.pslot = pslot; A.plan = v->dplan;
     const int threads = 256;
     const int blocks_ilp = (int)(((n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
@@ -1874,6 +1880,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     }
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
     P.partials = partials; P.vres = vres; P.counters = todo;
+    P.bcursor = v->bcursor; P.border = v->border; P.border_cap = v->cap_blk;
     {
         StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage (level 1: ONE event pair, so that the three
                                                          // kernels stay chained; the per-kernel split needs level 2)

@@ -40,6 +40,7 @@ constexpr uint32_t kVxStRgbNotU8 = 8u;        // a float colour is not k / 255 (
 constexpr int kVxDirChunk = 2048;             // directory words per scan block
 constexpr int kVxBrickChunk = 64;             // bricks per row-base chunk (8 warps x 8 bricks)
 constexpr int kVxMaxBrickChunks = 1 << 16;
+constexpr int kVxSizeClasses = 16;            // bricks are listed by size class (voxels / 32, capped): the search takes the large ones first
 
 // One pair split over the GPUs of a box: every rank holds both clouds, OWNS the queries of a slab of
 // 8-voxel z layers (cut so that the slabs hold equal numbers of points) and indexes only what those queries can see:
@@ -78,6 +79,8 @@ struct VoxBuildArgs {                         // everything the host knows when 
     uint32_t* dirsums;                        // [cap_dirw / kVxDirChunk + 1]
     uint2* rows;                              // [cap_blk][64] {occupancy word, rank of the row's first voxel}
     uint32_t* bricksums;                      // [cap_blk / kVxBrickChunk + 1]
+    uint32_t* bcursor;                        // [kVxSizeClasses] zeroed: bricks of each size class
+    uint32_t* border;                         // [kVxSizeClasses][cap_blk] slots of the bricks of each class (arrival order)
     uint2* vxyz;                              // [n_total]
     uint2* vkey;                              // [n_total] (0xFF-filled by vx_mark_kernel)
     uint32_t* prank;                          // [n_total]
@@ -521,6 +524,8 @@ __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__
     for (uint32_t j = threadIdx.x; j < c0; j += 256) off += A.bricksums[j];
     off = vx_block_sum_u32<256>(off, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ord_slot = kVxNone, ord_pos = 0;                // a brick of this lane waiting for its place in the size-class list
+    size_t ord_at = 0;
     for (uint32_t ch = c0; ch < c1; ++ch) {
         const uint32_t s0 = ch * kVxBrickChunk + warp * 8;
         uint2 m[8];
@@ -538,10 +543,33 @@ __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__
             in2[j] = v;
         }
         uint32_t bbase[8];                                   // base of brick j inside this warp's run
+        uint32_t mytot = 0;                                  // lane j < 8: voxels of brick j
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             bbase[j] = wtot;
-            wtot += __shfl_sync(0xffffffffu, in2[j], 31);
+            const uint32_t tot = __shfl_sync(0xffffffffu, in2[j], 31);
+            wtot += tot;
+            mytot = lane == j ? tot : mytot;
+        }
+        // list of the bricks by size class: the search kernel hands out the large bricks first, so that no warp
+        // starts a 500-voxel brick when the others are about to finish (the order inside a class does not matter)
+        // (the position comes back from the L2 while the chunk is finished: it is stored at the top of the next trip)
+        if (ord_slot != kVxNone) A.border[ord_at + ord_pos] = ord_slot;
+        ord_slot = kVxNone;
+        const bool isbrick = lane < 8 && s0 + lane + 1 < nb;   // (entry nb - 1 is the end marker, not a brick)
+        const unsigned bm = __ballot_sync(0xffffffffu, isbrick);
+        if (isbrick) {
+            // one atomic per size class present among the warp's eight bricks (neighbouring bricks are of similar size;
+            // a few counters taking one atomic per brick of the pair serialise at the L2)
+            const uint32_t cls = min(mytot >> 5, (uint32_t)kVxSizeClasses - 1u);
+            const unsigned peers = __match_any_sync(bm, cls);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(A.bcursor + cls, (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            ord_at = (size_t)cls * A.cap_blk;
+            ord_pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            ord_slot = s0 + lane;
         }
         __syncthreads();                                     // (s_wtot of the previous chunk has been read)
         if (lane == 0) s_wtot[warp] = wtot;
@@ -560,6 +588,7 @@ __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__
         }
         off += chunk_total;
     }
+    if (ord_slot != kVxNone) A.border[ord_at + ord_pos] = ord_slot;
     if (c1 == nchunks && threadIdx.x == 0) P->nvox_total = off;
 }
 
@@ -651,6 +680,9 @@ struct VxParams {
     uint4* vres;               // [n_total] by ranked position: {d2, packed (query - neighbour), neighbour idx, neighbour rgb};
                                // d2 == kVxNone while the voxel is undecided.  Pencil-round answers set the top bit of
                                // the neighbour idx and put the neighbour's position in the pencil records into .y
+    const uint32_t* bcursor;   // [kVxSizeClasses] bricks per size class and
+    const uint32_t* border;    // [kVxSizeClasses][border_cap] their slots (vx_rowbase_kernel)
+    uint32_t border_cap;
     uint32_t* counters;        // [0..1] undecided per direction, [2..3] far per direction, [4] brick ticket of the search kernel
     int32_t pass;              // vx_epilogue_kernel: 0 = brick answers, 1 = pencil-round answers only
 };
@@ -964,8 +996,16 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
     if (plan->status) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     VxWarpSmem& W = s_w[warp];
-    const uint32_t nblk_d0 = plan->view[P.dir[0].qc].nblk;
-    const uint32_t nwork = nblk_d0 + (P.ndirs > 1 ? plan->view[P.dir[1].qc].nblk : 0u);
+    // work list: every brick of the pair, largest size class first (bricks of a cloud that is not queried are skipped)
+    uint32_t cls_cnt = 0, cls_incl = 0;
+    if (lane < kVxSizeClasses) cls_cnt = __ldg(P.bcursor + (kVxSizeClasses - 1 - lane));
+    cls_incl = cls_cnt;
+#pragma unroll
+    for (int o = 1; o < kVxSizeClasses; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, cls_incl, o);
+        if (lane >= o) cls_incl += t;
+    }
+    const uint32_t nwork = __shfl_sync(full, cls_incl, kVxSizeClasses - 1);
 #ifndef PCCM_VX_TICKET
 #define PCCM_VX_TICKET 1          // bricks per ticket (measured: 4 per ticket costs 45 % -- the tail of the kernel is one ticket long)
 #endif
@@ -982,11 +1022,22 @@ vx_search_kernel(const __grid_constant__ VxParams P) {
             gw_end = min(gw + (uint32_t)PCCM_VX_TICKET, nwork);
             if (lane == 0) ticket = nwarps + atomicAdd(P.counters + 4, (uint32_t)PCCM_VX_TICKET);   // the next ticket travels while these bricks are searched
         }
-        const int d = gw >= nblk_d0 ? 1 : 0;
+        const int ci = __popc(__ballot_sync(full, lane < kVxSizeClasses && gw >= cls_incl));      // classes before the ticket's
+        const uint32_t cfirst = __shfl_sync(full, cls_incl - cls_cnt, ci);
+        const uint32_t slot = __ldg(P.border + (size_t)(kVxSizeClasses - 1 - ci) * P.border_cap + (gw - cfirst));
+        int d = 0;
+        {
+            const VoxView& Q0 = plan->view[P.dir[0].qc];
+            if (slot - Q0.slot0 >= Q0.nblk) {
+                if (P.ndirs < 2) continue;
+                const VoxView& Q1 = plan->view[P.dir[1].qc];
+                if (slot - Q1.slot0 >= Q1.nblk) continue;
+                d = 1;
+            }
+        }
         const VxDir& D = P.dir[d];
         const VoxView& Q = plan->view[D.qc];
         const VoxView& S = plan->view[D.sc];
-        const uint32_t slot = Q.slot0 + (gw - (d ? nblk_d0 : 0u));
         const uint32_t b0 = vx_brick_begin(Q, slot), b1 = vx_brick_begin(Q, slot + 1);
         uint32_t t_lo, t_hi;
         vx_slice(P, Q, t_lo, t_hi);
