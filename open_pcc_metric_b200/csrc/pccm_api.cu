@@ -1010,7 +1010,7 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
     if (rc) { pccm_cloud_destroy(ctx, c); return rc; }
     if (n) {
         StageTimer t(ctx, &ctx->tm.stats_ms);
-        c->stats_blocks = (int)std::min<int64_t>((n + kStatsThreads - 1) / kStatsThreads, (int64_t)ctx->sm_count * 4);
+        c->stats_blocks = (int)std::min<int64_t>((n + 2 * kStatsThreads - 1) / (2 * kStatsThreads), (int64_t)ctx->sm_count * 4);
         // ONE device block per cloud: partials, their fold, the colour flag, the DevStats record and -- for integer-capable
         // inputs -- the packed 8-byte coordinates the brick index is built from
         const bool want_packed = ctx->use_vox && xyz_dtype != PCCM_F32;
@@ -1028,8 +1028,13 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
             e = dzero(ctx, c->d_stats + c->stats_blocks, 2 * sizeof(StatsPartial) + hist_bytes, ctx->stream);
         }
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
-        launch_chain(ctx, stats_kernel, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
-                                                                                  nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);   // colours are classified apart
+        const bool f64rows = c->raw_dtype == PCCM_F64 && c->raw_stride == 24 && (reinterpret_cast<uintptr_t>(c->raw_xyz) & 7u) == 0;
+        if (f64rows)
+            launch_chain(ctx, stats_kernel<true>, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+                         nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);   // colours are classified apart
+        else
+            launch_chain(ctx, stats_kernel<false>, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+                         nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);
         ctx->tm.total_launches++;
         e = cudaGetLastError();
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats launch: %s", cudaGetErrorString(e)); }

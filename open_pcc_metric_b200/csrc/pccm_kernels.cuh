@@ -75,7 +75,11 @@ constexpr int kZHistBins = 4096;          // 8-voxel layers of a 15-bit coordina
 
 // K0: bounding box + classification of coordinates (and colours) in one pass; integer-valued coordinates are
 // also written as 8-byte {x | y << 16, z} records -- the form every later pass of the brick index reads.
-__global__ void __launch_bounds__(kStatsThreads)
+// F64ROWS: packed float64 rows (the form numpy / Open3D hand over): plain 8-byte loads instead of the per-element format
+// switch.  Values that are integers in [0, 32767] -- every coordinate of voxelised content -- take the short way: one round
+// trip through int, integer min / max; only other values pay for the float64 min / max and the float32 / finite checks.
+template <bool F64ROWS>
+__global__ void __launch_bounds__(kStatsThreads, 4)
 stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
              const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out, uint2* packed, DevStats* dev, uint32_t* zhist) {
     pdl_enter();
@@ -87,24 +91,48 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
         __syncthreads();
     }
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int imn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, imx[3] = {-1, -1, -1};        // over the values that are integers in [0, 32767]
     uint32_t not_int = 0, not_f32 = 0, not_fin = 0, rgb_bad = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double v3[3];
+    // two points of a thread are in flight (their loads are requested together): the pass is bound by memory latency
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t ib = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ib < n; ib += 2 * gstride) {
+      double w3[2][3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = ib + u * gstride;
+        if (i >= n) continue;
+        if (F64ROWS) {
+            const double* row = static_cast<const double*>(xyz) + 3 * i;
+            w3[u][0] = __ldg(row); w3[u][1] = __ldg(row + 1); w3[u][2] = __ldg(row + 2);
+        } else {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) w3[u][a] = load_coord(xyz, dtype, stride, i, a);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = ib + u * gstride;
+        if (i >= n) continue;
+        int i3[3];
+        double v3[3] = {w3[u][0], w3[u][1], w3[u][2]};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            double v = load_coord(xyz, dtype, stride, i, a);
-            v3[a] = v;
-            mn[a] = fmin(mn[a], v);
-            mx[a] = fmax(mx[a], v);
+            const double v = v3[a];
             const int iv = __double2int_rz(v);
-            if (!((double)iv == v && (unsigned)iv <= 32767u)) {      // the common case (voxelised content) costs one round trip through int
+            i3[a] = iv;
+            if ((double)iv == v && (unsigned)iv <= 32767u) {         // the common case (voxelised content): one round trip through int
+                imn[a] = min(imn[a], iv);
+                imx[a] = max(imx[a], iv);
+            } else {
                 not_int = 1;
+                mn[a] = fmin(mn[a], v);
+                mx[a] = fmax(mx[a], v);
                 if (!isfinite(v)) not_fin = 1;
                 if ((double)(float)v != v) not_f32 = 1;
             }
         }
-        if (packed) packed[i] = make_uint2(((uint32_t)(int)v3[0] & 0xffffu) | ((uint32_t)(int)v3[1] << 16), (uint32_t)(int)v3[2]);
-        if (zhist) atomicAdd(&s_hist[min(max((int)v3[2], 0) >> 3, kZHistBins - 1)], 1u);
+        if (packed) packed[i] = make_uint2(((uint32_t)i3[0] & 0xffffu) | ((uint32_t)i3[1] << 16), (uint32_t)i3[2]);
+        if (zhist) atomicAdd(&s_hist[min(max(i3[2], 0) >> 3, kZHistBins - 1)], 1u);
         if (rgb != nullptr && rgb_dtype == PCCM_F64) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -113,6 +141,7 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
                 if (!(k >= 0.0 && k <= 255.0 && k / 255.0 == c)) rgb_bad = 1;
             }
         }
+      }
     }
     __shared__ double s_mn[3][kStatsThreads / 32], s_mx[3][kStatsThreads / 32];
     __shared__ uint32_t s_flags[4];
@@ -124,6 +153,7 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+        if (imx[a] >= 0) { mn[a] = fmin(mn[a], (double)imn[a]); mx[a] = fmax(mx[a], (double)imx[a]); }
         for (int o = 16; o > 0; o >>= 1) {
             mn[a] = fmin(mn[a], __shfl_down_sync(0xffffffffu, mn[a], o));
             mx[a] = fmax(mx[a], __shfl_down_sync(0xffffffffu, mx[a], o));

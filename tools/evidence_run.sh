@@ -5,4 +5,4 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('dev ms',round(d['ms_per_step'],4),'frac',round(d['roofline']['frac'],4), {k:round(v,4) for k,v in d['stage_ms_per_step'].items() if v}, d['brick_path'])"
 done
-python tools/variants.py run base 2>&1 | head -30
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
