@@ -114,7 +114,7 @@ typedef struct pccm_timings {
     double vox_epilogue_ms;    /* per-point epilogue kernel of the brick path (D1 / D2 / colour + reduction records) */
     int64_t query_launches, knn_launches;
     int64_t total_launches;    /* kernels of this library (hand-written, sm_100a) */
-    int64_t library_launches;  /* CUB device-wide calls (radix sort passes, scans) */
+    int64_t library_launches;  /* kernels of a library (none: every sort and scan is hand-written; the field is kept and stays 0) */
     int64_t vox_undecided;     /* queries of the last brick-path evaluation that needed the general search */
     int64_t vox_far;           /* ... of which the pencil search had to finish (nearest point tens of voxels away) */
     int64_t vox_tail;          /* points that share a voxel with a smaller index (they reuse that voxel's search), last evaluation */
@@ -127,7 +127,8 @@ const char* pccm_last_error(const pccm_ctx* ctx);
 int pccm_ctx_create(int device, void* stream, pccm_ctx** out);
 int pccm_ctx_destroy(pccm_ctx* ctx);
 int pccm_ctx_synchronize(pccm_ctx* ctx);
-/* level 0 = off, 1 = time the query / k-NN kernels only, 2 = time every stage */
+/* level 0 = off, 1 = time the query stage (one event pair) / the k-NN kernels only, 2 = time every stage and every
+ * kernel of the query stage (the event pairs keep those kernels from overlapping their launches) */
 int pccm_ctx_set_profiling(pccm_ctx* ctx, int level);
 int pccm_ctx_reset_timings(pccm_ctx* ctx);
 /* One pair over several GPUs (one context per GPU, the same calls on every rank, both clouds given to every rank):
@@ -162,9 +163,12 @@ int pccm_cloud_info_get(pccm_ctx* ctx, pccm_cloud* cloud, pccm_cloud_info* out);
  * (both clouds of a pair must share one kind). */
 int pccm_cloud_build_index(pccm_ctx* ctx, pccm_cloud* cloud, double cell_size, int force_kind);
 
-/* Builds the indices of BOTH clouds of a pair (the two KDTreeFlann builds of cloud_pair.py:65)
- * in joint launches: one key pass, one radix sort, one scan, one reorder.  Same result as two
- * pccm_cloud_build_index calls with the common kind. */
+/* Builds the indices of BOTH clouds of a pair (the two KDTreeFlann builds of cloud_pair.py:65) in joint launches.
+ * Integer pairs (every coordinate an integer in [0, 32767]: voxelised content) get the occupancy-brick index -- a
+ * directory of occupied 32 x 8 x 8-voxel bricks, one occupancy word per brick row, one record per distinct voxel --
+ * enqueued WITHOUT a host synchronisation (the outcome is judged at the result read-back of pccm_pair_eval); other
+ * pairs get the pencil-grid index (counting sort by row + per-row sorting networks, no library sort).  Results are the
+ * same as with two pccm_cloud_build_index calls with the common kind. */
 int pccm_pair_build_index(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind);
 
 int pccm_cloud_set_normals(pccm_ctx* ctx, pccm_cloud* cloud, const void* normals, int nrm_dtype,
