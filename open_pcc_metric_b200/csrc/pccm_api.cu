@@ -1506,12 +1506,29 @@ static int vox_fetch(pccm_ctx* ctx, SharedVox* v) {
     CK(cudaMemcpyAsync(pin, v->dplan, sizeof(VoxPlan), cudaMemcpyDeviceToHost, ctx->stream));
     for (int c = 0; c < 2; ++c) {
         pccm_cloud* p = v->owner[c];
-        if (p && v->pending) { const int rc = stats_fetch(ctx, p, c); if (rc) return rc; }
         uint32_t* flag = reinterpret_cast<uint32_t*>(pin + sizeof(VoxPlan)) + c;
         *flag = 0;
         if (p && p->rgb_spec) CK(cudaMemcpyAsync(flag, p->d_rgbflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     return PCCM_OK;
+}
+
+// the same as entries of ONE gather launch (see gather_to_host_kernel)
+static void gather_add(GatherArgs& G, void* host_dst, const void* dev_src, size_t bytes) {
+    G.src[G.n] = static_cast<const uint32_t*>(dev_src);
+    G.dst[G.n] = static_cast<uint32_t*>(host_dst);
+    G.words[G.n] = (uint32_t)((bytes + 3) / 4);
+    G.n++;
+}
+static void vox_fetch_list(pccm_ctx* ctx, SharedVox* v, GatherArgs& G) {
+    char* pin = static_cast<char*>(ctx->pinned) + kVoxPinnedOffset;
+    gather_add(G, pin, v->dplan, sizeof(VoxPlan));
+    for (int c = 0; c < 2; ++c) {
+        pccm_cloud* p = v->owner[c];
+        uint32_t* flag = reinterpret_cast<uint32_t*>(pin + sizeof(VoxPlan)) + c;
+        *flag = 0;
+        if (p && p->rgb_spec) gather_add(G, flag, p->d_rgbflag, sizeof(uint32_t));
+    }
 }
 
 static int pair_build_classic(pccm_ctx* ctx, pccm_cloud* a, pccm_cloud* b, double cell_size, int force_kind, bool allow_vox);
@@ -1548,7 +1565,19 @@ static int vox_adopt(pccm_ctx* ctx, SharedVox* v, bool* redo) {
         }
     }
     if (rc || !was_pending) return rc;
-    for (int c = 0; c < 2 && !rc; ++c) if (cl[c]) rc = cl[c]->stats_fetched ? stats_adopt(ctx, cl[c]) : ensure_stats(ctx, cl[c]);
+    // statistics of the clouds: an integer pair (the plan says so) is fully described by the plan's bounding boxes;
+    // only when the coordinates turned out not to be integers do the per-block partials travel (a second wait)
+    for (int c = 0; c < 2 && !rc; ++c) {
+        pccm_cloud* p = cl[c];
+        if (!p) continue;
+        if (!(v->hplan.status & kVxStNotInt) && !p->stats_ready && !p->stats_fetched && p->n) {
+            for (int a = 0; a < 3; ++a) { p->mn[a] = (double)v->hplan.mn[c][a]; p->mx[a] = (double)v->hplan.mx[c][a]; }
+            p->data_kind = PCCM_KIND_INT;
+            p->stats_ready = true;
+        } else {
+            rc = p->stats_fetched ? stats_adopt(ctx, p) : ensure_stats(ctx, p);
+        }
+    }
     if (rc) {                                    // (NaN / Inf coordinates): no index
         for (int c = 0; c < 2; ++c)
             if (cl[c]) { release_vox(ctx, cl[c]); cl[c]->index_kind = -1; }
@@ -1928,20 +1957,27 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     Q.out = static_cast<BlockPartial*>(ctx->dscratch);
     Q.chunks = reinterpret_cast<BlockPartial*>(static_cast<char*>(ctx->dscratch) + kChunksOffset);
     uint32_t* hcnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->pinned) + kVoxPinnedOffset + sizeof(VoxPlan) + 16);
-    auto fold = [&](uint32_t passes) -> int {
+    auto fold = [&](uint32_t passes, bool copy) -> int {
         StageTimer t(ctx, &ctx->tm.finalize_ms);
-        for (int d = 0; d < ndirs; ++d) Q.dir[d].ntiles = passes * P.dir[d].ntiles;
-        launch_chain(ctx, finalize_kernel, Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream, Q);
+        uint32_t most = 0;
+        for (int d = 0; d < ndirs; ++d) { Q.dir[d].ntiles = passes * P.dir[d].ntiles; most = std::max(most, Q.dir[d].ntiles); }
+        if (most <= 2048) launch_chain(ctx, finalize_small_kernel, Q.ndirs, kFinalThreads, 0, ctx->stream, Q);
+        else launch_chain(ctx, finalize_kernel, Q.ndirs * kFinalChunks, kFinalThreads, 0, ctx->stream, Q);
         ctx->tm.total_launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
+        if (copy) CK(cudaMemcpyAsync(ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial), cudaMemcpyDeviceToHost, ctx->stream));
         return PCCM_OK;
     };
-    int rc = fold(1);
+    int rc = fold(1, false);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(hcnt, todo, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = vox_fetch(ctx, v);
-    if (rc) return rc;
+    {   // everything the host reads at its one wait, in one launch: results, counters, plan, statistics, colour flags
+        GatherArgs G{};
+        gather_add(G, ctx->pinned, ctx->dscratch, 2 * sizeof(BlockPartial));
+        gather_add(G, hcnt, todo, 8 * sizeof(uint32_t));
+        vox_fetch_list(ctx, v, G);
+        CK(launch_chain(ctx, gather_to_host_kernel, 1, 256, 0, ctx->stream, G));
+        ctx->tm.total_launches++;
+    }
     CK(cudaStreamSynchronize(ctx->stream));          // the one host wait of build + evaluation
     rc = vox_adopt(ctx, v, redo);
     if (rc || *redo) return rc;
@@ -1972,7 +2008,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
             ctx->tm.total_launches += 2;
             CK(cudaGetLastError());
         }
-        rc = fold(2);
+        rc = fold(2, true);
         if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
     }

@@ -30,6 +30,21 @@ __global__ void zero_words_kernel(uint32_t* __restrict__ p, size_t nwords) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
 }
 
+// The read-back of an evaluation as ONE kernel of the chain: up to eight small device blocks (result records, counters,
+// plan, statistics, colour flags) are copied word by word into the context's pinned host block (cudaMallocHost memory
+// is addressable from the device) -- instead of as many cudaMemcpyAsync calls, each a stream operation of its own.
+struct GatherArgs {
+    const uint32_t* src[8];
+    uint32_t* dst[8];
+    uint32_t words[8];
+    int n;
+};
+__global__ void __launch_bounds__(256) gather_to_host_kernel(const __grid_constant__ GatherArgs G) {
+    pdl_enter();
+    for (int k = 0; k < G.n; ++k)
+        for (uint32_t i = threadIdx.x; i < G.words[k]; i += 256) G.dst[k][i] = G.src[k][i];
+}
+
 constexpr int kStatsThreads = 256;
 constexpr int kQueryThreads = 128;
 constexpr int kKnnThreads = 64;
@@ -1183,6 +1198,19 @@ __device__ __forceinline__ void block_fold(BlockPartial& a, BlockPartial* sm, Bl
         for (int w = 1; w < kFinalThreads / 32; ++w) partial_merge(r, sm[w]);
         *dst = r;
     }
+}
+
+// a few hundred records per direction (the brick path's one-wave epilogue): one block per direction, no second phase
+__global__ void __launch_bounds__(kFinalThreads) finalize_small_kernel(const __grid_constant__ QueryParams P) {
+    pdl_enter();
+    __shared__ BlockPartial sm[kFinalThreads / 32];
+    const int d = blockIdx.x;
+    const uint32_t nrec = P.dir[d].ntiles;
+    const BlockPartial* in = P.partials + (size_t)d * P.rec_stride;
+    BlockPartial a;
+    partial_init(a);
+    for (uint32_t i = threadIdx.x; i < nrec; i += kFinalThreads) partial_merge(a, in[i]);
+    block_fold(a, sm, P.out + d);
 }
 
 __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const __grid_constant__ QueryParams P) {
