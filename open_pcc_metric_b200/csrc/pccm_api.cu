@@ -78,6 +78,11 @@ struct pccm_ctx {
     int host_threads = 0;                  // PCCM_HOST_THREADS (0 = min(hardware threads, 8))
     int shard_rank = 0, shard_world = 1;   // pccm_ctx_set_shard: pairs built from now on are split by z slabs over `world` ranks
     bool shard_sel = true;          // split pairs: fill / place walk a compacted list of the slab's points (PCCM_SHARD_SEL=0: every point)
+    int vxyz_rows = -1;             // voxel coordinates written from the occupancy rows, in rank order (1), or by every point, scattered (0);
+                                    // -1: by the number of points indexed here (PCCM_VXYZ_ROWS)
+    bool stats_tma = true;          // statistics pass: float64 rows staged by cp.async.bulk + mbarrier (PCCM_STATS_TMA=0: plain loads)
+    bool epi_compact = true;        // epilogue of a split pair / voxel slice works off a per-block queue of its own points (PCCM_EPI_COMPACT=0: every tile)
+    bool epi_tma = true;            // epilogue streams staged by cp.async.bulk + mbarrier (PCCM_EPI_TMA=0: plain loads)
     bool pdl = true;                // programmatic dependent launch along the kernel chains of an evaluation (PCCM_PDL=0: ordinary launches)
     int mark_sample = 32;           // the brick directory is marked by 1 / mark_sample of the points first (PCCM_MARK_SAMPLE, 0 = one pass)
 };
@@ -792,6 +797,10 @@ extern "C" int pccm_ctx_create(int device, void* stream, pccm_ctx** out) {
     if (const char* s = getenv("PCCM_EAGER_PENCIL")) ctx->eager_pencil = atoi(s) != 0;
     if (const char* s = getenv("PCCM_VX_BLOCKS")) ctx->vx_search_blocks = std::max(1, atoi(s));
     if (const char* s = getenv("PCCM_PDL")) ctx->pdl = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_EPI_TMA")) ctx->epi_tma = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_VXYZ_ROWS")) ctx->vxyz_rows = atoi(s);
+    if (const char* s = getenv("PCCM_STATS_TMA")) ctx->stats_tma = atoi(s) != 0;
+    if (const char* s = getenv("PCCM_EPI_COMPACT")) ctx->epi_compact = atoi(s) != 0;
     if (const char* s = getenv("PCCM_DEV_CACHE")) ctx->dev_cache = atoi(s) != 0;
     if (const char* s = getenv("PCCM_MARK_SAMPLE")) ctx->mark_sample = std::max(0, atoi(s));
     if (const char* s = getenv("PCCM_SHARD_SEL")) ctx->shard_sel = atoi(s) != 0;
@@ -1030,10 +1039,10 @@ extern "C" int pccm_cloud_create(pccm_ctx* ctx, const void* xyz, int xyz_dtype, 
         if (e != cudaSuccess) { pccm_cloud_destroy(ctx, c); return fail(ctx, PCCM_ERR_CUDA, "stats alloc: %s", cudaGetErrorString(e)); }
         const bool f64rows = c->raw_dtype == PCCM_F64 && c->raw_stride == 24 && (reinterpret_cast<uintptr_t>(c->raw_xyz) & 7u) == 0;
         if (f64rows)
-            launch_chain(ctx, stats_kernel<true>, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+            launch_chain(ctx, ctx->stats_tma ? stats_kernel<2> : stats_kernel<1>, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
                          nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);   // colours are classified apart
         else
-            launch_chain(ctx, stats_kernel<false>, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
+            launch_chain(ctx, stats_kernel<0>, c->stats_blocks, kStatsThreads, hist_bytes, ctx->stream, c->raw_xyz, c->raw_dtype, c->raw_stride, n,
                          nullptr, PCCM_F64, 0, c->d_stats, c->packed, c->d_dev, c->d_zhist);
         ctx->tm.total_launches++;
         e = cudaGetLastError();
@@ -1404,6 +1413,12 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     const size_t o_border = slice((size_t)kVxSizeClasses * cap_blk * 4);
     const size_t o_vxyz = slice((size_t)n_total * 8), o_vkey = slice((size_t)n_total * 8), o_prank = slice((size_t)n_total * 4);
     const size_t o_pslot = slice((size_t)n_total * 4);
+    // Scattered 8-byte stores of the coordinates are cheap while the voxel arrays sit in the L2 and ~0.8 ms of DRAM
+    // read-modify-writes on a 10 M + 10 M pair; the row walk costs a few microseconds per million voxels either way.
+    const bool sharded_here = ctx->shard_world > 1 && cl[0]->d_zhist && cl[1]->d_zhist && !full_need;
+    const size_t indexed_here = sharded_here ? (size_t)n_total / (size_t)ctx->shard_world : (size_t)n_total;
+    const bool vxyz_rows = ctx->vxyz_rows >= 0 ? ctx->vxyz_rows != 0 : indexed_here >= ((size_t)4 << 20);
+    const size_t o_bkey = slice(vxyz_rows ? (size_t)cap_blk * 4 : 0);
     const bool sharded = ctx->shard_world > 1 && cl[0]->d_zhist && cl[1]->d_zhist;
     const bool use_sel = sharded && !full_need && ctx->shard_sel;
     const size_t o_sel = slice(use_sel ? (size_t)n_total * 4 : 0);
@@ -1459,6 +1474,7 @@ static int vox_enqueue(pccm_ctx* ctx, pccm_cloud* cl[2], double cell_size, int f
     A.dirbits = v->dirbits; A.dirpre = v->dirpre; A.dirsums = v->dirsums; A.rows = v->rows;
     A.bcursor = v->bcursor; A.border = v->border;
     A.bricksums = v->bricksums; A.vxyz = v->vxyz; A.vkey = v->vkey; A.prank = v->prank; A.pslot = pslot; A.plan = v->dplan;
+    A.bkey = vxyz_rows ? reinterpret_cast<uint32_t*>(v->arena + o_bkey) : nullptr;
     const int threads = 256;
     const int blocks_ilp = (int)(((n_total + kVxIlp - 1) / kVxIlp + threads - 1) / threads);
     const int brick_grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count * 8u, nbrickchunks);
@@ -1915,6 +1931,10 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
     for (int d = 0; d < ndirs; ++d) P.dir[d].rec_off = (uint32_t)d * rec_stride;
     P.partials = partials; P.vres = vres; P.counters = todo;
     P.bcursor = v->bcursor; P.border = v->border; P.border_cap = v->cap_blk;
+    // a rank that evaluates a fraction of the points (split pair, voxel slice) queues them per block instead of walking every tile
+    const bool compact = ctx->epi_compact && (v->sharded || world > 1);
+    void (*epilogue_kernel)(VxParams) = compact ? vx_epilogue_kernel<false, true>
+                                                : (ctx->epi_tma ? vx_epilogue_kernel<true, false> : vx_epilogue_kernel<false, false>);
     {
         StageTimer stage(ctx, &ctx->tm.query_ms, 1);     // the whole query stage (level 1: ONE event pair, so that the three
                                                          // kernels stay chained; the per-kernel split needs level 2)
@@ -1945,7 +1965,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         }
         {
             StageTimer t(ctx, &ctx->tm.vox_epilogue_ms, 2);
-            launch_chain(ctx, vx_epilogue_kernel, ntiles, kVxEpiThreads, 0, ctx->stream, P);
+            launch_chain(ctx, epilogue_kernel, ntiles, kVxEpiThreads, 0, ctx->stream, P);
         }
         ctx->tm.total_launches += 3;
     }
@@ -2004,7 +2024,7 @@ static int launch_vox_query(pccm_ctx* ctx, int ndirs, pccm_cloud* qc[2], pccm_cl
         {
             StageTimer t(ctx, &ctx->tm.vox_tail_ms, 2);
             launch_chain(ctx, vx_far_kernel, ctx->sm_count * 8, 128, 0, ctx->stream, P);
-            launch_chain(ctx, vx_epilogue_kernel, ntiles, kVxEpiThreads, 0, ctx->stream, P);
+            launch_chain(ctx, epilogue_kernel, ntiles, kVxEpiThreads, 0, ctx->stream, P);
             ctx->tm.total_launches += 2;
             CK(cudaGetLastError());
         }

@@ -22,6 +22,34 @@ __device__ __forceinline__ void pdl_enter() {
     pdl_wait();
 }
 
+// Bulk asynchronous copies (the 1-D form of the TMA engine: cp.async.bulk, no tensor map) with completion counted in
+// bytes on a shared-memory mbarrier.  Used where a kernel streams contiguous arrays (stats_kernel: the float64 rows;
+// vx_epilogue_kernel: ranks, normals, colours of a tile): one elected thread requests whole tiles, tiles ahead, and the
+// loads cost the other threads neither registers nor issue slots while they travel.  Source, destination and size are
+// multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
 // Zeroing as a KERNEL of the chain instead of cudaMemsetAsync: a memset may be handed to a copy engine, where it queues
 // behind the attribute uploads of the copy stream (measured end to end: the index build then waits ~2 ms for 96 MB
 // of colours and normals it does not need), and a memset node also cuts the programmatic-launch chain.
@@ -93,10 +121,21 @@ constexpr int kZHistBins = 4096;          // 8-voxel layers of a 15-bit coordina
 // F64ROWS: packed float64 rows (the form numpy / Open3D hand over): plain 8-byte loads instead of the per-element format
 // switch.  Values that are integers in [0, 32767] -- every coordinate of voxelised content -- take the short way: one round
 // trip through int, integer min / max; only other values pay for the float64 min / max and the float32 / finite checks.
-template <bool F64ROWS>
+// MODE 2 = F64ROWS with the rows staged by bulk copies: tiles of kStatsThreads rows (6 KB), kStatsStages - 1 tiles of a
+// block in flight, no load instruction in the loop but the shared-memory reads (stride 24 bytes: conflict-free).
+constexpr int kStatsStages = 4;
+template <int MODE>
 __global__ void __launch_bounds__(kStatsThreads, 4)
 stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
              const void* rgb, int rgb_dtype, int64_t rgb_stride, StatsPartial* out, uint2* packed, DevStats* dev, uint32_t* zhist) {
+    constexpr bool F64ROWS = MODE != 0;
+    constexpr bool STAGED = MODE == 2;
+    __shared__ __align__(16) unsigned char s_rows[STAGED ? kStatsStages : 1][STAGED ? kStatsThreads * 24 + 16 : 16];
+    __shared__ unsigned long long s_bar[kStatsStages];
+    if (STAGED && threadIdx.x == 0) {
+        for (int k = 0; k < kStatsStages; ++k) mbar_init(&s_bar[k], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     pdl_enter();
     // zhist (sharded builds: one pair split over several GPUs by slabs of z): points per 8-voxel layer, kZHistBins
     // bins, accumulated per block in dynamic shared memory
@@ -108,28 +147,8 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     int imn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, imx[3] = {-1, -1, -1};        // over the values that are integers in [0, 32767]
     uint32_t not_int = 0, not_f32 = 0, not_fin = 0, rgb_bad = 0;
-    // two points of a thread are in flight (their loads are requested together): the pass is bound by memory latency
-    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t ib = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ib < n; ib += 2 * gstride) {
-      double w3[2][3];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int64_t i = ib + u * gstride;
-        if (i >= n) continue;
-        if (F64ROWS) {
-            const double* row = static_cast<const double*>(xyz) + 3 * i;
-            w3[u][0] = __ldg(row); w3[u][1] = __ldg(row + 1); w3[u][2] = __ldg(row + 2);
-        } else {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) w3[u][a] = load_coord(xyz, dtype, stride, i, a);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int64_t i = ib + u * gstride;
-        if (i >= n) continue;
+    auto point = [&](int64_t i, const double (&v3)[3]) {
         int i3[3];
-        double v3[3] = {w3[u][0], w3[u][1], w3[u][2]};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const double v = v3[a];
@@ -156,7 +175,64 @@ stats_kernel(const void* xyz, int dtype, int64_t stride, int64_t n,
                 if (!(k >= 0.0 && k <= 255.0 && k / 255.0 == c)) rgb_bad = 1;
             }
         }
+    };
+    if (STAGED) {
+        const unsigned char* base = static_cast<const unsigned char*>(xyz);
+        const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(xyz) & 15u);        // (0 or 8: rows of float64)
+        const int64_t ntiles = (n + kStatsThreads - 1) / kStatsThreads;
+        auto request = [&](int64_t tile, int st) {           // (thread 0) rows of the tile, from the 16-byte line below the first to the one above the last
+            const int64_t first = tile * kStatsThreads;
+            const uint32_t cnt = (uint32_t)min((int64_t)kStatsThreads, n - first);
+            const uint32_t bytes = (lead + cnt * 24u + 15u) & ~15u;
+            mbar_expect_tx(&s_bar[st], bytes);
+            bulk_g2s(s_rows[st], base + first * 24 - lead, bytes, &s_bar[st]);
+        };
+        __syncthreads();                                      // (barriers initialised)
+        if (threadIdx.x == 0)
+            for (int k = 0; k < kStatsStages - 1; ++k) {
+                const int64_t tile = blockIdx.x + (int64_t)k * gridDim.x;
+                if (tile < ntiles) request(tile, k);
+            }
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = (int)(it % kStatsStages);
+            if (threadIdx.x == 0) {                           // the stage consumed in the previous trip takes the tile kStatsStages - 1 ahead
+                const int64_t ahead = tile + (int64_t)(kStatsStages - 1) * gridDim.x;
+                if (ahead < ntiles) request(ahead, (int)((it + kStatsStages - 1) % kStatsStages));
+            }
+            mbar_wait(&s_bar[st], (it / kStatsStages) & 1u);
+            const int64_t i = tile * kStatsThreads + threadIdx.x;
+            if (i < n) {
+                const double* row = reinterpret_cast<const double*>(s_rows[st] + lead + threadIdx.x * 24);
+                const double v3[3] = {row[0], row[1], row[2]};
+                point(i, v3);
+            }
+            __syncthreads();                                  // everybody has read the stage before it is requested again
+        }
+    } else {
+    // two points of a thread are in flight (their loads are requested together): the pass is bound by memory latency
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t ib = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ib < n; ib += 2 * gstride) {
+      double w3[2][3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = ib + u * gstride;
+        if (i >= n) continue;
+        if (F64ROWS) {
+            const double* row = static_cast<const double*>(xyz) + 3 * i;
+            w3[u][0] = __ldg(row); w3[u][1] = __ldg(row + 1); w3[u][2] = __ldg(row + 2);
+        } else {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) w3[u][a] = load_coord(xyz, dtype, stride, i, a);
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = ib + u * gstride;
+        if (i >= n) continue;
+        point(i, w3[u]);
+      }
+    }
     }
     __shared__ double s_mn[3][kStatsThreads / 32], s_mx[3][kStatsThreads / 32];
     __shared__ uint32_t s_flags[4];

@@ -85,11 +85,11 @@ PCCM_HD void vx_atomic_or(uint32_t* p, uint32_t v) {     // (no result: a reduct
     *p |= v;
 #endif
 }
-PCCM_HD unsigned long long vx_atomic_min64(unsigned long long* p, unsigned long long v) {
+PCCM_HD void vx_atomic_min64(unsigned long long* p, unsigned long long v) {     // (no result: a reduction, not a round trip)
 #if defined(__CUDA_ARCH__)
-    return atomicMin(p, v);
+    atomicMin(p, v);
 #else
-    const unsigned long long o = *p; if (v < o) *p = v; return o;
+    if (v < *p) *p = v;
 #endif
 }
 PCCM_HD uint32_t vx_ld32(const uint32_t* p) {
@@ -197,8 +197,10 @@ PCCM_HD uint32_t vx_place_point(const uint2* rows, uint2* vxyz, uint2* vkey,
     const uint2 m = vx_ld64(rows + (size_t)slot * kVxRows + vx_row(y, z));
     const uint32_t rank = m.y + (uint32_t)vx_popc(m.x & ((1u << (x & 31)) - 1u));
     VX_CHECK((m.x >> (x & 31)) & 1u);
-    const unsigned long long old = vx_atomic_min64(reinterpret_cast<unsigned long long*>(vkey + rank), ((unsigned long long)idx << 32) | rgb);
-    if (old == ~0ull) {                                  // the first point to arrive at the voxel writes its coordinates
+    // a reduction, not a round trip: nobody waits for the old value.  Every point of the voxel writes the voxel's
+    // coordinates (the same 8 bytes) -- cheaper than learning from the atomic who came first
+    vx_atomic_min64(reinterpret_cast<unsigned long long*>(vkey + rank), ((unsigned long long)idx << 32) | rgb);
+    if (vxyz) {                                          // (null: the coordinates are written brick by brick, from the occupancy rows)
         uint2 c;
         c.x = (uint32_t)x | ((uint32_t)y << 16);
         c.y = (uint32_t)z;

@@ -85,6 +85,9 @@ struct VoxBuildArgs {                         // everything the host knows when 
     uint2* vkey;                              // [n_total] (0xFF-filled by vx_mark_kernel)
     uint32_t* prank;                          // [n_total]
     uint32_t* pslot;                          // [n_total] scratch: brick slot of input point i
+    uint32_t* bkey;                           // [cap_blk] directory key of every brick (written by its points in the fill pass), or null:
+                                              //   with it the voxel coordinates are written by vx_rowbase_kernel -- in rank order, from
+                                              //   the occupancy rows -- instead of by every point in the place pass (a scattered 8-byte store)
     VoxPlan* plan;
 };
 
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
     const uint32_t n_total = A.n[0] + A.n[1];
     uint2 p[kVxIlp];
     int c[kVxIlp];
-    uint32_t idx[kVxIlp], slot[kVxIlp];
+    uint32_t idx[kVxIlp], slot[kVxIlp], key[kVxIlp];
     bool on[kVxIlp];
 #pragma unroll
     for (int k = 0; k < kVxIlp; ++k) {
@@ -427,7 +430,8 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
         if (on[k]) {
             VX_UNPACK(p[k], x, y, z);
             const VoxView& V = P->view[c[k]];
-            slot[k] = vx_slot_of_key(V.dirbits, V.dirpre, vx_key(V.g, x, y, z));
+            key[k] = vx_key(V.g, x, y, z);
+            slot[k] = vx_slot_of_key(V.dirbits, V.dirpre, key[k]);
         }
     }
 #pragma unroll
@@ -437,6 +441,7 @@ __global__ void __launch_bounds__(256) vx_fill_kernel(const __grid_constant__ Vo
             VX_CHECK(slot[k] < P->view[0].nblk_total);
             vx_fill_point(A.rows, slot[k], x, y, z);
             A.pslot[idx[k]] = slot[k];
+            if (A.bkey) A.bkey[slot[k]] = key[k];
         }
 }
 
@@ -454,10 +459,12 @@ __global__ void __launch_bounds__(256) vx_fill_sel_kernel(const __grid_constant_
         const uint2 p = vx_point(A, i, c, li);
         VX_UNPACK(p, x, y, z);
         const VoxView& V = P->view[c];
-        const uint32_t slot = vx_slot_of_key(V.dirbits, V.dirpre, vx_key(V.g, x, y, z));
+        const uint32_t key = vx_key(V.g, x, y, z);
+        const uint32_t slot = vx_slot_of_key(V.dirbits, V.dirpre, key);
         VX_CHECK(slot < V.nblk_total);
         vx_fill_point(A.rows, slot, x, y, z);
         A.pslot[w] = slot;
+        if (A.bkey) A.bkey[slot] = key;
         A.vkey[w] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);       // (there are at most nsel voxels)
     }
 }
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(256) vx_place_sel_kernel(const __grid_constant
         const uint2 p = vx_point(A, i, c, li);
         VX_UNPACK(p, x, y, z);
         const uint32_t rgba = A.rgb[c] ? (__ldg(static_cast<const uint32_t*>(A.rgb[c]) + li) & 0xffffffu) : 0u;
-        A.prank[i] = vx_place_point(A.rows, A.vxyz, A.vkey, A.pslot[w], x, y, z, rgba, li);
+        A.prank[i] = vx_place_point(A.rows, A.bkey ? nullptr : A.vxyz, A.vkey, A.pslot[w], x, y, z, rgba, li);
     }
 }
 
@@ -585,6 +592,29 @@ __global__ void __launch_bounds__(256) vx_rowbase_kernel(const __grid_constant__
             const uint32_t a = (uint32_t)__popc(m[j].x), b = (uint32_t)__popc(m[j].y);
             const uint32_t base = wbase + bbase[j] + in2[j] - a - b;
             reinterpret_cast<uint4*>(A.rows + (size_t)(s0 + j) * kVxRows)[lane] = make_uint4(m[j].x, base, m[j].y, base + a);
+            if (A.bkey && s0 + j + 1 < nb) {
+                // coordinates of the brick's voxels, in rank order (a lane's two rows are neighbours in rank, the lanes of
+                // a warp follow each other: the stores of a brick fill consecutive sectors).  Measured against the whole
+                // warp taking the non-empty rows one after the other, one lane per bit (a coalesced store per row): this
+                // per-lane walk is faster (index build of the 10 M pair 1.53 vs 1.81 ms, of the 1 M pair 0.138 vs 0.195)
+                const int cl = s0 + j >= P->view[1].slot0 ? 1 : 0;
+                const VoxDims g = P->view[cl].g;
+                const uint32_t key = __ldg(A.bkey + s0 + j);
+                const uint32_t kx = key % (uint32_t)g.nbx, kyz = key / (uint32_t)g.nbx;
+                const uint32_t x0 = (kx + (uint32_t)g.obx) << 5, y0 = (kyz % (uint32_t)g.nby + (uint32_t)g.oby) << 3, z0 = (kyz / (uint32_t)g.nby + (uint32_t)g.obz) << 3;
+                uint32_t r = base;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t w = h ? m[j].y : m[j].x;
+                    const uint32_t row = 2u * (uint32_t)lane + (uint32_t)h;
+                    const uint32_t yz_lo = (y0 + (row & 7u)) << 16, zz = z0 + (row >> 3);
+                    while (w) {
+                        const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+                        w &= w - 1u;
+                        A.vxyz[r++] = make_uint2((x0 + b) | yz_lo, zz);
+                    }
+                }
+            }
         }
         off += chunk_total;
     }
@@ -622,7 +652,7 @@ __global__ void __launch_bounds__(256) vx_place_kernel(const __grid_constant__ V
         if (on[k]) {
             VX_UNPACK(p[k], x, y, z);
             VX_CHECK(slot[k] < P->view[0].nblk_total);
-            const uint32_t rank = vx_place_point(A.rows, A.vxyz, A.vkey, slot[k], x, y, z, rgba[k], li[k]);
+            const uint32_t rank = vx_place_point(A.rows, A.bkey ? nullptr : A.vxyz, A.vkey, slot[k], x, y, z, rgba[k], li[k]);
             VX_CHECK(rank < n_total);
             A.prank[idx[k]] = rank;
         }
@@ -705,7 +735,8 @@ struct VxAcc {
 // epilogue of ONE query point: D1 (+ per-point outputs), D2 with the other cloud's normals, colour.
 __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, const CloudView& qa, const CloudView& sa,
                                             uint32_t qidx, uint32_t qrgb, uint32_t d2,
-                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a) {
+                                            int ex, int ey, int ez, uint32_t nidx, uint32_t nrgb, VxAcc& a,
+                                            const double* staged_normal = nullptr) {
     a.s1 += d2;
     a.m1 = d2 > a.m1 ? d2 : a.m1;
     a.cnt++;
@@ -715,7 +746,8 @@ __device__ __forceinline__ void vx_epilogue(const VxParams& P, const VxDir& D, c
         const double e[3] = {(double)ex, (double)ey, (double)ez};
         double nv[3];
         const uint32_t ni = P.normals_mode == PCCM_NORMALS_BY_NEIGHBOUR ? nidx : qidx;
-        nv[0] = __ldg(sa.normals + 3 * (size_t)ni); nv[1] = __ldg(sa.normals + 3 * (size_t)ni + 1); nv[2] = __ldg(sa.normals + 3 * (size_t)ni + 2);
+        if (staged_normal) { nv[0] = staged_normal[0]; nv[1] = staged_normal[1]; nv[2] = staged_normal[2]; }   // (shared memory: the tile's bulk copy)
+        else { nv[0] = __ldg(sa.normals + 3 * (size_t)ni); nv[1] = __ldg(sa.normals + 3 * (size_t)ni + 1); nv[2] = __ldg(sa.normals + 3 * (size_t)ni + 2); }
         const double pe = plane_err2(e, nv);
         a.s2 = dadd(a.s2, pe);
         a.m2 = fmax(a.m2, pe);
@@ -1156,54 +1188,187 @@ constexpr int kVxEpiTile = kVxEpiThreads * kVxEpiPer;
 #define PCCM_VX_EPIGRID 740            // 148 SMs x 5 resident blocks on a B200 (measured: 592 / 740 / 888 / 1480 / 1776 blocks within 1 us)
 #endif
 constexpr uint32_t kVxEpiGrid = PCCM_VX_EPIGRID;
+
+// one query point and the 16-byte answer of its voxel (nothing to do when the voxel has none, or belongs to the other pass)
+__device__ __forceinline__ void vx_epilogue_answer(const VxParams& P, const VxDir& D, const VoxPlan* __restrict__ plan,
+                                                   const CloudView& qa, const CloudView& sa, uint32_t i, uint32_t rk, const uint4& v,
+                                                   uint32_t qrgb, const double* staged_normal, VxAcc& acc) {
+    if (v.x == kVxNone) return;
+    const bool far = (v.z & kVxFarBit) != 0u;
+    if (far != (P.pass == 1)) return;
+    int ex, ey, ez;
+    uint32_t nrgb = v.w;
+    if (!far) {
+        ex = (int)(v.y & 0xffu) - 128; ey = (int)((v.y >> 8) & 0xffu) - 128; ez = (int)((v.y >> 16) & 0xffu) - 128;
+    } else {                                  // pencil-round answer: any distance, coordinates from the records
+        const uint2 qv = __ldg(plan->view[D.qc].vxyz + rk);
+        const uint4 nr = __ldg(D.srecs + v.y);               // {xy, z, idx, rgb}
+        ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
+        nrgb = nr.w;
+    }
+    vx_epilogue(P, D, qa, sa, i, qrgb, v.x, ex, ey, ez, v.z & ~kVxFarBit, nrgb, acc, staged_normal);
+}
+
+// Bulk-copy staging (STAGED = true, the default; PCCM_EPI_TMA=0 selects the plain loads): the three arrays a tile reads
+// in the input's own order -- prank, the other cloud's normals at the query index, the packed own colours -- are
+// contiguous per tile, so ONE elected thread moves them into shared memory with cp.async.bulk (the 1-D form of the TMA
+// engine: no tensor map), one tile ahead, completion counted in bytes on an mbarrier.  The threads then wait for one
+// thing only, the gather of the voxel answers; the stream loads no longer queue behind it (they sat after the "does
+// this point belong to my slice" branch) and cost no registers while in flight.  Sources are taken from the 16-byte
+// boundary below a tile's first element to the one above its last (a 16-byte line never straddles a page).
+struct VxEpiStage {
+    alignas(16) unsigned char nrm[kVxEpiTile * 24 + 16];
+    alignas(16) unsigned char rnk[kVxEpiTile * 4 + 16];
+    alignas(16) unsigned char rgb[kVxEpiTile * 4 + 16];
+};
+struct VxEpiSrc {            // one staged array of a direction
+    const unsigned char* base;   // null: not staged (absent, or not read in the input's order)
+    uint32_t lead;               // bytes between the 16-byte boundary below the array and its first element
+    uint32_t elem;               // bytes per point
+    __device__ __forceinline__ void set(const void* p, uint32_t e) {
+        base = static_cast<const unsigned char*>(p);
+        lead = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+        elem = e;
+    }
+    __device__ __forceinline__ uint32_t issue(void* dst, uint32_t tile, uint32_t nq, unsigned long long* bar) const {
+        if (!base) return 0u;
+        const uint32_t first = tile * (uint32_t)kVxEpiTile, cnt = min((uint32_t)kVxEpiTile, nq - first);
+        const uint32_t bytes = (lead + cnt * elem + 15u) & ~15u;
+        bulk_g2s(dst, base + (size_t)first * elem - lead, bytes, bar);
+        return bytes;
+    }
+};
+
+// COMPACT (split pairs and voxel slices: this rank evaluates a fraction of the points): a tile only contributes the
+// points whose voxel is indexed here -- their {index, rank} go to a queue in shared memory, in the tile's order (prefix
+// sums, no atomics: the float sums stay reproducible), and the block works the queue off a full block of entries at a
+// time.  The cost of a tile this rank owns nothing of is one coalesced read of its ranks and a block scan, not a trip
+// through the epilogue with most lanes idle (measured on the 10 M pair split 8 ways: 205 -> @@COMPACT@@ us per rank).
+constexpr uint32_t kVxEpiQueue = 2 * kVxEpiTile;   // left-over entries (fewer than a block) + one tile; a power of two (ring)
+template <bool STAGED, bool COMPACT>
 __global__ void __launch_bounds__(kVxEpiThreads, PCCM_EPI_MINBLOCKS)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
     __shared__ double s_lut[256];
+    __shared__ VxEpiStage s_stage[STAGED ? 2 : 1];
+    __shared__ uint2 s_queue[COMPACT ? kVxEpiQueue : 1];
+    __shared__ uint32_t s_wcnt[kVxEpiThreads / 32];
+    __shared__ unsigned long long s_bar[2];
     pdl_launch();
     const int d = (P.ndirs > 1 && blockIdx.x >= P.dir[0].ntiles) ? 1 : 0;
     const VxDir& D = P.dir[d];
     const uint32_t blk = blockIdx.x - (d ? P.dir[0].ntiles : 0u);
     s_lut[threadIdx.x] = D.qa.lut255[threadIdx.x];       // k / 255.0 table: shared memory instead of six global loads per point
                                                          // (written when the context was created: read ahead of the wait)
+    VxEpiSrc src_rnk{nullptr, 0u, 0u}, src_nrm{nullptr, 0u, 0u}, src_rgb{nullptr, 0u, 0u};
+    if (STAGED) {
+        src_rnk.set(D.qprank, 4u);
+        if ((D.flags & PCCM_EVAL_D2) && P.normals_mode != PCCM_NORMALS_BY_NEIGHBOUR && D.sa.normals) src_nrm.set(D.sa.normals, 24u);
+        if ((D.flags & PCCM_EVAL_COLOR) && D.qa.rgb_mode == 2) src_rgb.set(D.qa.rgb_u8, 4u);
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1u);
+            mbar_init(&s_bar[1], 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     pdl_wait();
     const VoxPlan* __restrict__ plan = P.plan;
     if (plan->status) return;
-    __syncthreads();
+    auto stage_tile = [&](uint32_t tile, int s) {          // (thread 0 only)
+        uint32_t bytes = 0;
+        // the arrive comes first in program order; the byte count of the three copies is known up front
+        const uint32_t first = tile * (uint32_t)kVxEpiTile, cnt = min((uint32_t)kVxEpiTile, D.nq - first);
+        if (src_rnk.base) bytes += (src_rnk.lead + cnt * 4u + 15u) & ~15u;
+        if (src_nrm.base) bytes += (src_nrm.lead + cnt * 24u + 15u) & ~15u;
+        if (src_rgb.base) bytes += (src_rgb.lead + cnt * 4u + 15u) & ~15u;
+        mbar_expect_tx(&s_bar[s], bytes);
+        src_rnk.issue(s_stage[s].rnk, tile, D.nq, &s_bar[s]);
+        src_nrm.issue(s_stage[s].nrm, tile, D.nq, &s_bar[s]);
+        src_rgb.issue(s_stage[s].rgb, tile, D.nq, &s_bar[s]);
+    };
+    __syncthreads();                                       // (table and barriers)
+    if (STAGED && threadIdx.x == 0 && blk < D.npt_tiles) stage_tile(blk, 0);
     CloudView qa = D.qa, sa = D.sa;
     qa.lut255 = s_lut; sa.lut255 = s_lut;
+    if (STAGED && src_rgb.base) qa.rgb_mode = 1;           // own colour: the packed word of the staged tile
     uint32_t t_lo = 0u, t_hi = kVxNone;                   // (kVxNone itself marks "no voxel")
     if (P.world > 1) vx_slice(P, plan->view[D.qc], t_lo, t_hi);
     VxAcc acc;
     acc.init();
-    for (uint32_t tile = blk; tile < D.npt_tiles; tile += D.ntiles) {
+    if (COMPACT) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t head = 0, tail = 0;                       // (the same in every thread)
+        uint32_t rk[kVxEpiPer], nx[kVxEpiPer];
+        auto load_ranks = [&](uint32_t tile, uint32_t* out) {
+#pragma unroll
+            for (int j = 0; j < kVxEpiPer; ++j) {
+                const uint32_t i = tile * kVxEpiTile + threadIdx.x * kVxEpiPer + j;      // a thread's points are neighbours: queue order = input order
+                out[j] = (tile < D.npt_tiles && i < D.nq) ? __ldg(D.qprank + i) : kVxNone;
+            }
+        };
+        auto work_off = [&](uint32_t count) {              // entries head .. head + count (count <= block size)
+            if (threadIdx.x < count) {                     // (two entries per thread, gathered together: 149 vs 138 us -- spills)
+                const uint2 e = s_queue[(head + threadIdx.x) & (kVxEpiQueue - 1u)];
+                const uint4 v = __ldg(P.vres + e.y);
+                vx_epilogue_answer(P, D, plan, qa, sa, e.x, e.y, v, 0u, nullptr, acc);
+            }
+            head += count;
+        };
+        load_ranks(blk, nx);
+        for (uint32_t tile = blk; tile < D.npt_tiles; tile += D.ntiles) {
+#pragma unroll
+            for (int j = 0; j < kVxEpiPer; ++j) rk[j] = nx[j];
+            load_ranks(tile + D.ntiles, nx);               // (the next tile's ranks travel during this tile's scan)
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < kVxEpiPer; ++j) mine += (rk[j] >= t_lo && rk[j] < t_hi) ? 1u : 0u;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) s_wcnt[warp] = incl;
+            __syncthreads();
+            uint32_t off = tail + incl - mine, total = 0;
+#pragma unroll
+            for (int w = 0; w < kVxEpiThreads / 32; ++w) { const uint32_t c = s_wcnt[w]; if (w < warp) off += c; total += c; }
+#pragma unroll
+            for (int j = 0; j < kVxEpiPer; ++j)
+                if (rk[j] >= t_lo && rk[j] < t_hi)
+                    s_queue[(off++) & (kVxEpiQueue - 1u)] = make_uint2(tile * kVxEpiTile + threadIdx.x * kVxEpiPer + j, rk[j]);
+            tail += total;
+            __syncthreads();
+            while (tail - head >= (uint32_t)kVxEpiThreads) work_off(kVxEpiThreads);
+        }
+        work_off(tail - head);                               // (fewer than a block)
+    } else {
+    uint32_t it = 0;
+    for (uint32_t tile = blk; tile < D.npt_tiles; tile += D.ntiles, ++it) {
+    const int st = STAGED ? (int)(it & 1u) : 0;
     const uint32_t i0 = tile * kVxEpiTile + threadIdx.x;
+    if (STAGED) {
+        if (threadIdx.x == 0 && tile + D.ntiles < D.npt_tiles) stage_tile(tile + D.ntiles, st ^ 1);   // (its last readers passed the barrier below)
+        mbar_wait(&s_bar[st], (it >> 1) & 1u);
+    }
     uint32_t rk[kVxEpiPer];
     uint4 v[kVxEpiPer];
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
         const uint32_t i = i0 + j * kVxEpiThreads;
-        rk[j] = i < D.nq ? __ldg(D.qprank + i) : kVxNone;
+        if (STAGED) rk[j] = i < D.nq ? *reinterpret_cast<const uint32_t*>(s_stage[st].rnk + src_rnk.lead + (size_t)(threadIdx.x + j * kVxEpiThreads) * 4u) : kVxNone;
+        else rk[j] = i < D.nq ? __ldg(D.qprank + i) : kVxNone;
     }
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j)
         v[j] = (rk[j] >= t_lo && rk[j] < t_hi) ? __ldg(P.vres + rk[j]) : make_uint4(kVxNone, 0u, 0u, 0u);
 #pragma unroll
     for (int j = 0; j < kVxEpiPer; ++j) {
-        if (v[j].x == kVxNone) continue;
-        const uint32_t i = i0 + j * kVxEpiThreads;
-        const bool far = (v[j].z & kVxFarBit) != 0u;
-        if (far != (P.pass == 1)) continue;
-        int ex, ey, ez;
-        uint32_t nrgb = v[j].w;
-        if (!far) {
-            ex = (int)(v[j].y & 0xffu) - 128; ey = (int)((v[j].y >> 8) & 0xffu) - 128; ez = (int)((v[j].y >> 16) & 0xffu) - 128;
-        } else {                                  // pencil-round answer: any distance, coordinates from the records
-            const uint2 qv = __ldg(plan->view[D.qc].vxyz + rk[j]);
-            const uint4 nr = __ldg(D.srecs + v[j].y);               // {xy, z, idx, rgb}
-            ex = (int)(qv.x & 0xffffu) - (int)(nr.x & 0xffffu); ey = (int)(qv.x >> 16) - (int)(nr.x >> 16); ez = (int)qv.y - (int)nr.y;
-            nrgb = nr.w;
-        }
-        vx_epilogue(P, D, qa, sa, i, 0u, v[j].x, ex, ey, ez, v[j].z & ~kVxFarBit, nrgb, acc);
+        const uint32_t lp = threadIdx.x + j * kVxEpiThreads;         // position in the tile
+        const double* sn = (STAGED && src_nrm.base) ? reinterpret_cast<const double*>(s_stage[st].nrm + src_nrm.lead + (size_t)lp * 24u) : nullptr;
+        const uint32_t qrgb = (STAGED && src_rgb.base) ? *reinterpret_cast<const uint32_t*>(s_stage[st].rgb + src_rgb.lead + (size_t)lp * 4u) : 0u;
+        vx_epilogue_answer(P, D, plan, qa, sa, i0 + j * kVxEpiThreads, rk[j], v[j], qrgb, sn, acc);
+    }
+    if (STAGED) __syncthreads();                  // everybody is done with this stage before it is refilled (two tiles from now)
     }
     }
     BlockPartial r;

@@ -319,3 +319,92 @@ def test_host_narrowing_is_transparent(ctxs):
         c.build_index()
     c.close()
     vox.close()
+
+
+def test_bulk_copy_staging_is_transparent(ctxs):
+    """cp.async.bulk staging (statistics pass: float64 rows; epilogue: ranks / normals / colours of a tile) against the
+    plain-load builds of the same kernels (PCCM_STATS_TMA=0, PCCM_EPI_TMA=0): bit-identical evaluations -- host arrays,
+    device tensors whose first element sits 8 bytes above a 16-byte line (the copy starts at the line below), point
+    counts that leave partial tiles and put the second cloud's ranks at every offset within a line."""
+    import torch
+    from open_pcc_metric_b200 import _native as N
+    staged, _ = ctxs
+    os.environ["PCCM_STATS_TMA"] = "0"
+    os.environ["PCCM_EPI_TMA"] = "0"
+    try:
+        plain = N.Context(0)
+    finally:
+        del os.environ["PCCM_STATS_TMA"], os.environ["PCCM_EPI_TMA"]
+    A0, B0 = _case("surface")
+    rng = np.random.default_rng(21)
+    flags = N.EVAL_D2 | N.EVAL_COLOR
+
+    def shifted(x):                                   # device copy whose data pointer is 8 (mod 16)
+        flat = torch.empty(x.size + 3, dtype=torch.float64, device="cuda:0")
+        off = 1 if flat.data_ptr() % 16 == 0 else 2
+        view = flat[off:off + x.size].view(x.shape)
+        view.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+        assert view.data_ptr() % 16 == 8
+        return view
+
+    try:
+        n0 = min(len(A0), len(B0))
+        assert n0 > 5000
+        for n in (n0, n0 - 1, n0 - 2, n0 - 3, 513, 255):
+            A, B = A0[:n], B0[:n]
+            ca, na = _attrs(rng, n)
+            cb, nb = _attrs(rng, n)
+            outs = []
+            for ctx, dev in ((plain, False), (staged, False), (staged, True)):
+                f = shifted if dev else (lambda x: x)
+                keep = [f(A), f(ca), f(na), f(B), f(cb), f(nb)]
+                a, b = ctx.cloud(keep[0], keep[1], keep[2]), ctx.cloud(keep[3], keep[4], keep[5])
+                ctx.build_pair(a, b)
+                outs.append(bytes(ctx.pair_eval(a, b, flags, YUV)))
+                a.close(); b.close()
+            assert outs[0] == outs[1] == outs[2], n
+    finally:
+        plain.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_voxel_coordinates_from_rows_equal_scattered_stores(ctxs, name):
+    """The voxel coordinates of large pairs are written brick by brick from the occupancy rows (vx_rowbase_kernel),
+    those of small pairs by every point in the place pass; PCCM_VXYZ_ROWS forces either.  Same evaluation bit for bit --
+    whole pairs, a slab of a split pair, neighbour indices and distances, boundary distances."""
+    from open_pcc_metric_b200 import _native as N
+    A, B = _case(name)
+    n = min(len(A), len(B))
+    A, B = A[:n], B[:n]
+    rng = np.random.default_rng(31)
+    ca, na = _attrs(rng, n)
+    cb, nb = _attrs(rng, n)
+    flags = N.EVAL_D2 | N.EVAL_COLOR | N.EVAL_PERPOINT
+    outs = []
+    for mode in ("0", "1"):
+        os.environ["PCCM_VXYZ_ROWS"] = mode
+        try:
+            ctx = N.Context(0)
+        finally:
+            del os.environ["PCCM_VXYZ_ROWS"]
+        try:
+            got = []
+            for shard in ((0, 1), (1, 3)):
+                ctx.set_shard(*shard)
+                try:
+                    a, b = ctx.cloud(A, ca, na), ctx.cloud(B, cb, nb)
+                    ctx.build_pair(a, b)
+                finally:
+                    ctx.set_shard(0, 1)
+                got.append(bytes(ctx.pair_eval(a, b, flags, YUV, rank=shard[0], world=shard[1])))
+                if shard == (0, 1):
+                    for d in range(2):
+                        got.append(ctx.pair_get(N.GET_IDX, d, n).tobytes())
+                        got.append(ctx.pair_get(N.GET_D2, d, n).tobytes())
+                if n >= 2:
+                    got.append(a.self_nn_minmax()[:2])
+                a.close(); b.close()
+            outs.append(got)
+        finally:
+            ctx.close()
+    assert outs[0] == outs[1], name

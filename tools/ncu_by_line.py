@@ -4,6 +4,7 @@ thread-level efficiency and stall samples per CUDA source line.
 
     ncu -i prof.ncu-rep --page source --csv --print-source=sass > sass.csv
     python tools/ncu_by_line.py sass.csv open_pcc_metric_b200/libpccm.so pair_query_kernel [KInt]
+    python tools/ncu_by_line.py sass.csv open_pcc_metric_b200/libpccm.so vx_epilogue_kernel ILb1ELb0    # one instantiation of several
 """
 import collections
 import csv
@@ -52,7 +53,7 @@ def main():
     total = [0.0, 0.0, 0.0]
     for r in rows:
         if r and r[0] == "Kernel Name":
-            use = func in r[1] and all(e in r[1] for e in extra)
+            use = func in r[1] and all(e in r[1] for e in extra if not e.startswith("IL"))   # ("IL...": a mangled template argument list -- line map only)
             hdr = None
             base = None
             continue
