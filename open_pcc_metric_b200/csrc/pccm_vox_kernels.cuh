@@ -1243,7 +1243,7 @@ struct VxEpiSrc {            // one staged array of a direction
 // points whose voxel is indexed here -- their {index, rank} go to a queue in shared memory, in the tile's order (prefix
 // sums, no atomics: the float sums stay reproducible), and the block works the queue off a full block of entries at a
 // time.  The cost of a tile this rank owns nothing of is one coalesced read of its ranks and a block scan, not a trip
-// through the epilogue with most lanes idle (measured on the 10 M pair split 8 ways: 205 -> @@COMPACT@@ us per rank).
+// through the epilogue with most lanes idle (measured on the 10 M pair split 8 ways: 204 -> 137 us per rank).
 constexpr uint32_t kVxEpiQueue = 2 * kVxEpiTile;   // left-over entries (fewer than a block) + one tile; a power of two (ring)
 template <bool STAGED, bool COMPACT>
 __global__ void __launch_bounds__(kVxEpiThreads, PCCM_EPI_MINBLOCKS)
