@@ -120,15 +120,27 @@ class Workload:
     def _vox12(self, synth, attrs, oversample=3, tol=0.02):
         # (generating 10M voxelised surface points takes a minute of numpy: keep them for later runs on the same box)
         cache = os.path.join("/tmp", f"pccm_bench_vox12_{self.points}_{int(attrs)}_{oversample}.npz")
+        A = None
         if os.path.exists(cache):
-            z = np.load(cache)
-            A = synth.Cloud(z["p"], z["c"] if attrs else None, z["n"] if attrs else None)
-        else:
-            A = synth.synth_vox(12, self.points, synth.BASE_SEED + 3, with_colors=attrs, with_normals=attrs, oversample=oversample, tol=tol)
             try:
-                np.savez(cache, p=A.points, c=A.colors if attrs else np.zeros(0), n=A.normals if attrs else np.zeros(0))
-            except OSError:
-                pass
+                z = np.load(cache)
+                A = synth.Cloud(z["p"], z["c"] if attrs else None, z["n"] if attrs else None)
+            except Exception:                     # (a truncated file of an interrupted run: generate again)
+                A = None
+        if A is None:
+            A = synth.synth_vox(12, self.points, synth.BASE_SEED + 3, with_colors=attrs, with_normals=attrs, oversample=oversample, tol=tol)
+            # the ranks of one job all arrive here together: rank 0 alone keeps the arrays (0.7 GB for the 10 M pair), in a
+            # temporary file renamed over the cache name (atomic: a reader sees a complete file or none)
+            if int(os.environ.get("RANK", "0")) == 0:
+                tmp = f"{cache}.{os.getpid()}.tmp.npz"
+                try:
+                    np.savez(tmp, p=A.points, c=A.colors if attrs else np.zeros(0), n=A.normals if attrs else np.zeros(0))
+                    os.replace(tmp, cache)
+                except OSError:
+                    try:
+                        os.remove(tmp)
+                    except OSError:
+                        pass
         return A, synth.degrade(A, 2, synth.BASE_SEED + 3, 12, dedup=False)
 
     def _lidar(self, synth):
