@@ -30,9 +30,15 @@ def exchange_partials(vals, world: int, group=None, device="cpu"):
         rows.append([v["sum_d1"], v["max_d1"], v["sum_d2"], v["max_d2"], *v["csum"], *v["cmax"],
                      float(u >> 32), float(u & 0xffffffff), float(bool(v["d2_valid"])), float(v.get("n", 0))])
     fl = torch.tensor(rows, dtype=torch.float64, device=device)
-    parts = [torch.empty_like(fl) for _ in range(world)]
-    dist.all_gather(parts, fl, group=group)
-    fl_all = torch.stack(parts).cpu().numpy()    # (world, ndir, 14)
+    try:                                         # ONE output tensor: no per-rank list to copy in and out of
+        gathered = torch.empty((world * fl.shape[0], fl.shape[1]), dtype=torch.float64, device=device)   # (concatenated form: every backend)
+        dist.all_gather_into_tensor(gathered, fl, group=group)
+        gathered = gathered.view(world, fl.shape[0], fl.shape[1])
+    except (RuntimeError, NotImplementedError):  # a backend without the tensor form
+        parts = [torch.empty_like(fl) for _ in range(world)]
+        dist.all_gather(parts, fl, group=group)
+        gathered = torch.stack(parts)
+    fl_all = gathered.cpu().numpy()              # (world, ndir, 14)
     out = []
     for d, v in enumerate(vals):
         r = dict(v)
