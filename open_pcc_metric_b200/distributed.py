@@ -38,24 +38,30 @@ def exchange_partials(vals, world: int, group=None, device="cpu"):
         parts = [torch.empty_like(fl) for _ in range(world)]
         dist.all_gather(parts, fl, group=group)
         gathered = torch.stack(parts)
-    fl_all = gathered.cpu().numpy()              # (world, ndir, 14)
-    out = []
+    rows_all = gathered.cpu().tolist()           # [world][ndir][14] Python floats: the fold below is ~10 us at world 8
+    out = []                                     # (numpy scalars made it ~110 us -- inside every step of a split pair)
     for d, v in enumerate(vals):
         r = dict(v)
-        r["sum_u64"] = int(sum((int(x[10]) << 32) + int(x[11]) for x in fl_all[:, d]))
-        r["d2_valid"] = bool(fl_all[:, d, 12].min())
-        if "n" in v:
-            r["n"] = int(fl_all[:, d, 13].sum())
-        acc = np.zeros(10)
-        acc[list(MAX_SLOTS)] = -np.inf
-        for w in range(world):
-            row = fl_all[w, d]
+        u, valid, n = 0, True, 0
+        acc = [0.0] * 10
+        for j in MAX_SLOTS:
+            acc[j] = float("-inf")
+        for w in range(world):                   # fixed rank order: the float sums are reproducible for a given world
+            row = rows_all[w][d]
             for j in SUM_SLOTS:
                 acc[j] = acc[j] + row[j]
             for j in MAX_SLOTS:
-                acc[j] = max(acc[j], row[j])
+                if row[j] > acc[j]:
+                    acc[j] = row[j]
+            u += (int(row[10]) << 32) + int(row[11])
+            valid = valid and row[12] != 0.0
+            n += int(row[13])
+        r["sum_u64"] = u
+        r["d2_valid"] = valid
+        if "n" in v:
+            r["n"] = n
         r["sum_d1"], r["max_d1"], r["sum_d2"], r["max_d2"] = acc[0], acc[1], acc[2], acc[3]
-        r["csum"], r["cmax"] = acc[4:7].copy(), acc[7:10].copy()
+        r["csum"], r["cmax"] = np.array(acc[4:7]), np.array(acc[7:10])
         out.append(r)
     return out
 
