@@ -546,6 +546,32 @@ def main():
                                  "what": "same API, clouds held as uint16 / uchar / float32 (float32 normals change D2 only)",
                                  "d1_and_colour_identical_to_float64_inputs": bool(same)}
 
+    if not args.no_e2e and W.split:
+        # the split pair through the same public API: EVERY rank is handed both clouds as pinned host float64 arrays
+        # (that is the split's contract: a rank selects its slab on the device), uploads them inside the timed region,
+        # evaluates its slab and takes part in the exchanges; the metrics come back on every rank
+        try:
+            def pinned_t(t):
+                h = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+                h.copy_(t if t.dtype == torch.float64 else t.to(torch.float64) / 255.0)
+                return h.numpy()
+            hA = Cloud(pinned_t(dA[0]), pinned_t(dA[1]), pinned_t(dA[2]))
+            hB = Cloud(pinned_t(dB[0]), pinned_t(dB[1]), pinned_t(dB[2]))
+            torch.cuda.synchronize()
+            h2d = sum(x.nbytes for c in (hA, hB) for x in (c.points, c.colors, c.normals))
+            n_e2e = max(3, min(10, steps // 5))
+            ms_e2e, _, _, out = timed(lambda: step_e2e(hA, hB), n_e2e, 3, 0)
+            ms_e2e = max_over_ranks(ms_e2e)
+            e2e = {"value": nq * n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / n_e2e,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * 96 + 16),
+                   "h2d_note": "per RANK: every rank uploads both clouds (the whole job moves this many bytes times the number of ranks)",
+                   "api": "CloudPair(host float64 arrays, rank=, world=) + MetricCalculator.calculate(transform_options(color=yuv, point_to_plane)) "
+                          "on every rank; partial records and boundary distances exchanged with NCCL inside the step"}
+            del hA, hB
+        except Exception as exc:       # (never lose the device-timed line to the informational arm)
+            e2e = None
+            print(f"[bench] e2e arm of the split pair failed on rank {rank}: {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
+
     if not args.no_e2e and W.cfg == "4":
         # configs[3]: the sequence API from pinned host float64 frames, pipelined (two contexts alternate: the uploads of
         # frame t+1 run under the kernels of frame t) against one frame at a time.  Several contexts = several streams: timed
