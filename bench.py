@@ -31,7 +31,8 @@ Workloads (``config.workload`` names the one that ran):
   e2e    the same through the public drop-in API (CloudPair + MetricCalculator + transform_options) from
          PINNED HOST float64 arrays: host->device copies and the result read-back are inside the timed
          region; additionally includes the always-on MinSqrt/MaxSqrt self-NN pass of the reference's option
-         expansion.
+         expansion.  Split pair (N>1): every rank hands BOTH clouds to CloudPair(rank=, world=) -- the split's
+         contract -- so h2d_bytes_per_step is per rank; the NCCL exchanges are inside the step.
 
 --impl reference: the reference's CPU path timed on this host by the oracle port (oracle/cpu_baseline.py): per
 step ONE FULL evaluation of the same pair in batched form on all cores (cKDTree.query(workers=-1) + whole-array
