@@ -25,14 +25,20 @@ def host_cores() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def reference_structure(A, B, color_scheme="yuv", point_to_plane=True, sample=50_000, seed=0):
+def build_trees(A, B):
+    """The two KD-trees of a pair (cloud_pair.py:65) and the seconds they took."""
+    t0 = time.perf_counter()
+    trees = tuple(cKDTree(c.points, leafsize=15) for c in (A, B))
+    return trees, time.perf_counter() - t0
+
+
+def reference_structure(A, B, color_scheme="yuv", point_to_plane=True, sample=50_000, seed=0, prebuilt=None):
     """Times tree builds in full and the per-point work on `sample` queries per direction;
-    returns dict(queries_per_s, est_pair_seconds, sample, per_query_us, build_s)."""
+    returns dict(queries_per_s, est_pair_seconds, sample, per_query_us, build_s).
+    prebuilt = (trees, seconds) of build_trees: a 10 M-point tree is built once per bench run, not once per arm."""
     rng = np.random.default_rng(seed)
     clouds = (A, B)
-    t0 = time.perf_counter()
-    trees = tuple(cKDTree(c.points, leafsize=15) for c in clouds)      # cloud_pair.py:65
-    build_s = time.perf_counter() - t0
+    trees, build_s = prebuilt if prebuilt is not None else build_trees(A, B)      # cloud_pair.py:65
     T = COLOR_TRANSFORMS[color_scheme] if color_scheme else None
     n_total = len(A) + len(B)
     work_s = 0.0
@@ -73,9 +79,38 @@ def reference_structure(A, B, color_scheme="yuv", point_to_plane=True, sample=50
                 build_s=build_s, measured_s=build_s + work_s, cores=1)
 
 
-def cpu_best(A, B, color_scheme="yuv", point_to_plane=True, max_queries=None):
-    """Batched all-core version of the same pair evaluation (full workload unless capped)."""
+def cpu_best(A, B, color_scheme="yuv", point_to_plane=True, max_queries=None, prebuilt=None):
+    """Batched all-core version of the same pair evaluation (full workload unless capped).
+    With `prebuilt` = (trees, seconds) and `max_queries` the call is a BOUNDED SAMPLE of a large pair: the first
+    max_queries points of each direction are evaluated against the full trees and the pair's time is
+    build seconds + sample seconds x (queries of the pair / queries of the sample) -- `sampled` says so."""
     clouds = (A, B)
+    if prebuilt is not None and max_queries is not None:
+        trees, build_s = prebuilt
+        T = COLOR_TRANSFORMS[color_scheme] if color_scheme else None
+        est, n_s, t_s = build_s, 0, 0.0
+        for q, s in ((0, 1), (1, 0)):
+            Q, S = clouds[q], clouds[s]
+            m = min(max_queries, len(Q.points))
+            t0 = time.perf_counter()
+            pts = Q.points[:m]
+            _, idx = trees[s].query(pts, 1, workers=-1)
+            err = pts - S.points[idx]
+            d2 = (err[:, 0] * err[:, 0] + err[:, 1] * err[:, 1]) + err[:, 2] * err[:, 2]
+            _ = d2.sum() / len(d2), d2.max()
+            if point_to_plane and S.normals is not None:
+                nr = S.normals[:m] if len(S.normals) >= m else S.normals[idx]
+                _ = np.square((err * nr).sum(1)).sum()
+            if color_scheme and Q.colors is not None and S.colors is not None:
+                d = Q.colors[:m] @ T.T - S.colors[idx] @ T.T
+                _ = (d * d).mean(0)
+            dt = time.perf_counter() - t0
+            est += dt * (len(Q.points) / m)
+            n_s += m
+            t_s += dt
+        n = len(A.points) + len(B.points)
+        return dict(queries_per_s=n / est, seconds=est, queries=n, cores=host_cores(), sampled=True,
+                    sample_queries=n_s, sample_seconds=t_s, build_seconds=build_s)
     t0 = time.perf_counter()
     trees = tuple(cKDTree(c.points, leafsize=15) for c in clouds)
     T = COLOR_TRANSFORMS[color_scheme] if color_scheme else None
