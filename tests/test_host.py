@@ -226,3 +226,59 @@ def test_ply_roundtrip(tmp_path, binary):
     xyz = str(tmp_path / "c.xyz")
     np.savetxt(xyz, np.asarray(pc.points))
     assert np.array_equal(read_point_cloud(xyz).points, pc.points)
+
+
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pccm_bench", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_synthetic_cache_is_atomic_and_self_healing(monkeypatch):
+    """The ranks of one torchrun job generate the split pair at the same moment: only rank 0 keeps it (temporary file +
+    rename), the other ranks never write, and a damaged cache file is regenerated instead of crashing the run."""
+    import argparse
+    import glob
+    bench = _load_bench()
+    args = argparse.Namespace(config="split", points=12_000, mode="auto")
+    pat = "/tmp/pccm_bench_vox12_12000_*"
+    for f in glob.glob(pat):
+        os.remove(f)
+    try:
+        w = bench.Workload(args, 2)
+        monkeypatch.setenv("RANK", "1")
+        a1, b1 = w.gen(1)
+        assert glob.glob(pat) == []                                   # rank 1 keeps nothing
+        monkeypatch.setenv("RANK", "0")
+        a0, b0 = w.gen(0)
+        files = glob.glob(pat)
+        assert len(files) == 1 and not files[0].endswith(".tmp.npz")
+        a2, b2 = w.gen(0)                                             # read back from the cache
+        for x, y in ((a0, a1), (a0, a2), (b0, b1), (b0, b2)):
+            assert np.array_equal(x.points, y.points) and np.array_equal(x.colors, y.colors) and np.array_equal(x.normals, y.normals)
+        with open(files[0], "wb") as fh:
+            fh.write(b"not a zip file")
+        a3, _ = w.gen(0)
+        assert np.array_equal(a3.points, a0.points)
+        assert np.array_equal(np.load(files[0])["p"], a0.points)      # ... and repaired
+    finally:
+        for f in glob.glob(pat):
+            os.remove(f)
+
+
+def test_reference_arm_bounded_sample_scales_to_the_pair():
+    """bench.py --impl reference on the 10 M-point pair times a bounded sample per step (trees built once, the first
+    queries of each direction on all cores) and scales it to the pair; on a small pair the estimate agrees with the
+    full evaluation to within the noise of a sub-second measurement, and the bookkeeping is exact."""
+    from oracle import cpu_baseline as cb
+    from open_pcc_metric_b200 import synth
+    A, B = synth.synth_pair(9, 60_000, 3, dedup=False, oversample=4)
+    pre = cb.build_trees(A, B)
+    full = cb.cpu_best(A, B, "yuv", True)
+    samp = cb.cpu_best(A, B, "yuv", True, 20_000, pre)
+    assert samp["sampled"] is True and samp["sample_queries"] == 40_000
+    assert samp["queries"] == full["queries"] == len(A) + len(B)
+    assert samp["seconds"] > samp["build_seconds"] == pre[1]
+    assert 0.2 < samp["seconds"] / full["seconds"] < 5.0
