@@ -48,6 +48,15 @@ def _attr(cloud, name):
     return v if len(v) else None
 
 
+def _upload(cloud, name):
+    """What goes to the device for `name`: a cloud may carry the array in a narrower scalar type than the float64 view
+    its getters give (io.FileCloud: raw_points / raw_colors / raw_normals) -- every widening on the device is exact."""
+    v = getattr(cloud, "raw_" + name, None)
+    if v is not None and len(v):
+        return v
+    return _attr(cloud, name)
+
+
 class FusedDirection(typing.NamedTuple):
     n: int
     sum_d1: float          # exact for integer clouds
@@ -95,9 +104,9 @@ class CloudPair:
             self._ctx.set_shard(rank, world)
         try:
             for c in self.clouds:
-                self._dev.append(self._ctx.cloud(_attr(c, "points") if _attr(c, "points") is not None else np.zeros((0, 3))))
+                self._dev.append(self._ctx.cloud(_upload(c, "points") if _upload(c, "points") is not None else np.zeros((0, 3))))
             for c, d in zip(self.clouds, self._dev):
-                d.attach(_attr(c, "colors"), _attr(c, "normals"))
+                d.attach(_upload(c, "colors"), _upload(c, "normals"))
             self._ctx.build_pair(self._dev[0], self._dev[1], cell_size)
         except Exception:
             self.close()
@@ -108,9 +117,9 @@ class CloudPair:
         # everything above is only ENQUEUED (uploads, statistics, index build): what the host has to wait for -- coordinate
         # kind, bounding boxes -- is fetched on first use, so that a caller can prepare the next pair in the meantime
         self._infos = None
-        self._n = tuple(0 if _attr(c, "points") is None else len(c.points) for c in self.clouds)
-        self._has_normals = [_attr(c, "normals") is not None for c in self.clouds]
-        self._has_colors = tuple(_attr(c, "colors") is not None for c in self.clouds)
+        self._n = tuple(0 if _upload(c, "points") is None else len(_upload(c, "points")) for c in self.clouds)
+        self._has_normals = [_upload(c, "normals") is not None for c in self.clouds]
+        self._has_colors = tuple(_upload(c, "colors") is not None for c in self.clouds)
         if eager_normals:
             for k in range(2):
                 self._ensure_normals(k)

@@ -4,7 +4,13 @@
 PLY (ascii, binary_little_endian, binary_big_endian) with x/y/z of any scalar type,
 optional red/green/blue (uchar -> /255, floats kept) and nx/ny/nz; plus whitespace
 separated ``.xyz`` / ``.txt`` (x y z [r g b]).  Returns a ``geometry.PointCloud``
-holding float64 arrays like Open3D does.
+holding float64 arrays like Open3D does -- or, with ``native=True``, a ``FileCloud`` that
+keeps the file's own scalar types for the upload (a voxelised PLY with float / ushort
+coordinates, uchar colours and float normals is 21 bytes per point instead of the 72 of
+three float64 rows: the evaluation from host arrays is bound by PCIe, bench.py
+``e2e.compact_inputs``) and converts to float64 only when a getter asks.  Every widening the
+library then does on the device (uint16 / int32 / float32 -> float64, uchar -> k / 255.0) is
+exact, so the metrics are those of the float64 copy.
 """
 from __future__ import annotations
 
@@ -19,7 +25,57 @@ _PLY_TYPES = {
 }
 
 
-def _read_ply(path: str) -> PointCloud:
+_UPLOAD_DTYPES = ("f8", "f4", "i4", "u2")      # what pccm_cloud_create takes for coordinates (include/pccm.h; uchar coordinates are widened here)
+
+
+class FileCloud:
+    """A cloud as its file holds it.  ``raw_points`` / ``raw_colors`` / ``raw_normals`` are what ``CloudPair`` uploads
+    ((N, 3) arrays in the file's scalar types; uchar colours stay 0..255); ``points`` / ``colors`` / ``normals`` are the
+    float64 arrays Open3D would hold (colours in [0, 1]), made on first use."""
+
+    def __init__(self, raw_points, raw_colors=None, raw_normals=None):
+        self.raw_points = raw_points
+        self.raw_colors = raw_colors
+        self.raw_normals = raw_normals
+        self._f64 = {}
+
+    def _view(self, name, raw, scale=None):
+        if raw is None:
+            return None
+        if name not in self._f64:
+            a = np.asarray(raw, dtype=np.float64)
+            self._f64[name] = a / scale if scale else a
+        return self._f64[name]
+
+    @property
+    def points(self):
+        return self._view("points", self.raw_points)
+
+    @property
+    def colors(self):
+        c = self.raw_colors
+        return self._view("colors", c, 255.0 if c is not None and c.dtype == np.uint8 else None)
+
+    @property
+    def normals(self):
+        return self._view("normals", self.raw_normals)
+
+    @normals.setter
+    def normals(self, v):                       # (CloudPair writes estimated normals back into the caller's cloud)
+        self.raw_normals = None if v is None else np.asarray(v, dtype=np.float64)
+        self._f64.pop("normals", None)
+
+    def __len__(self):
+        return len(self.raw_points)
+
+    def has_colors(self):
+        return self.raw_colors is not None and len(self.raw_colors) == len(self.raw_points) > 0
+
+    def has_normals(self):
+        return self.raw_normals is not None and len(self.raw_normals) == len(self.raw_points) > 0
+
+
+def _read_ply(path: str, native: bool = False):
     with open(path, "rb") as f:
         if f.readline().strip() != b"ply":
             raise ValueError(f"{path}: not a PLY file")
@@ -54,6 +110,7 @@ def _read_ply(path: str) -> PointCloud:
             if any(p[1] == "list" for p in props):
                 raise ValueError(f"{path}: list property inside vertex element")
             names = [p[0] for p in props]
+            ftype = {p[0]: _PLY_TYPES[p[1]] for p in props}           # scalar type of every property, as declared
             if fmt == "ascii":
                 data = np.loadtxt(f, dtype=np.float64, max_rows=count, ndmin=2) if count else np.zeros((0, len(names)))
                 vertex = {n: data[:, i] for i, n in enumerate(names)}
@@ -70,6 +127,21 @@ def _read_ply(path: str) -> PointCloud:
     def cols(keys):
         return np.stack([np.asarray(vertex[k], dtype=np.float64) for k in keys], axis=1)
 
+    if native:
+        def raw(keys, allowed):
+            # one array in the file's scalar type when the three properties share one the library uploads; text files
+            # only keep INTEGER types (a decimal fraction is the float64 the default reader parses, not its float32)
+            t = {ftype[k] for k in keys}
+            dt = t.pop() if len(t) == 1 else None
+            if dt in allowed and (fmt != "ascii" or dt[0] in "iu"):
+                return np.stack([np.asarray(vertex[k]).astype(dt, copy=False) for k in keys], axis=1)
+            return cols(keys)
+        fc = FileCloud(raw(("x", "y", "z"), _UPLOAD_DTYPES))
+        if all(k in vertex for k in ("red", "green", "blue")):
+            fc.raw_colors = raw(("red", "green", "blue"), ("u1", "f8"))
+        if all(k in vertex for k in ("nx", "ny", "nz")):
+            fc.raw_normals = raw(("nx", "ny", "nz"), ("f4", "f8"))
+        return fc
     pc = PointCloud(cols(("x", "y", "z")))
     if all(k in vertex for k in ("red", "green", "blue")):
         c = cols(("red", "green", "blue"))
@@ -90,10 +162,11 @@ def _read_xyz(path: str) -> PointCloud:
     return pc
 
 
-def read_point_cloud(path: str) -> PointCloud:
+def read_point_cloud(path: str, native: bool = False):
+    """native=True (PLY): a FileCloud in the file's scalar types instead of a float64 PointCloud (see the module text)."""
     low = path.lower()
     if low.endswith(".ply"):
-        return _read_ply(path)
+        return _read_ply(path, native)
     if low.endswith((".xyz", ".txt", ".xyzrgb")):
         return _read_xyz(path)
     raise ValueError(f"unsupported point cloud format: {path}")

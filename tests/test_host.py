@@ -282,3 +282,69 @@ def test_reference_arm_bounded_sample_scales_to_the_pair():
     assert samp["queries"] == full["queries"] == len(A) + len(B)
     assert samp["seconds"] > samp["build_seconds"] == pre[1]
     assert 0.2 < samp["seconds"] / full["seconds"] < 5.0
+
+
+def _write_typed_ply(path, fields, rec, fmt):
+    names = {"f4": "float", "f8": "double", "u1": "uchar", "u2": "ushort", "i4": "int"}
+    header = ["ply", f"format {fmt} 1.0", "comment typed test file", f"element vertex {len(rec)}"]
+    header += [f"property {names[t]} {k}" for k, t in fields]
+    header.append("end_header")
+    with open(path, "wb") as f:
+        f.write(("\n".join(header) + "\n").encode("ascii"))
+        if fmt == "ascii":
+            for r in rec:
+                f.write((" ".join(repr(v.item()) for v in r) + "\n").encode("ascii"))
+        else:
+            end = "<" if fmt == "binary_little_endian" else ">"
+            f.write(rec.astype(np.dtype([(k, end + t) for k, t in fields])).tobytes())
+
+
+@pytest.mark.parametrize("fmt", ["binary_little_endian", "binary_big_endian", "ascii"])
+@pytest.mark.parametrize("xyz_t", ["f4", "u2", "i4", "f8"])
+def test_native_reader_keeps_file_types_and_the_float64_view(tmp_path, fmt, xyz_t):
+    """read_point_cloud(native=True): the arrays CloudPair uploads keep the file's scalar types (a third of the bytes of
+    the float64 copy on a voxelised PLY), the getters give exactly the float64 arrays of the default reader."""
+    from open_pcc_metric_b200.cloud_pair import _upload
+    from open_pcc_metric_b200.io import FileCloud
+    rng = np.random.default_rng(17)
+    n = 40
+    fields = [(k, xyz_t) for k in "xyz"] + [(k, "u1") for k in ("red", "green", "blue")] + [(k, "f4") for k in ("nx", "ny", "nz")]
+    rec = np.zeros(n, dtype=np.dtype([(k, t) for k, t in fields]))
+    for k in "xyz":
+        rec[k] = rng.integers(0, 1024, n) if xyz_t != "f4" and xyz_t != "f8" else rng.random(n).astype(xyz_t) * 100
+    for k in ("red", "green", "blue"):
+        rec[k] = rng.integers(0, 256, n)
+    for k in ("nx", "ny", "nz"):
+        rec[k] = rng.normal(0, 1, n).astype("f4")
+    path = str(tmp_path / "typed.ply")
+    _write_typed_ply(path, fields, rec, fmt)
+    ref = read_point_cloud(path)
+    got = read_point_cloud(path, native=True)
+    assert isinstance(got, FileCloud) and len(got) == n and got.has_colors() and got.has_normals()
+    text = fmt == "ascii"
+    assert got.raw_points.dtype == np.dtype("f8" if text and xyz_t == "f4" else xyz_t)   # text keeps integer types only
+    assert got.raw_colors.dtype == np.uint8
+    assert got.raw_normals.dtype == np.dtype("f8" if text else "f4")
+    assert got.raw_points.shape == got.raw_colors.shape == got.raw_normals.shape == (n, 3)
+    assert got.raw_points.flags.c_contiguous and got.raw_points.dtype.isnative
+    for name in ("points", "colors", "normals"):
+        assert np.array_equal(getattr(got, name), np.asarray(getattr(ref, name))), name
+        assert getattr(got, name).dtype == np.float64
+        assert _upload(got, name) is getattr(got, "raw_" + name)
+        assert _upload(ref, name) is getattr(ref, name)
+    est = rng.normal(0, 1, (n, 3))
+    got.normals = est                                    # what CloudPair does with estimated normals
+    assert np.array_equal(got.normals, est) and _upload(got, "normals").dtype == np.float64
+
+
+def test_native_reader_falls_back_to_float64_on_mixed_types(tmp_path):
+    fields = [("x", "f4"), ("y", "f8"), ("z", "f4"), ("red", "f4"), ("green", "f4"), ("blue", "f4")]
+    rec = np.zeros(5, dtype=np.dtype(fields))
+    for k, _ in fields:
+        rec[k] = np.arange(5) / 8.0
+    path = str(tmp_path / "mixed.ply")
+    _write_typed_ply(path, fields, rec, "binary_little_endian")
+    got = read_point_cloud(path, native=True)
+    assert got.raw_points.dtype == np.float64 and got.raw_colors.dtype == np.float64 and got.raw_normals is None
+    assert got.normals is None and not got.has_normals()
+    assert np.array_equal(got.colors, np.asarray(read_point_cloud(path).colors))     # float colours are kept as they are
