@@ -1245,6 +1245,8 @@ struct VxEpiSrc {            // one staged array of a direction
 // time.  The cost of a tile this rank owns nothing of is one coalesced read of its ranks and a block scan, not a trip
 // through the epilogue with most lanes idle (measured on the 10 M pair split 8 ways: 204 -> 137 us per rank).
 constexpr uint32_t kVxEpiQueue = 2 * kVxEpiTile;   // left-over entries (fewer than a block) + one tile; a power of two (ring)
+static_assert((kVxEpiQueue & (kVxEpiQueue - 1u)) == 0u && kVxEpiQueue >= (uint32_t)kVxEpiThreads + (uint32_t)kVxEpiTile,
+              "the epilogue's queue is a ring addressed by a mask");
 template <bool STAGED, bool COMPACT>
 __global__ void __launch_bounds__(kVxEpiThreads, PCCM_EPI_MINBLOCKS)
 vx_epilogue_kernel(const __grid_constant__ VxParams P) {
