@@ -35,6 +35,7 @@ def cli(ocloud, pcloud, color, hausdorff, point_to_plane, csv, device, peak, bit
 
     ctx = N.Context(device)
     ctx.set_profiling(2 if timings else 0)
+    # (pageable arrays: for ONE pair page-locking costs more than the staged copy it saves -- profiles/README.md)
     clouds = [read_point_cloud(p, native=native_dtypes) for p in (ocloud, pcloud)]
     pair = CloudPair(clouds[0], clouds[1], ctx=ctx, peak=peak, resolution_bits=bits, normals_mode=normals_mode)
     metrics = transform_options(CalculateOptions(color=color, hausdorff=hausdorff, point_to_plane=point_to_plane))

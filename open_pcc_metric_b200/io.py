@@ -75,7 +75,20 @@ class FileCloud:
         return self.raw_normals is not None and len(self.raw_normals) == len(self.raw_points) > 0
 
 
-def _read_ply(path: str, native: bool = False):
+def _pinned_like(shape, dtype):
+    """A page-locked (N, 3) host array when torch + CUDA are there (uploads from it are truly asynchronous: CloudPair only
+    enqueues), else an ordinary one."""
+    try:
+        import torch
+        tdt = {"f8": torch.float64, "f4": torch.float32, "i4": torch.int32, "u2": getattr(torch, "uint16", None), "u1": torch.uint8}[np.dtype(dtype).str[1:]]
+        if tdt is not None and torch.cuda.is_available():
+            return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+    except Exception:
+        pass
+    return np.empty(shape, dtype=dtype)
+
+
+def _read_ply(path: str, native: bool = False, pinned: bool = False):
     with open(path, "rb") as f:
         if f.readline().strip() != b"ply":
             raise ValueError(f"{path}: not a PLY file")
@@ -133,9 +146,12 @@ def _read_ply(path: str, native: bool = False):
             # only keep INTEGER types (a decimal fraction is the float64 the default reader parses, not its float32)
             t = {ftype[k] for k in keys}
             dt = t.pop() if len(t) == 1 else None
-            if dt in allowed and (fmt != "ascii" or dt[0] in "iu"):
-                return np.stack([np.asarray(vertex[k]).astype(dt, copy=False) for k in keys], axis=1)
-            return cols(keys)
+            if not (dt in allowed and (fmt != "ascii" or dt[0] in "iu")):
+                dt = "f8"
+            out = _pinned_like((len(vertex[keys[0]]), 3), dt) if pinned else np.empty((len(vertex[keys[0]]), 3), dtype=dt)
+            for j, k in enumerate(keys):                  # (interleaves the file's columns straight into the upload array)
+                out[:, j] = vertex[k]
+            return out
         fc = FileCloud(raw(("x", "y", "z"), _UPLOAD_DTYPES))
         if all(k in vertex for k in ("red", "green", "blue")):
             fc.raw_colors = raw(("red", "green", "blue"), ("u1", "f8"))
@@ -162,11 +178,12 @@ def _read_xyz(path: str) -> PointCloud:
     return pc
 
 
-def read_point_cloud(path: str, native: bool = False):
-    """native=True (PLY): a FileCloud in the file's scalar types instead of a float64 PointCloud (see the module text)."""
+def read_point_cloud(path: str, native: bool = False, pinned: bool = False):
+    """native=True (PLY): a FileCloud in the file's scalar types instead of a float64 PointCloud (see the module text);
+    pinned=True: its arrays are page-locked when a CUDA device is there."""
     low = path.lower()
     if low.endswith(".ply"):
-        return _read_ply(path, native)
+        return _read_ply(path, native, pinned)
     if low.endswith((".xyz", ".txt", ".xyzrgb")):
         return _read_xyz(path)
     raise ValueError(f"unsupported point cloud format: {path}")

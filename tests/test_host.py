@@ -319,7 +319,7 @@ def test_native_reader_keeps_file_types_and_the_float64_view(tmp_path, fmt, xyz_
     path = str(tmp_path / "typed.ply")
     _write_typed_ply(path, fields, rec, fmt)
     ref = read_point_cloud(path)
-    got = read_point_cloud(path, native=True)
+    got = read_point_cloud(path, native=True, pinned=(xyz_t == "u2"))    # (page-locked where CUDA is there, ordinary arrays here)
     assert isinstance(got, FileCloud) and len(got) == n and got.has_colors() and got.has_normals()
     text = fmt == "ascii"
     assert got.raw_points.dtype == np.dtype("f8" if text and xyz_t == "f4" else xyz_t)   # text keeps integer types only
